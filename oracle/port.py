@@ -1,7 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY: the unmodified reference (oracle/_ref/libkaori_ref.so).
+"""TEST INFRASTRUCTURE ONLY: the plain-C restatement (oracle/liboracle.so).
 
-Ground truth for the parity tests and for bench.py's cpu_baseline leg; see
-oracle/ref_harness.cpp.  Never imported by screencounter_b200/.
+See oracle/kaori_port.c.  Never imported by screencounter_b200/.
 """
 import os
 import sys
@@ -9,8 +8,7 @@ import sys
 from ._binding import OracleBinding, KaoriError, DUP_FIRST, DUP_LAST, DUP_NONE, DUP_ERROR  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_B = OracleBinding(os.path.join(_HERE, "_ref", "libkaori_ref.so"), "kref_",
-                   "run `make -C oracle ref` where /root/reference exists")
+_B = OracleBinding(os.path.join(_HERE, "liboracle.so"), "kport_", "run `make -C oracle liboracle.so`")
 
 available = _B.available
 for _name in dir(_B):

@@ -462,9 +462,11 @@ int kref_count_dual(const char* path1, const char* data1, size_t size1, const ch
 }
 
 // Per-pair outcome of DualBarcodesPairedEnd::process (handlers/DualBarcodesPairedEnd.hpp:353-381).
-// fresh_state != 0: the search cache is emptied before every pair, i.e. the
-// cache-free semantics ("Quirk C").  fresh_state == 0: one state
-// re-used for the whole file, which is what num.threads = 1 gives an R user.
+// fresh_state != 0: the search cache is emptied before every pair, so a pair's outcome
+// no longer depends on the pairs before it ("Quirk C"); the cache still
+// acts WITHIN a pair (the same variable strings at two hit positions with different
+// caps), which kaori_port.c reproduces in its CACHE_PER_PAIR mode.  fresh_state == 0:
+// one state re-used for the whole file, which is what num.threads = 1 gives an R user.
 int kref_trace_dual(const char* path1, const char* data1, size_t size1, const char* tmpl1, int reverse1, int mismatches1,
                     const char* const* pool1, int npool1,
                     const char* path2, const char* data2, size_t size2, const char* tmpl2, int reverse2, int mismatches2,
