@@ -1,0 +1,186 @@
+/*
+ * scg.h -- C ABI of the B200-native barcode-counting engine.
+ *
+ * Drop-in boundary for the hot path of crisprVerse/screenCounter (FASTQ reads ->
+ * template scan -> barcode lookup -> counts).  Each scg_count_* / scg_match_barcodes
+ * entry point replaces one Rcpp-exported function of the reference; argument order and
+ * meaning follow the reference (R/RcppExports.R:4-30, src/RcppExports.cpp:13-150), with
+ * R containers flattened to plain pointers and sizes.  The reference-side binding a
+ * maintainer adds (the Rcpp shim) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message (kaori's own
+ *     wording where the reference has one) is read with scg_last_error().  No C++
+ *     exception crosses this boundary.
+ *   - a FASTQ input is an scg_source: a file path (raw or gzip, sniffed from the magic
+ *     bytes like byteme::SomeFileReader, inst/include/byteme/SomeFileReader.hpp:25-66)
+ *     or a host memory buffer holding FASTQ text (like byteme::RawBufferReader).
+ *   - fixed-size outputs (count vectors, totals) are caller-owned; variable-size outputs
+ *     (combination tables, random-barcode tables, per-read traces) come back as an
+ *     scg_result handle that the caller reads with scg_result_* and frees.
+ *   - `nthreads` is the reference's num.threads; here it sizes the host FASTQ packer.
+ *   - CUDA is initialised lazily by the first call that needs the device (fork safety
+ *     under BiocParallel::MulticoreParam), never at library load.
+ *   - there is no CPU fallback: without a usable CUDA device every counting call fails.
+ */
+#ifndef SCG_H
+#define SCG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scg_ctx scg_ctx;
+typedef struct scg_result scg_result;
+typedef struct scg_reads scg_reads;   /* packed reads resident in device memory */
+typedef struct scg_plan scg_plan;     /* a compiled handler: template + libraries on the device */
+
+/* FASTQ input: path != NULL -> file (raw or .gz); else `data`/`size` hold FASTQ text. */
+typedef struct {
+    const char* path;
+    const char* data;
+    size_t size;
+} scg_source;
+
+/* strand codes: src/utils.cpp:33-41 (to_strand(int)) */
+enum { SCG_STRAND_ORIGINAL = 0, SCG_STRAND_REVERSE = 1, SCG_STRAND_BOTH = 2 };
+
+/* ---- context ------------------------------------------------------------------------ */
+int scg_ctx_create(scg_ctx** out, int device);       /* device = CUDA ordinal; lazy init */
+void scg_ctx_destroy(scg_ctx* ctx);
+const char* scg_last_error(const scg_ctx* ctx);       /* ctx may be NULL for creation errors */
+const char* scg_version(void);
+/* JSON with the stage timings of the most recent counting call on this context:
+ * parse_s, pack_s, h2d_s, device_s, reads, bytes_h2d, kernel launches. */
+const char* scg_timing_json(const scg_ctx* ctx);
+/* number of kernels this library has launched on behalf of the context so far */
+long long scg_kernel_launches(const scg_ctx* ctx);
+
+/* ---- results ------------------------------------------------------------------------ */
+size_t scg_result_rows(const scg_result* r);          /* table rows (combinations / barcodes) */
+int scg_result_width(const scg_result* r);            /* ints per key row, or chars per barcode */
+size_t scg_result_reads(const scg_result* r);         /* reads (pairs) in the per-read trace */
+/* Any pointer may be NULL.  keys: rows*width int32 (0-based pool indices, sorted ascending,
+ * one combination per row = one column of the reference's IntegerMatrix, src/utils.h:28-34);
+ * strings: rows*width chars, no terminators, sorted A<C<G<N<T (R/countRandomBarcodes.R:73);
+ * freq: rows int32. */
+int scg_result_copy_table(const scg_result* r, int32_t* keys, char* strings, int32_t* freq);
+/* Per-read trace (only filled when the call was made with want_trace != 0):
+ * index: reads*trace_width int32, -1 = no match; info: reads uint32,
+ * bit 31 found, bit 30 reverse strand, bits 20-24 mismatches, bits 25-29 variable mismatches,
+ * bits 0-19 position (meaningful for the single-barcode design only). */
+int scg_result_trace_width(const scg_result* r);
+int scg_result_copy_trace(const scg_result* r, int32_t* index, uint32_t* info);
+void scg_result_free(scg_result* r);
+
+/* ---- the seven entry points of the reference ---------------------------------------- */
+
+/* replaces count_single_barcodes, src/count_single_barcodes.cpp:29-50.
+ * counts: npool int32; total: reads seen.  trace (nullable out) receives per-read outcomes. */
+int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand,
+                     const char* const* pool, int npool, int mismatches, int use_first, int nthreads,
+                     int32_t* counts, int32_t* total, scg_result** trace);
+
+/* replaces count_random_barcodes, src/count_random_barcodes.cpp:41-60.
+ * table: distinct barcodes (strings) + frequencies. */
+int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, int strand,
+                     int mismatches, int use_first, int nthreads,
+                     scg_result** table, int32_t* total);
+
+/* replaces count_combo_barcodes_single, src/count_combo_barcodes_single.cpp:40-70 (two pools). */
+int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand,
+                           const char* const* pool1, int npool1, const char* const* pool2, int npool2,
+                           int mismatches, int use_first, int nthreads, int want_trace,
+                           scg_result** table, int32_t* total);
+
+/* replaces count_dual_barcodes_single_end, src/count_dual_barcodes_single_end.cpp:51-88.
+ * pools_flat: npools*nchoices strings, pool-major.  With diagnostics != 0, *table receives the
+ * invalid combinations (two pools only, as in the reference glue). */
+int scg_count_dual_single_end(scg_ctx* ctx, const scg_source* src, const char* constant,
+                              const char* const* pools_flat, int npools, int nchoices, int strand,
+                              int mismatches, int use_first, int diagnostics, int nthreads, int want_trace,
+                              int32_t* counts, int32_t* total, scg_result** table);
+
+/* replaces count_dual_barcodes, src/count_dual_barcodes.cpp:75-116. */
+int scg_count_dual(scg_ctx* ctx,
+                   const scg_source* src1, const char* constant1, int reverse1, int mismatches1,
+                   const char* const* pool1, int npool1,
+                   const scg_source* src2, const char* constant2, int reverse2, int mismatches2,
+                   const char* const* pool2, int npool2,
+                   int randomized, int use_first, int diagnostics, int nthreads, int want_trace,
+                   int32_t* counts, int32_t* total, scg_result** table, int32_t* barcode1_only, int32_t* barcode2_only);
+
+/* replaces count_combo_barcodes_paired, src/count_combo_barcodes_paired.cpp:55-95. */
+int scg_count_combo_paired(scg_ctx* ctx,
+                           const scg_source* src1, const char* constant1, int reverse1, int mismatches1,
+                           const char* const* pool1, int npool1,
+                           const scg_source* src2, const char* constant2, int reverse2, int mismatches2,
+                           const char* const* pool2, int npool2,
+                           int randomized, int use_first, int nthreads, int want_trace,
+                           scg_result** table, int32_t* total, int32_t* barcode1_only, int32_t* barcode2_only);
+
+/* replaces match_barcodes, src/match_barcodes.cpp:7-37.  index is 0-based with -1 where the
+ * reference returns NA_INTEGER (the shim adds 1); mismatches is -1 for NA. */
+int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequences,
+                       const char* const* choices, int nchoices, int substitutions, int reverse,
+                       int32_t* index, int32_t* mismatches);
+
+/* ---- resident objects (for callers that keep reads / libraries on the device) ---------- */
+
+/* Parse + pack a FASTQ into device memory (tile-planar 2-bit bases + N mask). */
+int scg_reads_from_source(scg_ctx* ctx, const scg_source* src, int nthreads, scg_reads** out);
+long long scg_reads_count(const scg_reads* r);
+long long scg_reads_device_bytes(const scg_reads* r);
+void scg_reads_free(scg_reads* r);
+
+/* Synthetic workload of BASELINE.json / SURVEY.md 8(d): counter-based generator, identical on
+ * the host (FASTQ text) and on the device (packed reads), any shard reproducible from
+ * (seed, first_read). */
+typedef struct {
+    uint64_t seed;
+    long long first_read;      /* global index of this shard's first read */
+    long long n_reads;
+    int read_len;              /* 75 */
+    const char* constant;      /* template with '-' runs, e.g. 12 + 20 + 12 */
+    int n_pools;               /* variable regions filled from pools (<= 2); 0 = random barcodes */
+    const char* const* pools[2];
+    int n_choices[2];
+    int paired_rows;           /* != 0: one row index picks (pools[0][i], pools[1][i]) */
+    int strand;                /* SCG_STRAND_*: BOTH = half the constructs reverse-complemented */
+    int construct_permille;    /* reads carrying a construct, e.g. 900 */
+    int sub_per_10k;           /* per-base substitution rate inside the construct, e.g. 100 = 1 % */
+    int n_per_10k;             /* per-base N rate anywhere, e.g. 10 = 0.1 % */
+    long long random_space;    /* n_pools == 0: number of distinct "true" random barcodes */
+} scg_synth_spec;
+
+int scg_reads_synthesize(scg_ctx* ctx, const scg_synth_spec* spec, scg_reads** out);
+/* FASTQ text of the same reads on the host.  Returns bytes needed in *used (call with out=NULL to size). */
+int scg_synth_fastq(const scg_synth_spec* spec, char* out, size_t capacity, size_t* used);
+
+/* Compiled single-barcode handler (template + library resident on the device). */
+int scg_single_plan_create(scg_ctx* ctx, const char* constant, int strand,
+                           const char* const* pool, int npool, int mismatches, int use_first,
+                           scg_plan** out);
+/* One pass of the hot path over resident reads.  d_counts (device, npool int32) is ACCUMULATED
+ * into; d_index (device, nullable) receives the per-read pool index.  Runs on `cuda_stream`
+ * (a cudaStream_t; NULL = the context's own stream) and does not synchronise. */
+int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_counts, int32_t* d_index,
+                        void* cuda_stream);
+void scg_plan_free(scg_plan* plan);
+
+/* Plain device-memory helpers so that a caller without a CUDA runtime of its own (R, ctypes)
+ * can own buffers for scg_single_plan_run. */
+int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out);   /* zero-initialised */
+int scg_device_free(scg_ctx* ctx, void* ptr);
+int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream);
+int scg_device_to_host(scg_ctx* ctx, void* host, const void* dev, size_t bytes);
+int scg_synchronize(scg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SCG_H */

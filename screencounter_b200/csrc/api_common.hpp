@@ -1,0 +1,143 @@
+// Glue shared by the C-ABI translation units: exception -> status code, pool marshalling,
+// template-instantiation dispatch.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../include/scg.h"
+#include "engine.hpp"
+#include "pipeline.hpp"
+
+namespace scg {
+
+std::string& creation_error();   // message of a failed scg_ctx_create
+
+// Runs f(); any exception becomes status 1 + ctx->last_error (BEGIN_RCPP/END_RCPP equivalent,
+// reference src/RcppExports.cpp:16,33).
+template <class F>
+int guarded(scg_ctx* ctx, F&& f) {
+    try {
+        if (!ctx) throw Error("null context");
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        if (ctx) {
+            ctx->impl.last_error = e.what();
+        } else {
+            creation_error() = e.what();
+        }
+        return 1;
+    } catch (...) {
+        if (ctx) ctx->impl.last_error = "unknown error";
+        return 1;
+    }
+}
+
+// format_pointers (reference src/utils.cpp:5-23): every sequence of a pool has the same length.
+struct Pool {
+    std::vector<std::string> seqs;
+    int length = 0;
+    Pool() {}
+    Pool(const char* const* p, int n);
+    std::vector<std::string> reverse_complemented() const;
+};
+
+// Owns one FASTQ input.
+struct Source {
+    std::unique_ptr<FastqReader> reader;
+    explicit Source(const scg_source* s);
+};
+
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+
+// Counter planes compiled: 0 (no mismatch allowed), 1 (<= 1), 2 (<= 3), 9 (anything up to 256).
+template <class F>
+void dispatch_cb(int cbits, F&& f) {
+    if (cbits <= 0) {
+        f(IntC<0>());
+    } else if (cbits == 1) {
+        f(IntC<1>());
+    } else if (cbits == 2) {
+        f(IntC<2>());
+    } else {
+        f(IntC<9>());
+    }
+}
+
+// Key words per plane compiled: 1 (<= 32 bases), 2 (<= 64), 8 (<= 256), 16 (<= 512).
+template <class F>
+void dispatch_kw(int kw, F&& f) {
+    if (kw <= 1) {
+        f(IntC<1>());
+    } else if (kw == 2) {
+        f(IntC<2>());
+    } else if (kw <= 8) {
+        f(IntC<8>());
+    } else {
+        f(IntC<16>());
+    }
+}
+
+// Device scratch for per-read outputs of one batch, copied back after each batch when tracing.
+struct TraceSink {
+    bool enabled = false;
+    int width = 1;
+    DeviceBuffer d_index, d_info;
+    std::vector<int32_t> index;
+    std::vector<uint32_t> info;
+    void prepare(long long n, bool want_info);
+    void collect(Context& ctx, long long n, bool want_info);
+};
+
+// A single-barcode matcher (template + forward/reverse libraries) resident on the device.
+struct SingleMatcher {
+    TemplateSpec tmpl;
+    DeviceLibrary lib_f, lib_r;
+    SingleParams params;
+    int npool = 0;
+    // SimpleSingleMatch constructor (reference inst/include/kaori/SimpleSingleMatch.hpp:61-97): host-only, throws
+    // the reference's validation errors; upload() then moves the tables to the device.
+    void prepare(const std::string& constant, int strand, const Pool& pool, int mismatches, bool use_first, Duplicates dup);
+    void upload(Context& ctx);
+};
+
+void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, int32_t* d_counts, int32_t* d_index,
+                   uint32_t* d_info, cudaStream_t stream);
+
+// Device count table (64- or 128-bit keys) that grows with the number of reads seen.
+struct CountTable {
+    bool wide = false;
+    DeviceBuffer keys, counts;
+    size_t capacity = 0;
+    void init(Context& ctx, bool wide128, size_t initial);
+    void ensure(Context& ctx, long long upcoming_inserts);   // keeps load factor <= 1/2
+    CountTable64 view64() const;
+    CountTable128 view128() const;
+    // live entries to the host
+    void download(Context& ctx, std::vector<unsigned long long>& keys_lo, std::vector<unsigned long long>& keys_hi,
+                  std::vector<uint32_t>& counts);
+    long long upper_bound = 0;
+};
+
+// Tally of (i, j) combinations: dense matrix when small, count table otherwise.
+struct ComboTally {
+    int n1 = 0, n2 = 0;
+    bool dense = false;
+    DeviceBuffer matrix;
+    CountTable table;
+    void init(Context& ctx, int n1, int n2);
+    ComboSink sink(Context& ctx, long long upcoming);
+    void harvest(Context& ctx, scg_result& out);   // sorted (i, j) rows + freq (reference src/utils.h:14-45)
+};
+
+} // namespace scg
+
+struct scg_plan {
+    scg_ctx* owner = nullptr;
+    int npool = 0;
+    scg::SingleMatcher matcher;
+};

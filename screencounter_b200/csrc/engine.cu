@@ -1,0 +1,265 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "pipeline.hpp"
+
+namespace scg {
+
+namespace {
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------
+void DeviceBuffer::alloc(size_t n, bool zero) {
+    release();
+    if (n == 0) n = 16;
+    SCG_CUDA_CHECK(cudaMalloc(&ptr, n));
+    bytes = n;
+    if (zero) SCG_CUDA_CHECK(cudaMemset(ptr, 0, n));
+}
+
+void DeviceBuffer::reserve(size_t n) {
+    if (n > bytes) alloc(n, false);
+}
+
+void DeviceBuffer::upload(const void* host, size_t n, cudaStream_t stream) {
+    reserve(std::max<size_t>(n, 16));
+    if (n) SCG_CUDA_CHECK(cudaMemcpyAsync(ptr, host, n, cudaMemcpyHostToDevice, stream));
+}
+
+void DeviceBuffer::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+}
+
+PinnedBuffer::~PinnedBuffer() {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+void PinnedBuffer::reserve(size_t n) {
+    if (n <= bytes) return;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    SCG_CUDA_CHECK(cudaMallocHost(&ptr, n));
+    bytes = n;
+}
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+Context::~Context() {
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Context::ensure_ready() {
+    if (ready) {
+        SCG_CUDA_CHECK(cudaSetDevice(device));
+        return;
+    }
+    int count = 0;
+    cudaError_t st = cudaGetDeviceCount(&count);
+    if (st != cudaSuccess || count == 0) {
+        throw Error(std::string("no usable CUDA device: this engine has no CPU fallback (") +
+                    (st != cudaSuccess ? cudaGetErrorString(st) : "device count is 0") + ")");
+    }
+    if (device < 0 || device >= count) {
+        throw Error("CUDA device " + std::to_string(device) + " does not exist (" + std::to_string(count) + " visible)");
+    }
+    SCG_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SCG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        throw Error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; this library carries sm_100a code only");
+    }
+    sm_count = prop.multiProcessorCount;
+    SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    ready = true;
+}
+
+int Context::grid_for(long long ntiles) const {
+    // persistent warps: 4 warps per block, up to 16 blocks per SM resident; never more blocks than work
+    long long blocks = (ntiles + 3) / 4;
+    long long cap = (long long)sm_count * 16;
+    return (int)std::max<long long>(1, std::min(blocks, cap));
+}
+
+void Context::finish_timing() {
+    char buf[512];
+    std::snprintf(buf, sizeof buf,
+                  "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"total_s\": %.6f, "
+                  "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld}",
+                  timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.total_s, timing.reads, timing.bytes_h2d,
+                  timing.launches);
+    timing_json = buf;
+}
+
+// ---------------------------------------------------------------------------------------
+// library upload
+// ---------------------------------------------------------------------------------------
+void DeviceLibrary::upload(Context& ctx) {
+    cudaStream_t st = ctx.stream;
+    slots.upload(host.slots.data(), host.slots.size() * sizeof(uint32_t), st);
+    ent_keys.upload(host.ent_keys.data(), host.ent_keys.size() * sizeof(uint32_t), st);
+    ent_idx.upload(host.ent_idx.data(), host.ent_idx.size() * sizeof(int32_t), st);
+    seed_masks.upload(host.seed_masks.data(), host.seed_masks.size() * sizeof(uint32_t), st);
+    buckets.upload(host.buckets.data(), host.buckets.size() * sizeof(uint2), st);
+    cands.upload(host.cands.data(), host.cands.size() * sizeof(int32_t), st);
+    prefix_slots.upload(host.prefix_slots.data(), host.prefix_slots.size() * sizeof(uint32_t), st);
+    SCG_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::memset(&dev, 0, sizeof dev);
+    dev.L = host.L;
+    dev.KW = host.KW;
+    dev.nentries = (int)host.nentries();
+    dev.dup_first = host.opt.duplicates == Duplicates::FIRST;
+    dev.slots = slots.as<uint32_t>();
+    dev.slot_words = host.slot_words;
+    dev.slot_mask = (uint32_t)(host.slots.size() / host.slot_words) - 1;
+    dev.ent_keys = ent_keys.as<uint32_t>();
+    dev.ent_idx = ent_idx.as<int32_t>();
+    dev.nseeds = host.nseeds;
+    dev.seed_masks = seed_masks.as<uint32_t>();
+    dev.buckets = buckets.as<uint2>();
+    dev.bucket_mask = host.nbuckets ? host.nbuckets - 1 : 0;
+    dev.cands = cands.as<int32_t>();
+    dev.seg1 = host.opt.segmented ? host.opt.seg1 : 0;
+    dev.prefix_slots = prefix_slots.as<uint32_t>();
+    dev.prefix_mask = host.prefix_slots.empty() ? 0 : (uint32_t)(host.prefix_slots.size() / host.slot_words) - 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// FASTQ -> pinned -> device pipeline
+// ---------------------------------------------------------------------------------------
+ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int nthreads, bool want_odd)
+    : ctx_(ctx), r1_(r1), r2_(r2), nthreads_(std::max(1, nthreads)), want_odd_(want_odd) {
+    for (int k = 0; k < kSlots; ++k) {
+        SCG_CUDA_CHECK(cudaEventCreateWithFlags(&slots_[k].done, cudaEventDisableTiming));
+    }
+}
+
+ReadPipeline::~ReadPipeline() {
+    for (int k = 0; k < kSlots; ++k) {
+        if (slots_[k].done) cudaEventDestroy(slots_[k].done);
+    }
+}
+
+void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count) {
+    Staged& s = slot.mate[mate];
+    uint32_t maxlen = 0, minlen = 0xFFFFFFFFu;
+    for (size_t i = 0; i < count; ++i) {
+        maxlen = std::max(maxlen, recs[i].len);
+        minlen = std::min(minlen, recs[i].len);
+    }
+    const int W = std::max(1, ceil_div((int)maxlen, 32));
+    const size_t padded = (count + TILE - 1) / TILE * TILE;
+    const size_t data_bytes = padded / TILE * tile_words(W) * sizeof(uint32_t);
+    const bool uniform = (minlen == maxlen);
+    s.pinned_data.reserve(data_bytes);
+    if (!uniform) s.pinned_lens.reserve(padded * sizeof(uint16_t));
+    if (want_odd_) {
+        s.odd_host.resize(padded);
+    }
+    double t0 = now_s();
+    pack_records(recs, count, W, s.pinned_data.as<uint32_t>(), uniform ? nullptr : s.pinned_lens.as<uint16_t>(),
+                 want_odd_ ? s.odd_host.data() : nullptr, nthreads_);
+    ctx_.timing.pack_s += now_s() - t0;
+
+    s.dev.data.reserve(data_bytes);
+    SCG_CUDA_CHECK(cudaMemcpyAsync(s.dev.data.ptr, s.pinned_data.ptr, data_bytes, cudaMemcpyHostToDevice, ctx_.stream));
+    ctx_.timing.bytes_h2d += (long long)data_bytes;
+    s.dev.view.data = s.dev.data.as<uint32_t>();
+    s.dev.view.W = W;
+    s.dev.view.n = (long long)count;
+    s.dev.view.uniform_len = (int)maxlen;
+    s.dev.view.lens = nullptr;
+    if (!uniform) {
+        s.dev.lens.reserve(padded * sizeof(uint16_t));
+        SCG_CUDA_CHECK(cudaMemcpyAsync(s.dev.lens.ptr, s.pinned_lens.ptr, padded * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx_.stream));
+        ctx_.timing.bytes_h2d += (long long)(padded * sizeof(uint16_t));
+        s.dev.view.lens = s.dev.lens.as<uint16_t>();
+    }
+    if (want_odd_) {
+        // pageable source: the copy is staged by the runtime before the call returns
+        s.dev.odd.reserve(padded);
+        SCG_CUDA_CHECK(cudaMemcpyAsync(s.dev.odd.ptr, s.odd_host.data(), padded, cudaMemcpyHostToDevice, ctx_.stream));
+        ctx_.timing.bytes_h2d += (long long)padded;
+    }
+}
+
+bool ReadPipeline::next(Batch& out) {
+    // refill the record windows
+    if (cur1_ >= n1_) {
+        const auto& b = r1_->next(kMaxBatchReads);
+        recs1_ = b.data();
+        n1_ = b.size();
+        cur1_ = 0;
+    }
+    if (r2_ && cur2_ >= n2_) {
+        const auto& b = r2_->next(kMaxBatchReads);
+        recs2_ = b.data();
+        n2_ = b.size();
+        cur2_ = 0;
+    }
+    size_t avail = n1_ - cur1_;
+    if (r2_) {
+        const size_t avail2 = n2_ - cur2_;
+        // process_data.hpp:284-285: both files must run out together
+        if ((avail == 0) != (avail2 == 0)) throw Error("different number of reads in paired FASTQ files");
+        avail = std::min(avail, avail2);
+    }
+    if (avail == 0) return false;
+
+    // bound the staging buffers: at most kMaxBatchBytes of packed data per mate
+    size_t count = avail;
+    {
+        uint32_t maxlen = 1;
+        const size_t probe = std::min<size_t>(avail, kMaxBatchReads);
+        for (size_t i = 0; i < probe; ++i) maxlen = std::max(maxlen, recs1_[cur1_ + i].len);
+        if (r2_) {
+            for (size_t i = 0; i < probe; ++i) maxlen = std::max(maxlen, recs2_[cur2_ + i].len);
+        }
+        const size_t per_read = (size_t)12 * ceil_div((int)maxlen, 32);
+        count = std::max<size_t>(TILE, std::min(probe, kMaxBatchBytes / per_read / TILE * TILE));
+        count = std::min(count, avail);
+    }
+
+    Slot& slot = slots_[next_slot_];
+    next_slot_ = (next_slot_ + 1) % kSlots;
+    if (slot.in_flight) {
+        double t0 = now_s();
+        SCG_CUDA_CHECK(cudaEventSynchronize(slot.done));  // the kernel that read this slot has finished
+        ctx_.timing.device_s += now_s() - t0;
+        slot.in_flight = false;
+    }
+    stage(slot, 0, recs1_ + cur1_, count);
+    if (r2_) stage(slot, 1, recs2_ + cur2_, count);
+    out.first_read = consumed_;
+    out.n = (long long)count;
+    out.reads1 = slot.mate[0].dev.view;
+    out.odd1 = want_odd_ ? slot.mate[0].dev.odd.as<uint8_t>() : nullptr;
+    out.recs1 = recs1_ + cur1_;
+    if (r2_) out.reads2 = slot.mate[1].dev.view;
+    out.slot = &slot;
+    cur1_ += count;
+    if (r2_) cur2_ += count;
+    consumed_ += (long long)count;
+    ctx_.timing.reads += (long long)count;
+    return true;
+}
+
+void ReadPipeline::submitted(Batch& b) {
+    Slot* slot = static_cast<Slot*>(b.slot);
+    SCG_CUDA_CHECK(cudaEventRecord(slot->done, ctx_.stream));
+    slot->in_flight = true;
+}
+
+} // namespace scg

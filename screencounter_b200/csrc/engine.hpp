@@ -1,0 +1,113 @@
+// Host-side runtime: context (device, stream, pinned staging), device images of libraries and
+// reads, and the FASTQ -> pinned -> HBM -> kernel pipeline.  This is what replaces the
+// reference's block driver and thread pool (inst/include/kaori/process_data.hpp:105-340).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "fastq.hpp"
+#include "handlers_params.hpp"
+#include "library.hpp"
+#include "template_spec.hpp"
+
+namespace scg {
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    DeviceBuffer() {}
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), bytes(o.bytes) { o.ptr = nullptr; o.bytes = 0; }
+    DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
+        if (this != &o) {
+            release();
+            ptr = o.ptr;
+            bytes = o.bytes;
+            o.ptr = nullptr;
+            o.bytes = 0;
+        }
+        return *this;
+    }
+    ~DeviceBuffer() { release(); }
+    void alloc(size_t n, bool zero);
+    void reserve(size_t n);  // grow-only, contents not preserved
+    void upload(const void* host, size_t n, cudaStream_t stream);
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct PinnedBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    ~PinnedBuffer();
+    void reserve(size_t n);
+    template <class T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct Timing {
+    double parse_s = 0, pack_s = 0, h2d_s = 0, device_s = 0, total_s = 0;
+    long long reads = 0, bytes_h2d = 0, launches = 0;
+};
+
+struct Context {
+    int device = 0;
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::string timing_json;
+    Timing timing;
+    long long launches = 0;
+
+    explicit Context(int dev) : device(dev) {}
+    ~Context();
+    void ensure_ready();   // lazy CUDA initialisation; throws when no usable device exists
+    int grid_for(long long ntiles) const;
+    void finish_timing();
+};
+
+// A library resident on the device.
+struct DeviceLibrary {
+    Library host;
+    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, prefix_slots;
+    LibDev dev;
+    void upload(Context& ctx);
+};
+
+// Packed reads of one batch resident on the device.
+struct DeviceBatch {
+    DeviceBuffer data, lens, odd;
+    ReadsDev view;
+};
+
+} // namespace scg
+
+// Opaque C-ABI types.
+struct scg_ctx {
+    scg::Context impl;
+    explicit scg_ctx(int dev) : impl(dev) {}
+};
+
+struct scg_reads {
+    scg_ctx* owner = nullptr;
+    std::vector<scg::DeviceBatch> batches;
+    long long n = 0;
+    long long device_bytes = 0;
+};
+
+struct scg_result {
+    int width = 0;
+    std::vector<int32_t> keys;
+    std::vector<char> strings;
+    std::vector<int32_t> freq;
+    int trace_width = 0;
+    std::vector<int32_t> trace_index;
+    std::vector<uint32_t> trace_info;
+    size_t rows() const { return freq.size(); }
+};

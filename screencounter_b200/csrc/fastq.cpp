@@ -1,0 +1,450 @@
+#include "fastq.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace scg {
+
+// ---------------------------------------------------------------------------------------
+// Inputs.  A window is a contiguous span of not-yet-consumed FASTQ text; `final` says that
+// nothing follows it.
+// ---------------------------------------------------------------------------------------
+class FastqInput {
+public:
+    virtual ~FastqInput() {}
+    // Makes [*base, *base + *avail) hold the unconsumed tail starting at `keep_from` (an
+    // offset into the previous window) plus as much further data as is convenient.
+    virtual void window(size_t keep_from, const char** base, size_t* avail, bool* final) = 0;
+};
+
+namespace {
+
+class MemoryInput : public FastqInput {
+public:
+    MemoryInput(const char* data, size_t size) : data_(data), size_(size) {}
+    void window(size_t keep_from, const char** base, size_t* avail, bool* final) override {
+        offset_ += keep_from;
+        *base = data_ + offset_;
+        *avail = size_ - offset_;
+        *final = true;
+    }
+
+protected:
+    const char* data_;
+    size_t size_;
+    size_t offset_ = 0;
+};
+
+class MmapInput : public MemoryInput {
+public:
+    MmapInput(int fd, void* map, size_t size) : MemoryInput(static_cast<const char*>(map), size), fd_(fd), map_(map), mapped_(size) {}
+    ~MmapInput() override {
+        if (map_ && mapped_) munmap(map_, mapped_);
+        if (fd_ >= 0) close(fd_);
+    }
+
+private:
+    int fd_;
+    void* map_;
+    size_t mapped_;
+};
+
+// gzip stream (byteme::GzipFileReader, inst/include/byteme/GzipFileReader.hpp:39-51), inflated in
+// large chunks; the unconsumed tail of a chunk is carried to the front of the next one.
+class GzInput : public FastqInput {
+public:
+    explicit GzInput(const char* path) {
+        gz_ = gzopen(path, "rb");
+        if (!gz_) throw Error(std::string("failed to open file at '") + path + "'");
+        gzbuffer(gz_, 1 << 20);
+        buf_.resize(kChunk);
+    }
+    ~GzInput() override {
+        if (gz_) gzclose(gz_);
+    }
+    void window(size_t keep_from, const char** base, size_t* avail, bool* final) override {
+        size_t tail = filled_ - keep_from;
+        if (keep_from > 0 && tail > 0) std::memmove(buf_.data(), buf_.data() + keep_from, tail);
+        filled_ = tail;
+        if (!eof_) {
+            if (buf_.size() - filled_ < kChunk / 2) buf_.resize(buf_.size() * 2);  // a record longer than the chunk
+            while (filled_ < buf_.size()) {
+                size_t want = std::min<size_t>(buf_.size() - filled_, 1u << 30);
+                int got = gzread(gz_, buf_.data() + filled_, (unsigned)want);
+                if (got < 0) {
+                    int dummy;
+                    throw Error(gzerror(gz_, &dummy));
+                }
+                if (got == 0) {
+                    eof_ = true;
+                    break;
+                }
+                filled_ += (size_t)got;
+            }
+        }
+        *base = buf_.data();
+        *avail = filled_;
+        *final = eof_;
+    }
+
+private:
+    static constexpr size_t kChunk = 64u << 20;
+    gzFile gz_ = nullptr;
+    std::vector<char> buf_;
+    size_t filled_ = 0;
+    bool eof_ = false;
+};
+
+std::unique_ptr<FastqInput> open_input(const char* path, const char* data, size_t size) {
+    if (!path) return std::unique_ptr<FastqInput>(new MemoryInput(data, size));
+    // byteme::SomeFileReader (inst/include/byteme/SomeFileReader.hpp:31-44): sniff the gzip magic.
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) throw Error(std::string("failed to open file at '") + path + "'");
+    unsigned char header[2];
+    ssize_t got = read(fd, header, 2);
+    if (got == 2 && header[0] == 0x1f && header[1] == 0x8b) {
+        close(fd);
+        return std::unique_ptr<FastqInput>(new GzInput(path));
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        throw Error(std::string("failed to open file at '") + path + "'");
+    }
+    if (st.st_size == 0) {
+        close(fd);
+        return std::unique_ptr<FastqInput>(new MemoryInput(nullptr, 0));
+    }
+    void* map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map == MAP_FAILED) {
+        close(fd);
+        throw Error(std::string("failed to read raw binary file (mmap of '") + path + "' failed)");
+    }
+    madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL);
+    return std::unique_ptr<FastqInput>(new MmapInput(fd, map, (size_t)st.st_size));
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// Record splitter
+// ---------------------------------------------------------------------------------------
+
+FastqReader::FastqReader(const char* path, const char* data, size_t size) : in_(open_input(path, data, size)) {}
+
+FastqReader::~FastqReader() {}
+
+void FastqReader::refill() {
+    in_->window(started_ ? pos_ : 0, &base_, &avail_, &final_);
+    started_ = true;
+    pos_ = 0;
+}
+
+// One record, following FastqReader::operator() (FastqReader.hpp:42-110).  Line numbers in the
+// messages: the reference counts exactly four lines per record whatever the wrapping, so record
+// k (0-based) "starts" at line 4k+1.
+bool FastqReader::parse_one(Record& out) {
+    const long long init_line = 4 * nrecords_;
+    const char* b = base_;
+    const size_t n = avail_;
+    size_t p = pos_;
+    if (p >= n) return false;  // needs more data; the caller knows whether that is the end
+
+    auto need_more = [&](int line_offset) -> bool {
+        if (final_) throw Error("premature end of the file at line " + std::to_string(init_line + line_offset));
+        return false;
+    };
+
+    if (b[p] != '@') {  // :54-57
+        throw Error("read name should start with '@' (starting line " + std::to_string(init_line + 1) + ")");
+    }
+    // name line: everything up to the first newline after '@' (:58-68)
+    const char* e1 = (p + 1 < n) ? static_cast<const char*>(std::memchr(b + p + 1, '\n', n - p - 1)) : nullptr;
+    if (!e1) return need_more(1);
+    // sequence: up to the first '+', newlines dropped, every other byte kept (:70-78)
+    size_t s0 = (size_t)(e1 - b) + 1;
+    const char* plus = (s0 < n) ? static_cast<const char*>(std::memchr(b + s0, '+', n - s0)) : nullptr;
+    if (!plus) return need_more(2);
+    size_t span = (size_t)(plus - (b + s0));
+    size_t len = span;
+    if (span > 0) {
+        // common case: one line, i.e. the only newline is the last byte of the span
+        const char* nl = static_cast<const char*>(std::memchr(b + s0, '\n', span));
+        if (nl == plus - 1) {
+            len = span - 1;
+        } else {
+            len = 0;
+            for (size_t i = 0; i < span; ++i) len += (b[s0 + i] != '\n');
+        }
+    }
+    // '+' line (:81-85): the reference advances past the '+' before looking for the newline
+    size_t q0 = (size_t)(plus - b) + 1;
+    const char* e3 = (q0 < n) ? static_cast<const char*>(std::memchr(b + q0, '\n', n - q0)) : nullptr;
+    if (!e3) return need_more(3);
+    // qualities (:91-105): lines are consumed until at least `len` characters were seen
+    size_t q = (size_t)(e3 - b) + 1;
+    size_t qual = 0;
+    bool ended = false, next_okay = false;
+    while (q < n) {
+        const char* e4 = static_cast<const char*>(std::memchr(b + q, '\n', n - q));
+        if (!e4) {
+            if (!final_) return false;  // quality line not complete yet
+            qual += n - q;
+            q = n;
+            break;
+        }
+        qual += (size_t)(e4 - (b + q));
+        q = (size_t)(e4 - b) + 1;
+        if (qual >= len) {
+            ended = true;
+            next_okay = q < n;
+            break;
+        }
+    }
+    if (!ended) {
+        if (!final_) return false;
+        next_okay = false;  // ran off the end of the file inside the quality string
+    } else if (!next_okay && !final_) {
+        // the record ended exactly at the window's edge: whether more input follows is not known yet
+        return false;
+    }
+    if (qual != len) {
+        throw Error("non-equal lengths for quality and sequence strings (starting line " + std::to_string(init_line + 1) + ")");
+    }
+    if (len > (size_t)MAX_READ_LEN) {
+        throw Error("reads longer than " + std::to_string(MAX_READ_LEN) + " bases are not supported by this engine (read " +
+                    std::to_string(nrecords_ + 1) + ")");
+    }
+    out.seq = b + s0;
+    out.span = (uint32_t)span;
+    out.len = (uint32_t)len;
+    pos_ = q;
+    okay_ = next_okay;
+    ++nrecords_;
+    return true;
+}
+
+const std::vector<Record>& FastqReader::next(size_t max_records) {
+    double t0 = now_s();
+    batch_.clear();
+    if (!started_ || (pos_ >= avail_ && !final_)) refill();
+    if (nrecords_ == 0 && avail_ == 0 && final_) okay_ = false;  // empty input: zero reads (FastqReader.hpp:30)
+    Record r;
+    while (okay_ && batch_.size() < max_records) {
+        if (parse_one(r)) {
+            batch_.push_back(r);
+            continue;
+        }
+        // needs more data
+        if (final_) break;
+        if (!batch_.empty()) break;  // hand out what is complete; records point into the current window
+        size_t before = avail_ - pos_;
+        refill();
+        if (avail_ == before && final_ && avail_ == 0) break;
+    }
+    parse_s_ += now_s() - t0;
+    return batch_;
+}
+
+// ---------------------------------------------------------------------------------------
+// Packer
+// ---------------------------------------------------------------------------------------
+
+namespace {
+
+struct Lut {
+    uint8_t code[256];  // 0..3 = ACGT (any case), 4 = anything else
+    uint8_t plain[256]; // 1 for upper-case A, C, G, T, N
+    Lut() {
+        std::memset(code, 4, sizeof code);
+        std::memset(plain, 0, sizeof plain);
+        const char* up = "ACGT";
+        const char* lo = "acgt";
+        for (int i = 0; i < 4; ++i) {
+            code[(unsigned char)up[i]] = (uint8_t)i;
+            code[(unsigned char)lo[i]] = (uint8_t)i;
+            plain[(unsigned char)up[i]] = 1;
+        }
+        plain[(unsigned char)'N'] = 1;
+    }
+};
+const Lut g_lut;
+
+// Packs up to 32 bases starting at s into one word of each plane; returns "all plain" flag.
+inline bool pack_word_scalar(const char* s, int count, uint32_t& h, uint32_t& l, uint32_t& n) {
+    uint32_t hh = 0, ll = 0, nn = 0;
+    uint8_t plain = 1;
+    for (int i = 0; i < count; ++i) {
+        unsigned char c = (unsigned char)s[i];
+        uint32_t code = g_lut.code[c];
+        plain &= g_lut.plain[c];
+        hh |= ((code >> 1) & 1u) << i;
+        ll |= (code & 1u) << i;
+        nn |= (code >> 2) << i;
+    }
+    h = hh;
+    l = ll;
+    n = nn;
+    return plain != 0;
+}
+
+#if defined(__x86_64__)
+// 32 bases at once.  ASCII trick: bit 2 of A/C/G/T (either case) is 0/0/1/1 = the H plane, and
+// bit 1 is 0/1/1/0, so L = bit1 ^ bit2.
+__attribute__((target("avx2"))) inline bool pack_word_avx2(const char* s, uint32_t& h, uint32_t& l, uint32_t& n) {
+    __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+    __m256i up = _mm256_and_si256(v, _mm256_set1_epi8((char)0xDF));  // fold case
+    __m256i isA = _mm256_cmpeq_epi8(up, _mm256_set1_epi8('A'));
+    __m256i isC = _mm256_cmpeq_epi8(up, _mm256_set1_epi8('C'));
+    __m256i isG = _mm256_cmpeq_epi8(up, _mm256_set1_epi8('G'));
+    __m256i isT = _mm256_cmpeq_epi8(up, _mm256_set1_epi8('T'));
+    // folding with 0xDF also maps a few non-letters onto letters (e.g. 0x61^0x20); require an alphabetic source byte
+    __m256i alpha = _mm256_cmpeq_epi8(_mm256_and_si256(v, _mm256_set1_epi8((char)0xC0)), _mm256_set1_epi8(0x40));
+    __m256i valid = _mm256_and_si256(_mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT)), alpha);
+    uint32_t vmask = (uint32_t)_mm256_movemask_epi8(valid);
+    uint32_t b2 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 5));
+    uint32_t b1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(v, 6));
+    h = b2 & vmask;
+    l = (b1 ^ b2) & vmask;
+    n = ~vmask;
+    __m256i plainv = _mm256_or_si256(
+        _mm256_or_si256(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(v, _mm256_set1_epi8('C'))),
+        _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(v, _mm256_set1_epi8('T'))),
+                        _mm256_cmpeq_epi8(v, _mm256_set1_epi8('N'))));
+    return (uint32_t)_mm256_movemask_epi8(plainv) == 0xFFFFFFFFu;
+}
+#endif
+
+bool have_avx2() {
+#if defined(__x86_64__)
+    static const bool yes = __builtin_cpu_supports("avx2");
+    return yes;
+#else
+    return false;
+#endif
+}
+
+// One read whose bases are contiguous (no embedded newline).  Returns the "plain" flag.
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+#endif
+bool pack_contiguous(const char* s, uint32_t len, int W, uint32_t* h, uint32_t* l, uint32_t* n, size_t stride, bool avx2) {
+    bool plain = true;
+    uint32_t full = len / 32, w = 0;
+    for (; w < full; ++w) {
+        uint32_t hh, ll, nn;
+#if defined(__x86_64__)
+        if (avx2) {
+            plain &= pack_word_avx2(s + 32 * w, hh, ll, nn);
+        } else
+#endif
+        {
+            plain &= pack_word_scalar(s + 32 * w, 32, hh, ll, nn);
+        }
+        h[w * stride] = hh;
+        l[w * stride] = ll;
+        n[w * stride] = nn;
+    }
+    uint32_t rem = len - 32 * full;
+    if (rem) {
+        uint32_t hh, ll, nn;
+        plain &= pack_word_scalar(s + 32 * w, (int)rem, hh, ll, nn);
+        h[w * stride] = hh;
+        l[w * stride] = ll;
+        n[w * stride] = nn;
+        ++w;
+    }
+    for (; w < (uint32_t)W; ++w) {
+        h[w * stride] = 0;
+        l[w * stride] = 0;
+        n[w * stride] = 0;
+    }
+    return plain;
+}
+
+} // namespace
+
+void pack_read_scalar(const char* seq, uint32_t span, int W, uint32_t* h, uint32_t* l, uint32_t* n, size_t stride) {
+    for (int w = 0; w < W; ++w) h[w * stride] = l[w * stride] = n[w * stride] = 0;
+    uint32_t i = 0;
+    for (uint32_t k = 0; k < span; ++k) {
+        char c = seq[k];
+        if (c == '\n') continue;
+        uint32_t code = g_lut.code[(unsigned char)c];
+        uint32_t bit = 1u << (i & 31);
+        if (code & 2) h[(i >> 5) * stride] |= bit;
+        if (code & 1) l[(i >> 5) * stride] |= bit;
+        if (code & 4) n[(i >> 5) * stride] |= bit;
+        ++i;
+    }
+}
+
+void pack_records(const Record* recs, size_t count, int W, uint32_t* out, uint16_t* lens, uint8_t* odd, int nthreads) {
+    const size_t ntiles = (count + TILE - 1) / TILE;
+    const size_t tw = tile_words(W);
+    const bool avx2 = have_avx2();
+    auto work = [&](size_t tile_begin, size_t tile_end) {
+        std::vector<char> scratch;
+        for (size_t t = tile_begin; t < tile_end; ++t) {
+            uint32_t* base = out + t * tw;
+            for (int lane = 0; lane < TILE; ++lane) {
+                size_t i = t * TILE + lane;
+                uint32_t* h = base + (size_t)(PLANE_H * W) * TILE + lane;
+                uint32_t* l = base + (size_t)(PLANE_L * W) * TILE + lane;
+                uint32_t* n = base + (size_t)(PLANE_N * W) * TILE + lane;
+                if (i >= count) {
+                    for (int w = 0; w < W; ++w) h[w * TILE] = l[w * TILE] = n[w * TILE] = 0;
+                    if (lens) lens[i] = 0;
+                    if (odd) odd[i] = 0;
+                    continue;
+                }
+                const Record& r = recs[i];
+                const char* s = r.seq;
+                bool plain;
+                if (r.span == r.len || (r.span == r.len + 1 && r.seq[r.len] == '\n')) {
+                    plain = pack_contiguous(s, r.len, W, h, l, n, TILE, avx2);
+                } else {
+                    scratch.clear();
+                    for (uint32_t k = 0; k < r.span; ++k) {
+                        if (s[k] != '\n') scratch.push_back(s[k]);
+                    }
+                    plain = pack_contiguous(scratch.data(), r.len, W, h, l, n, TILE, avx2);
+                }
+                if (lens) lens[i] = (uint16_t)r.len;
+                if (odd) odd[i] = plain ? 0 : 1;
+            }
+        }
+    };
+    int nt = std::max(1, std::min<int>(nthreads, (int)ntiles));
+    if (nt == 1 || ntiles < 64) {
+        work(0, ntiles);
+        return;
+    }
+    std::vector<std::thread> pool;
+    size_t per = (ntiles + nt - 1) / nt;
+    for (int k = 0; k < nt; ++k) {
+        size_t b = (size_t)k * per, e = std::min(ntiles, b + per);
+        if (b >= e) break;
+        pool.emplace_back(work, b, e);
+    }
+    for (auto& th : pool) th.join();
+}
+
+} // namespace scg

@@ -1,0 +1,63 @@
+// Host FASTQ reader + packer.  Replaces the reference's byte-at-a-time kaori::FastqReader
+// (inst/include/kaori/FastqReader.hpp:42-110) over byteme::PerByte with a chunked,
+// memchr-driven record splitter and a multi-threaded packer that writes the tile-planar
+// 2-bit + N-mask layout (layout.hpp) straight into pinned memory.  Grammar, line numbering
+// and error texts follow the reference.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "layout.hpp"
+
+namespace scg {
+
+struct Record {
+    const char* seq;     // first sequence byte (inside the reader's buffer)
+    uint32_t span;       // bytes from seq up to (not including) the '+' that ends the sequence
+    uint32_t len;        // bases = span minus embedded newlines
+};
+
+class FastqInput;  // raw file (mmap), gzip stream or caller memory
+
+class FastqReader {
+public:
+    FastqReader(const char* path, const char* data, size_t size);
+    ~FastqReader();
+
+    // Parses up to max_records further records.  The returned records point into an internal
+    // buffer that stays valid until the next call.  Empty result = end of input.
+    const std::vector<Record>& next(size_t max_records);
+
+    long long records_seen() const { return nrecords_; }
+    double parse_seconds() const { return parse_s_; }
+
+private:
+    bool parse_one(Record& out);  // false = needs more data (or clean end of input)
+    void refill();
+
+    std::unique_ptr<FastqInput> in_;
+    const char* base_ = nullptr;  // current window
+    size_t avail_ = 0;            // bytes in the window
+    size_t pos_ = 0;              // parse position inside the window
+    bool final_ = false;          // window reaches the end of the input
+    bool okay_ = true;            // reference's `okay` flag (FastqReader.hpp:44,93-99)
+    bool started_ = false;
+    long long nrecords_ = 0;
+    std::vector<Record> batch_;
+    double parse_s_ = 0;
+};
+
+// Packs records [first, first+count) into `out` (tile-planar, W words per plane, count padded
+// up to a multiple of 32 with empty reads).  lens receives the read lengths.  odd (nullable)
+// receives 1 for reads holding a character other than upper-case A, C, G, T, N.
+void pack_records(const Record* recs, size_t count, int W, uint32_t* out, uint16_t* lens, uint8_t* odd, int nthreads);
+
+// Scalar reference implementation of the packer for one read (also used for pool rows).
+void pack_read_scalar(const char* seq, uint32_t span, int W, uint32_t* h, uint32_t* l, uint32_t* n, size_t stride);
+
+} // namespace scg

@@ -1,0 +1,94 @@
+// Plain-old-data parameter blocks shared by the host runtime and the kernels (handlers.cuh).
+#pragma once
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+#include "layout.hpp"
+#include "library.hpp"
+#include "template_spec.hpp"
+
+namespace scg {
+
+// Packed reads of one batch on the device.
+struct ReadsDev {
+    const uint32_t* data;   // tile-planar words
+    const uint16_t* lens;   // nullptr when every read has length uniform_len
+    int uniform_len;
+    int W;
+    long long n;
+};
+
+struct SingleParams {
+    ScanSpec spec;
+    LibDev lib_f, lib_r;
+    int max_mm;
+    int use_first;
+};
+
+struct CountTable64 {
+    unsigned long long* keys;  // EMPTY = ~0
+    uint32_t* counts;
+    unsigned long long mask;   // capacity - 1
+};
+
+struct CountTable128 {
+    ulonglong2* keys;  // EMPTY = (~0, ~0); 16-byte aligned
+    uint32_t* counts;
+    unsigned long long mask;
+};
+
+struct RandomParams {
+    ScanSpec spec;
+    int max_mm;
+    int use_first;
+    int key_len;   // length of the first variable region
+};
+
+// Outcome for reads the packed representation cannot render as text (lower case, symbols other
+// than N): the host formats those keys from the raw read (handlers/RandomBarcodeSingleEnd.hpp:93-120).
+struct OddOutcome {
+    long long read;
+    int position;
+    int reverse;
+};
+
+struct ComboParams {
+    ScanSpec spec;
+    LibDev lib_f[2], lib_r[2];   // lib_r[r] is built from the reverse complement of pool[1 - r]
+    int max_mm;
+    int use_first;
+    int n1, n2;                  // pool sizes
+};
+
+// Where combinations are tallied: a dense n1 x n2 matrix when it is small, else the 64-bit hash.
+struct ComboSink {
+    int32_t* dense;        // n1 * n2 counters or nullptr
+    CountTable64 sparse;
+    int n2;
+};
+
+struct DualSEParams {
+    ScanSpec spec;
+    LibDev lib_f, lib_r;
+    int max_mm;
+    int use_first;
+};
+
+struct ComboPEParams {
+    SingleParams m1, m2;
+    int randomized;
+    int use_first;
+};
+
+struct DualPEParams {
+    ScanSpec spec1, spec2;   // each searches exactly one strand
+    LibDev lib;              // rows = [RC?]pool1[i] + [RC?]pool2[i], segments (len1, len2)
+    int mm1, mm2;
+    int randomized;
+    int use_first;
+    int len1, len2;
+};
+
+} // namespace scg

@@ -1,0 +1,89 @@
+// Barcode library: host-side construction (validation, IUPAC expansion, duplicate policy) and
+// the flat tables the kernels probe.  Replaces the reference's fill_library + MismatchTrie
+// (inst/include/kaori/BarcodeSearch.hpp:23-60, MismatchTrie.hpp:93-205) with
+//   * an open-addressing hash of packed barcodes for exact hits, and
+//   * pigeonhole seed buckets for the mismatch-tolerant search: a barcode within `cap`
+//     substitutions of the query agrees with it exactly on at least one of cap+1 disjoint
+//     segments, so probing one bucket per segment enumerates every candidate; candidates are
+//     verified by XOR/popcount on the packed planes and the best-unique / tie rules of
+//     MismatchTrie.hpp:266-343 are applied to the verified distances.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "common.hpp"
+#include "layout.hpp"
+
+namespace scg {
+
+enum class Duplicates { FIRST, ERROR };  // the two policies reachable from the R API
+
+// Device view (plain pointers; passed to kernels by value).
+struct LibDev {
+    int L;              // key length in bases
+    int KW;             // words per plane
+    int nentries;       // expanded (concrete) entries
+    int dup_first;      // ties between different indices resolve to the lowest index
+    // exact table: nslots slots of slot_words words: h[KW], l[KW], value (-1 = empty), padding
+    const uint32_t* slots;
+    uint32_t slot_mask;
+    int slot_words;
+    // expanded entries for verification: ent_keys[e*2KW ..] = h[KW], l[KW]; ent_idx[e] = pool index
+    const uint32_t* ent_keys;
+    const int32_t* ent_idx;
+    // pigeonhole seeds
+    int nseeds;
+    const uint32_t* seed_masks;  // nseeds * KW words: base positions of each seed (same mask for H and L)
+    const uint2* buckets;     // nseeds * (bucket_mask + 1) entries of (start, count) into cands
+    uint32_t bucket_mask;
+    const int32_t* cands;     // nseeds * nentries entry ids, grouped by bucket
+    // segmented search (dual paired-end): first segment = bases [0, seg1), second = [seg1, L)
+    int seg1;
+    // table of library rows with their last base dropped (SURVEY 8.1 T8 root rule)
+    const uint32_t* prefix_slots;
+    uint32_t prefix_mask;
+};
+
+struct LibraryOptions {
+    int max_mismatches = 0;          // any-mismatch search: cap never exceeds this
+    bool segmented = false;          // two segments with their own caps
+    int seg1 = 0;                    // length of the first segment
+    int max_mismatches1 = 0, max_mismatches2 = 0;
+    Duplicates duplicates = Duplicates::ERROR;
+};
+
+// Host image of the tables.
+struct Library {
+    int L = 0, KW = 0, nchoices = 0;
+    LibraryOptions opt;
+    std::vector<uint32_t> ent_keys;
+    std::vector<int32_t> ent_idx;
+    int slot_words = 0;
+    std::vector<uint32_t> slots;
+    int nseeds = 0;
+    std::vector<uint32_t> seed_masks;   // nseeds * KW
+    uint32_t nbuckets = 0;
+    std::vector<uint2> buckets;
+    std::vector<int32_t> cands;
+    std::vector<uint32_t> prefix_slots;
+
+    // `sequences` are the library rows as they must match the read (i.e. already
+    // reverse-complemented by the caller when the reverse strand is searched).
+    Library() {}
+    Library(const std::vector<std::string>& sequences, int length, const LibraryOptions& options);
+
+    size_t nentries() const { return ent_idx.size(); }
+};
+
+// Reverse complement of a pool sequence with IUPAC codes (utils.hpp:41-120, complement_base<true,true>).
+std::string reverse_complement_iupac(const std::string& s);
+
+// Pack a concrete ACGT string (any case) into planes; returns false if a non-ACGT char is present,
+// in which case its bit is set in n.
+bool pack_key(const char* s, int len, uint32_t* h, uint32_t* l, uint32_t* n);
+
+} // namespace scg

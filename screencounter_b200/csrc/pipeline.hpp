@@ -1,0 +1,65 @@
+// FASTQ -> pinned staging -> HBM, double-buffered.  While the GPU works on batch k the host parses
+// and packs batch k+1 into the other staging slot.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "engine.hpp"
+
+namespace scg {
+
+class ReadPipeline {
+public:
+    struct Batch {
+        long long first_read = 0;   // global index of the batch's first read (pair)
+        long long n = 0;
+        ReadsDev reads1, reads2;    // reads2 only for paired input
+        const uint8_t* odd1 = nullptr;   // device flags: read holds characters other than ACGTN (when asked for)
+        const Record* recs1 = nullptr;   // host records of mate 1 (valid until the next call)
+        void* slot = nullptr;
+    };
+
+    ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int nthreads, bool want_odd);
+    ~ReadPipeline();
+
+    // Stages the next batch on the context's stream.  false = input exhausted.
+    bool next(Batch& out);
+    // Call after the kernels that read the batch have been enqueued.
+    void submitted(Batch& b);
+
+    const std::vector<uint8_t>& odd_flags(const Batch& b) const { return static_cast<Slot*>(b.slot)->mate[0].odd_host; }
+
+private:
+    static constexpr int kSlots = 2;
+    static constexpr size_t kMaxBatchReads = 1u << 20;
+    static constexpr size_t kMaxBatchBytes = 64u << 20;
+
+    struct Staged {
+        PinnedBuffer pinned_data, pinned_lens;
+        std::vector<uint8_t> odd_host;
+        DeviceBatch dev;
+    };
+    struct Slot {
+        Staged mate[2];
+        cudaEvent_t done = nullptr;
+        bool in_flight = false;
+    };
+
+    void stage(Slot& slot, int mate, const Record* recs, size_t count);
+
+    Context& ctx_;
+    FastqReader* r1_;
+    FastqReader* r2_;
+    int nthreads_;
+    bool want_odd_;
+    Slot slots_[kSlots];
+    int next_slot_ = 0;
+    const Record* recs1_ = nullptr;
+    const Record* recs2_ = nullptr;
+    size_t n1_ = 0, cur1_ = 0, n2_ = 0, cur2_ = 0;
+    long long consumed_ = 0;
+};
+
+} // namespace scg

@@ -1,0 +1,385 @@
+// countSingleBarcodes / matchBarcodes / the resident single-barcode plan, plus the context and
+// result plumbing of the C ABI.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "api_common.hpp"
+#include "handlers.cuh"
+
+namespace scg {
+
+std::string& creation_error() {
+    static thread_local std::string msg;
+    return msg;
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+Pool::Pool(const char* const* p, int n) {
+    seqs.reserve(n);
+    size_t size = 0;
+    for (int i = 0; i < n; ++i) {
+        size_t cur = std::strlen(p[i]);
+        if (i == 0) {
+            size = cur;
+        } else if (cur != size) {
+            throw Error("variable regions should all have the same length (" + std::to_string(size) + ")");
+        }
+        seqs.emplace_back(p[i], cur);
+    }
+    length = (int)size;
+}
+
+std::vector<std::string> Pool::reverse_complemented() const {
+    std::vector<std::string> out;
+    out.reserve(seqs.size());
+    for (const auto& s : seqs) out.push_back(reverse_complement_iupac(s));
+    return out;
+}
+
+Source::Source(const scg_source* s) {
+    if (!s) throw Error("null FASTQ source");
+    reader.reset(new FastqReader(s->path, s->data, s->size));
+}
+
+void TraceSink::prepare(long long n, bool want_info) {
+    if (!enabled) return;
+    d_index.reserve((size_t)std::max<long long>(n, 1) * width * sizeof(int32_t));
+    if (want_info) d_info.reserve((size_t)std::max<long long>(n, 1) * sizeof(uint32_t));
+}
+
+void TraceSink::collect(Context& ctx, long long n, bool want_info) {
+    if (!enabled) return;
+    size_t at = index.size();
+    index.resize(at + (size_t)n * width);
+    SCG_CUDA_CHECK(cudaMemcpyAsync(index.data() + at, d_index.ptr, (size_t)n * width * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    if (want_info) {
+        size_t ai = info.size();
+        info.resize(ai + (size_t)n);
+        SCG_CUDA_CHECK(cudaMemcpyAsync(info.data() + ai, d_info.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    }
+    SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
+// SimpleSingleMatch constructor (reference inst/include/kaori/SimpleSingleMatch.hpp:61-97).
+void SingleMatcher::prepare(const std::string& constant, int strand, const Pool& pool, int mismatches, bool use_first, Duplicates dup) {
+    tmpl = TemplateSpec(constant, strand);
+    if (tmpl.fwd_regions.size() != 1) throw Error("expected one variable region in the constant template");
+    const int var_length = tmpl.fwd_regions[0].end - tmpl.fwd_regions[0].start;
+    if (var_length != pool.length) {
+        throw Error("length of barcode_pool sequences (" + std::to_string(pool.length) + ") should be the same as the barcode_pool region (" +
+                    std::to_string(var_length) + ")");
+    }
+    npool = (int)pool.seqs.size();
+    LibraryOptions opt;
+    opt.max_mismatches = mismatches;
+    opt.duplicates = dup;
+    std::memset(&params, 0, sizeof params);
+    if (tmpl.fwd) lib_f.host = Library(pool.seqs, pool.length, opt);
+    if (tmpl.rev) lib_r.host = Library(pool.reverse_complemented(), pool.length, opt);
+    params.spec = tmpl.scan_spec(mismatches);
+    params.max_mm = mismatches;
+    params.use_first = use_first ? 1 : 0;
+}
+
+void SingleMatcher::upload(Context& ctx) {
+    if (tmpl.fwd) {
+        lib_f.upload(ctx);
+        params.lib_f = lib_f.dev;
+    }
+    if (tmpl.rev) {
+        lib_r.upload(ctx);
+        params.lib_r = lib_r.dev;
+    }
+}
+
+void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, int32_t* d_counts, int32_t* d_index, uint32_t* d_info,
+                   cudaStream_t stream) {
+    if (reads.n <= 0) return;
+    const long long ntiles = (reads.n + TILE - 1) / TILE;
+    const int grid = ctx.grid_for(ntiles);
+    const int kw = std::max(P.spec.fwd ? P.lib_f.KW : 1, P.spec.rev ? P.lib_r.KW : 1);
+    dispatch_cb(P.spec.cbits, [&](auto CB) {
+        dispatch_kw(kw, [&](auto KW) {
+            single_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(reads, P, d_counts, d_index, d_info);
+        });
+    });
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    ++ctx.timing.launches;
+}
+
+} // namespace scg
+
+using namespace scg;
+
+extern "C" {
+
+const char* scg_version(void) { return "screencounter_b200 0.1.0 (sm_100a)"; }
+
+int scg_ctx_create(scg_ctx** out, int device) {
+    try {
+        *out = new scg_ctx(device);
+        return 0;
+    } catch (const std::exception& e) {
+        creation_error() = e.what();
+        return 1;
+    }
+}
+
+void scg_ctx_destroy(scg_ctx* ctx) { delete ctx; }
+
+const char* scg_last_error(const scg_ctx* ctx) { return ctx ? ctx->impl.last_error.c_str() : creation_error().c_str(); }
+
+const char* scg_timing_json(const scg_ctx* ctx) { return ctx ? ctx->impl.timing_json.c_str() : "{}"; }
+
+long long scg_kernel_launches(const scg_ctx* ctx) { return ctx ? ctx->impl.launches : 0; }
+
+size_t scg_result_rows(const scg_result* r) { return r ? r->rows() : 0; }
+int scg_result_width(const scg_result* r) { return r ? r->width : 0; }
+size_t scg_result_reads(const scg_result* r) { return (r && r->trace_width) ? r->trace_index.size() / r->trace_width : 0; }
+int scg_result_trace_width(const scg_result* r) { return r ? r->trace_width : 0; }
+
+int scg_result_copy_table(const scg_result* r, int32_t* keys, char* strings, int32_t* freq) {
+    if (!r) return 1;
+    if (keys && !r->keys.empty()) std::memcpy(keys, r->keys.data(), r->keys.size() * sizeof(int32_t));
+    if (strings && !r->strings.empty()) std::memcpy(strings, r->strings.data(), r->strings.size());
+    if (freq && !r->freq.empty()) std::memcpy(freq, r->freq.data(), r->freq.size() * sizeof(int32_t));
+    return 0;
+}
+
+int scg_result_copy_trace(const scg_result* r, int32_t* index, uint32_t* info) {
+    if (!r) return 1;
+    if (index && !r->trace_index.empty()) std::memcpy(index, r->trace_index.data(), r->trace_index.size() * sizeof(int32_t));
+    if (info && !r->trace_info.empty()) std::memcpy(info, r->trace_info.data(), r->trace_info.size() * sizeof(uint32_t));
+    return 0;
+}
+
+void scg_result_free(scg_result* r) { delete r; }
+
+// ---- countSingleBarcodes (reference src/count_single_barcodes.cpp:12-50) --------------------
+int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
+                     int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        const double t_start = now_s();
+        c.timing = Timing();
+        // same order as the reference glue: open the file, marshal the pool, build the handler, then read
+        Source source(src);
+        Pool p(pool, npool);
+        SingleMatcher m;
+        m.prepare(constant, strand, p, mismatches, use_first != 0, Duplicates::ERROR);  // all validation happens on the host
+        c.ensure_ready();
+        m.upload(c);
+
+        DeviceBuffer d_counts;
+        d_counts.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);
+        TraceSink sink;
+        sink.enabled = trace != nullptr;
+
+        ReadPipeline pipe(c, source.reader.get(), nullptr, nthreads, false);
+        ReadPipeline::Batch b;
+        long long nreads = 0;
+        while (pipe.next(b)) {
+            sink.prepare(b.n, true);
+            launch_single(c, b.reads1, m.params, d_counts.as<int32_t>(), sink.enabled ? sink.d_index.as<int32_t>() : nullptr,
+                          sink.enabled ? sink.d_info.as<uint32_t>() : nullptr, c.stream);
+            pipe.submitted(b);
+            sink.collect(c, b.n, true);
+            nreads += b.n;
+        }
+        double t0 = now_s();
+        SCG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts.ptr, (size_t)npool * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        c.timing.device_s += now_s() - t0;
+        *total = (int32_t)nreads;  // SingleBarcodeSingleEnd::process counts every read, matched or not (:103)
+        if (trace) {
+            auto* r = new scg_result;
+            r->trace_width = 1;
+            r->trace_index.swap(sink.index);
+            r->trace_info.swap(sink.info);
+            *trace = r;
+        }
+        c.timing.parse_s = source.reader->parse_seconds();
+        c.timing.total_s = now_s() - t_start;
+        c.finish_timing();
+    });
+}
+
+// ---- matchBarcodes (reference src/match_barcodes.cpp:7-37) -----------------------------------
+int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequences, const char* const* choices, int nchoices,
+                       int substitutions, int reverse, int32_t* index, int32_t* mismatches) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Pool lib_pool(choices, nchoices);
+        LibraryOptions opt;
+        opt.max_mismatches = substitutions;
+        opt.duplicates = Duplicates::ERROR;
+        Library host(reverse ? lib_pool.reverse_complemented() : lib_pool.seqs, lib_pool.length, opt);
+        Pool queries(sequences, nsequences);  // format_pointers on the queries too (:19)
+        if (nsequences == 0) return;
+        c.ensure_ready();
+        DeviceLibrary lib;
+        lib.host = std::move(host);
+        lib.upload(c);
+        // The reference hands each query's C string to a search of the library's length; queries are
+        // packed at that length (shorter queries would read past their terminator in the reference).
+        const int L = lib.host.L, KW = lib.host.KW;
+        // (a longer query is matched on its first L characters, as the trie walk does; a shorter one
+        // makes the reference read past the string's end, which is refused here)
+        if (queries.length < L) {
+            throw Error("sequences (" + std::to_string(queries.length) + " bp) are shorter than the choices (" + std::to_string(L) + " bp)");
+        }
+        std::vector<uint32_t> qk((size_t)nsequences * 3 * KW, 0);
+        for (int i = 0; i < nsequences; ++i) {
+            uint32_t* base = &qk[(size_t)i * 3 * KW];
+            pack_key(queries.seqs[i].data(), L, base, base + KW, base + 2 * KW);
+        }
+        DeviceBuffer d_q, d_idx, d_mm;
+        d_q.upload(qk.data(), qk.size() * sizeof(uint32_t), c.stream);
+        d_idx.alloc((size_t)nsequences * sizeof(int32_t), false);
+        d_mm.alloc((size_t)nsequences * sizeof(int32_t), false);
+        const int grid = (nsequences + 127) / 128;
+        dispatch_kw(KW, [&](auto KWC) {
+            constexpr int K = decltype(KWC)::value;
+            if (K == KW) {
+                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, lib.dev, substitutions, d_idx.as<int32_t>(),
+                                                            d_mm.as<int32_t>());
+            } else {
+                // repack to the compiled width
+                std::vector<uint32_t> wide((size_t)nsequences * 3 * K, 0);
+                for (int i = 0; i < nsequences; ++i) {
+                    for (int pl = 0; pl < 3; ++pl) {
+                        std::memcpy(&wide[((size_t)i * 3 + pl) * K], &qk[((size_t)i * 3 + pl) * KW], KW * sizeof(uint32_t));
+                    }
+                }
+                d_q.upload(wide.data(), wide.size() * sizeof(uint32_t), c.stream);
+                SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, lib.dev, substitutions, d_idx.as<int32_t>(),
+                                                            d_mm.as<int32_t>());
+            }
+        });
+        SCG_CUDA_CHECK(cudaGetLastError());
+        ++c.launches;
+        SCG_CUDA_CHECK(cudaMemcpyAsync(index, d_idx.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaMemcpyAsync(mismatches, d_mm.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---- resident reads ----------------------------------------------------------------------------
+int scg_reads_from_source(scg_ctx* ctx, const scg_source* src, int nthreads, scg_reads** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Source source(src);
+        c.ensure_ready();
+        std::unique_ptr<scg_reads> reads(new scg_reads);
+        reads->owner = ctx;
+        ReadPipeline pipe(c, source.reader.get(), nullptr, nthreads, false);
+        ReadPipeline::Batch b;
+        while (pipe.next(b)) {
+            // keep a private copy of the staged batch
+            DeviceBatch keep;
+            const size_t words = (size_t)((b.n + TILE - 1) / TILE) * tile_words(b.reads1.W);
+            keep.data.alloc(words * sizeof(uint32_t), false);
+            SCG_CUDA_CHECK(cudaMemcpyAsync(keep.data.ptr, b.reads1.data, words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+            keep.view = b.reads1;
+            keep.view.data = keep.data.as<uint32_t>();
+            reads->device_bytes += (long long)(words * sizeof(uint32_t));
+            if (b.reads1.lens) {
+                const size_t padded = (size_t)((b.n + TILE - 1) / TILE) * TILE;
+                keep.lens.alloc(padded * sizeof(uint16_t), false);
+                SCG_CUDA_CHECK(cudaMemcpyAsync(keep.lens.ptr, b.reads1.lens, padded * sizeof(uint16_t), cudaMemcpyDeviceToDevice, c.stream));
+                keep.view.lens = keep.lens.as<uint16_t>();
+                reads->device_bytes += (long long)(padded * sizeof(uint16_t));
+            }
+            pipe.submitted(b);
+            reads->n += b.n;
+            reads->batches.push_back(std::move(keep));
+        }
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        *out = reads.release();
+    });
+}
+
+long long scg_reads_count(const scg_reads* r) { return r ? r->n : 0; }
+long long scg_reads_device_bytes(const scg_reads* r) { return r ? r->device_bytes : 0; }
+void scg_reads_free(scg_reads* r) { delete r; }
+
+// ---- resident single-barcode plan ----------------------------------------------------------------
+int scg_single_plan_create(scg_ctx* ctx, const char* constant, int strand, const char* const* pool, int npool, int mismatches,
+                           int use_first, scg_plan** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Pool p(pool, npool);
+        std::unique_ptr<scg_plan> plan(new scg_plan);
+        plan->owner = ctx;
+        plan->npool = npool;
+        plan->matcher.prepare(constant, strand, p, mismatches, use_first != 0, Duplicates::ERROR);
+        c.ensure_ready();
+        plan->matcher.upload(c);
+        *out = plan.release();
+    });
+}
+
+int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_counts, int32_t* d_index, void* cuda_stream) {
+    if (!plan || !reads) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c.stream;
+        long long at = 0;
+        for (const auto& b : reads->batches) {
+            launch_single(c, b.view, plan->matcher.params, d_counts, d_index ? d_index + at : nullptr, nullptr, st);
+            at += b.view.n;
+        }
+    });
+}
+
+void scg_plan_free(scg_plan* plan) { delete plan; }
+
+// ---- plain device helpers ---------------------------------------------------------------------------
+int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        void* p = nullptr;
+        SCG_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        SCG_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(bytes, 16)));
+        *out = p;
+    });
+}
+
+int scg_device_free(scg_ctx* ctx, void* ptr) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        SCG_CUDA_CHECK(cudaFree(ptr));
+    });
+}
+
+int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->impl.stream;
+        SCG_CUDA_CHECK(cudaMemsetAsync(ptr, 0, bytes, st));
+    });
+}
+
+int scg_device_to_host(scg_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        SCG_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->impl.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(ctx->impl.stream));
+    });
+}
+
+int scg_synchronize(scg_ctx* ctx) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        SCG_CUDA_CHECK(cudaDeviceSynchronize());
+    });
+}
+
+} // extern "C"
