@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: countSingleBarcodes, BASELINE.json configs[1]
+(Brunello-sized 77,441-guide library, 1 mismatch, both strands, 75-bp synthetic reads).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                        the reference's own CPU path on the host cores
+
+One step = one pass of the hot path (template scan -> barcode lookup -> counts [-> NCCL all-reduce
+of the count vector when N > 1]) over the rank's reads, which are resident in HBM when the timed
+region starts.  Prints ONE JSON line (see the task contract): `value` is device-timed reads/s over
+all ranks, `e2e` the same metric through the file-level C-ABI call from host FASTQ text,
+`roofline` the dominant kernel against the measured HBM peak, `cpu_baseline` the compiled
+reference (kaori) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TEMPLATE = "CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG"   # 12 + 20 + 12, flanks of R/countSingleBarcodes.R:63
+N_GUIDES = 77441
+READ_LEN = 75
+MISMATCHES = 1
+STRAND = 2          # both
+USE_FIRST = True    # R default find.best = FALSE
+SEED = 42
+BYTES_PER_READ = 49  # 29 B packed read + 4 B outcome + 16 B table probe
+WORKLOAD = "countSingleBarcodes: 77,441 x 20-bp guides, 1 mismatch, both strands, 75-bp reads (BASELINE configs[1])"
+
+
+def make_library():
+    rng = np.random.default_rng(SEED)
+    seen, out = set(), []
+    while len(out) < N_GUIDES:
+        codes = rng.integers(0, 4, size=(4096, 20))
+        for row in codes:
+            s = "".join("ACGT"[c] for c in row)
+            if s not in seen:
+                seen.add(s)
+                out.append(s)
+                if len(out) == N_GUIDES:
+                    break
+    return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, library):
+    """The reference's own CPU implementation of the path (kaori compiled from /root/reference in
+    oracle/_ref, else the C restatement) on all host cores, on a bounded sample of the workload."""
+    from oracle import kref, port
+    from screencounter_b200.device import SynthSpec
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    engine, kind = (kref, "reference") if kref.available() else (port, "port")
+    cores = os.cpu_count() or 1
+    threads = cores if kind == "reference" else 1
+    sample = args.cpu_reads
+    spec = SynthSpec(TEMPLATE, [library], seed=SEED, read_len=READ_LEN, strand=STRAND)
+    text = spec.fastq(0, sample)
+    for _ in range(args.warmup):
+        engine.count_single(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        counts, total = engine.count_single(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_step": sample, "timing": "wall clock around kaori::process_single_end_data (parse + scan + lookup + reduce), FASTQ text in host memory"},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind,
+                         "sample": "%d reads of the same synthetic workload per step" % sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=200_000_000, help="reads resident per GPU (config 2: 200 M)")
+    ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host FASTQ text)")
+    ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    library = make_library()
+    if args.impl == "reference":
+        reference_arm(args, library)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from screencounter_b200 import rcpp
+    from screencounter_b200.device import SynthSpec, SinglePlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spec = SynthSpec(TEMPLATE, [library], seed=SEED, read_len=READ_LEN, strand=STRAND)
+    # contiguous read range per rank; weak scaling: `--reads` per GPU
+    first = rank * args.reads
+    reads = spec.on_device(first, args.reads, device=local_rank)
+    plan = SinglePlan(TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, device=local_rank)
+    counts = torch.zeros(len(library), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        counts.zero_()
+        plan.run(reads, counts.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(counts)   # one NCCL all-reduce of the count vector over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # --- kernel-only timing for the roofline (events around the kernel launches alone) ---
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_before = rcpp.kernel_launches(local_rank)
+    counts.zero_()
+    k0.record()
+    for _ in range(args.steps):
+        plan.run(reads, counts.data_ptr(), stream=stream.cuda_stream)
+    k1.record()
+    torch.cuda.synchronize()
+    launches_per_step = (rcpp.kernel_launches(local_rank) - launches_before) // args.steps
+    kernel_ms_per_step = k0.elapsed_time(k1) / args.steps
+    matched_per_step = int(counts.sum().item()) // args.steps
+
+    # --- the timed region: exactly K steps, barrier + synchronize on both sides, device clocks sampled ---
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches_before = rcpp.kernel_launches(local_rank)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    gpu_launches = rcpp.kernel_launches(local_rank) - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    total_reads = args.reads * world
+    value = total_reads * args.steps / (elapsed_ms / 1000.0)
+    final_counts = counts.cpu().numpy()
+
+    # --- end to end through the reference-facing call: host FASTQ text -> counts on the host ---
+    e2e_reads = args.e2e_reads
+    text = spec.fastq(first, e2e_reads)
+    nthreads = os.cpu_count() or 1
+    for _ in range(2):
+        rcpp.count_single_barcodes(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_counts, e2e_total = rcpp.count_single_barcodes(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_dt = float(e2e_dt.item())
+    stage = rcpp.timing(local_rank)
+    e2e_value = e2e_reads * world * e2e_steps / e2e_dt
+
+    # consistency: the end-to-end counts are the device-resident counts of the same read range
+    check_reads = min(e2e_reads, args.reads)
+    if check_reads == args.reads and world == 1:
+        assert np.array_equal(e2e_counts, final_counts), "end-to-end and resident counts differ"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # --- CPU baseline: the compiled reference on this box's host cores (N = 1 only) ---
+    cpu_baseline = None
+    if world == 1:
+        from oracle import kref, port
+        engine, kind = (kref, "reference") if kref.available() else (port, "port")
+        threads = nthreads if kind == "reference" else 1
+        sample = min(args.cpu_reads, e2e_reads)
+        sample_text = text[: sample * (2 * READ_LEN + 7)]
+        t0 = time.perf_counter()
+        ref_counts, ref_total = engine.count_single(sample_text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, threads)
+        cpu_dt = time.perf_counter() - t0
+        if sample == e2e_reads:
+            assert np.array_equal(ref_counts, e2e_counts), "GPU counts differ from the reference on the baseline sample"
+        else:
+            chk, _ = rcpp.count_single_barcodes(sample_text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
+            assert np.array_equal(ref_counts, chk), "GPU counts differ from the reference on the baseline sample"
+        cpu_baseline = {"value": sample / cpu_dt, "unit": "reads/s", "cores": threads, "kind": kind,
+                        "sample": "first %d reads of the workload, FASTQ text in host memory, counts checked equal to the GPU's" % sample}
+
+    peak, peak_src = measured_peaks()
+    reads_per_launch = args.reads / max(launches_per_step, 1)
+    kernel_ms_per_launch = kernel_ms_per_step / max(launches_per_step, 1)
+    achieved = BYTES_PER_READ * reads_per_launch / (kernel_ms_per_launch / 1000.0) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        # dram bytes per read from the committed ncu --set full capture, scaled to this launch size
+        traffic = t.get("dram_bytes_per_read", 0) * reads_per_launch or None
+    line = {
+        "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_gpu": args.reads, "library": N_GUIDES, "read_len": READ_LEN,
+                   "mismatches": MISMATCHES, "strand": "both", "find_best": False, "seed": SEED,
+                   "parallelism": "reads sharded by contiguous range, %d rank(s); count vector combined with one NCCL all-reduce" % world,
+                   "l2": "inputs (%.1f GB packed reads per GPU) are larger than the 126 MB L2; no flush needed" % (reads.device_bytes / 1e9),
+                   "matched_fraction": matched_per_step / args.reads},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
+                "d2h_bytes_per_step": 4 * len(library), "reads_per_step": e2e_reads, "host_threads": nthreads,
+                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "total_s")},
+                "note": "host FASTQ text -> scg_count_single (parse, pack to pinned, H2D, kernels, counts D2H)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "single_kernel<1,1>", "bytes_per_read": BYTES_PER_READ, "reads_per_launch": reads_per_launch,
+                     "kernel_ms_per_launch": kernel_ms_per_launch, "peak_source": peak_src,
+                     "note": "integer-pipe bound, not HBM bound: see DESIGN.md"},
+        "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

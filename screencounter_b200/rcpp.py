@@ -47,9 +47,9 @@ class _Src:
 
     def __init__(self, fastq):
         if isinstance(fastq, (bytes, bytearray, memoryview)):
-            self.keep = bytes(fastq)
-            self.buf = C.create_string_buffer(self.keep, len(self.keep)) if len(self.keep) else C.create_string_buffer(1)
-            self.struct = ScgSource(None, C.cast(self.buf, C.c_void_p), len(self.keep))
+            self.keep = fastq if isinstance(fastq, bytes) else bytes(fastq)
+            # a pointer INTO the bytes object: no copy of what can be gigabytes of text
+            self.struct = ScgSource(None, C.cast(C.c_char_p(self.keep), C.c_void_p), len(self.keep))
         else:
             self.keep = os.fsencode(fastq)
             self.struct = ScgSource(self.keep, None, 0)
