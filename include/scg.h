@@ -165,8 +165,10 @@ int scg_single_plan_create(scg_ctx* ctx, const char* constant, int strand,
                            const char* const* pool, int npool, int mismatches, int use_first,
                            scg_plan** out);
 /* One pass of the hot path over resident reads.  d_counts (device, npool int32) is ACCUMULATED
- * into; d_index (device, nullable) receives the per-read pool index.  Runs on `cuda_stream`
- * (a cudaStream_t; NULL = the context's own stream) and does not synchronise. */
+ * into; d_index (device, nullable) receives the per-read pool index.  Runs on `cuda_stream`, a
+ * cudaStream_t used as given (NULL is CUDA's legacy default stream, e.g. torch's default stream);
+ * SCG_STREAM_OWN selects the context's own stream.  Does not synchronise. */
+#define SCG_STREAM_OWN ((void*)(intptr_t)-1)
 int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_counts, int32_t* d_index,
                         void* cuda_stream);
 void scg_plan_free(scg_plan* plan);
@@ -175,7 +177,7 @@ void scg_plan_free(scg_plan* plan);
  * can own buffers for scg_single_plan_run. */
 int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out);   /* zero-initialised */
 int scg_device_free(scg_ctx* ctx, void* ptr);
-int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream);
+int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream);  /* stream as above */
 int scg_device_to_host(scg_ctx* ctx, void* host, const void* dev, size_t bytes);
 int scg_synchronize(scg_ctx* ctx);
 

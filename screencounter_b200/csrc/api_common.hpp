@@ -93,10 +93,14 @@ struct TraceSink {
     void collect(Context& ctx, long long n, bool want_info);
 };
 
+// Copies an array of library descriptors to the device (the kernels index it per lane).
+const LibDev* upload_lib_array(Context& ctx, const std::vector<LibDev>& libs, DeviceBuffer& storage);
+
 // A single-barcode matcher (template + forward/reverse libraries) resident on the device.
 struct SingleMatcher {
     TemplateSpec tmpl;
     DeviceLibrary lib_f, lib_r;
+    DeviceBuffer libs_dev;   // LibDev[2] on the device: forward, reverse
     SingleParams params;
     int npool = 0;
     // SimpleSingleMatch constructor (reference inst/include/kaori/SimpleSingleMatch.hpp:61-97): host-only, throws

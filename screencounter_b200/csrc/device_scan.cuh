@@ -20,8 +20,10 @@ struct ReadView {
     const uint32_t* __restrict__ ptr;
     int W;
     int len;
+    // No bounds check: the scan and the extraction may read up to two words past the read's last
+    // plane word; every buffer carries READ_GUARD_BYTES of slack and those bits are masked out.
     __device__ __forceinline__ uint32_t word(int plane, int w) const {
-        return (w < W) ? __ldg(ptr + (size_t)(plane * W + w) * TILE) : 0u;
+        return __ldg(ptr + (size_t)(plane * W + w) * TILE);
     }
 };
 
@@ -124,28 +126,47 @@ struct Key {
     uint32_t h[KW], l[KW], n[KW];
 };
 
-// Extract `len` bases starting at read bit `start` into key words [dst_bit / 32 ...] at bit offset
-// dst_bit (dst_bit = 0 for a single region; regions are concatenated for the dual single-end design).
+// Extract `len` bases starting at read bit `start` as a key (KW static words; no dynamic register
+// indexing, so the key stays in registers).
+template <int KW>
+__device__ __forceinline__ void extract_region(const ReadView& rd, int start, int len, Key<KW>& k) {
+    const int a = start >> 5, sh = start & 31;
+    uint32_t h0 = rd.word(PLANE_H, a), l0 = rd.word(PLANE_L, a), n0 = rd.word(PLANE_N, a);
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int rem = len - 32 * w;
+        if (rem > 0) {
+            const uint32_t h1 = rd.word(PLANE_H, a + w + 1), l1 = rd.word(PLANE_L, a + w + 1), n1 = rd.word(PLANE_N, a + w + 1);
+            const uint32_t m = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+            k.h[w] = __funnelshift_r(h0, h1, sh) & m;
+            k.l[w] = __funnelshift_r(l0, l1, sh) & m;
+            k.n[w] = __funnelshift_r(n0, n1, sh) & m;
+            h0 = h1;
+            l0 = l1;
+            n0 = n1;
+        } else {
+            k.h[w] = k.l[w] = k.n[w] = 0;
+        }
+    }
+}
+
+// OR `len` bases starting at read bit `start` into an existing key at bit offset dst_bit
+// (regions concatenated for the dual designs).  Every destination word is visited statically.
 template <int KW>
 __device__ __forceinline__ void extract_into(const ReadView& rd, int start, int len, int dst_bit, Key<KW>& k) {
-    // walk destination words
-    int done = 0;
-    while (done < len) {
-        const int d = dst_bit + done;
-        const int dw = d >> 5, db = d & 31;
-        const int take = min(32 - db, len - done);
-        const int sbit = start + done;
-        const int a = sbit >> 5, sh = sbit & 31;
-        uint32_t vh = __funnelshift_r(rd.word(PLANE_H, a), rd.word(PLANE_H, a + 1), sh);
-        uint32_t vl = __funnelshift_r(rd.word(PLANE_L, a), rd.word(PLANE_L, a + 1), sh);
-        uint32_t vn = __funnelshift_r(rd.word(PLANE_N, a), rd.word(PLANE_N, a + 1), sh);
-        const uint32_t m = take >= 32 ? 0xFFFFFFFFu : ((1u << take) - 1u);
-        if (dw < KW) {
-            k.h[dw] |= (vh & m) << db;
-            k.l[dw] |= (vl & m) << db;
-            k.n[dw] |= (vn & m) << db;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int d0 = max(dst_bit, 32 * w), d1 = min(dst_bit + len, 32 * w + 32);
+        if (d0 < d1) {
+            const int sbit = start + (d0 - dst_bit);
+            const int a = sbit >> 5, sh = sbit & 31;
+            const int take = d1 - d0;
+            const uint32_t m = take >= 32 ? 0xFFFFFFFFu : ((1u << take) - 1u);
+            const int db = d0 - 32 * w;
+            k.h[w] |= (__funnelshift_r(rd.word(PLANE_H, a), rd.word(PLANE_H, a + 1), sh) & m) << db;
+            k.l[w] |= (__funnelshift_r(rd.word(PLANE_L, a), rd.word(PLANE_L, a + 1), sh) & m) << db;
+            k.n[w] |= (__funnelshift_r(rd.word(PLANE_N, a), rd.word(PLANE_N, a + 1), sh) & m) << db;
         }
-        done += take;
     }
 }
 
@@ -234,7 +255,8 @@ __device__ __forceinline__ int probe_table(const uint32_t* __restrict__ slots, u
 // two segments [0, seg1) and [seg1, L).  Applies the best-unique / tie rules of
 // MismatchTrie.hpp:266-343 to the verified distances.
 template <int KW>
-__device__ __noinline__ Hit lookup_seeded(const LibDev& lib, const Key<KW>& q, int c1, int c2, int seg1) {
+__device__ __noinline__ Hit lookup_seeded(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2, int seg1) {
+    const LibDev lib = *libp;
     Hit out{ -1, 0 };
     const int kw = KW == 1 ? 1 : lib.KW;
     const bool segmented = seg1 >= 0;
@@ -301,22 +323,22 @@ __device__ __noinline__ Hit lookup_seeded(const LibDev& lib, const Key<KW>& q, i
 // the minimum distance over the library if it is <= cap and attained by one pool index, else a miss.
 // A query position holding N mismatches every barcode.
 template <int KW>
-__device__ __forceinline__ Hit lookup_any(const LibDev& lib, const Key<KW>& q, int cap) {
+__device__ __forceinline__ Hit lookup_any(const LibDev* __restrict__ lib, const Key<KW>& q, int cap) {
     Hit out{ -1, 0 };
-    const int kw = KW == 1 ? 1 : lib.KW;
+    const int kw = KW == 1 ? 1 : lib->KW;
     if (!key_has_n(q)) {
-        const int v = probe_table<KW>(lib.slots, lib.slot_mask, lib.slot_words, kw, q.h, q.l);
+        const int v = probe_table<KW>(lib->slots, lib->slot_mask, KW == 1 ? 4 : lib->slot_words, kw, q.h, q.l);
         if (v >= 0) {
             out.index = v;
             return out;
         }
     }
-    if (cap <= 0 || lib.nseeds == 0) return out;
+    if (cap <= 0 || lib->nseeds == 0) return out;
     int nbad = 0;
 #pragma unroll
     for (int w = 0; w < KW; ++w) nbad += __popc(q.n[w]);
     if (nbad > cap) return out;
-    return lookup_seeded<KW>(lib, q, min(cap, lib.L), 0, -1);
+    return lookup_seeded<KW>(lib, q, min(cap, lib->L), 0, -1);
 }
 
 // Best-unique search with one cap per segment (SegmentedMismatches<2>::search,
@@ -326,8 +348,9 @@ __device__ __forceinline__ Hit lookup_any(const LibDev& lib, const Key<KW>& q, i
 //                      row, the search reports no match ("root rule");
 //   c2 == 0, c1 >= 2 : not handled here -- the host refuses such budgets (runners_paired.cu).
 template <int KW>
-__device__ __forceinline__ Hit lookup_segmented(const LibDev& lib, const Key<KW>& q, int c1, int c2) {
+__device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
     Hit out{ -1, 0 };
+    const LibDev lib = *libp;
     const int kw = KW == 1 ? 1 : lib.KW;
     if (!key_has_n(q)) {
         const int v = probe_table<KW>(lib.slots, lib.slot_mask, lib.slot_words, kw, q.h, q.l);
@@ -356,7 +379,7 @@ __device__ __forceinline__ Hit lookup_segmented(const LibDev& lib, const Key<KW>
         }
         if (!pn && probe_table<KW>(lib.prefix_slots, lib.prefix_mask, lib.slot_words, kw, ph, pl) >= 0) return out;
     }
-    return lookup_seeded<KW>(lib, q, min(c1, lib.seg1), min(c2, lib.L - lib.seg1), lib.seg1);
+    return lookup_seeded<KW>(libp, q, min(c1, lib.seg1), min(c2, lib.L - lib.seg1), lib.seg1);
 }
 
 } // namespace scg

@@ -173,7 +173,7 @@ void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count)
                  want_odd_ ? s.odd_host.data() : nullptr, nthreads_);
     ctx_.timing.pack_s += now_s() - t0;
 
-    s.dev.data.reserve(data_bytes);
+    s.dev.data.reserve(data_bytes + READ_GUARD_BYTES);
     SCG_CUDA_CHECK(cudaMemcpyAsync(s.dev.data.ptr, s.pinned_data.ptr, data_bytes, cudaMemcpyHostToDevice, ctx_.stream));
     ctx_.timing.bytes_h2d += (long long)data_bytes;
     s.dev.view.data = s.dev.data.as<uint32_t>();

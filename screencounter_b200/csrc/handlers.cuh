@@ -61,45 +61,47 @@ __device__ __forceinline__ SingleOut single_search(const ReadView& rd, const Sin
         Counter<CB> cf, cr;
         scan_block<CB>(rd, s, pb, cf, cr);
         const uint32_t valid = valid_windows(rd.len, s.T, pb);
-        const uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
-        const uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
-        uint32_t both = okf | okr;
-        while (both) {
-            const int p = __ffs(both) - 1;
-            both &= both - 1;
-            // forward before reverse at each position (SimpleSingleMatch.hpp:226-242)
-            for (int rev = 0; rev < 2; ++rev) {
-                if (!(((rev ? okr : okf) >> p) & 1u)) continue;
-                const int c = rev ? cr.get(p) : cf.get(p);
-                Key<KW> key;
-                key_clear(key);
-                extract_into<KW>(rd, 32 * pb + p + (rev ? s.rstart[0] : s.fstart[0]), rev ? s.rlen_r[0] : s.rlen_f[0], 0, key);
-                const Hit h = lookup_any<KW>(rev ? P.lib_r : P.lib_f, key, P.max_mm - c);
-                if (h.index < 0) continue;
-                const int total = c + h.dist;
-                if (use_first) {
-                    out.found = true;
-                    out.index = h.index;
-                    out.position = 32 * pb + p;
-                    out.reverse = rev != 0;
-                    out.mismatches = total;
-                    out.var_mismatches = h.dist;
-                    return out;
+        uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
+        uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
+        // hits in the reference's order: positions ascending, forward before reverse at each
+        // position (SimpleSingleMatch.hpp:226-242); each lane walks its own list, one hit per trip,
+        // the strand being per-lane data so that forward and reverse hits share the instructions
+        while (okf | okr) {
+            const int p = __ffs(okf | okr) - 1;
+            const bool rev = !((okf >> p) & 1u);
+            if (rev) {
+                okr &= ~(1u << p);
+            } else {
+                okf &= ~(1u << p);
+            }
+            const int c = rev ? cr.get(p) : cf.get(p);
+            Key<KW> key;
+            extract_region<KW>(rd, 32 * pb + p + (rev ? s.rstart[0] : s.fstart[0]), s.rlen_f[0], key);
+            const Hit h = lookup_any<KW>(P.libs + (rev ? 1 : 0), key, P.max_mm - c);
+            if (h.index < 0) continue;
+            const int total = c + h.dist;
+            if (use_first) {
+                out.found = true;
+                out.index = h.index;
+                out.position = 32 * pb + p;
+                out.reverse = rev;
+                out.mismatches = total;
+                out.var_mismatches = h.dist;
+                return out;
+            }
+            if (total == best) {  // SimpleSingleMatch.hpp:270-275: equal total, different barcode -> ambiguous, sticky
+                if (out.index != h.index) {
+                    out.found = false;
+                    out.index = -1;
                 }
-                if (total == best) {  // SimpleSingleMatch.hpp:270-275: equal total, different barcode -> ambiguous, sticky
-                    if (out.index != h.index) {
-                        out.found = false;
-                        out.index = -1;
-                    }
-                } else if (total < best) {
-                    best = total;
-                    out.found = true;
-                    out.index = h.index;
-                    out.position = 32 * pb + p;
-                    out.reverse = rev != 0;
-                    out.mismatches = total;
-                    out.var_mismatches = h.dist;
-                }
+            } else if (total < best) {
+                best = total;
+                out.found = true;
+                out.index = h.index;
+                out.position = 32 * pb + p;
+                out.reverse = rev;
+                out.mismatches = total;
+                out.var_mismatches = h.dist;
             }
         }
     }
@@ -236,9 +238,8 @@ __global__ void __launch_bounds__(128) random_kernel(ReadsDev reads, RandomParam
                     odd_out[slot] = OddOutcome{ read_offset + i, best_pos, best_rev ? 1 : 0 };
                 } else {
                     Key<KW> key;
-                    key_clear(key);
                     // forward coordinates on BOTH strands (:106-108, SURVEY 8.1 T9 "Quirk B")
-                    extract_into<KW>(rd, best_pos + s.fstart[0], P.key_len, 0, key);
+                    extract_region<KW>(rd, best_pos + s.fstart[0], P.key_len, key);
                     if (best_rev) key_revcomp<KW>(key, P.key_len);
                     if (KW == 1 && P.key_len <= 21) {
                         const unsigned long long k = (unsigned long long)key.h[0] | ((unsigned long long)key.l[0] << 21) |
@@ -283,51 +284,56 @@ __device__ __forceinline__ ComboOut combo_search(const ReadView& rd, const Combo
         Counter<CB> cf, cr;
         scan_block<CB>(rd, s, pb, cf, cr);
         const uint32_t valid = valid_windows(rd.len, s.T, pb);
-        const uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
-        const uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
-        uint32_t both = okf | okr;
-        while (both) {
-            const int p = __ffs(both) - 1;
-            both &= both - 1;
-            for (int rev = 0; rev < 2; ++rev) {
-                if (!(((rev ? okr : okf) >> p) & 1u)) continue;
-                int obs = rev ? cr.get(p) : cf.get(p);
-                int ids[2] = { -1, -1 };
-                bool ok = true;
-                // regions in read order with the remaining budget (find_match, :149-186)
-                for (int r = 0; r < 2 && ok; ++r) {
-                    Key<KW> key;
-                    key_clear(key);
-                    extract_into<KW>(rd, 32 * pb + p + (rev ? s.rstart[r] : s.fstart[r]), rev ? s.rlen_r[r] : s.rlen_f[r], 0, key);
-                    const Hit h = lookup_any<KW>(rev ? P.lib_r[r] : P.lib_f[r], key, P.max_mm - obs);
-                    if (h.index < 0) {
-                        ok = false;
-                        break;
-                    }
-                    obs += h.dist;
-                    ids[rev ? 1 - r : r] = h.index;
-                }
+        uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
+        uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
+        while (okf | okr) {
+            const int p = __ffs(okf | okr) - 1;
+            const bool rev = !((okf >> p) & 1u);
+            if (rev) {
+                okr &= ~(1u << p);
+            } else {
+                okf &= ~(1u << p);
+            }
+            int obs = rev ? cr.get(p) : cf.get(p);
+            int ids[2] = { -1, -1 };
+            bool ok = true;
+            // regions in read order with the remaining budget (find_match, :149-186)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
                 if (!ok) continue;
-                if (P.use_first) {
-                    out.found = true;
-                    out.id0 = ids[0];
-                    out.id1 = ids[1];
-                    return out;
+                Key<KW> key;
+                extract_region<KW>(rd, 32 * pb + p + (rev ? s.rstart[r] : s.fstart[r]), rev ? s.rlen_r[r] : s.rlen_f[r], key);
+                const Hit h = lookup_any<KW>(P.libs + (rev ? 2 : 0) + r, key, P.max_mm - obs);
+                if (h.index < 0) {
+                    ok = false;
+                } else {
+                    obs += h.dist;
+                    if (rev) {
+                        ids[1 - r] = h.index;
+                    } else {
+                        ids[r] = h.index;
+                    }
                 }
-                if (obs == best) {  // :225-241
-                    if (out.id0 != ids[0] || out.id1 != ids[1]) out.found = false;
-                } else if (obs < best) {
-                    out.found = true;
-                    best = obs;
-                    out.id0 = ids[0];
-                    out.id1 = ids[1];
-                }
+            }
+            if (!ok) continue;
+            if (P.use_first) {
+                out.found = true;
+                out.id0 = ids[0];
+                out.id1 = ids[1];
+                return out;
+            }
+            if (obs == best) {  // :225-241
+                if (out.id0 != ids[0] || out.id1 != ids[1]) out.found = false;
+            } else if (obs < best) {
+                out.found = true;
+                best = obs;
+                out.id0 = ids[0];
+                out.id1 = ids[1];
             }
         }
     }
     return out;
 }
-
 
 __device__ __forceinline__ void combo_count(const ComboSink& k, int id0, int id1) {
     if (k.dense) {
@@ -383,39 +389,40 @@ __global__ void __launch_bounds__(128) dual_se_kernel(ReadsDev reads, DualSEPara
             Counter<CB> cf, cr;
             scan_block<CB>(rd, s, pb, cf, cr);
             const uint32_t valid = valid_windows(rd.len, s.T, pb);
-            const uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
-            const uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
-            uint32_t both = okf | okr;
-            while (both && !done) {
-                const int p = __ffs(both) - 1;
-                both &= both - 1;
-                for (int rev = 0; rev < 2 && !done; ++rev) {
-                    if (!(((rev ? okr : okf) >> p) & 1u)) continue;
-                    const int c = rev ? cr.get(p) : cf.get(p);
-                    Key<KW> key;
-                    key_clear(key);
-                    int off = 0;
-                    for (int r = 0; r < s.nreg; ++r) {  // find_match, :144-160
-                        const int rl = rev ? s.rlen_r[r] : s.rlen_f[r];
-                        extract_into<KW>(rd, 32 * pb + p + (rev ? s.rstart[r] : s.fstart[r]), rl, off, key);
-                        off += rl;
-                    }
-                    const Hit h = lookup_any<KW>(rev ? P.lib_r : P.lib_f, key, P.max_mm - c);
-                    if (h.index < 0) continue;
-                    if (P.use_first) {
-                        found = true;
-                        best_id = h.index;
-                        done = true;
-                        break;
-                    }
-                    const int tot = c + h.dist;
-                    if (tot == best) {  // :205-222
-                        if (best_id != h.index) found = false;
-                    } else if (tot < best) {
-                        found = true;
-                        best = tot;
-                        best_id = h.index;
-                    }
+            uint32_t okf = s.fwd ? (cf.le(s.mm) & valid) : 0u;
+            uint32_t okr = s.rev ? (cr.le(s.mm) & valid) : 0u;
+            while ((okf | okr) && !done) {
+                const int p = __ffs(okf | okr) - 1;
+                const bool rev = !((okf >> p) & 1u);
+                if (rev) {
+                    okr &= ~(1u << p);
+                } else {
+                    okf &= ~(1u << p);
+                }
+                const int c = rev ? cr.get(p) : cf.get(p);
+                Key<KW> key;
+                key_clear(key);
+                int off = 0;
+                for (int r = 0; r < s.nreg; ++r) {  // find_match, :144-160
+                    const int rl = rev ? s.rlen_r[r] : s.rlen_f[r];
+                    extract_into<KW>(rd, 32 * pb + p + (rev ? s.rstart[r] : s.fstart[r]), rl, off, key);
+                    off += rl;
+                }
+                const Hit h = lookup_any<KW>(P.libs + (rev ? 1 : 0), key, P.max_mm - c);
+                if (h.index < 0) continue;
+                if (P.use_first) {
+                    found = true;
+                    best_id = h.index;
+                    done = true;
+                    continue;
+                }
+                const int tot = c + h.dist;
+                if (tot == best) {  // :205-222
+                    if (best_id != h.index) found = false;
+                } else if (tot < best) {
+                    found = true;
+                    best = tot;
+                    best_id = h.index;
                 }
             }
         }
@@ -543,8 +550,7 @@ __device__ __forceinline__ DualOut dual_pe_search(const ReadView& ra, const Read
             ok1 &= ok1 - 1;
             const int m1 = c1.get(p1);
             Key<KW> key1;
-            key_clear(key1);
-            extract_into<KW>(ra, 32 * pb1 + p1 + (rev1 ? s1.rstart[0] : s1.fstart[0]), P.len1, 0, key1);
+            extract_region<KW>(ra, 32 * pb1 + p1 + (rev1 ? s1.rstart[0] : s1.fstart[0]), P.len1, key1);
             // every hit of template 2 on the other read, in position order
             for (int pb2 = 0; pb2 < nb2; ++pb2) {
                 Counter<CB> c2f, c2r;
@@ -615,7 +621,7 @@ __global__ void __launch_bounds__(128) dual_pe_kernel(ReadsDev reads1, ReadsDev 
 
 // matchBarcodes: one thread per query key (src/match_barcodes.cpp:7-37)
 template <int KW>
-__global__ void match_kernel(const uint32_t* __restrict__ qkeys /* n * 3KW: h, l, n */, int nq, LibDev lib, int cap,
+__global__ void match_kernel(const uint32_t* __restrict__ qkeys /* n * 3KW: h, l, n */, int nq, const LibDev* lib, int cap,
                              int32_t* __restrict__ index, int32_t* __restrict__ mm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
@@ -629,46 +635,6 @@ __global__ void match_kernel(const uint32_t* __restrict__ qkeys /* n * 3KW: h, l
     const Hit h = lookup_any<KW>(lib, q, cap);
     index[i] = h.index;
     mm[i] = h.index >= 0 ? h.dist : -1;
-}
-
-__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
-// re-insert the live entries of an old count table into a larger one
-__global__ void rehash64_kernel(const unsigned long long* keys, const uint32_t* counts, size_t n, CountTable64 dst) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (keys[i] != ~0ull) count_insert64(dst, keys[i], counts[i]);
-    }
-}
-
-__global__ void rehash128_kernel(const ulonglong2* keys, const uint32_t* counts, size_t n, CountTable128 dst) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (!(keys[i].x == ~0ull && keys[i].y == ~0ull)) count_insert128(dst, keys[i], counts[i]);
-    }
-}
-
-// compact the live entries of a count table: out_keys/out_counts sized by the live count
-__global__ void compact64_kernel(const unsigned long long* keys, const uint32_t* counts, size_t n,
-                                 unsigned long long* out_keys, uint32_t* out_counts, unsigned long long* cursor) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (keys[i] != ~0ull) {
-            const unsigned long long at = atomicAdd(cursor, 1ull);
-            out_keys[at] = keys[i];
-            out_counts[at] = counts[i];
-        }
-    }
-}
-
-__global__ void compact128_kernel(const ulonglong2* keys, const uint32_t* counts, size_t n,
-                                  ulonglong2* out_keys, uint32_t* out_counts, unsigned long long* cursor) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (!(keys[i].x == ~0ull && keys[i].y == ~0ull)) {
-            const unsigned long long at = atomicAdd(cursor, 1ull);
-            out_keys[at] = keys[i];
-            out_counts[at] = counts[i];
-        }
-    }
 }
 
 } // namespace scg

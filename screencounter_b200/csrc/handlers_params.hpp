@@ -22,7 +22,8 @@ struct ReadsDev {
 
 struct SingleParams {
     ScanSpec spec;
-    LibDev lib_f, lib_r;
+    const LibDev* libs;   // device array: [0] forward library, [1] reverse-complemented library
+    int kw;               // words per plane of the longest key (host-side dispatch)
     int max_mm;
     int use_first;
 };
@@ -56,7 +57,9 @@ struct OddOutcome {
 
 struct ComboParams {
     ScanSpec spec;
-    LibDev lib_f[2], lib_r[2];   // lib_r[r] is built from the reverse complement of pool[1 - r]
+    const LibDev* libs;          // device array indexed [2 * reverse + region]; reverse region r is built
+                                 // from the reverse complement of pool[1 - r]
+    int kw;
     int max_mm;
     int use_first;
     int n1, n2;                  // pool sizes
@@ -71,7 +74,8 @@ struct ComboSink {
 
 struct DualSEParams {
     ScanSpec spec;
-    LibDev lib_f, lib_r;
+    const LibDev* libs;   // device array: [0] concatenated rows, [1] their reverse complements
+    int kw;
     int max_mm;
     int use_first;
 };
@@ -84,7 +88,8 @@ struct ComboPEParams {
 
 struct DualPEParams {
     ScanSpec spec1, spec2;   // each searches exactly one strand
-    LibDev lib;              // rows = [RC?]pool1[i] + [RC?]pool2[i], segments (len1, len2)
+    const LibDev* lib;       // device: rows = [RC?]pool1[i] + [RC?]pool2[i], segments (len1, len2)
+    int kw;
     int mm1, mm2;
     int randomized;
     int use_first;

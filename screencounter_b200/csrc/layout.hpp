@@ -56,13 +56,21 @@ SCG_HD uint64_t mix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-// Hash of a (masked) key given as KW words per plane.
+// Hash of a (masked) key given as kw words per plane: 32-bit multiply/xorshift rounds (cheap on the
+// GPU's integer pipes; the same function builds the tables on the host).
 SCG_HD uint32_t hash_key(const uint32_t* h, const uint32_t* l, int kw, uint32_t salt) {
-    uint64_t acc = 0x243F6A8885A308D3ull ^ salt;
+    uint32_t acc = salt * 0x9E3779B1u + 0x7F4A7C15u;
     for (int i = 0; i < kw; ++i) {
-        acc = mix64(acc ^ (((uint64_t)h[i] << 32) | l[i]));
+        acc = (acc ^ h[i]) * 0x85EBCA6Bu;
+        acc ^= acc >> 13;
+        acc = (acc ^ l[i]) * 0xC2B2AE35u;
+        acc ^= acc >> 16;
     }
-    return (uint32_t)(acc >> 32);
+    return acc;
 }
+
+// Slack after every packed-read buffer: the scan may load up to two words past a read's last
+// plane word (bits that are masked out afterwards), so the loads need no bounds checks.
+constexpr size_t READ_GUARD_BYTES = 1024;
 
 } // namespace scg

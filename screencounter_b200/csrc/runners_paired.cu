@@ -1,0 +1,288 @@
+// countDualBarcodes (reference src/count_dual_barcodes.cpp:12-116) and countPairedComboBarcodes
+// (src/count_combo_barcodes_paired.cpp:12-95).
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "api_common.hpp"
+#include "handlers.cuh"
+
+namespace scg {
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// CombinatorialBarcodesPairedEnd (reference handlers/CombinatorialBarcodesPairedEnd.hpp:58-98): two
+// independent single-barcode matchers, each on its own configured strand.
+struct ComboPEMatcher {
+    SingleMatcher m1, m2;
+    ComboPEParams params;
+
+    void prepare(const std::string& c1, bool rev1, int mm1, const Pool& p1, const std::string& c2, bool rev2, int mm2, const Pool& p2,
+                 bool randomized, bool use_first, Duplicates dup) {
+        if (std::max(c1.size(), c2.size()) > (size_t)MAX_TEMPLATE) {
+            throw Error("lacking compile-time support for constant regions longer than 256 bp");
+        }
+        m1.prepare(c1, rev1 ? 1 : 0, p1, mm1, use_first, dup);
+        m2.prepare(c2, rev2 ? 1 : 0, p2, mm2, use_first, dup);
+        std::memset(&params, 0, sizeof params);
+        params.randomized = randomized ? 1 : 0;
+        params.use_first = use_first ? 1 : 0;
+    }
+
+    void upload(Context& ctx) {
+        m1.upload(ctx);
+        m2.upload(ctx);
+        params.m1 = m1.params;
+        params.m2 = m2.params;
+    }
+};
+
+static void launch_combo_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const ComboPEParams& P, const ComboSink& sink,
+                            int32_t* counters, const int32_t* skip_if_found, int32_t* out_pairs, int32_t* out_code) {
+    if (r1.n <= 0) return;
+    const long long ntiles = (r1.n + TILE - 1) / TILE;
+    const int grid = ctx.grid_for(ntiles);
+    const int cb = std::max(P.m1.spec.cbits, P.m2.spec.cbits);
+    const int kw = std::max(P.m1.kw, P.m2.kw);
+    dispatch_cb(cb, [&](auto CB) {
+        dispatch_kw(kw, [&](auto KW) {
+            combo_pe_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, ctx.stream>>>(r1, r2, P, sink, counters, skip_if_found,
+                                                                                                 out_pairs, out_code);
+        });
+    });
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    ++ctx.timing.launches;
+}
+
+// DualBarcodesPairedEnd (reference handlers/DualBarcodesPairedEnd.hpp:92-179).
+struct DualPEMatcher {
+    TemplateSpec t1, t2;
+    DeviceLibrary lib;
+    DeviceBuffer lib_dev;
+    DualPEParams params;
+
+    void prepare(const std::string& c1, bool rev1, int mm1, const Pool& p1, const std::string& c2, bool rev2, int mm2, const Pool& p2,
+                 bool randomized, bool use_first) {
+        if (std::max(c1.size(), c2.size()) > (size_t)MAX_TEMPLATE) {
+            throw Error("lacking compile-time support for constant regions longer than 256 bp");
+        }
+        t1 = TemplateSpec(c1, rev1 ? 1 : 0);
+        t2 = TemplateSpec(c2, rev2 ? 1 : 0);
+        if (p1.seqs.size() != p2.seqs.size()) throw Error("both barcode pools should be of the same length");
+        if (t1.fwd_regions.size() != 1) throw Error("expected one variable region in the first constant template");
+        const int len1 = t1.fwd_regions[0].end - t1.fwd_regions[0].start;
+        if (len1 != p1.length) {
+            throw Error("length of variable sequences (" + std::to_string(p1.length) + ") should be the same as the variable region (" +
+                        std::to_string(len1) + ")");
+        }
+        if (t2.fwd_regions.size() != 1) throw Error("expected one variable region in the second constant template");
+        const int len2 = t2.fwd_regions[0].end - t2.fwd_regions[0].start;
+        if (len2 != p2.length) {
+            throw Error("length of variable sequences (" + std::to_string(p2.length) + ") should be the same as the variable region (" +
+                        std::to_string(len2) + ")");
+        }
+        // rows = each half reverse-complemented on its own when its strand is reverse (:139-164)
+        std::vector<std::string> combined;
+        combined.reserve(p1.seqs.size());
+        for (size_t i = 0; i < p1.seqs.size(); ++i) {
+            combined.push_back((rev1 ? reverse_complement_iupac(p1.seqs[i]) : p1.seqs[i]) +
+                               (rev2 ? reverse_complement_iupac(p2.seqs[i]) : p2.seqs[i]));
+        }
+        // The reference's segmented trie search has a phantom result when the second cap is 0.
+        // The device search reproduces it for first-segment caps 0 and 1; larger budgets on read 1 need the
+        // trie-walk emulation, which this engine does not carry yet -- refuse rather than risk different counts.
+        if (mm1 >= 2) {
+            throw Error("countDualBarcodes with 2 or more substitutions on the first read is not supported by this engine yet");
+        }
+        LibraryOptions opt;
+        opt.segmented = true;
+        opt.seg1 = len1;
+        opt.max_mismatches1 = mm1;
+        opt.max_mismatches2 = mm2;
+        opt.duplicates = Duplicates::ERROR;
+        lib.host = Library(combined, len1 + len2, opt);
+        std::memset(&params, 0, sizeof params);
+        params.spec1 = t1.scan_spec(mm1);
+        params.spec2 = t2.scan_spec(mm2);
+        params.mm1 = mm1;
+        params.mm2 = mm2;
+        params.randomized = randomized ? 1 : 0;
+        params.use_first = use_first ? 1 : 0;
+        params.len1 = len1;
+        params.len2 = len2;
+    }
+
+    void upload(Context& ctx) {
+        lib.upload(ctx);
+        params.lib = upload_lib_array(ctx, std::vector<LibDev>{ lib.dev }, lib_dev);
+        params.kw = lib.dev.KW;
+    }
+};
+
+struct PairedSources {
+    Source s1, s2;
+    PairedSources(const scg_source* a, const scg_source* b) : s1(a), s2(b) {}
+};
+
+} // namespace scg
+
+using namespace scg;
+
+extern "C" {
+
+int scg_count_combo_paired(scg_ctx* ctx, const scg_source* src1, const char* constant1, int reverse1, int mismatches1,
+                           const char* const* pool1, int npool1, const scg_source* src2, const char* constant2, int reverse2,
+                           int mismatches2, const char* const* pool2, int npool2, int randomized, int use_first, int nthreads,
+                           int want_trace, scg_result** table, int32_t* total, int32_t* barcode1_only, int32_t* barcode2_only) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        const double t_start = now_s();
+        c.timing = Timing();
+        Source s1(src1);
+        Pool p1(pool1, npool1);
+        Source s2(src2);
+        Pool p2(pool2, npool2);
+        ComboPEMatcher m;
+        m.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0,
+                  Duplicates::ERROR);
+        c.ensure_ready();
+        m.upload(c);
+        ComboTally tally;
+        tally.init(c, npool1, npool2);
+        DeviceBuffer d_counters, d_pairs, d_code;
+        d_counters.alloc(2 * sizeof(int32_t), true);
+        std::vector<int32_t> trace_pairs, trace_code;
+
+        ReadPipeline pipe(c, s1.reader.get(), s2.reader.get(), nthreads, false);
+        ReadPipeline::Batch b;
+        long long npairs = 0;
+        while (pipe.next(b)) {
+            if (want_trace) {
+                d_pairs.reserve((size_t)b.n * 2 * sizeof(int32_t));
+                d_code.reserve((size_t)b.n * sizeof(int32_t));
+            }
+            launch_combo_pe(c, b.reads1, b.reads2, m.params, tally.sink(c, b.n), d_counters.as<int32_t>(), nullptr,
+                            want_trace ? d_pairs.as<int32_t>() : nullptr, want_trace ? d_code.as<int32_t>() : nullptr);
+            pipe.submitted(b);
+            if (want_trace) {
+                const size_t at = trace_pairs.size(), ac = trace_code.size();
+                trace_pairs.resize(at + (size_t)b.n * 2);
+                trace_code.resize(ac + (size_t)b.n);
+                SCG_CUDA_CHECK(cudaMemcpyAsync(trace_pairs.data() + at, d_pairs.ptr, (size_t)b.n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                SCG_CUDA_CHECK(cudaMemcpyAsync(trace_code.data() + ac, d_code.ptr, (size_t)b.n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            }
+            npairs += b.n;
+        }
+        int32_t only[2] = { 0, 0 };
+        SCG_CUDA_CHECK(cudaMemcpyAsync(only, d_counters.ptr, sizeof only, cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        auto* r = new scg_result;
+        tally.harvest(c, *r);
+        if (want_trace) {
+            r->trace_width = 2;
+            r->trace_index.swap(trace_pairs);
+            r->trace_info.assign(trace_code.begin(), trace_code.end());
+        }
+        *table = r;
+        *total = (int32_t)npairs;
+        *barcode1_only = only[0];
+        *barcode2_only = only[1];
+        c.timing.parse_s = s1.reader->parse_seconds() + s2.reader->parse_seconds();
+        c.timing.total_s = now_s() - t_start;
+        c.finish_timing();
+    });
+}
+
+int scg_count_dual(scg_ctx* ctx, const scg_source* src1, const char* constant1, int reverse1, int mismatches1, const char* const* pool1,
+                   int npool1, const scg_source* src2, const char* constant2, int reverse2, int mismatches2, const char* const* pool2,
+                   int npool2, int randomized, int use_first, int diagnostics, int nthreads, int want_trace, int32_t* counts,
+                   int32_t* total, scg_result** table, int32_t* barcode1_only, int32_t* barcode2_only) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        const double t_start = now_s();
+        c.timing = Timing();
+        Source s1(src1);
+        Pool p1(pool1, npool1);
+        Source s2(src2);
+        Pool p2(pool2, npool2);
+        DualPEMatcher m;
+        m.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0);
+        ComboPEMatcher combo;
+        if (diagnostics) {
+            // DualBarcodesPairedEndWithDiagnostics (reference handlers/DualBarcodesPairedEndWithDiagnostics.hpp:53-72):
+            // the combinatorial sub-handler allows duplicated single barcodes (DuplicateAction::FIRST)
+            combo.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0,
+                          use_first != 0, Duplicates::FIRST);
+        }
+        c.ensure_ready();
+        m.upload(c);
+        ComboTally tally;
+        DeviceBuffer d_counters;
+        d_counters.alloc(2 * sizeof(int32_t), true);
+        if (diagnostics) {
+            combo.upload(c);
+            tally.init(c, npool1, npool2);
+        }
+        DeviceBuffer d_counts, d_index;
+        d_counts.alloc((size_t)std::max(npool1, 1) * sizeof(int32_t), true);
+        const bool need_index = diagnostics || want_trace;
+        std::vector<int32_t> trace_index;
+
+        ReadPipeline pipe(c, s1.reader.get(), s2.reader.get(), nthreads, false);
+        ReadPipeline::Batch b;
+        long long npairs = 0;
+        while (pipe.next(b)) {
+            if (need_index) d_index.reserve((size_t)b.n * sizeof(int32_t));
+            const long long ntiles = (b.n + TILE - 1) / TILE;
+            const int grid = c.grid_for(ntiles);
+            const int cb = std::max(m.params.spec1.cbits, m.params.spec2.cbits);
+            dispatch_cb(cb, [&](auto CB) {
+                dispatch_kw(m.params.kw, [&](auto KW) {
+                    dual_pe_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, c.stream>>>(
+                        b.reads1, b.reads2, m.params, d_counts.as<int32_t>(), need_index ? d_index.as<int32_t>() : nullptr);
+                });
+            });
+            SCG_CUDA_CHECK(cudaGetLastError());
+            ++c.launches;
+            ++c.timing.launches;
+            if (diagnostics) {
+                // pairs without a valid combination go to the combinatorial handler (:115-120)
+                launch_combo_pe(c, b.reads1, b.reads2, combo.params, tally.sink(c, b.n), d_counters.as<int32_t>(), d_index.as<int32_t>(),
+                                nullptr, nullptr);
+            }
+            pipe.submitted(b);
+            if (want_trace) {
+                const size_t at = trace_index.size();
+                trace_index.resize(at + (size_t)b.n);
+                SCG_CUDA_CHECK(cudaMemcpyAsync(trace_index.data() + at, d_index.ptr, (size_t)b.n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            }
+            npairs += b.n;
+        }
+        SCG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts.ptr, (size_t)npool1 * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        int32_t only[2] = { 0, 0 };
+        SCG_CUDA_CHECK(cudaMemcpyAsync(only, d_counters.ptr, sizeof only, cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        *total = (int32_t)npairs;
+        if (barcode1_only) *barcode1_only = only[0];
+        if (barcode2_only) *barcode2_only = only[1];
+        if (table) {
+            auto* r = new scg_result;
+            if (diagnostics) tally.harvest(c, *r);
+            if (want_trace) {
+                r->trace_width = 1;
+                r->trace_index.swap(trace_index);
+            }
+            *table = r;
+        }
+        c.timing.parse_s = s1.reader->parse_seconds() + s2.reader->parse_seconds();
+        c.timing.total_s = now_s() - t_start;
+        c.finish_timing();
+    });
+}
+
+} // extern "C"

@@ -85,15 +85,27 @@ void SingleMatcher::prepare(const std::string& constant, int strand, const Pool&
     params.use_first = use_first ? 1 : 0;
 }
 
+const LibDev* upload_lib_array(Context& ctx, const std::vector<LibDev>& libs, DeviceBuffer& storage) {
+    storage.upload(libs.data(), libs.size() * sizeof(LibDev), ctx.stream);
+    SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    return storage.as<LibDev>();
+}
+
 void SingleMatcher::upload(Context& ctx) {
+    std::vector<LibDev> libs(2);
+    std::memset(libs.data(), 0, 2 * sizeof(LibDev));
+    params.kw = 1;
     if (tmpl.fwd) {
         lib_f.upload(ctx);
-        params.lib_f = lib_f.dev;
+        libs[0] = lib_f.dev;
+        params.kw = std::max(params.kw, lib_f.dev.KW);
     }
     if (tmpl.rev) {
         lib_r.upload(ctx);
-        params.lib_r = lib_r.dev;
+        libs[1] = lib_r.dev;
+        params.kw = std::max(params.kw, lib_r.dev.KW);
     }
+    params.libs = upload_lib_array(ctx, libs, libs_dev);
 }
 
 void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, int32_t* d_counts, int32_t* d_index, uint32_t* d_info,
@@ -101,7 +113,7 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, i
     if (reads.n <= 0) return;
     const long long ntiles = (reads.n + TILE - 1) / TILE;
     const int grid = ctx.grid_for(ntiles);
-    const int kw = std::max(P.spec.fwd ? P.lib_f.KW : 1, P.spec.rev ? P.lib_r.KW : 1);
+    const int kw = P.kw;
     dispatch_cb(P.spec.cbits, [&](auto CB) {
         dispatch_kw(kw, [&](auto KW) {
             single_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(reads, P, d_counts, d_index, d_info);
@@ -238,7 +250,8 @@ int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequence
             uint32_t* base = &qk[(size_t)i * 3 * KW];
             pack_key(queries.seqs[i].data(), L, base, base + KW, base + 2 * KW);
         }
-        DeviceBuffer d_q, d_idx, d_mm;
+        DeviceBuffer d_q, d_idx, d_mm, d_lib;
+        const LibDev* libp = upload_lib_array(c, std::vector<LibDev>{ lib.dev }, d_lib);
         d_q.upload(qk.data(), qk.size() * sizeof(uint32_t), c.stream);
         d_idx.alloc((size_t)nsequences * sizeof(int32_t), false);
         d_mm.alloc((size_t)nsequences * sizeof(int32_t), false);
@@ -246,7 +259,7 @@ int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequence
         dispatch_kw(KW, [&](auto KWC) {
             constexpr int K = decltype(KWC)::value;
             if (K == KW) {
-                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, lib.dev, substitutions, d_idx.as<int32_t>(),
+                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, libp, substitutions, d_idx.as<int32_t>(),
                                                             d_mm.as<int32_t>());
             } else {
                 // repack to the compiled width
@@ -258,7 +271,7 @@ int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequence
                 }
                 d_q.upload(wide.data(), wide.size() * sizeof(uint32_t), c.stream);
                 SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
-                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, lib.dev, substitutions, d_idx.as<int32_t>(),
+                match_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, libp, substitutions, d_idx.as<int32_t>(),
                                                             d_mm.as<int32_t>());
             }
         });
@@ -284,7 +297,7 @@ int scg_reads_from_source(scg_ctx* ctx, const scg_source* src, int nthreads, scg
             // keep a private copy of the staged batch
             DeviceBatch keep;
             const size_t words = (size_t)((b.n + TILE - 1) / TILE) * tile_words(b.reads1.W);
-            keep.data.alloc(words * sizeof(uint32_t), false);
+            keep.data.alloc(words * sizeof(uint32_t) + READ_GUARD_BYTES, false);
             SCG_CUDA_CHECK(cudaMemcpyAsync(keep.data.ptr, b.reads1.data, words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
             keep.view = b.reads1;
             keep.view.data = keep.data.as<uint32_t>();
@@ -330,7 +343,7 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
     return guarded(plan->owner, [&] {
         Context& c = plan->owner->impl;
         SCG_CUDA_CHECK(cudaSetDevice(c.device));
-        cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c.stream;
+        cudaStream_t st = cuda_stream == SCG_STREAM_OWN ? c.stream : static_cast<cudaStream_t>(cuda_stream);
         long long at = 0;
         for (const auto& b : reads->batches) {
             launch_single(c, b.view, plan->matcher.params, d_counts, d_index ? d_index + at : nullptr, nullptr, st);
@@ -362,7 +375,7 @@ int scg_device_free(scg_ctx* ctx, void* ptr) {
 int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream) {
     return guarded(ctx, [&] {
         ctx->impl.ensure_ready();
-        cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->impl.stream;
+        cudaStream_t st = cuda_stream == SCG_STREAM_OWN ? ctx->impl.stream : static_cast<cudaStream_t>(cuda_stream);
         SCG_CUDA_CHECK(cudaMemsetAsync(ptr, 0, bytes, st));
     });
 }

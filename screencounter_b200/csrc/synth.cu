@@ -202,7 +202,7 @@ int scg_reads_synthesize(scg_ctx* ctx, const scg_synth_spec* spec, scg_reads** o
             const long long n = std::min(per_batch, spec->n_reads - at);
             DeviceBatch b;
             const size_t words = (size_t)((n + TILE - 1) / TILE) * tile_words(W);
-            b.data.alloc(words * sizeof(uint32_t), false);
+            b.data.alloc(words * sizeof(uint32_t) + READ_GUARD_BYTES, false);
             b.view.data = b.data.as<uint32_t>();
             b.view.lens = nullptr;
             b.view.uniform_len = spec->read_len;

@@ -35,6 +35,11 @@ def _synth_spec(seed, first_read, n_reads, read_len, constant, pools, paired_row
     return spec, keep
 
 
+def _stream(stream):
+    # SCG_STREAM_OWN = (void*)-1 selects the context's stream; anything else is a cudaStream_t used as given
+    return C.c_void_p(-1 & (2 ** (8 * C.sizeof(C.c_void_p)) - 1)) if stream is None else C.c_void_p(int(stream))
+
+
 class SynthSpec:
     """The synthetic workload of SURVEY.md 8(d): identical reads on the host (FASTQ text) and on the device."""
 
@@ -120,10 +125,10 @@ class SinglePlan:
                                                       int(mismatches), int(bool(use_first)), C.byref(self.handle)))
 
     def run(self, reads, counts_ptr, index_ptr=None, stream=None):
-        """One pass over `reads`; counts (device int32[npool]) are accumulated into.  Asynchronous."""
+        """One pass over `reads`; counts (device int32[npool]) are accumulated into.  Asynchronous.
+        stream: None = the context's own stream; an int = that cudaStream_t (0 = CUDA's default stream)."""
         _check(self.ctx, lib().scg_single_plan_run(self.handle, reads.handle, C.c_void_p(counts_ptr),
-                                                   C.c_void_p(index_ptr) if index_ptr else None,
-                                                   C.c_void_p(stream) if stream else None))
+                                                   C.c_void_p(index_ptr) if index_ptr else None, _stream(stream)))
 
     def free(self):
         if self.handle:
@@ -148,7 +153,7 @@ class DeviceArray:
         self.ptr = p.value
 
     def zero(self):
-        _check(self.ctx, lib().scg_device_zero(self.ctx, C.c_void_p(self.ptr), C.c_size_t(self.nbytes), None))
+        _check(self.ctx, lib().scg_device_zero(self.ctx, C.c_void_p(self.ptr), C.c_size_t(self.nbytes), _stream(None)))
 
     def to_numpy(self, dtype):
         out = np.zeros(self.nbytes // np.dtype(dtype).itemsize, dtype=dtype)

@@ -144,3 +144,122 @@ def timing(device=None):
 
 def kernel_launches(device=None):
     return int(lib().scg_kernel_launches(context(device)))
+
+
+def count_random_barcodes(path, constant, strand, mismatches, use_first, nthreads, device=None):
+    """reference: src/count_random_barcodes.cpp:41-60 -> list(list(sequences, frequencies), total).
+    Sequences come back sorted (R sorts them anyway, R/countRandomBarcodes.R:73-74)."""
+    ctx = context(device)
+    src = _Src(path)
+    handle = C.c_void_p()
+    total = C.c_int32()
+    _check(ctx, lib().scg_count_random(ctx, src.ref(), constant.encode("latin-1"), int(strand), int(mismatches), int(bool(use_first)),
+                                       int(nthreads), C.byref(handle), C.byref(total)))
+    seqs, freq = _table(handle, "random")
+    lib().scg_result_free(handle)
+    return [[seqs, freq], total.value]
+
+
+def count_combo_barcodes_single(path, constant, strand, pool, mismatches, use_first, nthreads, trace=False, device=None):
+    """reference: src/count_combo_barcodes_single.cpp:40-70 -> list(2 x k matrix (0-based), freq, total)."""
+    if len(pool) != 2:
+        raise ScreenCounterError("currently expecting only 2 variable regions for single-end combinatorial barcodes")
+    ctx = context(device)
+    src = _Src(path)
+    a1, k1 = _strs(pool[0])
+    a2, k2 = _strs(pool[1])
+    handle = C.c_void_p()
+    total = C.c_int32()
+    _check(ctx, lib().scg_count_combo_single(ctx, src.ref(), constant.encode("latin-1"), int(strand), a1, len(pool[0]), a2, len(pool[1]),
+                                             int(mismatches), int(bool(use_first)), int(nthreads), int(bool(trace)),
+                                             C.byref(handle), C.byref(total)))
+    keys, freq = _table(handle, "combo")
+    out = [keys.T.copy(), freq, np.array([total.value], dtype=np.int32)]
+    if trace:
+        out.append(_trace(handle)[0])
+    lib().scg_result_free(handle)
+    return out
+
+
+def count_dual_barcodes_single_end(path, constant, pools, strand, mismatches, use_first, diagnostics, nthreads, trace=False, device=None):
+    """reference: src/count_dual_barcodes_single_end.cpp:51-88 -> list(counts, total) or
+    list(counts, list(2 x k matrix, freq), total) with diagnostics."""
+    ctx = context(device)
+    src = _Src(path)
+    nchoices = len(pools[0]) if len(pools) else 0
+    flat = []
+    for p in pools:
+        if len(p) != nchoices:
+            raise ScreenCounterError("all entries of 'barcode_pools' should have the same length")
+        flat.extend(p)
+    arr, keep = _strs(flat)
+    counts = np.zeros(nchoices, dtype=np.int32)
+    total = C.c_int32()
+    handle = C.c_void_p()
+    _check(ctx, lib().scg_count_dual_single_end(ctx, src.ref(), constant.encode("latin-1"), arr, len(pools), nchoices, int(strand),
+                                                int(mismatches), int(bool(use_first)), int(bool(diagnostics)), int(nthreads),
+                                                int(bool(trace)), _ip(counts), C.byref(total), C.byref(handle)))
+    tot = np.array([total.value], dtype=np.int32)
+    if diagnostics:
+        keys, freq = _table(handle, "combo")
+        out = [counts, [keys.T.copy(), freq], tot]
+    else:
+        out = [counts, tot]
+    if trace:
+        out.append(_trace(handle)[0][:, 0])
+    lib().scg_result_free(handle)
+    return out
+
+
+def count_dual_barcodes(path1, constant1, reverse1, mismatches1, pool1, path2, constant2, reverse2, mismatches2, pool2,
+                        randomized, use_first, diagnostics, nthreads, trace=False, device=None):
+    """reference: src/count_dual_barcodes.cpp:75-116 -> list(counts, total) or
+    list(counts, list(2 x k matrix, freq), total, barcode1_only, barcode2_only) with diagnostics."""
+    ctx = context(device)
+    s1, s2 = _Src(path1), _Src(path2)
+    a1, k1 = _strs(pool1)
+    a2, k2 = _strs(pool2)
+    counts = np.zeros(len(pool1), dtype=np.int32)
+    total = C.c_int32()
+    b1 = C.c_int32()
+    b2 = C.c_int32()
+    handle = C.c_void_p()
+    _check(ctx, lib().scg_count_dual(ctx, s1.ref(), constant1.encode("latin-1"), int(bool(reverse1)), int(mismatches1), a1, len(pool1),
+                                     s2.ref(), constant2.encode("latin-1"), int(bool(reverse2)), int(mismatches2), a2, len(pool2),
+                                     int(bool(randomized)), int(bool(use_first)), int(bool(diagnostics)), int(nthreads), int(bool(trace)),
+                                     _ip(counts), C.byref(total), C.byref(handle), C.byref(b1), C.byref(b2)))
+    tot = np.array([total.value], dtype=np.int32)
+    if diagnostics:
+        keys, freq = _table(handle, "combo")
+        out = [counts, [keys.T.copy(), freq], tot, np.array([b1.value], dtype=np.int32), np.array([b2.value], dtype=np.int32)]
+    else:
+        out = [counts, tot]
+    if trace:
+        out.append(_trace(handle)[0][:, 0])
+    lib().scg_result_free(handle)
+    return out
+
+
+def count_combo_barcodes_paired(path1, constant1, reverse1, mismatches1, pool1, path2, constant2, reverse2, mismatches2, pool2,
+                                randomized, use_first, nthreads, trace=False, device=None):
+    """reference: src/count_combo_barcodes_paired.cpp:55-95 -> list(2 x k matrix, freq, total, barcode1_only, barcode2_only)."""
+    ctx = context(device)
+    s1, s2 = _Src(path1), _Src(path2)
+    a1, k1 = _strs(pool1)
+    a2, k2 = _strs(pool2)
+    total = C.c_int32()
+    b1 = C.c_int32()
+    b2 = C.c_int32()
+    handle = C.c_void_p()
+    _check(ctx, lib().scg_count_combo_paired(ctx, s1.ref(), constant1.encode("latin-1"), int(bool(reverse1)), int(mismatches1), a1, len(pool1),
+                                             s2.ref(), constant2.encode("latin-1"), int(bool(reverse2)), int(mismatches2), a2, len(pool2),
+                                             int(bool(randomized)), int(bool(use_first)), int(nthreads), int(bool(trace)),
+                                             C.byref(handle), C.byref(total), C.byref(b1), C.byref(b2)))
+    keys, freq = _table(handle, "combo")
+    out = [keys.T.copy(), freq, np.array([total.value], dtype=np.int32), np.array([b1.value], dtype=np.int32),
+           np.array([b2.value], dtype=np.int32)]
+    if trace:
+        index, info = _trace(handle)
+        out.append((index, info.astype(np.int32)))
+    lib().scg_result_free(handle)
+    return out
