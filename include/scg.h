@@ -173,6 +173,13 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
                         void* cuda_stream);
 void scg_plan_free(scg_plan* plan);
 
+/* Host-only check of the FASTQ reader + packer (no device needed): parses `src`, packs every read into
+ * the tile-planar 2-bit + N-mask layout and unpacks it again.  bases receives the concatenated
+ * sequences as upper-case A/C/G/T with N for every other character; offsets (n_reads + 1 entries)
+ * delimit them.  Call with bases == NULL to size the outputs (*n_reads, *n_bases). */
+int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, long long* offsets,
+                            long long* n_reads, long long* n_bases);
+
 /* Plain device-memory helpers so that a caller without a CUDA runtime of its own (R, ctypes)
  * can own buffers for scg_single_plan_run. */
 int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out);   /* zero-initialised */

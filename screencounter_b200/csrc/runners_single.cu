@@ -354,6 +354,49 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
 
 void scg_plan_free(scg_plan* plan) { delete plan; }
 
+// ---- host-only reader/packer check ---------------------------------------------------------------------
+int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, long long* offsets, long long* n_reads,
+                            long long* n_bases) {
+    try {
+        Source source(src);
+        long long nr = 0, nb = 0;
+        if (offsets) offsets[0] = 0;
+        std::vector<uint32_t> packed;
+        std::vector<uint16_t> lens;
+        for (;;) {
+            const auto& recs = source.reader->next(1u << 16);
+            if (recs.empty()) break;
+            uint32_t maxlen = 0;
+            for (const auto& r : recs) maxlen = std::max(maxlen, r.len);
+            const int W = std::max(1, ceil_div((int)maxlen, 32));
+            const size_t padded = (recs.size() + TILE - 1) / TILE * TILE;
+            packed.assign(padded / TILE * tile_words(W), 0xDEADBEEFu);
+            lens.assign(padded, 0);
+            pack_records(recs.data(), recs.size(), W, packed.data(), lens.data(), nullptr, nthreads);
+            for (size_t i = 0; i < recs.size(); ++i) {
+                const uint32_t* base = packed.data() + (i / TILE) * tile_words(W) + (i % TILE);
+                if (bases) {
+                    for (uint32_t k = 0; k < lens[i]; ++k) {
+                        const uint32_t h = (base[(size_t)(PLANE_H * W + (k >> 5)) * TILE] >> (k & 31)) & 1u;
+                        const uint32_t l = (base[(size_t)(PLANE_L * W + (k >> 5)) * TILE] >> (k & 31)) & 1u;
+                        const uint32_t n = (base[(size_t)(PLANE_N * W + (k >> 5)) * TILE] >> (k & 31)) & 1u;
+                        bases[nb + k] = n ? 'N' : "ACGT"[(h << 1) | l];
+                    }
+                }
+                nb += lens[i];
+                ++nr;
+                if (offsets) offsets[nr] = nb;
+            }
+        }
+        if (n_reads) *n_reads = nr;
+        if (n_bases) *n_bases = nb;
+        return 0;
+    } catch (const std::exception& e) {
+        creation_error() = e.what();
+        return 1;
+    }
+}
+
 // ---- plain device helpers ---------------------------------------------------------------------------
 int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out) {
     return guarded(ctx, [&] {

@@ -263,3 +263,20 @@ def count_combo_barcodes_paired(path1, constant1, reverse1, mismatches1, pool1, 
         out.append((index, info.astype(np.int32)))
     lib().scg_result_free(handle)
     return out
+
+
+def host_pack_roundtrip(fastq, nthreads=1):
+    """Host-only: parse + pack + unpack a FASTQ; returns the reads as the packed layout sees them
+    (upper-case ACGT, N for anything else).  Needs no device."""
+    src = _Src(fastq)
+    nr = C.c_longlong()
+    nb = C.c_longlong()
+    if lib().scg_host_pack_roundtrip(src.ref(), int(nthreads), None, None, C.byref(nr), C.byref(nb)) != 0:
+        raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+    bases = C.create_string_buffer(max(nb.value, 1))
+    offsets = np.zeros(nr.value + 1, dtype=np.int64)
+    src = _Src(fastq)
+    if lib().scg_host_pack_roundtrip(src.ref(), int(nthreads), bases, _ip(offsets), C.byref(nr), C.byref(nb)) != 0:
+        raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+    raw = bases.raw
+    return [raw[offsets[i]:offsets[i + 1]].decode("latin-1") for i in range(nr.value)]

@@ -1,0 +1,158 @@
+"""Host-side logic of the product that needs no GPU: the C ABI loads and exports what include/scg.h
+declares, the FASTQ reader/packer agrees with the reference's parser, validation errors carry the
+reference's texts, the synthetic generator is reproducible, and -- without a device -- counting
+fails loudly instead of falling back to a CPU path."""
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fastq_cases import GOOD, BAD
+from util import fastq, random_seq, mutate
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_abi_exports_every_declared_symbol():
+    from screencounter_b200._lib import lib, EXPORTS
+    header = open(os.path.join(ROOT, "include", "scg.h")).read()
+    declared = set(re.findall(r"\b(scg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    L = lib()
+    for name in EXPORTS:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.scg_version()
+
+
+def test_product_does_not_use_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "screencounter_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "kaori_port" not in text and "libkaori_ref" not in text and "liboracle" not in text, f
+
+
+def _norm(seq):
+    return "".join(c.upper() if c in "ACGTacgt" else "N" for c in seq)
+
+
+@pytest.mark.parametrize("name", sorted(GOOD))
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_reader_matches_reference_parser(kref, name, nthreads):
+    from screencounter_b200 import rcpp
+    data = GOOD[name]
+    assert rcpp.host_pack_roundtrip(data, nthreads) == [_norm(s) for s in kref.parse(data)]
+
+
+@pytest.mark.parametrize("name", sorted(BAD))
+def test_reader_errors(name):
+    from screencounter_b200 import rcpp
+    data, msg = BAD[name]
+    with pytest.raises(Exception) as err:
+        rcpp.host_pack_roundtrip(data)
+    assert str(err.value) == msg
+
+
+def test_reader_large_ragged_files_raw_and_gz(kref, tmp_path):
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(0)
+    reads = [mutate(rng, random_seq(rng, int(rng.integers(0, 300))), 0, 0.02, 0.05) for _ in range(30000)]
+    reads[5] = random_seq(rng, 5000)
+    data = fastq(reads)
+    want = [_norm(s) for s in reads]
+    assert [_norm(s) for s in kref.parse(data)] == want
+    raw = tmp_path / "x.fastq"
+    raw.write_bytes(data)
+    gz = tmp_path / "x.fastq.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(data)
+    for src in (data, str(raw), str(gz)):
+        assert rcpp.host_pack_roundtrip(src, 4) == want
+    with pytest.raises(Exception, match="failed to open file at"):
+        rcpp.host_pack_roundtrip(str(tmp_path / "missing.fastq"))
+
+
+VALIDATION = [
+    # (call, args, message) -- texts of the reference
+    ("single", dict(constant="ACGN--", pool=["AA"]), "unknown base 'N'"),
+    ("single", dict(constant="ACGN--", pool=["AA"], strand=1), "cannot complement unknown base 'N'"),
+    ("single", dict(constant="ACGT", pool=["AA"]), "expected one variable region in the constant template"),
+    ("single", dict(constant="AC--GT--", pool=["AA"]), "expected one variable region in the constant template"),
+    ("single", dict(constant="AC---", pool=["AA"]), "length of barcode_pool sequences (2) should be the same as the barcode_pool region (3)"),
+    ("single", dict(constant="AC--", pool=["AA", "AAA"]), "variable regions should all have the same length (2)"),
+    ("single", dict(constant="AC--", pool=["AA", "CC", "AA"]), "duplicate sequences detected (1, 3) when constructing the trie"),
+    ("single", dict(constant="AC--", pool=["AR", "AG"]), "duplicate sequences detected (1, 2) when constructing the trie"),
+    ("single", dict(constant="AC--", pool=["A!"]), "unknown base '!' detected when constructing the trie"),
+    ("single", dict(constant="A" * 250 + "-" * 7, pool=["ACGTACG"]), "lacking compile-time support for constant regions longer than 256 bp"),
+]
+
+
+@pytest.mark.parametrize("kind,kw,msg", VALIDATION)
+def test_validation_errors_need_no_device(kref, kind, kw, msg):
+    from screencounter_b200 import rcpp
+    args = (fastq(["ACGT"]), kw["constant"], kw.get("strand", 0), kw["pool"], 0, True)
+    with pytest.raises(Exception) as err:
+        rcpp.count_single_barcodes(*args, 1)
+    assert str(err.value) == msg
+    with pytest.raises(Exception) as ref_err:   # and the reference says the same
+        kref.count_single(*args)
+    assert str(ref_err.value) == msg
+
+
+def test_other_entry_points_validate_like_the_reference():
+    from screencounter_b200 import rcpp
+    f = fastq(["ACGT"])
+    with pytest.raises(Exception, match="expected 2 variable regions in the constant template"):
+        rcpp.count_combo_barcodes_single(f, "AC--", 0, [["AA"], ["CC"]], 0, True, 1)
+    with pytest.raises(Exception, match="currently expecting only 2 variable regions"):
+        rcpp.count_combo_barcodes_single(f, "AC--", 0, [["AA"]], 0, True, 1)
+    with pytest.raises(Exception, match=re.escape("length of variable region 2 (3) should be the same as its sequences (2)")):
+        rcpp.count_combo_barcodes_single(f, "AC--G---", 0, [["AA"], ["CC"]], 0, True, 1)
+    with pytest.raises(Exception, match="length of 'barcode_pools' should equal the number of variable regions"):
+        rcpp.count_dual_barcodes_single_end(f, "AC--", [["AA"], ["CC"]], 0, 0, True, False, 1)
+    with pytest.raises(Exception, match="both barcode pools should be of the same length"):
+        rcpp.count_dual_barcodes(f, "AC--", False, 0, ["AA", "CC"], f, "AC--", False, 0, ["AA"], False, True, False, 1)
+    with pytest.raises(Exception, match="expected one variable region in the second constant template"):
+        rcpp.count_dual_barcodes(f, "AC--", False, 0, ["AA"], f, "ACGT", False, 0, ["AA"], False, True, False, 1)
+    with pytest.raises(Exception, match=re.escape("duplicate sequences detected (1, 2) when constructing the trie")):
+        rcpp.count_dual_barcodes(f, "AC--", False, 0, ["AA", "AA"], f, "AC--", False, 0, ["CC", "CC"], False, True, False, 1)
+    with pytest.raises(Exception, match="expected at least one variable region"):
+        rcpp.count_random_barcodes(f, "ACGT", 0, 0, True, 1)
+    with pytest.raises(Exception, match="variable regions should all have the same length"):
+        rcpp.match_barcodes(["AAA"], ["AAA", "AA"], 0, False)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful where no CUDA device exists")
+def test_no_device_is_a_loud_error_not_a_cpu_fallback():
+    from screencounter_b200 import rcpp
+    with pytest.raises(Exception, match="no usable CUDA device: this engine has no CPU fallback"):
+        rcpp.count_single_barcodes(fastq(["ACGTAA"]), "AC--", 0, ["GT"], 0, True, 1)
+
+
+def test_synthetic_generator_is_shard_reproducible(kref):
+    from screencounter_b200.device import SynthSpec
+    rng = np.random.default_rng(0)
+    pool = ["".join("ACGT"[i] for i in rng.integers(0, 4, 20)) for _ in range(64)]
+    template = "CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG"
+    spec = SynthSpec(template, [pool], seed=42, read_len=75, strand=2)
+    whole = spec.fastq(0, 3000)
+    per = 2 * 75 + 7
+    assert len(whole) == 3000 * per
+    assert spec.fastq(1000, 500) == whole[1000 * per:1500 * per]
+    reads = kref.parse(whole)
+    assert all(len(r) == 75 for r in reads)
+    index, info = kref.trace_single(whole, template, 2, pool, 1, True)
+    assert 0.75 < (index >= 0).mean() < 0.95           # ~90 % carry a construct, 1 % substitutions
+    assert 0.3 < info[index >= 0, 1].mean() < 0.7      # about half on the reverse strand
+    assert sum("N" in r for r in reads) > 0
