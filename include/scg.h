@@ -172,6 +172,9 @@ int scg_single_plan_create(scg_ctx* ctx, const char* constant, int strand,
 int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_counts, int32_t* d_index,
                         void* cuda_stream);
 void scg_plan_free(scg_plan* plan);
+/* Which kernel variant the plan's last run used: "specialised (NVRTC)" = the template compiled into the
+ * kernel at run time, or "generic (<why>)". */
+const char* scg_plan_kernel(const scg_plan* plan);
 
 /* Host-only check of the FASTQ reader + packer (no device needed): parses `src`, packs every read into
  * the tile-planar 2-bit + N-mask layout and unpacks it again.  bases receives the concatenated
@@ -179,6 +182,11 @@ void scg_plan_free(scg_plan* plan);
  * delimit them.  Call with bases == NULL to size the outputs (*n_reads, *n_bases). */
 int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, long long* offsets,
                             long long* n_reads, long long* n_bases);
+
+/* Compiles the run-time specialised single-barcode kernel for a template (NVRTC) and, when a device is
+ * present, loads it.  Returns 0 = compiled and loaded, 2 = compiled but no device to load it on,
+ * 1 = failed; `message` receives the details.  Diagnostic only. */
+int scg_jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, char* message, size_t capacity);
 
 /* Plain device-memory helpers so that a caller without a CUDA runtime of its own (R, ctypes)
  * can own buffers for scg_single_plan_run. */

@@ -68,6 +68,8 @@ def lib():
         L.scg_reads_free.restype = None
         L.scg_plan_free.argtypes = [C.c_void_p]
         L.scg_plan_free.restype = None
+        L.scg_plan_kernel.restype = C.c_char_p
+        L.scg_plan_kernel.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -81,7 +83,7 @@ EXPORTS = [
     "scg_count_combo_paired", "scg_match_barcodes",
     "scg_reads_from_source", "scg_reads_count", "scg_reads_device_bytes", "scg_reads_free",
     "scg_reads_synthesize", "scg_synth_fastq",
-    "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free",
-    "scg_host_pack_roundtrip",
+    "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",
+    "scg_host_pack_roundtrip", "scg_jit_selftest",
     "scg_device_alloc", "scg_device_free", "scg_device_zero", "scg_device_to_host", "scg_synchronize",
 ]

@@ -103,13 +103,16 @@ struct SingleMatcher {
     DeviceBuffer libs_dev;   // LibDev[2] on the device: forward, reverse
     SingleParams params;
     int npool = 0;
+    mutable std::string kernel_note;   // which kernel the last launch used, and why
     // SimpleSingleMatch constructor (reference inst/include/kaori/SimpleSingleMatch.hpp:61-97): host-only, throws
     // the reference's validation errors; upload() then moves the tables to the device.
     void prepare(const std::string& constant, int strand, const Pool& pool, int mismatches, bool use_first, Duplicates dup);
     void upload(Context& ctx);
 };
 
-void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, int32_t* d_counts, int32_t* d_index,
+// Runs the single-barcode kernel over one batch: the run-time specialised kernel (jit.hpp) when it
+// can be had, the generic one otherwise.
+void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, int32_t* d_counts, int32_t* d_index,
                    uint32_t* d_info, cudaStream_t stream);
 
 // Device count table (64- or 128-bit keys) that grows with the number of reads seen.

@@ -1,0 +1,369 @@
+// Device-side building blocks shared by every handler kernel (nvcc-built and NVRTC-specialised):
+//   * the bit-sliced mismatch counter of the position-parallel scan;
+//   * extraction of a variable region from the read's bit planes;
+//   * the barcode lookups (replace SimpleBarcodeSearch::search / SegmentedBarcodeSearch::search,
+//     BarcodeSearch.hpp:243-251, 478-487 and the trie searches of MismatchTrie.hpp:446-660).
+#pragma once
+
+#include "layout.hpp"
+#include "libdev.hpp"
+
+namespace scg {
+
+// One lane's view of its read inside a tile (layout.hpp): word w of plane p is ptr[(p*W + w)*32].
+struct ReadView {
+    const uint32_t* __restrict__ ptr;
+    int W;
+    int len;
+    // No bounds check: the scan and the extraction may read up to two words past the read's last
+    // plane word; every buffer carries READ_GUARD_BYTES of slack and those bits are masked out.
+    __device__ __forceinline__ uint32_t word(int plane, int w) const {
+        return __ldg(ptr + (size_t)(plane * W + w) * TILE);
+    }
+};
+
+// Bit-sliced saturating counter over 32 window positions: CB planes + a sticky overflow plane.
+// add(m) adds 1 at every position whose bit is set in m.
+template <int CB>
+struct Counter {
+    uint32_t c[CB > 0 ? CB : 1];
+    uint32_t ovf;
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < CB; ++i) c[i] = 0;
+        ovf = 0;
+    }
+    __device__ __forceinline__ void add(uint32_t m) {
+        uint32_t carry = m;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+            uint32_t t = c[i] & carry;
+            c[i] ^= carry;
+            carry = t;
+        }
+        ovf |= carry;
+    }
+    // positions whose count is <= mm (mm < 2^CB; the caller clamps)
+    __device__ __forceinline__ uint32_t le(int mm) const {
+        if (mm < 0) return 0u;
+        // count <= mm  <=>  not overflowed and not (count > mm); compare bit-sliced from the top
+        uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = CB - 1; i >= 0; --i) {
+            uint32_t mbit = ((mm >> i) & 1) ? 0xFFFFFFFFu : 0u;
+            gt |= eq & c[i] & ~mbit;
+            eq &= ~(c[i] ^ mbit);
+        }
+        return ~ovf & ~gt;
+    }
+    __device__ __forceinline__ int get(int p) const {
+        int v = 0;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) v |= ((c[i] >> p) & 1u) << i;
+        return v;
+    }
+};
+
+// Windows of block pb that exist in a read of length len: positions p with 32*pb + p + T <= len.
+__device__ __forceinline__ uint32_t valid_windows(int len, int T, int pb) {
+    int npos = len - T + 1 - 32 * pb;
+    if (npos <= 0) return 0u;
+    return npos >= 32 ? 0xFFFFFFFFu : ((1u << npos) - 1u);
+}
+
+
+__device__ __forceinline__ ReadView read_view(const ReadsDev& r, long long tile, int lane) {
+    ReadView v;
+    v.ptr = r.data + (size_t)tile * tile_words(r.W) + lane;
+    v.W = r.W;
+    const long long i = tile * TILE + lane;
+    v.len = (i < r.n) ? (r.lens ? (int)r.lens[i] : r.uniform_len) : 0;
+    return v;
+}
+
+__device__ __forceinline__ int window_blocks(int len, int T) {
+    const int npos = len - T + 1;
+    return npos <= 0 ? 0 : (npos + 31) >> 5;
+}
+
+// info word of the per-read trace (include/scg.h, scg_result_copy_trace)
+__device__ __forceinline__ uint32_t pack_info(bool found, bool reverse, int mismatches, int var_mismatches, int position) {
+    if (!found) return 0u;
+    return 0x80000000u | (reverse ? 0x40000000u : 0u) | ((uint32_t)min(var_mismatches, 31) << 25) |
+           ((uint32_t)min(mismatches, 31) << 20) | ((uint32_t)position & 0xFFFFFu);
+}
+
+// outcome of one single-barcode search (SimpleSingleMatch::State, SimpleSingleMatch.hpp:103-140)
+struct SingleOut {
+    bool found;
+    int index;
+    int position;
+    bool reverse;
+    int mismatches;
+    int var_mismatches;
+};
+
+// ---- keys ---------------------------------------------------------------------------------
+
+template <int KW>
+struct Key {
+    uint32_t h[KW], l[KW], n[KW];
+};
+
+// Extract `len` bases starting at read bit `start` as a key (KW static words; no dynamic register
+// indexing, so the key stays in registers).
+template <int KW>
+__device__ __forceinline__ void extract_region(const ReadView& rd, int start, int len, Key<KW>& k) {
+    const int a = start >> 5, sh = start & 31;
+    uint32_t h0 = rd.word(PLANE_H, a), l0 = rd.word(PLANE_L, a), n0 = rd.word(PLANE_N, a);
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int rem = len - 32 * w;
+        if (rem > 0) {
+            const uint32_t h1 = rd.word(PLANE_H, a + w + 1), l1 = rd.word(PLANE_L, a + w + 1), n1 = rd.word(PLANE_N, a + w + 1);
+            const uint32_t m = rem >= 32 ? 0xFFFFFFFFu : ((1u << rem) - 1u);
+            k.h[w] = __funnelshift_r(h0, h1, sh) & m;
+            k.l[w] = __funnelshift_r(l0, l1, sh) & m;
+            k.n[w] = __funnelshift_r(n0, n1, sh) & m;
+            h0 = h1;
+            l0 = l1;
+            n0 = n1;
+        } else {
+            k.h[w] = k.l[w] = k.n[w] = 0;
+        }
+    }
+}
+
+// OR `len` bases starting at read bit `start` into an existing key at bit offset dst_bit
+// (regions concatenated for the dual designs).  Every destination word is visited statically.
+template <int KW>
+__device__ __forceinline__ void extract_into(const ReadView& rd, int start, int len, int dst_bit, Key<KW>& k) {
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int d0 = max(dst_bit, 32 * w), d1 = min(dst_bit + len, 32 * w + 32);
+        if (d0 < d1) {
+            const int sbit = start + (d0 - dst_bit);
+            const int a = sbit >> 5, sh = sbit & 31;
+            const int take = d1 - d0;
+            const uint32_t m = take >= 32 ? 0xFFFFFFFFu : ((1u << take) - 1u);
+            const int db = d0 - 32 * w;
+            k.h[w] |= (__funnelshift_r(rd.word(PLANE_H, a), rd.word(PLANE_H, a + 1), sh) & m) << db;
+            k.l[w] |= (__funnelshift_r(rd.word(PLANE_L, a), rd.word(PLANE_L, a + 1), sh) & m) << db;
+            k.n[w] |= (__funnelshift_r(rd.word(PLANE_N, a), rd.word(PLANE_N, a + 1), sh) & m) << db;
+        }
+    }
+}
+
+template <int KW>
+__device__ __forceinline__ void key_clear(Key<KW>& k) {
+#pragma unroll
+    for (int w = 0; w < KW; ++w) k.h[w] = k.l[w] = k.n[w] = 0;
+}
+
+// Reverse complement of a key of `len` bases (used by the random-barcode handler).
+template <int KW>
+__device__ __forceinline__ void key_revcomp(Key<KW>& k, int len) {
+    // reverse all KW*32 bits, then shift right by (KW*32 - len); complement = flip both planes
+    uint32_t rh[KW], rl[KW], rn[KW];
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        rh[w] = __brev(k.h[KW - 1 - w]);
+        rl[w] = __brev(k.l[KW - 1 - w]);
+        rn[w] = __brev(k.n[KW - 1 - w]);
+    }
+    const int shift = KW * 32 - len;
+    const int ws = shift >> 5, bs = shift & 31;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        uint32_t lo_h = (w + ws < KW) ? rh[w + ws] : 0u, hi_h = (w + ws + 1 < KW) ? rh[w + ws + 1] : 0u;
+        uint32_t lo_l = (w + ws < KW) ? rl[w + ws] : 0u, hi_l = (w + ws + 1 < KW) ? rl[w + ws + 1] : 0u;
+        uint32_t lo_n = (w + ws < KW) ? rn[w + ws] : 0u, hi_n = (w + ws + 1 < KW) ? rn[w + ws + 1] : 0u;
+        k.h[w] = __funnelshift_r(lo_h, hi_h, bs);
+        k.l[w] = __funnelshift_r(lo_l, hi_l, bs);
+        k.n[w] = __funnelshift_r(lo_n, hi_n, bs);
+    }
+    // complement the called bases only (an N stays an N with H = L = 0)
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int rem = len - 32 * w;
+        const uint32_t m = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+        k.h[w] = (~k.h[w]) & m & ~k.n[w];
+        k.l[w] = (~k.l[w]) & m & ~k.n[w];
+    }
+}
+
+// ---- lookups --------------------------------------------------------------------------------
+
+struct Hit {
+    int index;  // pool index, or -1 (missing or ambiguous; the handlers treat both alike)
+    int dist;
+};
+
+template <int KW>
+__device__ __forceinline__ bool key_has_n(const Key<KW>& k) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) any |= k.n[w];
+    return any != 0;
+}
+
+// Probe an open-addressing table of packed keys (library.cpp insert_slot).  Returns the slot's
+// value or -1.  hm/lm are the (masked) key planes to look for; kw (<= KW) is the table's own
+// number of words per plane.
+template <int KW>
+__device__ __forceinline__ int probe_table(const uint32_t* __restrict__ slots, uint32_t mask, int slot_words, int kw,
+                                           const uint32_t* hm, const uint32_t* lm) {
+    uint32_t pos = hash_key(hm, lm, KW == 1 ? 1 : kw, 0) & mask;
+    for (;;) {
+        const uint32_t* s = slots + (size_t)pos * slot_words;
+        if (KW == 1) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(s));
+            if ((int)v.z == -1) return -1;
+            if (v.x == hm[0] && v.y == lm[0]) return (int)v.z;
+        } else {
+            const int val = (int)__ldg(s + 2 * kw);
+            if (val == -1) return -1;
+            bool same = true;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) {
+                if (w < kw) same &= (__ldg(s + w) == hm[w]) & (__ldg(s + kw + w) == lm[w]);
+            }
+            if (same) return val;
+        }
+        pos = (pos + 1) & mask;
+    }
+}
+
+// Candidate enumeration through the pigeonhole seeds + verification (the mismatch-tolerant part of
+// both searches).  seg1 < 0: one cap (c1) on the total distance; seg1 >= 0: caps (c1, c2) on the
+// two segments [0, seg1) and [seg1, L).  Applies the best-unique / tie rules of
+// MismatchTrie.hpp:266-343 to the verified distances.
+template <int KW>
+__device__ __noinline__ Hit lookup_seeded(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2, int seg1) {
+    const LibDev lib = *libp;
+    Hit out{ -1, 0 };
+    const int kw = KW == 1 ? 1 : lib.KW;
+    const bool segmented = seg1 >= 0;
+    uint32_t s1m[KW];  // base positions of the first segment
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        const int rem = (segmented ? seg1 : 0) - 32 * w;
+        s1m[w] = rem >= 32 ? 0xFFFFFFFFu : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+    }
+    const int cap = segmented ? c1 + c2 : c1;
+    int best = cap + 1, bidx = -1;
+    bool ambiguous = false;
+    for (int sd = 0; sd < lib.nseeds; ++sd) {
+        const uint32_t* sm = lib.seed_masks + sd * kw;
+        uint32_t mh[KW], ml[KW], bad = 0;
+#pragma unroll
+        for (int w = 0; w < KW; ++w) {
+            const uint32_t m = (w < kw) ? __ldg(sm + w) : 0u;
+            mh[w] = q.h[w] & m;
+            ml[w] = q.l[w] & m;
+            bad |= q.n[w] & m;
+        }
+        if (bad) continue;  // an N inside the seed: no barcode agrees with the query there
+        const uint32_t b = hash_key(mh, ml, kw, 0x5EED0000u + sd) & lib.bucket_mask;
+        const uint2 bk = __ldg(lib.buckets + (size_t)sd * (lib.bucket_mask + 1) + b);
+        const int32_t* cd = lib.cands + (size_t)sd * lib.nentries + bk.x;
+        for (uint32_t c = 0; c < bk.y; ++c) {
+            const int e = __ldg(cd + c);
+            const uint32_t* ek = lib.ent_keys + (size_t)e * 2 * kw;
+            int d1 = 0, d2 = 0;
+#pragma unroll
+            for (int w = 0; w < KW; ++w) {
+                if (w < kw) {
+                    const uint32_t diff = (q.h[w] ^ __ldg(ek + w)) | (q.l[w] ^ __ldg(ek + kw + w)) | q.n[w];
+                    d1 += __popc(diff & s1m[w]);
+                    d2 += __popc(diff & ~s1m[w]);
+                }
+            }
+            if (segmented ? (d1 > c1 || d2 > c2) : (d2 > c1)) continue;
+            const int d = d1 + d2;
+            if (d > best) continue;
+            const int idx = __ldg(lib.ent_idx + e);
+            if (d < best) {
+                best = d;
+                bidx = idx;
+                ambiguous = false;
+            } else if (idx != bidx) {  // d == best
+                if (lib.dup_first) {
+                    bidx = min(bidx, idx);
+                } else {
+                    ambiguous = true;
+                }
+            }
+        }
+    }
+    if (bidx >= 0 && !ambiguous) {
+        out.index = bidx;
+        out.dist = best;
+    }
+    return out;
+}
+
+// Best-unique search with a single cap (AnyMismatches::search semantics, MismatchTrie.hpp:446-501):
+// the minimum distance over the library if it is <= cap and attained by one pool index, else a miss.
+// A query position holding N mismatches every barcode.
+template <int KW>
+__device__ __forceinline__ Hit lookup_any(const LibDev* __restrict__ lib, const Key<KW>& q, int cap) {
+    Hit out{ -1, 0 };
+    const int kw = KW == 1 ? 1 : lib->KW;
+    if (!key_has_n(q)) {
+        const int v = probe_table<KW>(lib->slots, lib->slot_mask, KW == 1 ? 4 : lib->slot_words, kw, q.h, q.l);
+        if (v >= 0) {
+            out.index = v;
+            return out;
+        }
+    }
+    if (cap <= 0 || lib->nseeds == 0) return out;
+    int nbad = 0;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) nbad += __popc(q.n[w]);
+    if (nbad > cap) return out;
+    return lookup_seeded<KW>(lib, q, min(cap, lib->L), 0, -1);
+}
+
+// Best-unique search with one cap per segment (SegmentedMismatches<2>::search,
+// MismatchTrie.hpp:577-660), cache-free semantics, including the phantom result of :608-617
+// when the second segment's cap is 0 ("Quirk A"):
+//   c2 == 0, c1 == 1 : if the query minus its last base is free of N and is a prefix of a library
+//                      row, the search reports no match ("root rule");
+//   c2 == 0, c1 >= 2 : not handled here -- the host refuses such budgets (runners_paired.cu).
+template <int KW>
+__device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
+    Hit out{ -1, 0 };
+    const LibDev lib = *libp;
+    const int kw = KW == 1 ? 1 : lib.KW;
+    if (!key_has_n(q)) {
+        const int v = probe_table<KW>(lib.slots, lib.slot_mask, lib.slot_words, kw, q.h, q.l);
+        if (v >= 0) {
+            out.index = v;
+            return out;
+        }
+    }
+    if ((c1 <= 0 && c2 <= 0) || lib.nseeds == 0) return out;
+    if (c2 == 0 && c1 >= 1) {
+        // root rule: the exact chain down to the last base exists -> the phantom (MISSING, 1) ties or beats every hit
+        uint32_t ph[KW], pl[KW], pn = 0;
+        const int lw = (lib.L - 1) >> 5;
+        const uint32_t lastbit = 1u << ((lib.L - 1) & 31);
+#pragma unroll
+        for (int w = 0; w < KW; ++w) {
+            ph[w] = q.h[w];
+            pl[w] = q.l[w];
+            uint32_t nn = q.n[w];
+            if (w == lw) {
+                ph[w] &= ~lastbit;
+                pl[w] &= ~lastbit;
+                nn &= ~lastbit;
+            }
+            pn |= nn;
+        }
+        if (!pn && probe_table<KW>(lib.prefix_slots, lib.prefix_mask, lib.slot_words, kw, ph, pl) >= 0) return out;
+    }
+    return lookup_seeded<KW>(libp, q, min(c1, lib.seg1), min(c2, lib.L - lib.seg1), lib.seg1);
+}
+
+} // namespace scg

@@ -97,10 +97,15 @@ void Context::finish_timing() {
     char buf[512];
     std::snprintf(buf, sizeof buf,
                   "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"total_s\": %.6f, "
-                  "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld}",
+                  "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld, \"kernel\": \"",
                   timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.total_s, timing.reads, timing.bytes_h2d,
                   timing.launches);
     timing_json = buf;
+    for (char ch : kernel_note) {
+        if (ch == '"' || ch == '\\' || ch == '\n') ch = ' ';
+        timing_json.push_back(ch);
+    }
+    timing_json += "\"}";
 }
 
 // ---------------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     std::string last_error;
     std::string timing_json;
+    std::string kernel_note;   // which kernel variant the last launch used
     Timing timing;
     long long launches = 0;
 

@@ -17,39 +17,10 @@
 namespace scg {
 
 
-__device__ __forceinline__ ReadView read_view(const ReadsDev& r, long long tile, int lane) {
-    ReadView v;
-    v.ptr = r.data + (size_t)tile * tile_words(r.W) + lane;
-    v.W = r.W;
-    const long long i = tile * TILE + lane;
-    v.len = (i < r.n) ? (r.lens ? (int)r.lens[i] : r.uniform_len) : 0;
-    return v;
-}
-
-__device__ __forceinline__ int window_blocks(int len, int T) {
-    const int npos = len - T + 1;
-    return npos <= 0 ? 0 : (npos + 31) >> 5;
-}
-
-// info word of the per-read trace (include/scg.h, scg_result_copy_trace)
-__device__ __forceinline__ uint32_t pack_info(bool found, bool reverse, int mismatches, int var_mismatches, int position) {
-    if (!found) return 0u;
-    return 0x80000000u | (reverse ? 0x40000000u : 0u) | ((uint32_t)min(var_mismatches, 31) << 25) |
-           ((uint32_t)min(mismatches, 31) << 20) | ((uint32_t)position & 0xFFFFFu);
-}
-
 // -------------------------------------------------------------------------------------------
 // single barcode (also the building block of the paired combinatorial design)
 // -------------------------------------------------------------------------------------------
 
-struct SingleOut {
-    bool found;
-    int index;
-    int position;
-    bool reverse;
-    int mismatches;
-    int var_mismatches;
-};
 
 template <int CB, int KW>
 __device__ __forceinline__ SingleOut single_search(const ReadView& rd, const SingleParams& P, bool use_first) {

@@ -6,19 +6,12 @@
 #include <cuda_runtime.h>
 
 #include "layout.hpp"
+#include "libdev.hpp"
 #include "library.hpp"
 #include "template_spec.hpp"
 
 namespace scg {
 
-// Packed reads of one batch on the device.
-struct ReadsDev {
-    const uint32_t* data;   // tile-planar words
-    const uint16_t* lens;   // nullptr when every read has length uniform_len
-    int uniform_len;
-    int W;
-    long long n;
-};
 
 struct SingleParams {
     ScanSpec spec;

@@ -1,0 +1,198 @@
+#include "jit.hpp"
+
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <vector>
+
+#include "common.hpp"
+
+namespace scg {
+
+namespace {
+
+struct EmbeddedSource {
+    const char* name;
+    const char* text;
+};
+#include "embedded_sources.inc"
+
+// the handful of NVRTC entry points used, resolved at run time
+typedef struct _nvrtcProgram* nvrtcProgram;
+typedef int nvrtcResult;
+struct Nvrtc {
+    void* handle = nullptr;
+    std::string where;
+    nvrtcResult (*Version)(int*, int*) = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    std::string problem;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        std::vector<std::string> candidates;
+        if (const char* env = std::getenv("SCG_NVRTC_PATH")) candidates.push_back(env);
+        for (const char* name : { "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                                  "libnvrtc.so.13", "libnvrtc.so" }) {
+            candidates.push_back(name);
+        }
+        for (const auto& c : candidates) {
+            n.handle = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (n.handle) {
+                n.where = c;
+                break;
+            }
+        }
+        if (!n.handle) {
+            n.problem = "libnvrtc not found (set SCG_NVRTC_PATH)";
+            return;
+        }
+#define SCG_NVRTC_SYM(field, name)                                                       \
+    n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.handle, name));                \
+    if (!n.field) {                                                                      \
+        n.problem = std::string("libnvrtc lacks ") + name;                               \
+        return;                                                                          \
+    }
+        SCG_NVRTC_SYM(Version, "nvrtcVersion")
+        SCG_NVRTC_SYM(CreateProgram, "nvrtcCreateProgram")
+        SCG_NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram")
+        SCG_NVRTC_SYM(CompileProgram, "nvrtcCompileProgram")
+        SCG_NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+        SCG_NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog")
+        SCG_NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+        SCG_NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN")
+        SCG_NVRTC_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef SCG_NVRTC_SYM
+    });
+    return n;
+}
+
+struct Cached {
+    cudaLibrary_t library = nullptr;
+    cudaKernel_t kernel = nullptr;
+    std::string problem;
+};
+
+std::mutex g_mutex;
+std::map<std::string, Cached> g_cache;
+
+} // namespace
+
+std::string SpecSingleConfig::key() const {
+    std::ostringstream o;
+    o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
+      << fstart << '|' << rstart << '|' << keylen;
+    return o.str();
+}
+
+std::string jit_status() {
+    Nvrtc& n = nvrtc();
+    if (!n.problem.empty()) return n.problem;
+    int major = 0, minor = 0;
+    n.Version(&major, &minor);
+    return "nvrtc " + std::to_string(major) + "." + std::to_string(minor) + " from " + n.where;
+}
+
+cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why) {
+    auto fail = [&](const std::string& msg) -> cudaKernel_t {
+        if (why) *why = msg;
+        return nullptr;
+    };
+    if (const char* env = std::getenv("SCG_NO_SPECIALIZE")) {
+        if (env[0] && env[0] != '0') return fail("disabled by SCG_NO_SPECIALIZE");
+    }
+    // register budget: 4 mismatch planes of W + 2 words must stay in registers
+    if (cfg.W > 6) return fail("reads longer than 192 bases use the generic kernel");
+    if (cfg.T > 128) return fail("templates longer than 128 bases use the generic kernel");
+    if (cfg.cb > 3) return fail("mismatch budgets above 7 use the generic kernel");
+    if (cfg.keylen > 512) return fail("key too long");
+    Nvrtc& n = nvrtc();
+    if (!n.problem.empty()) return fail(n.problem);
+
+    const std::string key = std::to_string(device) + "#" + cfg.key();
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end()) {
+        if (!it->second.kernel && why) *why = it->second.problem;
+        return it->second.kernel;
+    }
+    Cached entry;
+    auto remember = [&](const std::string& problem) -> cudaKernel_t {
+        entry.problem = problem;
+        g_cache[key] = entry;
+        if (why) *why = problem;
+        return nullptr;
+    };
+
+    std::ostringstream src;
+    const int nb = (32 * cfg.W - cfg.T + 1 + 31) / 32;
+    src << "#define SPEC_CUSTOM 1\n"
+        << "#define SPEC_T " << cfg.T << "\n"
+        << "#define SPEC_FBASES \"" << cfg.fbases << "\"\n"
+        << "#define SPEC_RBASES \"" << cfg.rbases << "\"\n"
+        << "#define SPEC_FWD " << cfg.fwd << "\n"
+        << "#define SPEC_REV " << cfg.rev << "\n"
+        << "#define SPEC_W " << cfg.W << "\n"
+        << "#define SPEC_NB " << (nb < 1 ? 1 : nb) << "\n"
+        << "#define SPEC_CB " << cfg.cb << "\n"
+        << "#define SPEC_MM " << cfg.mm << "\n"
+        << "#define SPEC_MAXMM " << cfg.maxmm << "\n"
+        << "#define SPEC_USE_FIRST " << cfg.use_first << "\n"
+        << "#define SPEC_FSTART " << cfg.fstart << "\n"
+        << "#define SPEC_RSTART " << cfg.rstart << "\n"
+        << "#define SPEC_KEYLEN " << cfg.keylen << "\n"
+        << "#define SPEC_NAME spec_single_kernel\n"
+        << "#include \"spec_single.cuh\"\n";
+    const std::string program_text = src.str();
+
+    std::vector<const char*> header_text, header_name;
+    for (const auto& e : kEmbeddedSources) {
+        header_text.push_back(e.text);
+        header_name.push_back(e.name);
+    }
+    nvrtcProgram prog = nullptr;
+    nvrtcResult rc = n.CreateProgram(&prog, program_text.c_str(), "spec_single_jit.cu", (int)header_text.size(), header_text.data(),
+                                     header_name.data());
+    if (rc != 0) return remember(std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc));
+    const char* options[] = { "--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device" };
+    rc = n.CompileProgram(prog, 3, options);
+    if (rc != 0) {
+        size_t log_size = 0;
+        n.GetProgramLogSize(prog, &log_size);
+        std::string log(log_size, '\0');
+        if (log_size) n.GetProgramLog(prog, &log[0]);
+        n.DestroyProgram(&prog);
+        return remember(std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log);
+    }
+    size_t cubin_size = 0;
+    n.GetCUBINSize(prog, &cubin_size);
+    std::vector<char> cubin(cubin_size);
+    rc = n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    if (rc != 0 || cubin_size == 0) return remember("nvrtcGetCUBIN failed");
+
+    cudaError_t st = cudaLibraryLoadData(&entry.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (st != cudaSuccess) return remember(std::string("cudaLibraryLoadData: ") + cudaGetErrorString(st));
+    st = cudaLibraryGetKernel(&entry.kernel, entry.library, "spec_single_kernel");
+    if (st != cudaSuccess) {
+        entry.kernel = nullptr;
+        return remember(std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(st));
+    }
+    g_cache[key] = entry;
+    return entry.kernel;
+}
+
+} // namespace scg

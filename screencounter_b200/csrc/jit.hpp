@@ -1,0 +1,32 @@
+// Run-time specialisation of the scan kernel: the template in use is compiled into the kernel with
+// NVRTC (libnvrtc is opened with dlopen; nothing links against it), the cubin is loaded through the
+// CUDA runtime's library API and cached for the life of the process.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "handlers_params.hpp"
+#include "template_spec.hpp"
+
+namespace scg {
+
+struct SpecSingleConfig {
+    std::string fbases, rbases;   // forward / reverse-complemented template, '-' for variable positions
+    int T = 0, fwd = 0, rev = 0;
+    int W = 0;                    // words per plane of the batch
+    int cb = 0, mm = 0, maxmm = 0, use_first = 1;
+    int fstart = 0, rstart = 0, keylen = 0;
+    std::string key() const;
+};
+
+// Returns a launchable kernel for the configuration, or nullptr (with the reason in *why) when
+// run-time compilation is unavailable or disabled (SCG_NO_SPECIALIZE=1); callers then use the
+// generic kernel.  Thread-safe.
+cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why);
+
+// Human-readable status of the run-time compiler ("nvrtc 12.9 from <path>" or why it is missing).
+std::string jit_status();
+
+} // namespace scg

@@ -16,7 +16,18 @@
 // per plane; an extracted variable region also carries its N plane.
 #pragma once
 
+#if defined(__CUDACC_RTC__)
+// run-time compilation: no standard headers, so the fixed-width types are spelled out
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
+#include <cstddef>
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define SCG_HD __host__ __device__ __forceinline__

@@ -1,0 +1,44 @@
+// Plain-old-data views of device-resident objects, readable by nvcc-built kernels and by the
+// run-time specialised kernels (NVRTC) alike: no standard headers.
+#pragma once
+
+#include "layout.hpp"
+
+namespace scg {
+
+// Device view of a library (library.hpp builds it): plain pointers into device memory.
+struct LibDev {
+    int L;              // key length in bases
+    int KW;             // words per plane
+    int nentries;       // expanded (concrete) entries
+    int dup_first;      // ties between different indices resolve to the lowest index
+    // exact table: nslots slots of slot_words words: h[KW], l[KW], value (-1 = empty), padding
+    const uint32_t* slots;
+    uint32_t slot_mask;
+    int slot_words;
+    // expanded entries for verification: ent_keys[e*2KW ..] = h[KW], l[KW]; ent_idx[e] = pool index
+    const uint32_t* ent_keys;
+    const int32_t* ent_idx;
+    // pigeonhole seeds
+    int nseeds;
+    const uint32_t* seed_masks;  // nseeds * KW words: base positions of each seed (same mask for H and L)
+    const uint2* buckets;     // nseeds * (bucket_mask + 1) entries of (start, count) into cands
+    uint32_t bucket_mask;
+    const int32_t* cands;     // nseeds * nentries entry ids, grouped by bucket
+    // segmented search (dual paired-end): first segment = bases [0, seg1), second = [seg1, L)
+    int seg1;
+    // table of library rows with their last base dropped (SURVEY 8.1 T8 root rule)
+    const uint32_t* prefix_slots;
+    uint32_t prefix_mask;
+};
+
+// Packed reads of one batch on the device.
+struct ReadsDev {
+    const uint32_t* data;   // tile-planar words
+    const uint16_t* lens;   // nullptr when every read has length uniform_len
+    int uniform_len;
+    int W;
+    long long n;
+};
+
+} // namespace scg

@@ -6,6 +6,7 @@
 
 #include "api_common.hpp"
 #include "handlers.cuh"
+#include "jit.hpp"
 
 namespace scg {
 
@@ -108,17 +109,46 @@ void SingleMatcher::upload(Context& ctx) {
     params.libs = upload_lib_array(ctx, libs, libs_dev);
 }
 
-void launch_single(Context& ctx, const ReadsDev& reads, const SingleParams& P, int32_t* d_counts, int32_t* d_index, uint32_t* d_info,
+void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, int32_t* d_counts, int32_t* d_index, uint32_t* d_info,
                    cudaStream_t stream) {
     if (reads.n <= 0) return;
+    const SingleParams& P = m.params;
     const long long ntiles = (reads.n + TILE - 1) / TILE;
     const int grid = ctx.grid_for(ntiles);
-    const int kw = P.kw;
-    dispatch_cb(P.spec.cbits, [&](auto CB) {
-        dispatch_kw(kw, [&](auto KW) {
-            single_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(reads, P, d_counts, d_index, d_info);
+
+    // the template folded into the kernel at run time (spec_single.cuh via NVRTC)
+    SpecSingleConfig cfg;
+    cfg.fbases = m.tmpl.fwd_seq;
+    cfg.rbases = m.tmpl.rev ? m.tmpl.rev_seq : std::string(m.tmpl.length, '-');
+    cfg.T = m.tmpl.length;
+    cfg.fwd = m.tmpl.fwd ? 1 : 0;
+    cfg.rev = m.tmpl.rev ? 1 : 0;
+    cfg.W = reads.W;
+    cfg.cb = P.spec.cbits;
+    cfg.mm = P.spec.mm;
+    cfg.maxmm = P.max_mm;
+    cfg.use_first = P.use_first;
+    cfg.fstart = P.spec.fstart[0];
+    cfg.rstart = P.spec.rstart[0];
+    cfg.keylen = P.spec.rlen_f[0];
+    std::string why;
+    cudaKernel_t spec = (P.spec.mm >= 0 && cfg.T > 0) ? specialised_single_kernel(cfg, ctx.device, &why) : nullptr;
+    if (spec) {
+        ReadsDev reads_arg = reads;
+        const LibDev* libs = P.libs;
+        void* args[] = { &reads_arg, &libs, &d_counts, &d_index, &d_info };
+        SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(grid), dim3(128), args, 0, stream));
+        m.kernel_note = "specialised (NVRTC)";
+        ctx.kernel_note = m.kernel_note;
+    } else {
+        dispatch_cb(P.spec.cbits, [&](auto CB) {
+            dispatch_kw(P.kw, [&](auto KW) {
+                single_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(reads, P, d_counts, d_index, d_info);
+            });
         });
-    });
+        m.kernel_note = "generic (" + why + ")";
+        ctx.kernel_note = m.kernel_note;
+    }
     SCG_CUDA_CHECK(cudaGetLastError());
     ++ctx.launches;
     ++ctx.timing.launches;
@@ -197,7 +227,7 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         long long nreads = 0;
         while (pipe.next(b)) {
             sink.prepare(b.n, true);
-            launch_single(c, b.reads1, m.params, d_counts.as<int32_t>(), sink.enabled ? sink.d_index.as<int32_t>() : nullptr,
+            launch_single(c, b.reads1, m, d_counts.as<int32_t>(), sink.enabled ? sink.d_index.as<int32_t>() : nullptr,
                           sink.enabled ? sink.d_info.as<uint32_t>() : nullptr, c.stream);
             pipe.submitted(b);
             sink.collect(c, b.n, true);
@@ -346,13 +376,57 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
         cudaStream_t st = cuda_stream == SCG_STREAM_OWN ? c.stream : static_cast<cudaStream_t>(cuda_stream);
         long long at = 0;
         for (const auto& b : reads->batches) {
-            launch_single(c, b.view, plan->matcher.params, d_counts, d_index ? d_index + at : nullptr, nullptr, st);
+            launch_single(c, b.view, plan->matcher, d_counts, d_index ? d_index + at : nullptr, nullptr, st);
             at += b.view.n;
         }
     });
 }
 
 void scg_plan_free(scg_plan* plan) { delete plan; }
+
+const char* scg_plan_kernel(const scg_plan* plan) { return plan ? plan->matcher.kernel_note.c_str() : ""; }
+
+// ---- run-time compiler check (no device needed for the compile step) --------------------------------------
+int scg_jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, char* message, size_t capacity) {
+    std::string msg;
+    int status = 1;
+    try {
+        TemplateSpec t(constant, strand);
+        if (t.fwd_regions.size() != 1) throw Error("expected one variable region in the constant template");
+        const ScanSpec s = t.scan_spec(mismatches);
+        SpecSingleConfig cfg;
+        cfg.fbases = t.fwd_seq;
+        cfg.rbases = t.rev ? t.rev_seq : std::string(t.length, '-');
+        cfg.T = t.length;
+        cfg.fwd = t.fwd;
+        cfg.rev = t.rev;
+        cfg.W = words_per_plane;
+        cfg.cb = s.cbits;
+        cfg.mm = s.mm;
+        cfg.maxmm = mismatches;
+        cfg.use_first = 1;
+        cfg.fstart = s.fstart[0];
+        cfg.rstart = s.rstart[0];
+        cfg.keylen = s.rlen_f[0];
+        std::string why;
+        cudaKernel_t k = specialised_single_kernel(cfg, 0, &why);
+        if (k) {
+            msg = "ok: " + jit_status();
+            status = 0;
+        } else {
+            msg = why + " [" + jit_status() + "]";
+            // compiling worked if the only failure is loading the cubin onto a (missing) device
+            status = why.rfind("cudaLibraryLoadData", 0) == 0 ? 2 : 1;
+        }
+    } catch (const std::exception& e) {
+        msg = e.what();
+    }
+    if (message && capacity) {
+        std::strncpy(message, msg.c_str(), capacity - 1);
+        message[capacity - 1] = 0;
+    }
+    return status;
+}
 
 // ---- host-only reader/packer check ---------------------------------------------------------------------
 int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, long long* offsets, long long* n_reads,

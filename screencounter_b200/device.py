@@ -130,6 +130,10 @@ class SinglePlan:
         _check(self.ctx, lib().scg_single_plan_run(self.handle, reads.handle, C.c_void_p(counts_ptr),
                                                    C.c_void_p(index_ptr) if index_ptr else None, _stream(stream)))
 
+    @property
+    def kernel(self):
+        return lib().scg_plan_kernel(self.handle).decode()
+
     def free(self):
         if self.handle:
             lib().scg_plan_free(self.handle)

@@ -156,3 +156,19 @@ def test_synthetic_generator_is_shard_reproducible(kref):
     assert 0.75 < (index >= 0).mean() < 0.95           # ~90 % carry a construct, 1 % substitutions
     assert 0.3 < info[index >= 0, 1].mean() < 0.7      # about half on the reverse strand
     assert sum("N" in r for r in reads) > 0
+
+
+@pytest.mark.parametrize("template,strand,mm,words", [
+    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 1, 3),
+    ("ACGT----------TGCA", 0, 0, 2),
+    ("ACGT----------TGCA", 1, 3, 5),
+    ("A" * 60 + "-" * 8 + "C" * 60, 2, 2, 6),
+])
+def test_runtime_specialised_kernel_compiles(template, strand, mm, words):
+    """The NVRTC step of the specialised scan kernel needs no device: 0 = compiled and loaded,
+    2 = compiled, nothing to load it on."""
+    import ctypes as C
+    from screencounter_b200._lib import lib
+    buf = C.create_string_buffer(16384)
+    rc = lib().scg_jit_selftest(template.encode(), strand, mm, words, buf, C.c_size_t(16384))
+    assert rc in (0, 2), buf.value.decode()
