@@ -207,30 +207,37 @@ __device__ __forceinline__ bool key_has_n(const Key<KW>& k) {
     return any != 0;
 }
 
-// Probe an open-addressing table of packed keys (library.cpp insert_slot).  Returns the slot's
-// value or -1.  hm/lm are the (masked) key planes to look for; kw (<= KW) is the table's own
-// number of words per plane.
+// Probe a two-table cuckoo hash of packed keys (library.cpp CuckooTable): the key, if present, sits
+// at one of exactly two slots, so both are fetched at once -- two independent loads, no loop, no
+// divergence between lanes.  Returns the slot's value or -1.  hm/lm are the (masked) key planes to
+// look for; kw (<= KW) is the table's own number of words per plane.
 template <int KW>
 __device__ __forceinline__ int probe_table(const uint32_t* __restrict__ slots, uint32_t mask, int slot_words, int kw,
                                            const uint32_t* hm, const uint32_t* lm) {
-    uint32_t pos = hash_key(hm, lm, KW == 1 ? 1 : kw, 0) & mask;
-    for (;;) {
-        const uint32_t* s = slots + (size_t)pos * slot_words;
-        if (KW == 1) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(s));
-            if ((int)v.z == -1) return -1;
-            if (v.x == hm[0] && v.y == lm[0]) return (int)v.z;
-        } else {
+    const uint32_t acc = hash_key(hm, lm, KW == 1 ? 1 : kw, 0);
+    const uint32_t* s1 = slots + (size_t)(acc & mask) * slot_words;
+    const uint32_t* s2 = slots + ((size_t)(mask + 1) + (hash_second(acc) & mask)) * slot_words;
+    if (KW == 1) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(s1));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(s2));
+        // values are >= 0; an empty slot holds -1 (and zero key planes, which a poly-A query also has)
+        const int ra = (a.x == hm[0] && a.y == lm[0]) ? (int)a.z : -1;
+        const int rb = (b.x == hm[0] && b.y == lm[0]) ? (int)b.z : -1;
+        return max(ra, rb);
+    } else {
+        int out = -1;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t* s = t ? s2 : s1;
             const int val = (int)__ldg(s + 2 * kw);
-            if (val == -1) return -1;
-            bool same = true;
+            bool same = val != -1;
 #pragma unroll
             for (int w = 0; w < KW; ++w) {
                 if (w < kw) same &= (__ldg(s + w) == hm[w]) & (__ldg(s + kw + w) == lm[w]);
             }
-            if (same) return val;
+            if (same) out = val;
         }
-        pos = (pos + 1) & mask;
+        return out;
     }
 }
 
@@ -239,7 +246,7 @@ __device__ __forceinline__ int probe_table(const uint32_t* __restrict__ slots, u
 // two segments [0, seg1) and [seg1, L).  Applies the best-unique / tie rules of
 // MismatchTrie.hpp:266-343 to the verified distances.
 template <int KW>
-__device__ __noinline__ Hit lookup_seeded(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2, int seg1) {
+__device__ __forceinline__ Hit lookup_seeded_body(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2, int seg1) {
     const LibDev lib = *libp;
     Hit out{ -1, 0 };
     const int kw = KW == 1 ? 1 : lib.KW;
@@ -303,10 +310,16 @@ __device__ __noinline__ Hit lookup_seeded(const LibDev* __restrict__ libp, const
     return out;
 }
 
+// Out of line by default (the handler kernels call it from several places); INLINE = true folds it into the caller.
+template <int KW>
+__device__ __noinline__ Hit lookup_seeded(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2, int seg1) {
+    return lookup_seeded_body<KW>(libp, q, c1, c2, seg1);
+}
+
 // Best-unique search with a single cap (AnyMismatches::search semantics, MismatchTrie.hpp:446-501):
 // the minimum distance over the library if it is <= cap and attained by one pool index, else a miss.
 // A query position holding N mismatches every barcode.
-template <int KW>
+template <int KW, bool INLINE = false>
 __device__ __forceinline__ Hit lookup_any(const LibDev* __restrict__ lib, const Key<KW>& q, int cap) {
     Hit out{ -1, 0 };
     const int kw = KW == 1 ? 1 : lib->KW;
@@ -322,6 +335,7 @@ __device__ __forceinline__ Hit lookup_any(const LibDev* __restrict__ lib, const 
 #pragma unroll
     for (int w = 0; w < KW; ++w) nbad += __popc(q.n[w]);
     if (nbad > cap) return out;
+    if (INLINE) return lookup_seeded_body<KW>(lib, q, min(cap, lib->L), 0, -1);
     return lookup_seeded<KW>(lib, q, min(cap, lib->L), 0, -1);
 }
 

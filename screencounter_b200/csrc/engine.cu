@@ -128,7 +128,7 @@ void DeviceLibrary::upload(Context& ctx) {
     dev.dup_first = host.opt.duplicates == Duplicates::FIRST;
     dev.slots = slots.as<uint32_t>();
     dev.slot_words = host.slot_words;
-    dev.slot_mask = (uint32_t)(host.slots.size() / host.slot_words) - 1;
+    dev.slot_mask = host.slot_mask;
     dev.ent_keys = ent_keys.as<uint32_t>();
     dev.ent_idx = ent_idx.as<int32_t>();
     dev.nseeds = host.nseeds;
@@ -138,7 +138,7 @@ void DeviceLibrary::upload(Context& ctx) {
     dev.cands = cands.as<int32_t>();
     dev.seg1 = host.opt.segmented ? host.opt.seg1 : 0;
     dev.prefix_slots = prefix_slots.as<uint32_t>();
-    dev.prefix_mask = host.prefix_slots.empty() ? 0 : (uint32_t)(host.prefix_slots.size() / host.slot_words) - 1;
+    dev.prefix_mask = host.prefix_mask;
 }
 
 // ---------------------------------------------------------------------------------------

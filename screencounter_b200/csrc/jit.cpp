@@ -2,6 +2,8 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -93,9 +95,25 @@ std::map<std::string, Cached> g_cache;
 
 std::string SpecSingleConfig::key() const {
     std::ostringstream o;
-    o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
+    o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << nb << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
       << fstart << '|' << rstart << '|' << keylen;
     return o.str();
+}
+
+int specialised_blocks_per_sm(cudaKernel_t kernel) {
+    static std::mutex m;
+    static std::map<cudaKernel_t, int> cache;
+    std::lock_guard<std::mutex> lock(m);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int blocks = 0;
+    cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, reinterpret_cast<const void*>(kernel), 128, 0);
+    if (st != cudaSuccess || blocks < 1) {
+        cudaGetLastError();
+        blocks = 4;
+    }
+    cache[kernel] = blocks;
+    return blocks;
 }
 
 std::string jit_status() {
@@ -118,11 +136,20 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     if (cfg.W > 6) return fail("reads longer than 192 bases use the generic kernel");
     if (cfg.T > 128) return fail("templates longer than 128 bases use the generic kernel");
     if (cfg.cb > 3) return fail("mismatch budgets above 7 use the generic kernel");
-    if (cfg.keylen > 512) return fail("key too long");
+    if (cfg.keylen > 32) return fail("variable regions longer than 32 bases use the generic kernel");
     Nvrtc& n = nvrtc();
     if (!n.problem.empty()) return fail(n.problem);
 
-    const std::string key = std::to_string(device) + "#" + cfg.key();
+    // tuning knobs (occupancy target and TMA ring depth) can be overridden for experiments
+    auto env_int = [](const char* name, int fallback, int lo, int hi) {
+        const char* v = std::getenv(name);
+        if (!v || !*v) return fallback;
+        int x = std::atoi(v);
+        return x < lo ? lo : (x > hi ? hi : x);
+    };
+    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", 5, 1, 16);
+    const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
+    const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages);
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
@@ -138,7 +165,8 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     };
 
     std::ostringstream src;
-    const int nb = (32 * cfg.W - cfg.T + 1 + 31) / 32;
+    const int nb_max = (32 * cfg.W - cfg.T + 1 + 31) / 32;
+    const int nb = std::max(1, std::min(cfg.nb, nb_max));
     src << "#define SPEC_CUSTOM 1\n"
         << "#define SPEC_T " << cfg.T << "\n"
         << "#define SPEC_FBASES \"" << cfg.fbases << "\"\n"
@@ -146,7 +174,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_FWD " << cfg.fwd << "\n"
         << "#define SPEC_REV " << cfg.rev << "\n"
         << "#define SPEC_W " << cfg.W << "\n"
-        << "#define SPEC_NB " << (nb < 1 ? 1 : nb) << "\n"
+        << "#define SPEC_NB " << nb << "\n"
         << "#define SPEC_CB " << cfg.cb << "\n"
         << "#define SPEC_MM " << cfg.mm << "\n"
         << "#define SPEC_MAXMM " << cfg.maxmm << "\n"
@@ -155,6 +183,8 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_RSTART " << cfg.rstart << "\n"
         << "#define SPEC_KEYLEN " << cfg.keylen << "\n"
         << "#define SPEC_NAME spec_single_kernel\n"
+        << "#define SPEC_MIN_BLOCKS " << min_blocks << "\n"
+        << "#define SPEC_STAGES " << stages << "\n"
         << "#include \"spec_single.cuh\"\n";
     const std::string program_text = src.str();
 

@@ -16,6 +16,7 @@ struct SpecSingleConfig {
     std::string fbases, rbases;   // forward / reverse-complemented template, '-' for variable positions
     int T = 0, fwd = 0, rev = 0;
     int W = 0;                    // words per plane of the batch
+    int nb = 1;                   // window blocks needed by the longest read of the batch
     int cb = 0, mm = 0, maxmm = 0, use_first = 1;
     int fstart = 0, rstart = 0, keylen = 0;
     std::string key() const;
@@ -25,6 +26,9 @@ struct SpecSingleConfig {
 // run-time compilation is unavailable or disabled (SCG_NO_SPECIALIZE=1); callers then use the
 // generic kernel.  Thread-safe.
 cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why);
+
+// Blocks of 128 threads of a specialised kernel that fit on one SM (occupancy query, cached per kernel).
+int specialised_blocks_per_sm(cudaKernel_t kernel);
 
 // Human-readable status of the run-time compiler ("nvrtc 12.9 from <path>" or why it is missing).
 std::string jit_status();

@@ -80,6 +80,12 @@ SCG_HD uint32_t hash_key(const uint32_t* h, const uint32_t* l, int kw, uint32_t 
     return acc;
 }
 
+// Second position of a key in the two-table cuckoo layout of the exact tables, derived from the first hash.
+SCG_HD uint32_t hash_second(uint32_t acc) {
+    const uint32_t x = acc * 0x9E3779B1u;
+    return x ^ (x >> 15);
+}
+
 // Slack after every packed-read buffer: the scan may load up to two words past a read's last
 // plane word (bits that are masked out afterwards), so the loads need no bounds checks.
 constexpr size_t READ_GUARD_BYTES = 1024;

@@ -12,7 +12,8 @@ struct LibDev {
     int KW;             // words per plane
     int nentries;       // expanded (concrete) entries
     int dup_first;      // ties between different indices resolve to the lowest index
-    // exact table: nslots slots of slot_words words: h[KW], l[KW], value (-1 = empty), padding
+    // exact table, two-table cuckoo: T1 then T2, slot_mask + 1 slots of slot_words words each:
+    // h[KW], l[KW], value (-1 = empty), padding; a key is at T1[hash & mask] or T2[hash_second(hash) & mask]
     const uint32_t* slots;
     uint32_t slot_mask;
     int slot_words;

@@ -80,22 +80,77 @@ struct Builder {
     }
 };
 
-void insert_slot(std::vector<uint32_t>& slots, uint32_t mask, int slot_words, int KW,
-                 const uint32_t* h, const uint32_t* l, int32_t value, bool keep_first) {
-    uint32_t pos = hash_key(h, l, KW, 0) & mask;
+// Two-table cuckoo hash (device_keys.cuh probe_table reads it): slot = h[KW], l[KW], value (-1 = empty),
+// padding.  A key lives in T1 at hash & mask or in T2 at hash_second(hash) & mask.
+struct CuckooTable {
+    int KW, slot_words;
+    uint32_t n = 0;   // slots per table
+    std::vector<uint32_t> slots;
+
+    void reset(uint32_t per_table) {
+        n = per_table;
+        slots.assign((size_t)2 * n * slot_words, 0);
+        for (size_t s = 0; s < (size_t)2 * n; ++s) slots[s * slot_words + 2 * KW] = 0xFFFFFFFFu;
+    }
+    uint32_t* at(int table, uint32_t pos) { return &slots[((size_t)table * n + pos) * slot_words]; }
+    uint32_t position(int table, const uint32_t* key) const {
+        const uint32_t acc = hash_key(key, key + KW, KW, 0);
+        return (table == 0 ? acc : hash_second(acc)) & (n - 1);
+    }
+    bool same(const uint32_t* slot, const uint32_t* key) const { return std::memcmp(slot, key, 2 * KW * sizeof(uint32_t)) == 0; }
+    static bool empty(const uint32_t* slot, int KW) { return (int32_t)slot[2 * KW] == -1; }
+
+    // false = gave up after too many evictions (the caller rebuilds with larger tables)
+    bool insert(const uint32_t* h, const uint32_t* l, int32_t value, bool keep_first) {
+        std::vector<uint32_t> cur(2 * KW + 1), tmp(2 * KW + 1);
+        std::memcpy(cur.data(), h, KW * sizeof(uint32_t));
+        std::memcpy(cur.data() + KW, l, KW * sizeof(uint32_t));
+        cur[2 * KW] = (uint32_t)value;
+        for (int t = 0; t < 2; ++t) {
+            uint32_t* s = at(t, position(t, cur.data()));
+            if (!empty(s, KW) && same(s, cur.data())) {
+                if (!keep_first) s[2 * KW] = (uint32_t)value;
+                return true;
+            }
+        }
+        int table = 0;
+        for (int kicks = 0; kicks < 2000; ++kicks) {
+            uint32_t* s = at(table, position(table, cur.data()));
+            if (empty(s, KW)) {
+                std::memcpy(s, cur.data(), (2 * KW + 1) * sizeof(uint32_t));
+                return true;
+            }
+            if (kicks == 0) {  // try the other home before evicting anyone
+                uint32_t* o = at(1, position(1, cur.data()));
+                if (empty(o, KW)) {
+                    std::memcpy(o, cur.data(), (2 * KW + 1) * sizeof(uint32_t));
+                    return true;
+                }
+            }
+            std::memcpy(tmp.data(), s, (2 * KW + 1) * sizeof(uint32_t));
+            std::memcpy(s, cur.data(), (2 * KW + 1) * sizeof(uint32_t));
+            cur.swap(tmp);
+            table ^= 1;
+        }
+        return false;
+    }
+};
+
+// Builds the table for `count` keys produced by key(e, h, l) / value(e).
+template <class KeyFn, class ValueFn>
+void build_cuckoo(CuckooTable& t, size_t count, KeyFn key, ValueFn value) {
+    uint32_t per_table = std::max<uint32_t>(16, next_pow2((uint32_t)std::min<size_t>(count + 1, 1u << 29)));
+    std::vector<uint32_t> h(t.KW), l(t.KW);
     for (;;) {
-        uint32_t* s = &slots[(size_t)pos * slot_words];
-        if ((int32_t)s[2 * KW] == -1) {
-            std::memcpy(s, h, KW * sizeof(uint32_t));
-            std::memcpy(s + KW, l, KW * sizeof(uint32_t));
-            s[2 * KW] = (uint32_t)value;
-            return;
+        t.reset(per_table);
+        bool ok = true;
+        for (size_t e = 0; e < count && ok; ++e) {
+            key(e, h.data(), l.data());
+            ok = t.insert(h.data(), l.data(), value(e), true);
         }
-        if (std::memcmp(s, h, KW * sizeof(uint32_t)) == 0 && std::memcmp(s + KW, l, KW * sizeof(uint32_t)) == 0) {
-            if (!keep_first) s[2 * KW] = (uint32_t)value;
-            return;
-        }
-        pos = (pos + 1) & mask;
+        if (ok) return;
+        if (per_table >= (1u << 30)) throw Error("could not build the barcode hash table");
+        per_table *= 2;
     }
 }
 
@@ -171,11 +226,19 @@ Library::Library(const std::vector<std::string>& sequences, int length, const Li
 
     // Exact table.  Slot = h[KW], l[KW], value, padded to a multiple of 4 words (16-byte loads).
     slot_words = ((2 * KW + 1) + 3) / 4 * 4;
-    uint32_t nslots = std::max<uint32_t>(16, next_pow2((uint32_t)std::min<size_t>(E * 2 + 1, 1u << 30)));
-    slots.assign((size_t)nslots * slot_words, 0);
-    for (uint32_t s = 0; s < nslots; ++s) slots[(size_t)s * slot_words + 2 * KW] = 0xFFFFFFFFu;
-    for (size_t e = 0; e < E; ++e) {
-        insert_slot(slots, nslots - 1, slot_words, KW, &ent_keys[e * 2 * KW], &ent_keys[e * 2 * KW + KW], ent_idx[e], true);
+    {
+        CuckooTable t;
+        t.KW = KW;
+        t.slot_words = slot_words;
+        build_cuckoo(
+            t, E,
+            [&](size_t e, uint32_t* h, uint32_t* l) {
+                std::memcpy(h, &ent_keys[e * 2 * KW], KW * sizeof(uint32_t));
+                std::memcpy(l, &ent_keys[e * 2 * KW + KW], KW * sizeof(uint32_t));
+            },
+            [&](size_t e) { return ent_idx[e]; });
+        slots.swap(t.slots);
+        slot_mask = t.n - 1;
     }
 
     // Seeds.
@@ -260,20 +323,21 @@ Library::Library(const std::vector<std::string>& sequences, int length, const Li
 
     // Rows with the last base dropped (only the segmented search consults it).
     if (options.segmented && L > 0) {
-        uint32_t nps = std::max<uint32_t>(16, next_pow2((uint32_t)std::min<size_t>(E * 2 + 1, 1u << 30)));
-        prefix_slots.assign((size_t)nps * slot_words, 0);
-        for (uint32_t s = 0; s < nps; ++s) prefix_slots[(size_t)s * slot_words + 2 * KW] = 0xFFFFFFFFu;
-        std::vector<uint32_t> ph(KW), pl(KW);
-        uint32_t lastbit = 1u << ((L - 1) & 31);
-        for (size_t e = 0; e < E; ++e) {
-            for (int w = 0; w < KW; ++w) {
-                ph[w] = ent_keys[e * 2 * KW + w];
-                pl[w] = ent_keys[e * 2 * KW + KW + w];
-            }
-            ph[(L - 1) >> 5] &= ~lastbit;
-            pl[(L - 1) >> 5] &= ~lastbit;
-            insert_slot(prefix_slots, nps - 1, slot_words, KW, ph.data(), pl.data(), 0, true);
-        }
+        CuckooTable t;
+        t.KW = KW;
+        t.slot_words = slot_words;
+        const uint32_t lastbit = 1u << ((L - 1) & 31);
+        build_cuckoo(
+            t, E,
+            [&](size_t e, uint32_t* h, uint32_t* l) {
+                std::memcpy(h, &ent_keys[e * 2 * KW], KW * sizeof(uint32_t));
+                std::memcpy(l, &ent_keys[e * 2 * KW + KW], KW * sizeof(uint32_t));
+                h[(L - 1) >> 5] &= ~lastbit;
+                l[(L - 1) >> 5] &= ~lastbit;
+            },
+            [&](size_t) { return 0; });
+        prefix_slots.swap(t.slots);
+        prefix_mask = t.n - 1;
     }
 }
 

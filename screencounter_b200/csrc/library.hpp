@@ -1,7 +1,8 @@
 // Barcode library: host-side construction (validation, IUPAC expansion, duplicate policy) and
 // the flat tables the kernels probe.  Replaces the reference's fill_library + MismatchTrie
 // (inst/include/kaori/BarcodeSearch.hpp:23-60, MismatchTrie.hpp:93-205) with
-//   * an open-addressing hash of packed barcodes for exact hits, and
+//   * a two-table cuckoo hash of packed barcodes for exact hits (a key lives at one of exactly two
+//     positions, so a probe is two independent 16-byte loads and no loop), and
 //   * pigeonhole seed buckets for the mismatch-tolerant search: a barcode within `cap`
 //     substitutions of the query agrees with it exactly on at least one of cap+1 disjoint
 //     segments, so probing one bucket per segment enumerates every candidate; candidates are
@@ -38,13 +39,15 @@ struct Library {
     std::vector<uint32_t> ent_keys;
     std::vector<int32_t> ent_idx;
     int slot_words = 0;
-    std::vector<uint32_t> slots;
+    std::vector<uint32_t> slots;        // tables T1 | T2, slot_mask + 1 slots each
+    uint32_t slot_mask = 0;
     int nseeds = 0;
     std::vector<uint32_t> seed_masks;   // nseeds * KW
     uint32_t nbuckets = 0;
     std::vector<uint2> buckets;
     std::vector<int32_t> cands;
-    std::vector<uint32_t> prefix_slots;
+    std::vector<uint32_t> prefix_slots; // same layout, rows with the last base dropped
+    uint32_t prefix_mask = 0;
 
     // `sequences` are the library rows as they must match the read (i.e. already
     // reverse-complemented by the caller when the reverse strand is searched).

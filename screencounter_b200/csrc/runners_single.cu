@@ -124,6 +124,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
     cfg.fwd = m.tmpl.fwd ? 1 : 0;
     cfg.rev = m.tmpl.rev ? 1 : 0;
     cfg.W = reads.W;
+    // uniform_len is the longest read of the batch (also when per-read lengths are present)
+    cfg.nb = std::max(1, (reads.uniform_len - m.tmpl.length + 1 + 31) / 32);
     cfg.cb = P.spec.cbits;
     cfg.mm = P.spec.mm;
     cfg.maxmm = P.max_mm;
@@ -137,7 +139,10 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
         ReadsDev reads_arg = reads;
         const LibDev* libs = P.libs;
         void* args[] = { &reads_arg, &libs, &d_counts, &d_index, &d_info };
-        SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(grid), dim3(128), args, 0, stream));
+        // persistent warps: as many blocks as are resident at once, each warp strides over the tiles
+        const int resident = specialised_blocks_per_sm(spec);
+        const int spec_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * resident));
+        SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
         m.kernel_note = "specialised (NVRTC)";
         ctx.kernel_note = m.kernel_note;
     } else {
@@ -401,6 +406,7 @@ int scg_jit_selftest(const char* constant, int strand, int mismatches, int words
         cfg.fwd = t.fwd;
         cfg.rev = t.rev;
         cfg.W = words_per_plane;
+        cfg.nb = std::max(1, (32 * words_per_plane - t.length + 1 + 31) / 32);
         cfg.cb = s.cbits;
         cfg.mm = s.mm;
         cfg.maxmm = mismatches;

@@ -1,11 +1,24 @@
 // countSingleBarcodes kernel with the TEMPLATE FOLDED IN AT COMPILE TIME.
 //
-// The generic kernel (handlers.cuh, single_kernel) receives the template as bit masks and spends
-// most of its issue slots on uniform bookkeeping (which template position is constant, which base
-// it holds).  Here every template position is a compile-time constant, so after unrolling the scan
-// is exactly, per constant position and strand,
-//     one funnel shift (the 32-window view of that base's mismatch plane) + the counter update
-// -- the position-parallel formulation at its minimum instruction count.
+// One warp owns a tile of 32 reads (layout.hpp), one lane one read.  Work per tile:
+//
+//   FAST PATH (every lane, no divergence)
+//     1. the read's bit planes (3 x W words) arrive with coalesced 128-byte loads, the next tile's
+//        words are requested before this tile is processed (software prefetch);
+//     2. four "is not base X" planes are derived once; the constant-flank scan is then, per constant
+//        template position and strand, ONE funnel shift (the 32-window view of that base's plane) plus
+//        a carry-save update of a bit-sliced saturating counter -- bit p of every register is window p
+//        (replaces ScanTemplate::next / strand_match, ScanTemplate.hpp:183-252);
+//     3. the first window that passes (positions ascending, forward before reverse,
+//        SimpleSingleMatch.hpp:226-242) has its variable region cut out of the registers and probed
+//        in the exact table (one 16-byte load); an exact hit resolves the read on the spot.
+//   SLOW PATH (compacted)
+//     Reads the fast path cannot settle -- the exact probe missed with budget left for the
+//     mismatch-tolerant search, an N inside the variable region, several candidate windows -- are
+//     appended to a per-warp queue in shared memory.  Whenever 32 are waiting the warp runs the full
+//     per-read search (every window, pigeonhole-seeded mismatch search, first / best rules) with all
+//     32 lanes busy on 32 different deferred reads, instead of a few lanes of every tile dragging the
+//     rest of the warp through the long path.
 //
 // This file is compiled twice:
 //   * by nvcc at build time for the default configuration below (BASELINE configs[1]'s template),
@@ -17,7 +30,7 @@
 //   as a string of A C G T and '-', SPEC_FWD / SPEC_REV strands searched, SPEC_W words per plane of
 //   the batch, SPEC_NB window blocks (ceil((32*W - T + 1) / 32)), SPEC_CB counter planes, SPEC_MM
 //   clamped scan budget, SPEC_MAXMM the caller's budget, SPEC_USE_FIRST, SPEC_FSTART / SPEC_RSTART /
-//   SPEC_KEYLEN the variable region, SPEC_NAME the kernel's name.
+//   SPEC_KEYLEN the variable region (at most 32 bases), SPEC_NAME the kernel's name.
 #pragma once
 
 #include "device_keys.cuh"
@@ -40,6 +53,16 @@
 #define SPEC_NAME spec_single_kernel_default
 #endif
 
+#ifndef SPEC_BLOCK
+#define SPEC_BLOCK 128
+#endif
+#ifndef SPEC_MIN_BLOCKS
+#define SPEC_MIN_BLOCKS 6
+#endif
+#ifndef SPEC_STAGES
+#define SPEC_STAGES 2
+#endif
+
 namespace scg {
 namespace spec {
 
@@ -47,15 +70,57 @@ constexpr int T = SPEC_T;
 constexpr int W = SPEC_W;
 constexpr int NB = SPEC_NB;
 constexpr int CB = SPEC_CB;
-constexpr int KW = (SPEC_KEYLEN + 31) / 32;
+constexpr int KEYLEN = SPEC_KEYLEN;
+constexpr int WARPS = SPEC_BLOCK / 32;
+constexpr int QCAP = 64;   // per-warp queue of deferred reads: < 32 waiting + at most 32 new ones
+constexpr int STAGES = SPEC_STAGES;                 // tiles in flight per warp
+constexpr int TILE_WORDS = 3 * W * TILE;            // one tile = 3 planes x W words x 32 lanes, contiguous
+constexpr uint32_t TILE_BYTES = TILE_WORDS * 4u;    // a multiple of 16, as the bulk copy requires
 constexpr char FB[] = SPEC_FBASES;
 constexpr char RB[] = SPEC_RBASES;
 
-// mismatch planes of one read: bit i of X?[w] is set when base 32*w + i is NOT that base
+__host__ __device__ constexpr int count_constant(const char* s) {
+    int n = 0;
+    for (int j = 0; j < T; ++j) n += s[j] != '-';
+    return n;
+}
+// template position of the k-th constant base of a strand
+__host__ __device__ constexpr int kth_constant(const char* s, int k) {
+    int n = 0;
+    for (int j = 0; j < T; ++j) {
+        if (s[j] != '-') {
+            if (n == k) return j;
+            ++n;
+        }
+    }
+    return 0;
+}
+constexpr int NCF = SPEC_FWD ? count_constant(FB) : 0;
+constexpr int NCR = SPEC_REV ? count_constant(RB) : 0;
+
+// The read's words in registers; two zero guard words so that every funnel shift has a partner.
+struct Words {
+    uint32_t h[W + 2], l[W + 2], n[W + 2];
+};
+
+// mismatch planes of one read: bit i of x?[w] is set when base 32*w + i is NOT that base
 // (an N, or anything else that is not ACGT, mismatches all four)
 struct Planes {
     uint32_t xa[W + 2], xc[W + 2], xg[W + 2], xt[W + 2];
 };
+
+__device__ __forceinline__ void make_planes(const Words& R, Planes& P) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint32_t h = R.h[w], l = R.l[w], n = R.n[w];
+        P.xa[w] = h | l | n;
+        P.xc[w] = h | ~l | n;
+        P.xg[w] = ~h | l | n;
+        P.xt[w] = ~h | ~l | n;
+    }
+    P.xa[W] = P.xc[W] = P.xg[W] = P.xt[W] = 0;
+    P.xa[W + 1] = P.xc[W + 1] = P.xg[W + 1] = P.xt[W + 1] = 0;
+}
 
 template <char B>
 __device__ __forceinline__ uint32_t window(const Planes& P, int word, int shift) {
@@ -63,106 +128,389 @@ __device__ __forceinline__ uint32_t window(const Planes& P, int word, int shift)
     return __funnelshift_r(x[word], x[word + 1], shift);
 }
 
-template <int J>
-struct ScanStep {
-    static __device__ __forceinline__ void run(const Planes& P, int pb, Counter<CB>& cf, Counter<CB>& cr) {
-        if constexpr (SPEC_FWD && FB[J] != '-') cf.add(window<FB[J]>(P, pb + J / 32, J % 32));
-        if constexpr (SPEC_REV && RB[J] != '-') cr.add(window<RB[J]>(P, pb + J / 32, J % 32));
-        ScanStep<J + 1>::run(P, pb, cf, cr);
+// 32-window mismatch plane of the K-th constant position of a strand, window block pb
+template <bool REV, int K>
+__device__ __forceinline__ uint32_t cplane(const Planes& P, int pb) {
+    constexpr int j = REV ? kth_constant(RB, K) : kth_constant(FB, K);
+    constexpr char b = REV ? RB[j] : FB[j];
+    return window<b>(P, pb + j / 32, j % 32);
+}
+
+// one LOP3 with a chosen truth table (a = 0xF0, b = 0xCC, c = 0xAA)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0x96>(a, b, c); }
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xE8>(a, b, c); }
+__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xFE>(a, b, c); }
+
+// ---- TMA (1-D bulk copy global -> shared) signalled on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// dst, bar: shared-memory addresses; src: global pointer, 16-byte aligned
+__device__ __forceinline__ void tma_tile(uint32_t dst, const void* src, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TILE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(TILE_BYTES), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// Accumulates constant positions K .. N-1 of a strand into the bit-sliced counter.
+//   CB == 0 (no mismatch allowed): only "any mismatch" is kept            -> 1/2 LOP3 per position
+//   CB == 1 (budget 1): ones / "two or more" planes, carry-save, 4 at once -> 5/4 LOP3 per position
+//   otherwise: ripple add, one position at a time
+template <bool REV, int K, int N>
+struct Accumulate {
+    static __device__ __forceinline__ void run(const Planes& P, int pb, Counter<CB>& c) {
+        if constexpr (K < N) {
+            if constexpr (CB == 0) {
+                if constexpr (N - K >= 2) {
+                    c.ovf = or3(c.ovf, cplane<REV, K>(P, pb), cplane<REV, K + 1>(P, pb));
+                    Accumulate<REV, K + 2, N>::run(P, pb, c);
+                } else {
+                    c.ovf |= cplane<REV, K>(P, pb);
+                }
+            } else if constexpr (CB == 1) {
+                if constexpr (N - K >= 4) {
+                    const uint32_t a = cplane<REV, K>(P, pb), b = cplane<REV, K + 1>(P, pb), d = cplane<REV, K + 2>(P, pb),
+                                   e = cplane<REV, K + 3>(P, pb);
+                    const uint32_t s = xor3(a, b, d);
+                    const uint32_t t = maj3(a, b, d);
+                    c.ovf = or3(c.ovf, t, maj3(s, e, c.c[0]));
+                    c.c[0] = xor3(c.c[0], s, e);
+                    Accumulate<REV, K + 4, N>::run(P, pb, c);
+                } else if constexpr (N - K >= 2) {
+                    const uint32_t a = cplane<REV, K>(P, pb), b = cplane<REV, K + 1>(P, pb);
+                    c.ovf |= maj3(a, b, c.c[0]);
+                    c.c[0] = xor3(c.c[0], a, b);
+                    Accumulate<REV, K + 2, N>::run(P, pb, c);
+                } else {
+                    const uint32_t a = cplane<REV, K>(P, pb);
+                    c.ovf |= a & c.c[0];
+                    c.c[0] ^= a;
+                }
+            } else {
+                c.add(cplane<REV, K>(P, pb));
+                Accumulate<REV, K + 1, N>::run(P, pb, c);
+            }
+        }
     }
 };
 
-template <>
-struct ScanStep<T> {
-    static __device__ __forceinline__ void run(const Planes&, int, Counter<CB>&, Counter<CB>&) {}
-};
+// value of arr[base + d] for a run-time d in [0, DMAX]; arr lives in registers
+template <int DMAX, int LEN>
+__device__ __forceinline__ uint32_t pick(const uint32_t (&arr)[LEN], int base, int d) {
+    uint32_t v = arr[base];
+#pragma unroll
+    for (int k = 1; k <= DMAX; ++k) {
+        if (base + k < LEN) v = (d == k) ? arr[base + k] : v;
+    }
+    return v;
+}
+
+// the variable region's first word index is one of a few consecutive values known at compile time
+__host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int SMIN = (SPEC_FWD && SPEC_REV) ? cmin(SPEC_FSTART, SPEC_RSTART) : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
+constexpr int SMAX = (SPEC_FWD && SPEC_REV) ? cmax(SPEC_FSTART, SPEC_RSTART) : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
+
+// The full per-read search (every window, mismatch-tolerant lookups, first / best rules): the
+// reference's SimpleSingleMatch::search_first / search_best (SimpleSingleMatch.hpp:200-306) for one
+// read, reading its words from global memory.  Run by a full warp on 32 deferred reads.
+__device__ __noinline__ void slow_single(const ReadsDev& reads, const LibDev* __restrict__ libs, long long i, bool active,
+                                         int32_t* __restrict__ counts, int32_t* __restrict__ out_index, uint32_t* __restrict__ out_info) {
+    if (!active) return;
+    const ReadView rd = read_view(reads, i / TILE, (int)(i % TILE));
+    Words R;
+    Planes P;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        R.h[w] = rd.word(PLANE_H, w);
+        R.l[w] = rd.word(PLANE_L, w);
+        R.n[w] = rd.word(PLANE_N, w);
+    }
+    R.h[W] = R.l[W] = R.n[W] = 0;
+    R.h[W + 1] = R.l[W + 1] = R.n[W + 1] = 0;
+    make_planes(R, P);
+
+    SingleOut out{ false, -1, 0, false, 0, 0 };
+    int best = SPEC_MAXMM + 1;
+    bool done = false;
+    const int nblocks = window_blocks(rd.len, T);
+#pragma unroll
+    for (int pb = 0; pb < NB; ++pb) {
+        if (pb >= nblocks || done) continue;
+        Counter<CB> cf, cr;
+        cf.clear();
+        cr.clear();
+        if constexpr (SPEC_FWD) Accumulate<false, 0, NCF>::run(P, pb, cf);
+        if constexpr (SPEC_REV) Accumulate<true, 0, NCR>::run(P, pb, cr);
+        const uint32_t valid = valid_windows(rd.len, T, pb);
+        uint32_t okf = SPEC_FWD ? (cf.le(SPEC_MM) & valid) : 0u;
+        uint32_t okr = SPEC_REV ? (cr.le(SPEC_MM) & valid) : 0u;
+        // hits in the reference's order: positions ascending, forward before reverse
+        // (SimpleSingleMatch.hpp:226-242); the strand is per-lane data
+        while ((okf | okr) && !done) {
+            const int p = __ffs(okf | okr) - 1;
+            const bool rev = !((okf >> p) & 1u);
+            if (rev) {
+                okr &= ~(1u << p);
+            } else {
+                okf &= ~(1u << p);
+            }
+            const int c = rev ? cr.get(p) : cf.get(p);
+            Key<1> key;
+            extract_region<1>(rd, 32 * pb + p + (rev ? SPEC_RSTART : SPEC_FSTART), KEYLEN, key);
+            const Hit h = lookup_any<1, true>(libs + (rev ? 1 : 0), key, SPEC_MAXMM - c);
+            if (h.index < 0) continue;
+            const int total = c + h.dist;
+            if (SPEC_USE_FIRST) {
+                out.found = true;
+                out.index = h.index;
+                out.position = 32 * pb + p;
+                out.reverse = rev;
+                out.mismatches = total;
+                out.var_mismatches = h.dist;
+                done = true;
+            } else if (total == best) {  // SimpleSingleMatch.hpp:270-275
+                if (out.index != h.index) {
+                    out.found = false;
+                    out.index = -1;
+                }
+            } else if (total < best) {
+                best = total;
+                out.found = true;
+                out.index = h.index;
+                out.position = 32 * pb + p;
+                out.reverse = rev;
+                out.mismatches = total;
+                out.var_mismatches = h.dist;
+            }
+        }
+    }
+    if (out.found) atomicAdd(counts + out.index, 1);
+    if (out_index) out_index[i] = out.found ? out.index : -1;
+    if (out_info) out_info[i] = pack_info(out.found, out.reverse, out.mismatches, out.var_mismatches, out.position);
+}
 
 } // namespace spec
 } // namespace scg
 
-extern "C" __global__ void __launch_bounds__(128) SPEC_NAME(scg::ReadsDev reads, const scg::LibDev* __restrict__ libs,
-                                                            int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
-                                                            uint32_t* __restrict__ out_info) {
+// What a lane remembers about its read between the scan and the arrival of the table slots.
+struct Pending {
+    uint4 a, b;        // the two cuckoo slots of the first candidate's variable region
+    uint32_t kh, kl;   // that region, packed
+    uint32_t meta;     // PM_* flags | constant mismatches << 16 | window position
+    uint32_t i;        // read index inside the batch
+};
+constexpr uint32_t PM_CAND = 1u << 31;    // at least one window passed the constant-flank filter
+constexpr uint32_t PM_PROBED = 1u << 30;  // slots a, b were requested (the region holds no N and sits in the first block)
+constexpr uint32_t PM_MANY = 1u << 29;    // more than one candidate window
+constexpr uint32_t PM_REV = 1u << 28;     // the first candidate is on the reverse strand
+constexpr uint32_t PM_LATE = 1u << 27;    // the first candidate lies beyond the first window block
+constexpr uint32_t PM_INRANGE = 1u << 26; // the lane holds a real read
+
+extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
+    SPEC_NAME(scg::ReadsDev reads, const scg::LibDev* __restrict__ libs, int32_t* __restrict__ counts,
+              int32_t* __restrict__ out_index, uint32_t* __restrict__ out_info) {
     using namespace scg;
     using namespace scg::spec;
+    static_assert(KEYLEN <= 32, "the specialised kernel handles variable regions of at most 32 bases");
+    // per warp: a ring of STAGES tile buffers filled by the TMA (1-D bulk copies, one per tile, issued by
+    // lane 0 and signalled on an mbarrier), and the queue of deferred reads
+    __shared__ __align__(128) uint32_t stage_all[WARPS][STAGES][TILE_WORDS];
+    __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
+    __shared__ uint32_t queue_all[WARPS][QCAP];
+    const int wib = threadIdx.x >> 5;
+    uint32_t* queue = queue_all[wib];
+    int waiting = 0;   // warp-uniform
+
     const int lane = threadIdx.x & 31;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ntiles = (reads.n + TILE - 1) / TILE;
-    for (long long tile = warp; tile < ntiles; tile += nwarps) {
-        const long long i = tile * TILE + lane;
-        const ReadView rd = read_view(reads, tile, lane);
+    // the exact tables of both strands (library.cpp CuckooTable): slot = (h, l, value, pad), 16 bytes;
+    // a key sits in T1 at hash & mask or in T2 (mask + 1 slots further on) at hash_second(hash) & mask
+    const uint4* __restrict__ slots_f = SPEC_FWD ? reinterpret_cast<const uint4*>(libs[0].slots) : nullptr;
+    const uint4* __restrict__ slots_r = SPEC_REV ? reinterpret_cast<const uint4*>(libs[1].slots) : nullptr;
+    const uint32_t mask_f = SPEC_FWD ? libs[0].slot_mask : 0u;
+    const uint32_t mask_r = SPEC_REV ? libs[1].slot_mask : 0u;
+    constexpr uint32_t keymask = KEYLEN >= 32 ? 0xFFFFFFFFu : ((1u << KEYLEN) - 1u);
 
-        Planes P;
+    const uint32_t stage_base = smem_addr(&stage_all[wib][0][0]);
+    const uint32_t bar_base = smem_addr(&bar_all[wib][0]);
+    if (lane == 0) {
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const uint32_t h = rd.word(PLANE_H, w), l = rd.word(PLANE_L, w), n = rd.word(PLANE_N, w);
-            P.xa[w] = h | l | n;
-            P.xc[w] = h | ~l | n;
-            P.xg[w] = ~h | l | n;
-            P.xt[w] = ~h | ~l | n;
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar_base + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    const char* src = reinterpret_cast<const char*>(reads.data) + (size_t)warp * TILE_BYTES;
+    const size_t src_stride = (size_t)nwarps * TILE_BYTES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            if (warp + s * nwarps < ntiles) tma_tile(stage_base + s * TILE_BYTES, src + s * src_stride, bar_base + 8u * s);
         }
-        P.xa[W] = P.xc[W] = P.xg[W] = P.xt[W] = 0;
-        P.xa[W + 1] = P.xc[W + 1] = P.xg[W + 1] = P.xt[W + 1] = 0;
+    }
+    src += STAGES * src_stride;   // the next tile to request
 
-        SingleOut out{ false, -1, 0, false, 0, 0 };
-        int best = SPEC_MAXMM + 1;
-        bool done = false;
-        const int nblocks = window_blocks(rd.len, T);
+    Pending pend;
+    pend.meta = 0;
+    pend.a = pend.b = make_uint4(0, 0, 0, 0);
+    pend.kh = pend.kl = pend.i = 0;
+    long long tile = warp;
+    uint32_t stage = 0, parity = 0;
+    for (;;) {
+        const bool have = tile < ntiles;   // warp-uniform
+        Words R;
+        uint32_t meta = 0;
+        if (have) {
+            // ---- this tile's words: wait for the TMA, registers <- shared memory, hand the buffer back ----
+            mbar_wait(bar_base + 8u * stage, parity);
+            const uint32_t* buf = stage_all[wib][stage] + lane;
 #pragma unroll
-        for (int pb = 0; pb < NB; ++pb) {
-            if (pb >= nblocks || done) continue;
-            Counter<CB> cf, cr;
-            cf.clear();
-            cr.clear();
-            ScanStep<0>::run(P, pb, cf, cr);
-            const uint32_t valid = valid_windows(rd.len, T, pb);
-            uint32_t okf = SPEC_FWD ? (cf.le(SPEC_MM) & valid) : 0u;
-            uint32_t okr = SPEC_REV ? (cr.le(SPEC_MM) & valid) : 0u;
-            // hits in the reference's order: positions ascending, forward before reverse
-            // (SimpleSingleMatch.hpp:226-242); the strand is per-lane data
-            while ((okf | okr) && !done) {
-                const int p = __ffs(okf | okr) - 1;
-                const bool rev = !((okf >> p) & 1u);
-                if (rev) {
-                    okr &= ~(1u << p);
-                } else {
-                    okf &= ~(1u << p);
+            for (int w = 0; w < W; ++w) {
+                R.h[w] = buf[(PLANE_H * W + w) * TILE];
+                R.l[w] = buf[(PLANE_L * W + w) * TILE];
+                R.n[w] = buf[(PLANE_N * W + w) * TILE];
+            }
+            R.h[W] = R.l[W] = R.n[W] = 0;
+            R.h[W + 1] = R.l[W + 1] = R.n[W + 1] = 0;
+
+            const long long i = tile * TILE + lane;
+            const bool inrange = i < reads.n;
+            const int len = inrange ? (reads.lens ? (int)reads.lens[i] : reads.uniform_len) : 0;
+            Planes P;
+            make_planes(R, P);
+
+            // ---- scan: every window of every block, both strands ----
+            int ncand = 0;            // windows (position, strand) that pass the constant-flank filter
+            int fp = 0, fc = 0;       // first candidate in the reference's order: position, constant mismatches
+            bool frev = false;
+            const int nblocks = window_blocks(len, T);
+#pragma unroll
+            for (int pb = 0; pb < NB; ++pb) {
+                // later blocks only exist for reads longer than T + 31 bases: skipped when no lane has one
+                if (pb > 0 && !__any_sync(0xFFFFFFFFu, pb < nblocks)) continue;
+                Counter<CB> cf, cr;
+                cf.clear();
+                cr.clear();
+                if constexpr (SPEC_FWD) Accumulate<false, 0, NCF>::run(P, pb, cf);
+                if constexpr (SPEC_REV) Accumulate<true, 0, NCR>::run(P, pb, cr);
+                const uint32_t valid = valid_windows(len, T, pb);
+                const uint32_t okf = SPEC_FWD ? (cf.le(SPEC_MM) & valid) : 0u;
+                const uint32_t okr = SPEC_REV ? (cr.le(SPEC_MM) & valid) : 0u;
+                const uint32_t any = okf | okr;
+                if (any && ncand == 0) {
+                    const int p = __ffs(any) - 1;
+                    frev = !((okf >> p) & 1u);
+                    fc = frev ? cr.get(p) : cf.get(p);
+                    fp = 32 * pb + p;
                 }
-                const int c = rev ? cr.get(p) : cf.get(p);
-                Key<KW> key;
-                extract_region<KW>(rd, 32 * pb + p + (rev ? SPEC_RSTART : SPEC_FSTART), SPEC_KEYLEN, key);
-                const Hit h = lookup_any<KW>(libs + (rev ? 1 : 0), key, SPEC_MAXMM - c);
-                if (h.index < 0) continue;
-                const int total = c + h.dist;
-                if (SPEC_USE_FIRST) {
-                    out.found = true;
-                    out.index = h.index;
-                    out.position = 32 * pb + p;
-                    out.reverse = rev;
-                    out.mismatches = total;
-                    out.var_mismatches = h.dist;
-                    done = true;
-                } else if (total == best) {  // SimpleSingleMatch.hpp:270-275
-                    if (out.index != h.index) {
-                        out.found = false;
-                        out.index = -1;
-                    }
-                } else if (total < best) {
-                    best = total;
-                    out.found = true;
-                    out.index = h.index;
-                    out.position = 32 * pb + p;
-                    out.reverse = rev;
-                    out.mismatches = total;
-                    out.var_mismatches = h.dist;
+                ncand += __popc(okf) + __popc(okr);
+            }
+            // the buffer goes back to the TMA once every lane has consumed the words it read from it
+            __syncwarp();
+            if (lane == 0 && tile + (long long)STAGES * nwarps < ntiles) {
+                tma_tile(stage_base + stage * TILE_BYTES, src, bar_base + 8u * stage);
+            }
+            src += src_stride;
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+            meta = (inrange ? PM_INRANGE : 0u) | (ncand > 0 ? PM_CAND : 0u) | (ncand > 1 ? PM_MANY : 0u) | (frev ? PM_REV : 0u) |
+                   ((NB > 1 && fp >= 32) ? PM_LATE : 0u) | ((uint32_t)fc << 16) | (uint32_t)fp;
+        }
+
+        // ---- settle the PREVIOUS tile: its table slots were requested one scan ago ----
+        if (__any_sync(0xFFFFFFFFu, pend.meta != 0)) {
+            const uint32_t m = pend.meta;
+            int index = -1;
+            if (m & PM_PROBED) {
+                const int ra = (pend.a.x == pend.kh && pend.a.y == pend.kl) ? (int)pend.a.z : -1;
+                const int rb = (pend.b.x == pend.kh && pend.b.y == pend.kl) ? (int)pend.b.z : -1;
+                index = max(ra, rb);
+            }
+            const int pfc = (int)((m >> 16) & 0xFFu), pfp = (int)(m & 0xFFFFu);
+            // an exact hit at the first window is the answer in first mode, and in best mode when it is the only window
+            const bool found = index >= 0 && (SPEC_USE_FIRST || !(m & PM_MANY));
+            // otherwise the mismatch-tolerant search may still find something there (budget left), or another window may
+            const bool defer = (m & PM_CAND) && !found && ((SPEC_MAXMM - pfc >= 1) || (m & (PM_MANY | PM_LATE)));
+            if ((m & PM_INRANGE) && !defer) {
+                if (found) atomicAdd(counts + index, 1);
+                if (out_index) out_index[pend.i] = found ? index : -1;
+                if (out_info) out_info[pend.i] = pack_info(found, (m & PM_REV) != 0, pfc, 0, pfp);
+            }
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+            if (dm) {
+                if (defer) queue[waiting + __popc(dm & lanes_below)] = pend.i;
+                waiting += __popc(dm);
+                __syncwarp();
+            }
+        }
+
+        // ---- this tile's first candidate: cut the variable region out of the registers, request its two slots ----
+        pend.meta = meta;
+        if (have) {
+            pend.i = (uint32_t)(tile * TILE + lane);
+            if ((meta & PM_CAND) && !(meta & PM_LATE)) {
+                const bool frev = (meta & PM_REV) != 0;
+                const int start = (int)(meta & 0xFFFFu) + (frev ? SPEC_RSTART : SPEC_FSTART);
+                const int a = start >> 5, sh = start & 31;
+                // a - base is in [0, DMAX] inside the first block; candidates of later blocks (long reads) take the slow path
+                constexpr int base = SMIN >> 5;
+                constexpr int DMAX = ((SMAX + 31) >> 5) - base;
+                const int d = a - base;
+                const uint32_t kh = __funnelshift_r(pick<DMAX>(R.h, base, d), pick<DMAX>(R.h, base + 1, d), sh) & keymask;
+                const uint32_t kl = __funnelshift_r(pick<DMAX>(R.l, base, d), pick<DMAX>(R.l, base + 1, d), sh) & keymask;
+                const uint32_t kn = __funnelshift_r(pick<DMAX>(R.n, base, d), pick<DMAX>(R.n, base + 1, d), sh) & keymask;
+                if (kn == 0) {
+                    const uint4* __restrict__ slots = frev ? slots_r : slots_f;
+                    const uint32_t mask = frev ? mask_r : mask_f;
+                    const uint32_t acc = hash_key(&kh, &kl, 1, 0);
+                    pend.a = __ldg(slots + (acc & mask));
+                    pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+                    pend.kh = kh;
+                    pend.kl = kl;
+                    pend.meta |= PM_PROBED;
                 }
             }
         }
-        if (i < reads.n) {
-            if (out.found) atomicAdd(counts + out.index, 1);
-            if (out_index) out_index[i] = out.found ? out.index : -1;
-            if (out_info) out_info[i] = pack_info(out.found, out.reverse, out.mismatches, out.var_mismatches, out.position);
+
+        // ---- the full search runs when a warp's worth of deferred reads is waiting, and once more at the end ----
+        while (waiting >= 32 || (!have && waiting > 0)) {
+            const int take = waiting < 32 ? waiting : 32;
+            waiting -= take;
+            const bool active = lane < take;
+            const uint32_t j = active ? queue[waiting + lane] : 0u;
+            __syncwarp();
+            slow_single(reads, libs, (long long)j, active, counts, out_index, out_info);
         }
+        if (!have) break;
+        tile += nwarps;
     }
 }

@@ -53,3 +53,26 @@ def test_reads_from_fastq_resident(kref):
     plan.run(reads, counts.ptr)
     want, _ = kref.count_single(text, TEMPLATE, 2, pool, 1, False)
     assert np.array_equal(counts.to_numpy(np.int32), want)
+
+
+@pytest.mark.parametrize("use_first", [True, False])
+def test_many_tiles_per_warp(kref, use_first):
+    """Enough reads that every persistent warp walks many tiles: exercises the TMA ring, the probe
+    carried from one tile to the next and the deferred-read queue (filled, drained mid-way and
+    flushed at the end).  Every read must come back, exactly as the reference decides it."""
+    from screencounter_b200.device import SynthSpec, SinglePlan, DeviceArray
+    rng = np.random.default_rng(5)
+    pool = distinct_pool(rng, 2000, 20)
+    # noisy constructs: many reads need the mismatch-tolerant search (the deferred path)
+    spec = SynthSpec(TEMPLATE, [pool], seed=11, read_len=75, strand=2, sub_per_10k=300, n_per_10k=30)
+    n = 1_500_003
+    reads = spec.on_device(0, n)
+    plan = SinglePlan(TEMPLATE, 2, pool, 1, use_first)
+    counts = DeviceArray(4 * len(pool))
+    index = DeviceArray(4 * n)
+    plan.run(reads, counts.ptr, index.ptr)
+    got_index = index.to_numpy(np.int32)
+    got_counts = counts.to_numpy(np.int32)
+    want_index, _ = kref.trace_single(spec.fastq(0, n), TEMPLATE, 2, pool, 1, use_first)
+    assert np.array_equal(got_index, want_index)
+    assert np.array_equal(got_counts, np.bincount(want_index[want_index >= 0], minlength=len(pool)))
