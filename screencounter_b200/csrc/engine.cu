@@ -119,6 +119,7 @@ void DeviceLibrary::upload(Context& ctx) {
     seed_masks.upload(host.seed_masks.data(), host.seed_masks.size() * sizeof(uint32_t), st);
     buckets.upload(host.buckets.data(), host.buckets.size() * sizeof(uint2), st);
     cands.upload(host.cands.data(), host.cands.size() * sizeof(int32_t), st);
+    cand_rows.upload(host.cand_rows.data(), host.cand_rows.size() * sizeof(uint32_t), st);
     prefix_slots.upload(host.prefix_slots.data(), host.prefix_slots.size() * sizeof(uint32_t), st);
     SCG_CUDA_CHECK(cudaStreamSynchronize(st));
     std::memset(&dev, 0, sizeof dev);
@@ -136,6 +137,7 @@ void DeviceLibrary::upload(Context& ctx) {
     dev.buckets = buckets.as<uint2>();
     dev.bucket_mask = host.nbuckets ? host.nbuckets - 1 : 0;
     dev.cands = cands.as<int32_t>();
+    dev.cand_rows = host.cand_rows.empty() ? nullptr : cand_rows.as<uint4>();
     dev.seg1 = host.opt.segmented ? host.opt.seg1 : 0;
     dev.prefix_slots = prefix_slots.as<uint32_t>();
     dev.prefix_mask = host.prefix_mask;

@@ -76,7 +76,7 @@ struct Context {
 // A library resident on the device.
 struct DeviceLibrary {
     Library host;
-    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, prefix_slots;
+    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots;
     LibDev dev;
     void upload(Context& ctx);
 };

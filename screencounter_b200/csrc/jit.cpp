@@ -96,7 +96,8 @@ std::map<std::string, Cached> g_cache;
 std::string SpecSingleConfig::key() const {
     std::ostringstream o;
     o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << nb << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
-      << fstart << '|' << rstart << '|' << keylen;
+      << fstart << '|' << rstart << '|' << keylen << '|' << dup_first;
+    for (uint32_t m : seed_masks) o << '|' << m;
     return o.str();
 }
 
@@ -147,7 +148,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         int x = std::atoi(v);
         return x < lo ? lo : (x > hi ? hi : x);
     };
-    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", 5, 1, 16);
+    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
     const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages);
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -164,6 +165,10 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         return nullptr;
     };
 
+    std::string seed_list = "{ ";
+    for (size_t k = 0; k < cfg.seed_masks.size(); ++k) seed_list += (k ? ", " : "") + std::to_string(cfg.seed_masks[k]) + "u";
+    if (cfg.seed_masks.empty()) seed_list += "0u";
+    seed_list += " }";
     std::ostringstream src;
     const int nb_max = (32 * cfg.W - cfg.T + 1 + 31) / 32;
     const int nb = std::max(1, std::min(cfg.nb, nb_max));
@@ -182,6 +187,9 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_FSTART " << cfg.fstart << "\n"
         << "#define SPEC_RSTART " << cfg.rstart << "\n"
         << "#define SPEC_KEYLEN " << cfg.keylen << "\n"
+        << "#define SPEC_NSEEDS " << cfg.seed_masks.size() << "\n"
+        << "#define SPEC_SEEDMASKS " << seed_list << "\n"
+        << "#define SPEC_DUP_FIRST " << cfg.dup_first << "\n"
         << "#define SPEC_NAME spec_single_kernel\n"
         << "#define SPEC_MIN_BLOCKS " << min_blocks << "\n"
         << "#define SPEC_STAGES " << stages << "\n"

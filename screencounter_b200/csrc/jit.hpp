@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "handlers_params.hpp"
 #include "template_spec.hpp"
@@ -19,6 +20,8 @@ struct SpecSingleConfig {
     int nb = 1;                   // window blocks needed by the longest read of the batch
     int cb = 0, mm = 0, maxmm = 0, use_first = 1;
     int fstart = 0, rstart = 0, keylen = 0;
+    std::vector<uint32_t> seed_masks;   // pigeonhole seeds of the libraries (empty = deferred reads take the generic search)
+    int dup_first = 0;
     std::string key() const;
 };
 

@@ -26,11 +26,25 @@ struct LibDev {
     const uint2* buckets;     // nseeds * (bucket_mask + 1) entries of (start, count) into cands
     uint32_t bucket_mask;
     const int32_t* cands;     // nseeds * nentries entry ids, grouped by bucket
+    // KW == 1 only: the same candidates as rows (h, l, pool index, 0), so that a candidate costs one 16-byte load
+    const uint4* cand_rows;
     // segmented search (dual paired-end): first segment = bases [0, seg1), second = [seg1, L)
     int seg1;
     // table of library rows with their last base dropped (SURVEY 8.1 T8 root rule)
     const uint32_t* prefix_slots;
     uint32_t prefix_mask;
+};
+
+// What the specialised single-barcode kernel (spec_single.cuh) needs of the two strands' libraries, passed by
+// value as a kernel argument so that the table pointers sit in the constant bank.  [0] forward, [1] reverse.
+struct SpecTables {
+    const uint4* slots[2];      // exact cuckoo tables (16-byte slots)
+    const uint2* buckets[2];    // pigeonhole seed buckets
+    const uint4* cand_rows[2];  // candidates as rows
+    uint32_t slot_mask[2];
+    uint32_t bucket_mask[2];
+    int nentries[2];
+    const LibDev* libs;         // the full descriptors, for the generic search of the rare complicated reads
 };
 
 // Packed reads of one batch on the device.

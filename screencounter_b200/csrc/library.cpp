@@ -319,6 +319,15 @@ Library::Library(const std::vector<std::string>& sequences, int length, const Li
                 ++slot.y;
             }
         }
+        if (KW == 1) {
+            cand_rows.assign((size_t)nseeds * E * 4, 0);
+            for (size_t k = 0; k < (size_t)nseeds * E; ++k) {
+                const size_t e = (size_t)cands[k];
+                cand_rows[4 * k + 0] = ent_keys[e * 2];
+                cand_rows[4 * k + 1] = ent_keys[e * 2 + 1];
+                cand_rows[4 * k + 2] = (uint32_t)ent_idx[e];
+            }
+        }
     }
 
     // Rows with the last base dropped (only the segmented search consults it).

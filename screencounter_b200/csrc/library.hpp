@@ -46,6 +46,7 @@ struct Library {
     uint32_t nbuckets = 0;
     std::vector<uint2> buckets;
     std::vector<int32_t> cands;
+    std::vector<uint32_t> cand_rows;    // KW == 1: 4 words (h, l, pool index, 0) per (seed, candidate), in `cands` order
     std::vector<uint32_t> prefix_slots; // same layout, rows with the last base dropped
     uint32_t prefix_mask = 0;
 

@@ -109,6 +109,23 @@ void SingleMatcher::upload(Context& ctx) {
     params.libs = upload_lib_array(ctx, libs, libs_dev);
 }
 
+// The pigeonhole seeds the specialised kernel may fold in: both strands' libraries have the same ones (same length,
+// same budget); more than four seeds, or the "every entry is a candidate" seed, leave the list empty and the
+// kernel sends its deferred reads through the generic search.
+static void spec_seeds(const SingleMatcher& m, SpecSingleConfig& cfg) {
+    cfg.seed_masks.clear();
+    const Library& lib = m.tmpl.fwd ? m.lib_f.host : m.lib_r.host;
+    cfg.dup_first = lib.opt.duplicates == Duplicates::FIRST ? 1 : 0;
+    if (lib.KW != 1 || lib.nseeds < 1 || lib.nseeds > 4 || lib.cand_rows.empty()) return;
+    for (int s = 0; s < lib.nseeds; ++s) {
+        if (lib.seed_masks[s] == 0) {
+            cfg.seed_masks.clear();
+            return;
+        }
+        cfg.seed_masks.push_back(lib.seed_masks[s]);
+    }
+}
+
 void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, int32_t* d_counts, int32_t* d_index, uint32_t* d_info,
                    cudaStream_t stream) {
     if (reads.n <= 0) return;
@@ -133,12 +150,25 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
     cfg.fstart = P.spec.fstart[0];
     cfg.rstart = P.spec.rstart[0];
     cfg.keylen = P.spec.rlen_f[0];
+    spec_seeds(m, cfg);
     std::string why;
     cudaKernel_t spec = (P.spec.mm >= 0 && cfg.T > 0) ? specialised_single_kernel(cfg, ctx.device, &why) : nullptr;
     if (spec) {
         ReadsDev reads_arg = reads;
-        const LibDev* libs = P.libs;
-        void* args[] = { &reads_arg, &libs, &d_counts, &d_index, &d_info };
+        SpecTables tables;
+        std::memset(&tables, 0, sizeof tables);
+        const DeviceLibrary* both[2] = { m.tmpl.fwd ? &m.lib_f : nullptr, m.tmpl.rev ? &m.lib_r : nullptr };
+        for (int s = 0; s < 2; ++s) {
+            if (!both[s]) continue;
+            tables.slots[s] = reinterpret_cast<const uint4*>(both[s]->dev.slots);
+            tables.buckets[s] = both[s]->dev.buckets;
+            tables.cand_rows[s] = both[s]->dev.cand_rows;
+            tables.slot_mask[s] = both[s]->dev.slot_mask;
+            tables.bucket_mask[s] = both[s]->dev.bucket_mask;
+            tables.nentries[s] = both[s]->dev.nentries;
+        }
+        tables.libs = P.libs;
+        void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info };
         // persistent warps: as many blocks as are resident at once, each warp strides over the tiles
         const int resident = specialised_blocks_per_sm(spec);
         const int spec_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * resident));
@@ -414,6 +444,16 @@ int scg_jit_selftest(const char* constant, int strand, int mismatches, int words
         cfg.fstart = s.fstart[0];
         cfg.rstart = s.rstart[0];
         cfg.keylen = s.rlen_f[0];
+        // the seeds library.cpp would build for this budget: cap + 1 contiguous parts of the variable region
+        const int cap = std::min(std::max(mismatches, 0), cfg.keylen);
+        if (cap >= 1 && cap + 1 <= 4 && cfg.keylen <= 32) {
+            for (int p = 0; p < cap + 1; ++p) {
+                const int from = (int)((long long)cfg.keylen * p / (cap + 1)), to = (int)((long long)cfg.keylen * (p + 1) / (cap + 1));
+                uint32_t mask = 0;
+                for (int b = from; b < to; ++b) mask |= 1u << b;
+                cfg.seed_masks.push_back(mask);
+            }
+        }
         std::string why;
         cudaKernel_t k = specialised_single_kernel(cfg, 0, &why);
         if (k) {

@@ -12,13 +12,17 @@
 //     3. the first window that passes (positions ascending, forward before reverse,
 //        SimpleSingleMatch.hpp:226-242) has its variable region cut out of the registers and probed
 //        in the exact table (one 16-byte load); an exact hit resolves the read on the spot.
+//        The two table slots are requested right after the scan and looked at one tile later, so the
+//        L2 latency of the probe hides behind the next tile's scan.
 //   SLOW PATH (compacted)
 //     Reads the fast path cannot settle -- the exact probe missed with budget left for the
 //     mismatch-tolerant search, an N inside the variable region, several candidate windows -- are
-//     appended to a per-warp queue in shared memory.  Whenever 32 are waiting the warp runs the full
-//     per-read search (every window, pigeonhole-seeded mismatch search, first / best rules) with all
-//     32 lanes busy on 32 different deferred reads, instead of a few lanes of every tile dragging the
-//     rest of the warp through the long path.
+//     appended, with their variable region, to a per-warp queue in shared memory.  Whenever 32 are
+//     waiting the warp runs the mismatch-tolerant search (pigeonhole seeds, every candidate row one
+//     16-byte load, best-unique / tie rules of MismatchTrie.hpp:266-343) with all 32 lanes busy on 32
+//     different deferred reads, instead of a few lanes of every tile dragging the rest of the warp
+//     through the long path.  The rare read with several candidate windows gets the full per-read
+//     search (every window, first / best rules) out of line.
 //
 // This file is compiled twice:
 //   * by nvcc at build time for the default configuration below (BASELINE configs[1]'s template),
@@ -30,7 +34,8 @@
 //   as a string of A C G T and '-', SPEC_FWD / SPEC_REV strands searched, SPEC_W words per plane of
 //   the batch, SPEC_NB window blocks (ceil((32*W - T + 1) / 32)), SPEC_CB counter planes, SPEC_MM
 //   clamped scan budget, SPEC_MAXMM the caller's budget, SPEC_USE_FIRST, SPEC_FSTART / SPEC_RSTART /
-//   SPEC_KEYLEN the variable region (at most 32 bases), SPEC_NAME the kernel's name.
+//   SPEC_KEYLEN the variable region (at most 32 bases), SPEC_NSEEDS / SPEC_SEEDMASKS the libraries' pigeonhole
+//   seeds (0 = deferred reads all take the generic search), SPEC_NAME the kernel's name.
 #pragma once
 
 #include "device_keys.cuh"
@@ -61,6 +66,14 @@
 #endif
 #ifndef SPEC_STAGES
 #define SPEC_STAGES 2
+#endif
+// pigeonhole seeds of the libraries (library.cpp): number (0 = none usable here) and base-position masks
+#ifndef SPEC_NSEEDS
+#define SPEC_NSEEDS 2
+#define SPEC_SEEDMASKS { 0x3FFu, 0xFFC00u }
+#endif
+#ifndef SPEC_DUP_FIRST
+#define SPEC_DUP_FIRST 0
 #endif
 
 namespace scg {
@@ -282,7 +295,7 @@ __device__ __noinline__ void slow_single(const ReadsDev& reads, const LibDev* __
             const int c = rev ? cr.get(p) : cf.get(p);
             Key<1> key;
             extract_region<1>(rd, 32 * pb + p + (rev ? SPEC_RSTART : SPEC_FSTART), KEYLEN, key);
-            const Hit h = lookup_any<1, true>(libs + (rev ? 1 : 0), key, SPEC_MAXMM - c);
+            const Hit h = lookup_any<1>(libs + (rev ? 1 : 0), key, SPEC_MAXMM - c);
             if (h.index < 0) continue;
             const int total = c + h.dist;
             if (SPEC_USE_FIRST) {
@@ -314,12 +327,10 @@ __device__ __noinline__ void slow_single(const ReadsDev& reads, const LibDev* __
     if (out_info) out_info[i] = pack_info(out.found, out.reverse, out.mismatches, out.var_mismatches, out.position);
 }
 
-} // namespace spec
-} // namespace scg
 
 // What a lane remembers about its read between the scan and the arrival of the table slots.
 struct Pending {
-    uint4 a, b;        // the two cuckoo slots of the first candidate's variable region
+    uint4 a, b;        // the two cuckoo slots of the first candidate's variable region (a.x = its N plane when not probed)
     uint32_t kh, kl;   // that region, packed
     uint32_t meta;     // PM_* flags | constant mismatches << 16 | window position
     uint32_t i;        // read index inside the batch
@@ -331,19 +342,95 @@ constexpr uint32_t PM_REV = 1u << 28;     // the first candidate is on the rever
 constexpr uint32_t PM_LATE = 1u << 27;    // the first candidate lies beyond the first window block
 constexpr uint32_t PM_INRANGE = 1u << 26; // the lane holds a real read
 
+constexpr int NSEEDS = SPEC_NSEEDS;
+__host__ __device__ constexpr uint32_t seed_mask(int sd) {
+    constexpr uint32_t masks[] = SPEC_SEEDMASKS;   // at least one element (a dummy when there are no seeds)
+    return masks[sd];
+}
+constexpr uint32_t KEYMASK = KEYLEN >= 32 ? 0xFFFFFFFFu : ((1u << KEYLEN) - 1u);
+
+// best-unique bookkeeping of the mismatch-tolerant search (MismatchTrie.hpp:266-343)
+struct Best {
+    int dist, index;
+    bool ambiguous;
+    __device__ __forceinline__ void consider(const uint4 row, uint32_t kh, uint32_t kl, uint32_t kn, int cap, bool valid) {
+        const int d = __popc(((kh ^ row.x) | (kl ^ row.y) | kn) & KEYMASK);
+        if (!valid || d > cap || d > dist) return;
+        const int idx = (int)row.z;
+        if (d < dist) {
+            dist = d;
+            index = idx;
+            ambiguous = false;
+        } else if (idx != index) {
+            if (SPEC_DUP_FIRST) {
+                index = min(index, idx);
+            } else {
+                ambiguous = true;
+            }
+        }
+    }
+};
+
+// AnyMismatches::search (MismatchTrie.hpp:446-501) for a region whose exact probe already missed (or that holds an
+// N): a barcode within `cap` substitutions agrees with the region on at least one of the cap + 1 seeds, so one
+// bucket per seed enumerates every candidate.  Uniform control flow: the bucket loads of all seeds go out
+// together, then the first candidate row of each; further rows of a bucket are rare.
+__device__ __forceinline__ Hit seeded_search(const SpecTables& tb, bool rev, uint32_t kh, uint32_t kl, uint32_t kn, int cap, bool active) {
+    Hit out{ -1, 0 };
+    cap = min(cap, KEYLEN);
+    active = active && cap > 0 && __popc(kn) <= cap;
+    const uint2* __restrict__ buckets = rev ? tb.buckets[1] : tb.buckets[0];
+    const uint4* __restrict__ rows = rev ? tb.cand_rows[1] : tb.cand_rows[0];
+    const uint32_t bmask = rev ? tb.bucket_mask[1] : tb.bucket_mask[0];
+    const int nent = rev ? tb.nentries[1] : tb.nentries[0];
+    uint2 bk[NSEEDS > 0 ? NSEEDS : 1];
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        const uint32_t m = seed_mask(sd);
+        const uint32_t mh = kh & m, ml = kl & m;
+        bk[sd] = make_uint2(0, 0);
+        // an N inside the seed: no barcode agrees with the region there
+        if (active && !(kn & m)) {
+            const uint32_t b = hash_key(&mh, &ml, 1, 0x5EED0000u + sd) & bmask;
+            bk[sd] = __ldg(buckets + (size_t)sd * (bmask + 1) + b);
+        }
+    }
+    uint4 first[NSEEDS > 0 ? NSEEDS : 1];
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        first[sd] = make_uint4(0, 0, 0, 0);
+        if (bk[sd].y > 0) first[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x);
+    }
+    Best best{ cap + 1, -1, false };
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) best.consider(first[sd], kh, kl, kn, cap, bk[sd].y > 0);
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        for (uint32_t c = 1; c < bk[sd].y; ++c) best.consider(__ldg(rows + (size_t)sd * nent + bk[sd].x + c), kh, kl, kn, cap, true);
+    }
+    if (best.index >= 0 && !best.ambiguous) {
+        out.index = best.index;
+        out.dist = best.dist;
+    }
+    return out;
+}
+
+} // namespace spec
+} // namespace scg
+
 extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
-    SPEC_NAME(scg::ReadsDev reads, const scg::LibDev* __restrict__ libs, int32_t* __restrict__ counts,
-              int32_t* __restrict__ out_index, uint32_t* __restrict__ out_info) {
+    SPEC_NAME(const scg::ReadsDev reads, const scg::SpecTables tb, int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
+              uint32_t* __restrict__ out_info) {
     using namespace scg;
     using namespace scg::spec;
     static_assert(KEYLEN <= 32, "the specialised kernel handles variable regions of at most 32 bases");
     // per warp: a ring of STAGES tile buffers filled by the TMA (1-D bulk copies, one per tile, issued by
-    // lane 0 and signalled on an mbarrier), and the queue of deferred reads
+    // lane 0 and signalled on an mbarrier), and the queue of deferred reads (index, meta word, variable region)
     __shared__ __align__(128) uint32_t stage_all[WARPS][STAGES][TILE_WORDS];
     __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
-    __shared__ uint32_t queue_all[WARPS][QCAP];
+    __shared__ uint32_t queue_all[WARPS][5][QCAP];
     const int wib = threadIdx.x >> 5;
-    uint32_t* queue = queue_all[wib];
+    uint32_t(*queue)[QCAP] = queue_all[wib];
     int waiting = 0;   // warp-uniform
 
     const int lane = threadIdx.x & 31;
@@ -351,13 +438,6 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long ntiles = (reads.n + TILE - 1) / TILE;
-    // the exact tables of both strands (library.cpp CuckooTable): slot = (h, l, value, pad), 16 bytes;
-    // a key sits in T1 at hash & mask or in T2 (mask + 1 slots further on) at hash_second(hash) & mask
-    const uint4* __restrict__ slots_f = SPEC_FWD ? reinterpret_cast<const uint4*>(libs[0].slots) : nullptr;
-    const uint4* __restrict__ slots_r = SPEC_REV ? reinterpret_cast<const uint4*>(libs[1].slots) : nullptr;
-    const uint32_t mask_f = SPEC_FWD ? libs[0].slot_mask : 0u;
-    const uint32_t mask_r = SPEC_REV ? libs[1].slot_mask : 0u;
-    constexpr uint32_t keymask = KEYLEN >= 32 ? 0xFFFFFFFFu : ((1u << KEYLEN) - 1u);
 
     const uint32_t stage_base = smem_addr(&stage_all[wib][0][0]);
     const uint32_t bar_base = smem_addr(&bar_all[wib][0]);
@@ -388,7 +468,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         Words R;
         uint32_t meta = 0;
         if (have) {
-            // ---- this tile's words: wait for the TMA, registers <- shared memory, hand the buffer back ----
+            // ---- this tile's words: wait for the TMA, registers <- shared memory ----
             mbar_wait(bar_base + 8u * stage, parity);
             const uint32_t* buf = stage_all[wib][stage] + lane;
 #pragma unroll
@@ -467,7 +547,14 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             }
             const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
             if (dm) {
-                if (defer) queue[waiting + __popc(dm & lanes_below)] = pend.i;
+                if (defer) {
+                    const int at = waiting + __popc(dm & lanes_below);
+                    queue[0][at] = pend.i;
+                    queue[1][at] = m;
+                    queue[2][at] = pend.kh;
+                    queue[3][at] = pend.kl;
+                    queue[4][at] = (m & PM_PROBED) ? 0u : pend.a.x;
+                }
                 waiting += __popc(dm);
                 __syncwarp();
             }
@@ -485,30 +572,52 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                 constexpr int base = SMIN >> 5;
                 constexpr int DMAX = ((SMAX + 31) >> 5) - base;
                 const int d = a - base;
-                const uint32_t kh = __funnelshift_r(pick<DMAX>(R.h, base, d), pick<DMAX>(R.h, base + 1, d), sh) & keymask;
-                const uint32_t kl = __funnelshift_r(pick<DMAX>(R.l, base, d), pick<DMAX>(R.l, base + 1, d), sh) & keymask;
-                const uint32_t kn = __funnelshift_r(pick<DMAX>(R.n, base, d), pick<DMAX>(R.n, base + 1, d), sh) & keymask;
+                const uint32_t kh = __funnelshift_r(pick<DMAX>(R.h, base, d), pick<DMAX>(R.h, base + 1, d), sh) & KEYMASK;
+                const uint32_t kl = __funnelshift_r(pick<DMAX>(R.l, base, d), pick<DMAX>(R.l, base + 1, d), sh) & KEYMASK;
+                const uint32_t kn = __funnelshift_r(pick<DMAX>(R.n, base, d), pick<DMAX>(R.n, base + 1, d), sh) & KEYMASK;
+                pend.kh = kh;
+                pend.kl = kl;
+                pend.a.x = kn;
                 if (kn == 0) {
-                    const uint4* __restrict__ slots = frev ? slots_r : slots_f;
-                    const uint32_t mask = frev ? mask_r : mask_f;
+                    // library.cpp CuckooTable: a key sits in T1 at hash & mask or in T2 (mask + 1 slots on) at hash_second(hash) & mask
+                    const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
+                    const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
                     const uint32_t acc = hash_key(&kh, &kl, 1, 0);
                     pend.a = __ldg(slots + (acc & mask));
                     pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
-                    pend.kh = kh;
-                    pend.kl = kl;
                     pend.meta |= PM_PROBED;
                 }
             }
         }
 
-        // ---- the full search runs when a warp's worth of deferred reads is waiting, and once more at the end ----
+        // ---- deferred reads: searched when a warp's worth is waiting, and whatever is left at the end ----
         while (waiting >= 32 || (!have && waiting > 0)) {
             const int take = waiting < 32 ? waiting : 32;
             waiting -= take;
             const bool active = lane < take;
-            const uint32_t j = active ? queue[waiting + lane] : 0u;
+            const uint32_t qi = active ? queue[0][waiting + lane] : 0u;
+            const uint32_t qm = active ? queue[1][waiting + lane] : 0u;
+            const uint32_t qh = active ? queue[2][waiting + lane] : 0u;
+            const uint32_t ql = active ? queue[3][waiting + lane] : 0u;
+            const uint32_t qn = active ? queue[4][waiting + lane] : 0u;
             __syncwarp();
-            slow_single(reads, libs, (long long)j, active, counts, out_index, out_info);
+            // one candidate window in the first block: only its variable region is still open
+            const bool simple = active && NSEEDS > 0 && !(qm & (PM_MANY | PM_LATE));
+            if (NSEEDS > 0) {
+                const bool rev = (qm & PM_REV) != 0;
+                const int fc = (int)((qm >> 16) & 0xFFu);
+                const Hit h = seeded_search(tb, rev, qh, ql, qn, SPEC_MAXMM - fc, simple);
+                if (simple) {
+                    const bool found = h.index >= 0;
+                    if (found) atomicAdd(counts + h.index, 1);
+                    if (out_index) out_index[qi] = h.index;
+                    if (out_info) out_info[qi] = pack_info(found, rev, fc + h.dist, h.dist, (int)(qm & 0xFFFFu));
+                }
+            }
+            // several candidate windows (or one beyond the first block): the full per-read search
+            if (__any_sync(0xFFFFFFFFu, active && !simple)) {
+                slow_single(reads, tb.libs, (long long)qi, active && !simple, counts, out_index, out_info);
+            }
         }
         if (!have) break;
         tile += nwarps;
