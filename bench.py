@@ -306,7 +306,7 @@ def main():
                    "matched_fraction": matched_per_step / args.reads},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
                 "d2h_bytes_per_step": 4 * len(library), "reads_per_step": e2e_reads, "host_threads": nthreads,
-                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "total_s")},
+                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "total_s")},
                 "note": "host FASTQ text -> scg_count_single (parse, pack to pinned, H2D, kernels, counts D2H)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "countSingleBarcodes scan+lookup+count, " + plan.kernel, "bytes_per_read": BYTES_PER_READ, "reads_per_launch": reads_per_launch,

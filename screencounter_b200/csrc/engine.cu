@@ -57,6 +57,11 @@ void PinnedBuffer::reserve(size_t n) {
 // context
 // ---------------------------------------------------------------------------------------
 Context::~Context() {
+    if (ready) cudaSetDevice(device);
+    for (auto& slot : staging) {
+        if (slot.done) cudaEventDestroy(slot.done);
+    }
+    single_cache.clear();
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -96,9 +101,9 @@ int Context::grid_for(long long ntiles) const {
 void Context::finish_timing() {
     char buf[512];
     std::snprintf(buf, sizeof buf,
-                  "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"total_s\": %.6f, "
+                  "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"setup_s\": %.6f, \"total_s\": %.6f, "
                   "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld, \"kernel\": \"",
-                  timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.total_s, timing.reads, timing.bytes_h2d,
+                  timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.setup_s, timing.total_s, timing.reads, timing.bytes_h2d,
                   timing.launches);
     timing_json = buf;
     for (char ch : kernel_note) {
@@ -148,14 +153,20 @@ void DeviceLibrary::upload(Context& ctx) {
 // ---------------------------------------------------------------------------------------
 ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int nthreads, bool want_odd)
     : ctx_(ctx), r1_(r1), r2_(r2), nthreads_(std::max(1, nthreads)), want_odd_(want_odd) {
+    if (r1_) r1_->set_threads(nthreads_);
+    if (r2_) r2_->set_threads(nthreads_);
+    slots_ = ctx_.staging;
     for (int k = 0; k < kSlots; ++k) {
-        SCG_CUDA_CHECK(cudaEventCreateWithFlags(&slots_[k].done, cudaEventDisableTiming));
+        if (!slots_[k].done) SCG_CUDA_CHECK(cudaEventCreateWithFlags(&slots_[k].done, cudaEventDisableTiming));
+        slots_[k].in_flight = false;
     }
 }
 
 ReadPipeline::~ReadPipeline() {
+    // whatever still reads the staging buffers must finish before the next call reuses them
     for (int k = 0; k < kSlots; ++k) {
-        if (slots_[k].done) cudaEventDestroy(slots_[k].done);
+        if (slots_[k].in_flight) cudaEventSynchronize(slots_[k].done);
+        slots_[k].in_flight = false;
     }
 }
 

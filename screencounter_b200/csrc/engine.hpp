@@ -52,10 +52,49 @@ struct PinnedBuffer {
 
 struct Timing {
     double parse_s = 0, pack_s = 0, h2d_s = 0, device_s = 0, total_s = 0;
+    double setup_s = 0;   // library tables built + uploaded, kernels specialised (zero when the context had them cached)
     long long reads = 0, bytes_h2d = 0, launches = 0;
 };
 
+// A library resident on the device.
+struct DeviceLibrary {
+    Library host;
+    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots;
+    LibDev dev;
+    void upload(struct Context& ctx);
+};
+
+// Packed reads of one batch resident on the device.
+struct DeviceBatch {
+    DeviceBuffer data, lens, odd;
+    ReadsDev view;
+};
+
+// One slot of the FASTQ -> pinned -> HBM double buffer (pipeline.hpp).  The slots belong to the context so that
+// consecutive calls (one per file in matrixOf*-style loops) reuse the pinned and device allocations.
+struct Staged {
+    PinnedBuffer pinned_data, pinned_lens;
+    std::vector<uint8_t> odd_host;
+    DeviceBatch dev;
+};
+struct StagingSlot {
+    Staged mate[2];
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
+struct SingleMatcher;
+
 struct Context {
+    static constexpr int kStagingSlots = 2;
+    StagingSlot staging[kStagingSlots];
+    // single-barcode matchers (template + both strands' tables on the device) of recent calls, keyed by a
+    // 128-bit hash of everything that defines them
+    struct CachedMatcher {
+        unsigned long long key1 = 0, key2 = 0;
+        std::shared_ptr<SingleMatcher> matcher;
+    };
+    std::vector<CachedMatcher> single_cache;
     int device = 0;
     bool ready = false;
     int sm_count = 0;
@@ -71,20 +110,6 @@ struct Context {
     void ensure_ready();   // lazy CUDA initialisation; throws when no usable device exists
     int grid_for(long long ntiles) const;
     void finish_timing();
-};
-
-// A library resident on the device.
-struct DeviceLibrary {
-    Library host;
-    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots;
-    LibDev dev;
-    void upload(Context& ctx);
-};
-
-// Packed reads of one batch resident on the device.
-struct DeviceBatch {
-    DeviceBuffer data, lens, odd;
-    ReadsDev view;
 };
 
 } // namespace scg

@@ -157,18 +157,17 @@ void FastqReader::refill() {
     pos_ = 0;
 }
 
-// One record, following FastqReader::operator() (FastqReader.hpp:42-110).  Line numbers in the
-// messages: the reference counts exactly four lines per record whatever the wrapping, so record
-// k (0-based) "starts" at line 4k+1.
-bool FastqReader::parse_one(Record& out) {
-    const long long init_line = 4 * nrecords_;
-    const char* b = base_;
-    const size_t n = avail_;
-    size_t p = pos_;
+// One record starting at b[p], following FastqReader::operator() (FastqReader.hpp:42-110).  Returns false when
+// the window [b, b + n) ends before the record is complete (the caller knows whether more data can follow;
+// with `final` set a truncated record throws like the reference).  Line numbers in the messages: the reference
+// counts exactly four lines per record whatever the wrapping, so record k (0-based) "starts" at line 4k+1.
+static bool parse_record(const char* b, size_t n, bool final, size_t& pos, long long rec_index, Record& out, bool& okay_after) {
+    const long long init_line = 4 * rec_index;
+    size_t p = pos;
     if (p >= n) return false;  // needs more data; the caller knows whether that is the end
 
     auto need_more = [&](int line_offset) -> bool {
-        if (final_) throw Error("premature end of the file at line " + std::to_string(init_line + line_offset));
+        if (final) throw Error("premature end of the file at line " + std::to_string(init_line + line_offset));
         return false;
     };
 
@@ -205,7 +204,7 @@ bool FastqReader::parse_one(Record& out) {
     while (q < n) {
         const char* e4 = static_cast<const char*>(std::memchr(b + q, '\n', n - q));
         if (!e4) {
-            if (!final_) return false;  // quality line not complete yet
+            if (!final) return false;  // quality line not complete yet
             qual += n - q;
             q = n;
             break;
@@ -219,9 +218,9 @@ bool FastqReader::parse_one(Record& out) {
         }
     }
     if (!ended) {
-        if (!final_) return false;
+        if (!final) return false;
         next_okay = false;  // ran off the end of the file inside the quality string
-    } else if (!next_okay && !final_) {
+    } else if (!next_okay && !final) {
         // the record ended exactly at the window's edge: whether more input follows is not known yet
         return false;
     }
@@ -230,15 +229,114 @@ bool FastqReader::parse_one(Record& out) {
     }
     if (len > (size_t)MAX_READ_LEN) {
         throw Error("reads longer than " + std::to_string(MAX_READ_LEN) + " bases are not supported by this engine (read " +
-                    std::to_string(nrecords_ + 1) + ")");
+                    std::to_string(rec_index + 1) + ")");
     }
     out.seq = b + s0;
     out.span = (uint32_t)span;
     out.len = (uint32_t)len;
-    pos_ = q;
+    pos = q;
+    okay_after = next_okay;
+    return true;
+}
+
+bool FastqReader::parse_one(Record& out) {
+    bool next_okay = false;
+    if (!parse_record(base_, avail_, final_, pos_, nrecords_, out, next_okay)) return false;
     okay_ = next_okay;
     ++nrecords_;
     return true;
+}
+
+// A likely record start at or after `from`: a line starting with '@' whose line after next starts with '+'.
+// Only a guess (the grammar allows wrapped sequences and '@' is a legal quality character): the caller checks it
+// against where the preceding chunk's exact parse really ends.
+static size_t guess_record_start(const char* b, size_t n, size_t from) {
+    const char* nl = from < n ? static_cast<const char*>(std::memchr(b + from, '\n', n - from)) : nullptr;
+    for (int tries = 0; nl && tries < 64; ++tries) {
+        const size_t q = (size_t)(nl - b) + 1;
+        if (q >= n) break;
+        const char* e1 = static_cast<const char*>(std::memchr(b + q, '\n', n - q));
+        if (!e1) break;
+        if (b[q] == '@') {
+            const size_t s = (size_t)(e1 - b) + 1;
+            const char* e2 = s < n ? static_cast<const char*>(std::memchr(b + s, '\n', n - s)) : nullptr;
+            if (e2 && (size_t)(e2 - b) + 1 < n && e2[1] == '+') return q;
+        }
+        nl = e1;
+    }
+    return (size_t)-1;
+}
+
+// Splits the next stretch of an in-memory input into chunks, parses them concurrently with the exact grammar and
+// keeps the longest prefix of chunks whose parses chain up (each ends exactly where the next one started).  Whatever
+// does not chain -- a wrong guess, a malformed record -- is left for the serial path, which then reproduces the
+// reference's behaviour (and error text) at exactly that record.
+bool FastqReader::next_parallel(size_t max_records) {
+    const char* b = base_;
+    const size_t n = avail_;
+    size_t probe = pos_;
+    Record first;
+    bool dummy = false;
+    if (!parse_record(b, n, true, probe, nrecords_, first, dummy)) return false;
+    const size_t rec_bytes = std::max<size_t>(probe - pos_, 8);
+    const size_t region_end = std::min(n, pos_ + std::max<size_t>(max_records, 1) * rec_bytes);
+    const size_t region = region_end - pos_;
+    int K = (int)std::min<size_t>((size_t)threads_, region / (1u << 20));
+    if (K < 2) return false;
+    std::vector<size_t> starts;
+    starts.push_back(pos_);
+    for (int k = 1; k < K; ++k) {
+        const size_t g = guess_record_start(b, n, pos_ + region / K * k);
+        if (g == (size_t)-1 || g <= starts.back() || g >= region_end) continue;
+        starts.push_back(g);
+    }
+    K = (int)starts.size();
+    if (K < 2) return false;
+    struct Chunk {
+        std::vector<Record> recs;
+        size_t end = 0;
+        bool okay_after = true, failed = false;
+    };
+    std::vector<Chunk> chunks(K);
+    auto work = [&](int k) {
+        Chunk& c = chunks[k];
+        size_t p = starts[k];
+        const size_t stop = k + 1 < K ? starts[k + 1] : region_end;
+        c.recs.reserve((stop - p) / rec_bytes + 16);
+        try {
+            Record r;
+            bool ok = true;
+            while (ok && p < stop) {
+                if (!parse_record(b, n, true, p, 0, r, ok)) break;
+                c.recs.push_back(r);
+            }
+            c.okay_after = ok;
+        } catch (const std::exception&) {
+            c.failed = true;  // records before the bad one stay valid; the serial path raises the error
+        }
+        c.end = p;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int k = 1; k < K; ++k) pool.emplace_back(work, k);
+        work(0);
+        for (auto& t : pool) t.join();
+    }
+    size_t total = 0;
+    int accepted = 0;
+    for (int k = 0; k < K; ++k) {
+        total += chunks[k].recs.size();
+        ++accepted;
+        if (chunks[k].failed || !chunks[k].okay_after) break;
+        if (k + 1 < K && chunks[k].end != starts[k + 1]) break;
+    }
+    batch_.reserve(total);
+    for (int k = 0; k < accepted; ++k) batch_.insert(batch_.end(), chunks[k].recs.begin(), chunks[k].recs.end());
+    const Chunk& last = chunks[accepted - 1];
+    pos_ = last.end;
+    okay_ = last.okay_after;
+    nrecords_ += (long long)batch_.size();
+    return !batch_.empty();
 }
 
 const std::vector<Record>& FastqReader::next(size_t max_records) {
@@ -246,6 +344,20 @@ const std::vector<Record>& FastqReader::next(size_t max_records) {
     batch_.clear();
     if (!started_ || (pos_ >= avail_ && !final_)) refill();
     if (nrecords_ == 0 && avail_ == 0 && final_) okay_ = false;  // empty input: zero reads (FastqReader.hpp:30)
+    // the whole remaining input is in memory (caller's buffer or mmap): parse it on all the threads we were given
+    if (threads_ > 1 && final_ && okay_ && avail_ - pos_ >= (4u << 20)) {
+        bool done = false;
+        try {
+            done = next_parallel(max_records);
+        } catch (const std::exception&) {
+            done = false;  // the serial path below raises the same error with the right line number
+            batch_.clear();
+        }
+        if (done) {
+            parse_s_ += now_s() - t0;
+            return batch_;
+        }
+    }
     Record r;
     while (okay_ && batch_.size() < max_records) {
         if (parse_one(r)) {

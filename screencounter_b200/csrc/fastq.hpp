@@ -33,11 +33,15 @@ public:
     // buffer that stays valid until the next call.  Empty result = end of input.
     const std::vector<Record>& next(size_t max_records);
 
+    // Threads the record splitter may use on inputs that are entirely in memory (caller's buffer, mmap'd file).
+    void set_threads(int n) { threads_ = n < 1 ? 1 : n; }
+
     long long records_seen() const { return nrecords_; }
     double parse_seconds() const { return parse_s_; }
 
 private:
     bool parse_one(Record& out);  // false = needs more data (or clean end of input)
+    bool next_parallel(size_t max_records);
     void refill();
 
     std::unique_ptr<FastqInput> in_;
@@ -50,6 +54,7 @@ private:
     long long nrecords_ = 0;
     std::vector<Record> batch_;
     double parse_s_ = 0;
+    int threads_ = 1;
 };
 
 // Packs records [first, first+count) into `out` (tile-planar, W words per plane, count padded

@@ -29,23 +29,13 @@ public:
     // Call after the kernels that read the batch have been enqueued.
     void submitted(Batch& b);
 
-    const std::vector<uint8_t>& odd_flags(const Batch& b) const { return static_cast<Slot*>(b.slot)->mate[0].odd_host; }
+    const std::vector<uint8_t>& odd_flags(const Batch& b) const { return static_cast<StagingSlot*>(b.slot)->mate[0].odd_host; }
 
 private:
-    static constexpr int kSlots = 2;
+    static constexpr int kSlots = Context::kStagingSlots;
     static constexpr size_t kMaxBatchReads = 1u << 20;
     static constexpr size_t kMaxBatchBytes = 64u << 20;
-
-    struct Staged {
-        PinnedBuffer pinned_data, pinned_lens;
-        std::vector<uint8_t> odd_host;
-        DeviceBatch dev;
-    };
-    struct Slot {
-        Staged mate[2];
-        cudaEvent_t done = nullptr;
-        bool in_flight = false;
-    };
+    using Slot = StagingSlot;
 
     void stage(Slot& slot, int mate, const Record* recs, size_t count);
 
@@ -54,7 +44,7 @@ private:
     FastqReader* r2_;
     int nthreads_;
     bool want_odd_;
-    Slot slots_[kSlots];
+    Slot* slots_;   // the context's staging slots
     int next_slot_ = 0;
     const Record* recs1_ = nullptr;
     const Record* recs2_ = nullptr;

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 #include "api_common.hpp"
 #include "handlers.cuh"
@@ -79,8 +81,31 @@ void SingleMatcher::prepare(const std::string& constant, int strand, const Pool&
     opt.max_mismatches = mismatches;
     opt.duplicates = dup;
     std::memset(&params, 0, sizeof params);
-    if (tmpl.fwd) lib_f.host = Library(pool.seqs, pool.length, opt);
-    if (tmpl.rev) lib_r.host = Library(pool.reverse_complemented(), pool.length, opt);
+    // the two strands' tables are independent: build them side by side (errors surface in the reference's order,
+    // forward library first, SimpleSingleMatch.hpp:88-96)
+    std::exception_ptr err_f, err_r;
+    std::thread side;
+    if (tmpl.fwd && tmpl.rev) {
+        side = std::thread([&] {
+            try {
+                lib_r.host = Library(pool.reverse_complemented(), pool.length, opt);
+            } catch (...) {
+                err_r = std::current_exception();
+            }
+        });
+    }
+    try {
+        if (tmpl.fwd) lib_f.host = Library(pool.seqs, pool.length, opt);
+    } catch (...) {
+        err_f = std::current_exception();
+    }
+    if (side.joinable()) {
+        side.join();
+    } else if (tmpl.rev) {
+        lib_r.host = Library(pool.reverse_complemented(), pool.length, opt);
+    }
+    if (err_f) std::rethrow_exception(err_f);
+    if (err_r) std::rethrow_exception(err_r);
     params.spec = tmpl.scan_spec(mismatches);
     params.max_mm = mismatches;
     params.use_first = use_first ? 1 : 0;
@@ -107,6 +132,38 @@ void SingleMatcher::upload(Context& ctx) {
         params.kw = std::max(params.kw, lib_r.dev.KW);
     }
     params.libs = upload_lib_array(ctx, libs, libs_dev);
+}
+
+// A matcher for these arguments, from the context's cache when an earlier call (another file of the same screen)
+// already built and uploaded it.  Only successful builds are cached, so validation errors are raised every time.
+std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const std::string& constant, int strand, const Pool& pool,
+                                                     int mismatches, bool use_first) {
+    unsigned long long k1 = 1469598103934665603ull, k2 = 0x9E3779B97F4A7C15ull;
+    auto feed = [&](const void* data, size_t n) {
+        const unsigned char* p = static_cast<const unsigned char*>(data);
+        for (size_t i = 0; i < n; ++i) {
+            k1 = (k1 ^ p[i]) * 1099511628211ull;
+            k2 = mix64(k2 + p[i] + 0x100 * (i & 0xFF));
+        }
+    };
+    const int header[4] = { strand, mismatches, use_first ? 1 : 0, (int)pool.seqs.size() };
+    feed(header, sizeof header);
+    feed(constant.data(), constant.size() + 1);
+    for (const auto& s : pool.seqs) feed(s.data(), s.size() + 1);
+    for (auto& e : ctx.single_cache) {
+        if (e.key1 == k1 && e.key2 == k2) return e.matcher;
+    }
+    auto m = std::make_shared<SingleMatcher>();
+    m->prepare(constant, strand, pool, mismatches, use_first, Duplicates::ERROR);  // all validation happens on the host
+    ctx.ensure_ready();
+    m->upload(ctx);
+    if (ctx.single_cache.size() >= 4) ctx.single_cache.erase(ctx.single_cache.begin());
+    Context::CachedMatcher entry;
+    entry.key1 = k1;
+    entry.key2 = k2;
+    entry.matcher = m;
+    ctx.single_cache.push_back(entry);
+    return m;
 }
 
 // The pigeonhole seeds the specialised kernel may fold in: both strands' libraries have the same ones (same length,
@@ -247,10 +304,11 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         // same order as the reference glue: open the file, marshal the pool, build the handler, then read
         Source source(src);
         Pool p(pool, npool);
-        SingleMatcher m;
-        m.prepare(constant, strand, p, mismatches, use_first != 0, Duplicates::ERROR);  // all validation happens on the host
+        const double t_setup = now_s();
+        const std::shared_ptr<SingleMatcher> matcher = cached_single_matcher(c, constant, strand, p, mismatches, use_first != 0);
+        const SingleMatcher& m = *matcher;
         c.ensure_ready();
-        m.upload(c);
+        c.timing.setup_s += now_s() - t_setup;
 
         DeviceBuffer d_counts;
         d_counts.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);
@@ -479,6 +537,7 @@ int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, lo
                             long long* n_bases) {
     try {
         Source source(src);
+        source.reader->set_threads(nthreads);
         long long nr = 0, nb = 0;
         if (offsets) offsets[0] = 0;
         std::vector<uint32_t> packed;

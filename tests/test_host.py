@@ -172,3 +172,50 @@ def test_runtime_specialised_kernel_compiles(template, strand, mm, words):
     buf = C.create_string_buffer(16384)
     rc = lib().scg_jit_selftest(template.encode(), strand, mm, words, buf, C.c_size_t(16384))
     assert rc in (0, 2), buf.value.decode()
+
+
+def _tricky_fastq(rng, n, wrap_every=0, bad_at=None):
+    """Records that defeat naive boundary guessing: qualities starting with '@' or '+', wrapped
+    sequences and qualities, names holding '@' and '+', an occasional empty read."""
+    out = []
+    for i in range(n):
+        L = int(rng.integers(0, 120)) if rng.random() < 0.9 else 0
+        s = random_seq(rng, L)
+        q = "".join("@+I#"[int(x)] for x in rng.integers(0, 4, size=L))
+        if L and rng.random() < 0.3:
+            q = "@" + q[1:]
+        if wrap_every and L > wrap_every and rng.random() < 0.3:
+            s = "\n".join(s[k:k + wrap_every] for k in range(0, L, wrap_every))
+            q = "\n".join(q[k:k + wrap_every] for k in range(0, L, wrap_every))
+        if bad_at is not None and i == bad_at:
+            q = q + "I"   # one quality too many
+        out.append("@r%d @x+y\n%s\n+anything@here\n%s\n" % (i, s, q))
+    return "".join(out).encode("latin-1")
+
+
+@pytest.mark.parametrize("wrap", [0, 40])
+def test_parallel_splitter_equals_serial_and_reference(kref, wrap):
+    """Inputs above 4 MB are split and parsed on several threads; the result must be the serial parse."""
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(11 + wrap)
+    data = _tricky_fastq(rng, 60000, wrap_every=wrap)
+    assert len(data) > (4 << 20)
+    serial = rcpp.host_pack_roundtrip(data, 1)
+    assert serial == [_norm(s) for s in kref.parse(data)]
+    for threads in (2, 5, 16):
+        assert rcpp.host_pack_roundtrip(data, threads) == serial
+
+
+def test_parallel_splitter_reports_the_serial_error(kref):
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(3)
+    data = _tricky_fastq(rng, 60000, bad_at=41234)
+    msgs = []
+    for threads in (1, 8):
+        with pytest.raises(Exception) as err:
+            rcpp.host_pack_roundtrip(data, threads)
+        msgs.append(str(err.value))
+    assert msgs[0] == msgs[1] == "non-equal lengths for quality and sequence strings (starting line %d)" % (4 * 41234 + 1)
+    with pytest.raises(Exception) as err:
+        kref.parse(data)
+    assert msgs[0] in str(err.value)
