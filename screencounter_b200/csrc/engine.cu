@@ -170,13 +170,8 @@ ReadPipeline::~ReadPipeline() {
     }
 }
 
-void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count) {
+void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count, uint32_t minlen, uint32_t maxlen) {
     Staged& s = slot.mate[mate];
-    uint32_t maxlen = 0, minlen = 0xFFFFFFFFu;
-    for (size_t i = 0; i < count; ++i) {
-        maxlen = std::max(maxlen, recs[i].len);
-        minlen = std::min(minlen, recs[i].len);
-    }
     const int W = std::max(1, ceil_div((int)maxlen, 32));
     const size_t padded = (count + TILE - 1) / TILE * TILE;
     const size_t data_bytes = padded / TILE * tile_words(W) * sizeof(uint32_t);
@@ -239,16 +234,31 @@ bool ReadPipeline::next(Batch& out) {
     // bound the staging buffers: at most kMaxBatchBytes of packed data per mate
     size_t count = avail;
     {
-        uint32_t maxlen = 1;
+        // the reader already knows the longest read of what it handed out
+        uint32_t maxlen = std::max<uint32_t>(1, r1_->batch_max_len());
+        if (r2_) maxlen = std::max(maxlen, r2_->batch_max_len());
         const size_t probe = std::min<size_t>(avail, kMaxBatchReads);
-        for (size_t i = 0; i < probe; ++i) maxlen = std::max(maxlen, recs1_[cur1_ + i].len);
-        if (r2_) {
-            for (size_t i = 0; i < probe; ++i) maxlen = std::max(maxlen, recs2_[cur2_ + i].len);
-        }
         const size_t per_read = (size_t)12 * ceil_div((int)maxlen, 32);
         count = std::max<size_t>(TILE, std::min(probe, kMaxBatchBytes / per_read / TILE * TILE));
         count = std::min(count, avail);
     }
+    // exact shortest / longest read of this batch: the reader's figures when the batch is everything it returned
+    auto extent = [&](FastqReader* r, const Record* recs, size_t cur, size_t n_all, uint32_t& lo, uint32_t& hi) {
+        if (cur == 0 && count == n_all) {
+            lo = r->batch_min_len();
+            hi = r->batch_max_len();
+            return;
+        }
+        lo = 0xFFFFFFFFu;
+        hi = 0;
+        for (size_t i = 0; i < count; ++i) {
+            lo = std::min(lo, recs[cur + i].len);
+            hi = std::max(hi, recs[cur + i].len);
+        }
+    };
+    uint32_t lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+    extent(r1_, recs1_, cur1_, n1_, lo1, hi1);
+    if (r2_) extent(r2_, recs2_, cur2_, n2_, lo2, hi2);
 
     Slot& slot = slots_[next_slot_];
     next_slot_ = (next_slot_ + 1) % kSlots;
@@ -258,8 +268,8 @@ bool ReadPipeline::next(Batch& out) {
         ctx_.timing.device_s += now_s() - t0;
         slot.in_flight = false;
     }
-    stage(slot, 0, recs1_ + cur1_, count);
-    if (r2_) stage(slot, 1, recs2_ + cur2_, count);
+    stage(slot, 0, recs1_ + cur1_, count, lo1, hi1);
+    if (r2_) stage(slot, 1, recs2_ + cur2_, count, lo2, hi2);
     out.first_read = consumed_;
     out.n = (long long)count;
     out.reads1 = slot.mate[0].dev.view;

@@ -1,5 +1,7 @@
 #include "fastq.hpp"
 
+#include "hostpool.hpp"
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -292,23 +294,26 @@ bool FastqReader::next_parallel(size_t max_records) {
     }
     K = (int)starts.size();
     if (K < 2) return false;
-    struct Chunk {
-        std::vector<Record> recs;
-        size_t end = 0;
-        bool okay_after = true, failed = false;
-    };
-    std::vector<Chunk> chunks(K);
+    // chunk scratch lives in the reader: after the first call no memory is allocated (or page-faulted) here
+    if ((int)chunks_.size() < K) chunks_.resize(K);
+    std::vector<ParseChunk>& chunks = chunks_;
     auto work = [&](int k) {
-        Chunk& c = chunks[k];
+        ParseChunk& c = chunks[k];
+        c.recs.clear();
+        c.min_len = 0xFFFFFFFFu;
+        c.max_len = 0;
+        c.failed = false;
+        c.okay_after = true;
         size_t p = starts[k];
         const size_t stop = k + 1 < K ? starts[k + 1] : region_end;
-        c.recs.reserve((stop - p) / rec_bytes + 16);
         try {
             Record r;
             bool ok = true;
             while (ok && p < stop) {
                 if (!parse_record(b, n, true, p, 0, r, ok)) break;
                 c.recs.push_back(r);
+                c.min_len = std::min(c.min_len, r.len);
+                c.max_len = std::max(c.max_len, r.len);
             }
             c.okay_after = ok;
         } catch (const std::exception&) {
@@ -316,23 +321,26 @@ bool FastqReader::next_parallel(size_t max_records) {
         }
         c.end = p;
     };
-    {
-        std::vector<std::thread> pool;
-        for (int k = 1; k < K; ++k) pool.emplace_back(work, k);
-        work(0);
-        for (auto& t : pool) t.join();
-    }
+    HostPool::instance().parallel_for(K, K, work);
     size_t total = 0;
     int accepted = 0;
+    std::vector<size_t> offset(K + 1, 0);
     for (int k = 0; k < K; ++k) {
         total += chunks[k].recs.size();
+        offset[k + 1] = total;
         ++accepted;
         if (chunks[k].failed || !chunks[k].okay_after) break;
         if (k + 1 < K && chunks[k].end != starts[k + 1]) break;
     }
-    batch_.reserve(total);
-    for (int k = 0; k < accepted; ++k) batch_.insert(batch_.end(), chunks[k].recs.begin(), chunks[k].recs.end());
-    const Chunk& last = chunks[accepted - 1];
+    batch_.resize(total);
+    HostPool::instance().parallel_for(accepted, accepted, [&](int k) {
+        if (!chunks[k].recs.empty()) std::memcpy(batch_.data() + offset[k], chunks[k].recs.data(), chunks[k].recs.size() * sizeof(Record));
+    });
+    for (int k = 0; k < accepted; ++k) {
+        batch_min_len_ = std::min(batch_min_len_, chunks[k].min_len);
+        batch_max_len_ = std::max(batch_max_len_, chunks[k].max_len);
+    }
+    const ParseChunk& last = chunks[accepted - 1];
     pos_ = last.end;
     okay_ = last.okay_after;
     nrecords_ += (long long)batch_.size();
@@ -342,6 +350,8 @@ bool FastqReader::next_parallel(size_t max_records) {
 const std::vector<Record>& FastqReader::next(size_t max_records) {
     double t0 = now_s();
     batch_.clear();
+    batch_min_len_ = 0xFFFFFFFFu;
+    batch_max_len_ = 0;
     if (!started_ || (pos_ >= avail_ && !final_)) refill();
     if (nrecords_ == 0 && avail_ == 0 && final_) okay_ = false;  // empty input: zero reads (FastqReader.hpp:30)
     // the whole remaining input is in memory (caller's buffer or mmap): parse it on all the threads we were given
@@ -362,6 +372,8 @@ const std::vector<Record>& FastqReader::next(size_t max_records) {
     while (okay_ && batch_.size() < max_records) {
         if (parse_one(r)) {
             batch_.push_back(r);
+            batch_min_len_ = std::min(batch_min_len_, r.len);
+            batch_max_len_ = std::max(batch_max_len_, r.len);
             continue;
         }
         // needs more data
@@ -549,14 +561,13 @@ void pack_records(const Record* recs, size_t count, int W, uint32_t* out, uint16
         work(0, ntiles);
         return;
     }
-    std::vector<std::thread> pool;
-    size_t per = (ntiles + nt - 1) / nt;
-    for (int k = 0; k < nt; ++k) {
-        size_t b = (size_t)k * per, e = std::min(ntiles, b + per);
-        if (b >= e) break;
-        pool.emplace_back(work, b, e);
-    }
-    for (auto& th : pool) th.join();
+    // more pieces than threads, so that a slow core does not hold everyone up
+    const int pieces = nt * 4;
+    const size_t per = (ntiles + pieces - 1) / pieces;
+    HostPool::instance().parallel_for(pieces, nt, [&](int k) {
+        const size_t b = (size_t)k * per, e = std::min(ntiles, b + per);
+        if (b < e) work(b, e);
+    });
 }
 
 } // namespace scg

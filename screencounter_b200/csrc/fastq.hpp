@@ -24,6 +24,14 @@ struct Record {
 
 class FastqInput;  // raw file (mmap), gzip stream or caller memory
 
+// Scratch of one chunk of the multi-threaded record splitter.
+struct ParseChunk {
+    std::vector<Record> recs;
+    uint32_t min_len = 0xFFFFFFFFu, max_len = 0;
+    size_t end = 0;
+    bool okay_after = true, failed = false;
+};
+
 class FastqReader {
 public:
     FastqReader(const char* path, const char* data, size_t size);
@@ -35,6 +43,10 @@ public:
 
     // Threads the record splitter may use on inputs that are entirely in memory (caller's buffer, mmap'd file).
     void set_threads(int n) { threads_ = n < 1 ? 1 : n; }
+
+    // shortest / longest read of the batch returned by the last next()
+    uint32_t batch_min_len() const { return batch_min_len_; }
+    uint32_t batch_max_len() const { return batch_max_len_; }
 
     long long records_seen() const { return nrecords_; }
     double parse_seconds() const { return parse_s_; }
@@ -55,6 +67,8 @@ private:
     std::vector<Record> batch_;
     double parse_s_ = 0;
     int threads_ = 1;
+    std::vector<ParseChunk> chunks_;
+    uint32_t batch_min_len_ = 0xFFFFFFFFu, batch_max_len_ = 0;
 };
 
 // Packs records [first, first+count) into `out` (tile-planar, W words per plane, count padded

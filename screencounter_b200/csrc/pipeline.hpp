@@ -37,7 +37,7 @@ private:
     static constexpr size_t kMaxBatchBytes = 64u << 20;
     using Slot = StagingSlot;
 
-    void stage(Slot& slot, int mate, const Record* recs, size_t count);
+    void stage(Slot& slot, int mate, const Record* recs, size_t count, uint32_t minlen, uint32_t maxlen);
 
     Context& ctx_;
     FastqReader* r1_;

@@ -58,9 +58,27 @@ class _Src:
         return C.byref(self.struct)
 
 
+_STRS_CACHE = {}
+
+
 def _strs(seqs):
+    """ctypes char*[] for a list of sequences.  Large pools (a guide library handed to one call per
+    FASTQ file) are marshalled once and found again by content hash."""
+    key = None
+    if len(seqs) >= 1024:
+        try:
+            key = (len(seqs), hash(tuple(seqs)))
+        except TypeError:
+            key = None
+        hit = _STRS_CACHE.get(key) if key is not None else None
+        if hit is not None and hit[2] == seqs[0] and hit[3] == seqs[-1]:
+            return hit[0], hit[1]
     enc = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
     arr = (C.c_char_p * max(len(enc), 1))(*enc)
+    if key is not None:
+        if len(_STRS_CACHE) >= 8:
+            _STRS_CACHE.pop(next(iter(_STRS_CACHE)))
+        _STRS_CACHE[key] = (arr, enc, seqs[0], seqs[-1])
     return arr, enc
 
 
