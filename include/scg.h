@@ -196,6 +196,13 @@ int scg_device_zero(scg_ctx* ctx, void* ptr, size_t bytes, void* cuda_stream);  
 int scg_device_to_host(scg_ctx* ctx, void* host, const void* dev, size_t bytes);
 int scg_synchronize(scg_ctx* ctx);
 
+/* Page-locked host memory.  FASTQ text handed over in such a buffer (scg_source.data) goes to the device
+ * by DMA straight from it; text in ordinary memory is first copied through the library's own pinned
+ * bounce buffers.  Either way the records are split and packed on the device (the device-side
+ * counterpart of kaori::FastqReader, inst/include/kaori/FastqReader.hpp:42-110). */
+int scg_host_alloc(scg_ctx* ctx, size_t bytes, void** out);
+int scg_host_free(scg_ctx* ctx, void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

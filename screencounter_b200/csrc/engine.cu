@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstring>
 
+#include "ingest.hpp"
 #include "pipeline.hpp"
 
 namespace scg {
@@ -62,6 +63,7 @@ Context::~Context() {
         if (slot.done) cudaEventDestroy(slot.done);
     }
     single_cache.clear();
+    ingest.reset();
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -102,9 +104,9 @@ void Context::finish_timing() {
     char buf[512];
     std::snprintf(buf, sizeof buf,
                   "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"setup_s\": %.6f, \"total_s\": %.6f, "
-                  "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld, \"kernel\": \"",
+                  "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld, \"reader\": \"%s\", \"kernel\": \"",
                   timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.setup_s, timing.total_s, timing.reads, timing.bytes_h2d,
-                  timing.launches);
+                  timing.launches, timing.reader.c_str());
     timing_json = buf;
     for (char ch : kernel_note) {
         if (ch == '"' || ch == '\\' || ch == '\n') ch = ' ';
@@ -160,6 +162,14 @@ ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int n
         if (!slots_[k].done) SCG_CUDA_CHECK(cudaEventCreateWithFlags(&slots_[k].done, cudaEventDisableTiming));
         slots_[k].in_flight = false;
     }
+    // Single-end text that is entirely in host memory is read on the device (ingest.hpp).  Paired input (the two
+    // mates' chunks would have to be cut at the same record) and callers that need the raw characters of a read back
+    // (random barcodes) keep the host reader.
+    const char* text = nullptr;
+    size_t size = 0;
+    if (r1_ && !r2_ && !want_odd_ && device_ingest_enabled() && r1_->memory_text(&text, &size) && size > 0) {
+        ingest_.reset(new DeviceIngest(ctx_, text, size, nthreads_));
+    }
 }
 
 ReadPipeline::~ReadPipeline() {
@@ -209,6 +219,33 @@ void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count,
 }
 
 bool ReadPipeline::next(Batch& out) {
+    while (ingest_) {
+        if (handover_pending_) {
+            // the device reader met something that is not a four-line record: the host reader takes over at that byte
+            r1_->resume_at(handover_offset_, ingest_->records());
+            ingest_.reset();
+            handover_pending_ = false;
+            ctx_.timing.reader += ", then host from byte " + std::to_string(handover_offset_);
+            break;
+        }
+        DeviceIngest::Result res;
+        const bool more = ingest_->next(res);
+        if (res.handover) {
+            handover_pending_ = true;
+            handover_offset_ = res.resume_offset;
+        }
+        if (res.n > 0) {
+            out = Batch();
+            out.first_read = consumed_;
+            out.n = res.n;
+            out.reads1 = res.reads;
+            out.slot = nullptr;
+            consumed_ += res.n;
+            ctx_.timing.reads += res.n;
+            return true;
+        }
+        if (!more && !handover_pending_) return false;
+    }
     // refill the record windows
     if (cur1_ >= n1_) {
         const auto& b = r1_->next(kMaxBatchReads);
@@ -285,6 +322,7 @@ bool ReadPipeline::next(Batch& out) {
 }
 
 void ReadPipeline::submitted(Batch& b) {
+    if (!b.slot) return;   // device reader: its buffers are recycled in stream order
     Slot* slot = static_cast<Slot*>(b.slot);
     SCG_CUDA_CHECK(cudaEventRecord(slot->done, ctx_.stream));
     slot->in_flight = true;

@@ -54,6 +54,7 @@ struct Timing {
     double parse_s = 0, pack_s = 0, h2d_s = 0, device_s = 0, total_s = 0;
     double setup_s = 0;   // library tables built + uploaded, kernels specialised (zero when the context had them cached)
     long long reads = 0, bytes_h2d = 0, launches = 0;
+    std::string reader = "host";   // which FASTQ reader fed the call: the host parser/packer or the device one (ingest.hpp)
 };
 
 // A library resident on the device.
@@ -84,6 +85,7 @@ struct StagingSlot {
 };
 
 struct SingleMatcher;
+struct IngestBuffers;   // ingest.hpp
 
 struct Context {
     static constexpr int kStagingSlots = 2;
@@ -95,6 +97,7 @@ struct Context {
         std::shared_ptr<SingleMatcher> matcher;
     };
     std::vector<CachedMatcher> single_cache;
+    std::shared_ptr<IngestBuffers> ingest;   // text ring, line tables and streams of the device-side FASTQ reader
     int device = 0;
     bool ready = false;
     int sm_count = 0;

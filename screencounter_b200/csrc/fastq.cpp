@@ -30,6 +30,12 @@ public:
     // Makes [*base, *base + *avail) hold the unconsumed tail starting at `keep_from` (an
     // offset into the previous window) plus as much further data as is convenient.
     virtual void window(size_t keep_from, const char** base, size_t* avail, bool* final) = 0;
+    // Inputs that are entirely in host memory (caller's buffer, mmap'd raw file) say where.
+    virtual bool memory(const char** data, size_t* size) const {
+        (void)data;
+        (void)size;
+        return false;
+    }
 };
 
 namespace {
@@ -42,6 +48,11 @@ public:
         *base = data_ + offset_;
         *avail = size_ - offset_;
         *final = true;
+    }
+    bool memory(const char** data, size_t* size) const override {
+        *data = data_;
+        *size = size_;
+        return true;
     }
 
 protected:
@@ -152,6 +163,17 @@ double now_s() {
 FastqReader::FastqReader(const char* path, const char* data, size_t size) : in_(open_input(path, data, size)) {}
 
 FastqReader::~FastqReader() {}
+
+bool FastqReader::memory_text(const char** data, size_t* size) const {
+    return !started_ && in_->memory(data, size);
+}
+
+void FastqReader::resume_at(size_t offset, long long nrecords) {
+    if (!started_) refill();
+    pos_ = offset;
+    nrecords_ = nrecords;
+    okay_ = pos_ < avail_;
+}
 
 void FastqReader::refill() {
     in_->window(started_ ? pos_ : 0, &base_, &avail_, &final_);

@@ -48,6 +48,13 @@ public:
     uint32_t batch_min_len() const { return batch_min_len_; }
     uint32_t batch_max_len() const { return batch_max_len_; }
 
+    // The whole input as one span of host memory, for inputs that are (caller's buffer, mmap'd raw file) and have not
+    // been read from yet: the device-side reader (ingest.hpp) takes the text from there.
+    bool memory_text(const char** data, size_t* size) const;
+    // Continues the host parse at byte `offset` of such an input -- the start of record number `nrecords` (0-based),
+    // everything before it having been consumed elsewhere as four-line records.
+    void resume_at(size_t offset, long long nrecords);
+
     long long records_seen() const { return nrecords_; }
     double parse_seconds() const { return parse_s_; }
 

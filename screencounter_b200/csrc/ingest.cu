@@ -1,0 +1,483 @@
+// Device-side FASTQ reader: see ingest.hpp.
+//
+// WHY A LINE SPLIT IS ENOUGH FOR FOUR-LINE RECORDS.  kaori::FastqReader::operator() (FastqReader.hpp:42-110) reads,
+// from a record start: '@' (else it throws), the rest of that line; then every character up to the first '+'
+// ANYWHERE, dropping newlines, as the sequence (:70-78); the rest of the '+' line (:81-85); then characters until a
+// newline at which at least as many quality characters as bases have been seen (:91-105), the two counts having to be
+// equal.  Number the lines of the text from a record start as L0 L1 L2 L3.  If (a) L0 starts with '@', (b) L1 holds no
+// '+', (c) L2 starts with '+' and (d) |L3| = |L1|, the reference's walk consumes exactly L0, takes L1 as the sequence
+// (its first '+' is L2's first character), consumes L2, and stops at the newline that ends L3 because |L3| >= |L1|
+// there and not before (there is no earlier newline): the next record starts at the next line.  By induction a text
+// whose every group of four lines satisfies (a)-(d) is parsed by the reference into exactly those groups -- including
+// '\r' before the newlines (kept as a base), empty sequences, and a last line without newline.
+// `validate_records` checks (a)-(d) per group; the first group that fails ends the device reader's part of the text.
+#include "ingest.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+#include "hostpool.hpp"
+#include "layout.hpp"
+
+namespace scg {
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+constexpr int kBlockThreads = 256;
+constexpr int kBytesPerThread = 16;
+constexpr uint32_t kBlockBytes = kBlockThreads * kBytesPerThread;   // 4096
+
+enum : uint32_t {
+    ST_LINECAP = 1u,    // more lines than the position buffer holds
+    ST_BADREC = 2u,     // a group of four lines is not a four-line record
+    ST_REMAINDER = 4u,  // the last chunk does not end on a record boundary
+    ST_CARRY = 8u,      // the unfinished tail does not fit the carry area
+};
+
+} // namespace
+
+struct IngestState {
+    uint32_t begin;      // ring position of the first unconsumed text byte of the chunk about to be parsed
+    uint32_t nlines;     // complete lines in [begin, end), capped at the position buffer's size
+    uint32_t nrec;       // records accepted from this chunk
+    uint32_t bad_rec;    // lowest group of four lines that failed the record checks (>= nrec: none)
+    uint32_t min_len, max_len;
+    uint32_t status;     // ST_* flags: the device reader stops after this chunk
+    uint32_t tail;       // ring position just past the last accepted record
+};
+
+namespace {
+
+// ---- kernels ---------------------------------------------------------------------------------------------------
+
+__global__ void ingest_init(IngestState* st, uint32_t begin) {
+    st->begin = begin;
+    st->nlines = st->nrec = st->bad_rec = 0;
+    st->min_len = 0xFFFFFFFFu;
+    st->max_len = 0;
+    st->status = 0;
+    st->tail = begin;
+}
+
+// newlines among the 16 bytes at ring position p that lie in [begin, end): bit j of the result = byte j is one
+__device__ __forceinline__ uint32_t newline_mask(const uint4 v, uint32_t p, uint32_t begin, uint32_t end) {
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = w[k] ^ 0x0A0A0A0Au;
+        // exact zero-byte detector: 0x80 in every byte of x that is zero
+        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        m |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * k);
+    }
+    // clip to [begin, end)
+    if (p < begin) m &= (begin - p >= 16) ? 0u : (0xFFFFu << (begin - p));
+    if (p + 16 > end) m &= (p >= end) ? 0u : ((1u << (end - p)) - 1u);
+    return m & 0xFFFFu;
+}
+
+// pass 1: newlines per 4 KiB block of the slot
+__global__ void __launch_bounds__(kBlockThreads) count_newlines(const uint8_t* __restrict__ ring, uint32_t slot0, uint32_t end,
+                                                                const IngestState* __restrict__ st, uint32_t* __restrict__ block_counts) {
+    const uint32_t begin = st->begin;
+    const uint32_t bpos = slot0 + blockIdx.x * kBlockBytes;
+    __shared__ uint32_t warp_sums[kBlockThreads / 32];
+    uint32_t c = 0;
+    if (bpos + kBlockBytes > begin && bpos < end) {
+        const uint32_t p = bpos + threadIdx.x * kBytesPerThread;
+        const uint4 v = *reinterpret_cast<const uint4*>(ring + p);
+        c = __popc(newline_mask(v, p, begin, end));
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int k = 0; k < kBlockThreads / 32; ++k) t += warp_sums[k];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// pass 2: exclusive scan of the block counts (one block), number of lines and of candidate records
+__global__ void __launch_bounds__(1024) scan_blocks(uint32_t* __restrict__ block_counts, int nblocks, IngestState* st, uint32_t line_cap) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_counts[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t t = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, t, d);
+                if (lane >= d) t += y;
+            }
+            warp_tot[lane] = t;   // inclusive totals of the warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + (wid ? warp_tot[wid - 1] : 0u) + (x - v);
+        if (i < nblocks) block_counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t lines = carry, status = 0;
+        if (lines > line_cap) {
+            lines = line_cap;
+            status |= ST_LINECAP;
+        }
+        st->nlines = lines;
+        st->nrec = lines / 4;
+        st->bad_rec = lines / 4;
+        st->min_len = 0xFFFFFFFFu;
+        st->max_len = 0;
+        st->status = status;
+    }
+}
+
+// pass 3: positions of the newlines, in text order
+__global__ void __launch_bounds__(kBlockThreads) scatter_newlines(const uint8_t* __restrict__ ring, uint32_t slot0, uint32_t end,
+                                                                  const IngestState* __restrict__ st, const uint32_t* __restrict__ block_offsets,
+                                                                  uint32_t* __restrict__ lines, uint32_t line_cap) {
+    const uint32_t begin = st->begin;
+    const uint32_t bpos = slot0 + blockIdx.x * kBlockBytes;
+    if (!(bpos + kBlockBytes > begin && bpos < end)) return;   // block-uniform
+    __shared__ uint32_t warp_sums[kBlockThreads / 32];
+    const uint32_t p = bpos + threadIdx.x * kBytesPerThread;
+    const uint4 v = *reinterpret_cast<const uint4*>(ring + p);
+    uint32_t m = newline_mask(v, p, begin, end);
+    const uint32_t c = __popc(m);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    uint32_t at = block_offsets[blockIdx.x] + (x - c);
+    for (int k = 0; k < wid; ++k) at += warp_sums[k];
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        if (at < line_cap) lines[at] = p + j;
+        ++at;
+    }
+}
+
+// pass 4: conditions (a)-(d) for every group of four lines; sequence offsets and lengths
+__global__ void __launch_bounds__(256) validate_records(const uint8_t* __restrict__ ring, const uint32_t* __restrict__ lines, IngestState* st,
+                                                        uint32_t* __restrict__ seq_off, uint16_t* __restrict__ seq_len) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= st->nrec) return;
+    const uint32_t e0 = lines[4 * r], e1 = lines[4 * r + 1], e2 = lines[4 * r + 2], e3 = lines[4 * r + 3];
+    const uint32_t start = r ? lines[4 * r - 1] + 1 : st->begin;
+    const uint32_t s = e0 + 1, len = e1 - s, qlen = e3 - (e2 + 1);
+    bool ok = ring[start] == '@' && ring[e1 + 1] == '+' && qlen == len && len <= (uint32_t)MAX_READ_LEN;
+    if (ok) {
+        for (uint32_t k = 0; k < len; ++k) {
+            if (ring[s + k] == '+') {
+                ok = false;
+                break;
+            }
+        }
+    }
+    seq_off[r] = s;
+    seq_len[r] = (uint16_t)(ok ? len : 0u);
+    if (!ok) atomicMin(&st->bad_rec, r);
+}
+
+// pass 5: shortest and longest sequence among the accepted records
+__global__ void __launch_bounds__(256) record_extent(const uint16_t* __restrict__ seq_len, IngestState* st) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = min(st->nrec, st->bad_rec);
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    if (r < n) lo = hi = seq_len[r];
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0 && lo != 0xFFFFFFFFu) {
+        atomicMin(&st->min_len, lo);
+        atomicMax(&st->max_len, hi);
+    }
+}
+
+// pass 6 (one block): settles what this chunk contributes, moves the unfinished tail in front of the next slot
+__global__ void __launch_bounds__(1024) finish_chunk(uint8_t* __restrict__ ring, const uint32_t* __restrict__ lines, IngestState* st, uint32_t end,
+                                                     int final_chunk, uint32_t next_data0, uint32_t carry_room) {
+    __shared__ uint32_t s_tail, s_len, s_copy;
+    if (threadIdx.x == 0) {
+        uint32_t status = st->status;
+        uint32_t n = st->nrec;
+        if (st->bad_rec < n) {
+            n = st->bad_rec;
+            status |= ST_BADREC;
+        }
+        const uint32_t tail = n ? lines[4 * n - 1] + 1 : st->begin;
+        const uint32_t left = end - tail;
+        if (final_chunk) {
+            if (left) status |= ST_REMAINDER;
+        } else if (left > carry_room) {
+            status |= ST_CARRY;
+        }
+        st->nrec = n;
+        st->tail = tail;
+        st->status = status;
+        s_tail = tail;
+        s_len = left;
+        s_copy = (!final_chunk && status == 0) ? 1u : 0u;
+        if (s_copy) st->begin = next_data0 - left;
+    }
+    __syncthreads();
+    if (!s_copy) return;
+    const uint32_t tail = s_tail, left = s_len, dst = next_data0 - left;
+    for (uint32_t k = threadIdx.x; k < left; k += blockDim.x) ring[dst + k] = ring[tail + k];
+}
+
+// pass 7: bases -> tile-planar bit planes (layout.hpp); one warp per tile, one lane per record
+__global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restrict__ ring, const uint32_t* __restrict__ seq_off,
+                                                        uint16_t* __restrict__ seq_len, uint32_t nrec, int W, uint32_t* __restrict__ out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ntiles = (nrec + TILE - 1) / TILE;
+    if (warp >= ntiles) return;
+    const uint32_t r = warp * TILE + lane;
+    uint32_t len = 0;
+    const uint8_t* s = ring;
+    if (r < nrec) {
+        len = seq_len[r];
+        s = ring + seq_off[r];
+    } else {
+        seq_len[r] = 0;   // the length array is padded to whole tiles like the host packer's
+    }
+    uint32_t* base = out + (size_t)warp * 3 * W * TILE + lane;
+    for (int w = 0; w < W; ++w) {
+        uint32_t hh = 0, ll = 0, nn = 0;
+        const int first = 32 * w;
+        const int cnt = (int)len > first ? min(32, (int)len - first) : 0;
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t c = s[first + j];
+            const uint32_t u = c & 0xDFu;   // fold case: only X and x map to X
+            const bool valid = u == 'A' || u == 'C' || u == 'G' || u == 'T';
+            // ASCII: bit 2 of A/C/G/T (either case) is 0/0/1/1 = plane H, bit 1 is 0/1/1/0, so L = bit 1 ^ bit 2
+            const uint32_t hb = (c >> 2) & 1u, lb = ((c >> 1) ^ (c >> 2)) & 1u;
+            hh |= (valid ? hb : 0u) << j;
+            ll |= (valid ? lb : 0u) << j;
+            nn |= (valid ? 0u : 1u) << j;
+        }
+        base[(size_t)(PLANE_H * W + w) * TILE] = hh;
+        base[(size_t)(PLANE_L * W + w) * TILE] = ll;
+        base[(size_t)(PLANE_N * W + w) * TILE] = nn;
+    }
+}
+
+} // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------------
+
+bool device_ingest_enabled() {
+    const char* v = std::getenv("SCG_HOST_PARSE");
+    return !(v && *v && *v != '0');
+}
+
+IngestBuffers::~IngestBuffers() {
+    for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+        if (copied[k]) cudaEventDestroy(copied[k]);
+        if (bounced[k]) cudaEventDestroy(bounced[k]);
+        if (released[k]) cudaEventDestroy(released[k]);
+    }
+    if (meta_ready) cudaEventDestroy(meta_ready);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+}
+
+void IngestBuffers::ensure(size_t chunk, size_t carry, bool need_bounce) {
+    const size_t stride = carry + chunk + 256, line_cap = (carry + chunk) / 4;
+    if (!copy_stream) {
+        SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+            SCG_CUDA_CHECK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+            SCG_CUDA_CHECK(cudaEventCreateWithFlags(&bounced[k], cudaEventDisableTiming));
+            SCG_CUDA_CHECK(cudaEventCreateWithFlags(&released[k], cudaEventDisableTiming));
+        }
+        SCG_CUDA_CHECK(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming));
+    }
+    text.reserve(DeviceIngest::kSlots * stride + 2 * kBlockBytes);
+    lines.reserve((line_cap + 4) * sizeof(uint32_t));
+    block_counts.reserve((stride / kBlockBytes + 2) * sizeof(uint32_t));
+    seq_off.reserve((line_cap / 4 + 1) * sizeof(uint32_t));
+    state.reserve(sizeof(IngestState));
+    meta.reserve(sizeof(IngestState));
+    for (int k = 0; k < 2; ++k) lens[k].reserve((line_cap / 4 + TILE) * sizeof(uint16_t));
+    if (need_bounce) {
+        for (int k = 0; k < DeviceIngest::kSlots; ++k) bounce[k].reserve(chunk);
+    }
+    for (int k = 0; k < DeviceIngest::kSlots; ++k) released_valid[k] = bounced_valid[k] = false;
+}
+
+DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads)
+    : ctx_(ctx), text_(text), size_(size), nthreads_(std::max(1, nthreads)) {
+    ctx_.ensure_ready();
+    // a page-locked source (scg_host_alloc, cudaHostRegister) feeds the copy engine directly
+    cudaPointerAttributes a0, a1;
+    const bool ok0 = cudaPointerGetAttributes(&a0, text_) == cudaSuccess && a0.type == cudaMemoryTypeHost;
+    const bool ok1 = ok0 && cudaPointerGetAttributes(&a1, text_ + size_ - 1) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered pointer may leave a sticky-free error behind on old drivers
+    pinned_source_ = ok0 && ok1;
+    virtual_newline_ = text_[size_ - 1] != '\n';
+    auto env_size = [](const char* name, size_t fallback, size_t lo, size_t hi) {
+        const char* v = std::getenv(name);
+        if (!v || !*v) return fallback;
+        const long long x = std::atoll(v);
+        return (size_t)std::min<long long>((long long)hi, std::max<long long>((long long)lo, x));
+    };
+    // multiples of 16 keep the slots' data areas aligned for the 16-byte loads of the line kernels
+    chunk_ = env_size("SCG_INGEST_CHUNK", kChunk, 64, 1u << 30) / 16 * 16;
+    carry_ = env_size("SCG_INGEST_CARRY", kCarry, 16, 64u << 20) / 16 * 16;
+    stride_ = carry_ + chunk_ + 256;
+    line_cap_ = (carry_ + chunk_) / 4;
+    if (!ctx_.ingest) ctx_.ingest.reset(new IngestBuffers);
+    IngestBuffers& B = *ctx_.ingest;
+    B.ensure(chunk_, carry_, !pinned_source_);
+    ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_));
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx_.launches;
+    ctx_.timing.reader = pinned_source_ ? "device (text copied from page-locked memory)" : "device (text staged through pinned bounce buffers)";
+}
+
+DeviceIngest::~DeviceIngest() {
+    // copies still in flight read the caller's text (or the bounce buffers): let them finish
+    if (ctx_.ingest && ctx_.ingest->copy_stream) cudaStreamSynchronize(ctx_.ingest->copy_stream);
+}
+
+void DeviceIngest::issue_copy(size_t chunk) {
+    IngestBuffers& B = *ctx_.ingest;
+    const int s = (int)(chunk % kSlots);
+    const size_t off = chunk * chunk_;
+    const size_t bytes = std::min(chunk_, size_ - off);
+    uint8_t* dst = B.text.as<uint8_t>() + slot_base(chunk) + carry_;
+    // the slot's previous text must have been parsed and packed
+    if (B.released_valid[s]) SCG_CUDA_CHECK(cudaStreamWaitEvent(B.copy_stream, B.released[s], 0));
+    const void* src = text_ + off;
+    if (!pinned_source_) {
+        if (B.bounced_valid[s]) SCG_CUDA_CHECK(cudaEventSynchronize(B.bounced[s]));
+        const double t0 = now_s();
+        char* bb = B.bounce[s].as<char>();
+        const int pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads_, bytes >> 20));
+        const size_t per = (bytes + pieces - 1) / pieces;
+        HostPool::instance().parallel_for(pieces, pieces, [&](int k) {
+            const size_t b = (size_t)k * per, e = std::min(bytes, b + per);
+            if (b < e) std::memcpy(bb + b, text_ + off + b, e - b);
+        });
+        ctx_.timing.pack_s += now_s() - t0;
+        src = bb;
+    }
+    SCG_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, B.copy_stream));
+    if (chunk + 1 == nchunks() && virtual_newline_) SCG_CUDA_CHECK(cudaMemsetAsync(dst + bytes, '\n', 1, B.copy_stream));
+    if (!pinned_source_) {
+        SCG_CUDA_CHECK(cudaEventRecord(B.bounced[s], B.copy_stream));
+        B.bounced_valid[s] = true;
+    }
+    SCG_CUDA_CHECK(cudaEventRecord(B.copied[s], B.copy_stream));
+    ctx_.timing.bytes_h2d += (long long)bytes;
+}
+
+bool DeviceIngest::next(Result& out) {
+    out = Result();
+    if (stopped_ || parsed_ >= nchunks()) return false;
+    IngestBuffers& B = *ctx_.ingest;
+    const size_t k = parsed_;
+    // chunk k + kSlots - 1 reuses the slot of chunk k - 1, whose kernels (and `released` event) are already enqueued;
+    // one further would need the slot this call is about to parse
+    while (issued_ < nchunks() && issued_ <= k + kSlots - 1) {
+        issue_copy(issued_);
+        ++issued_;
+    }
+    const int s = (int)(k % kSlots);
+    const bool final_chunk = k + 1 == nchunks();
+    const size_t bytes = std::min(chunk_, size_ - k * chunk_) + ((final_chunk && virtual_newline_) ? 1 : 0);
+    const uint32_t slot0 = (uint32_t)slot_base(k);
+    const uint32_t data0 = slot0 + (uint32_t)carry_;
+    const uint32_t end = data0 + (uint32_t)bytes;
+    const uint32_t next_data0 = (uint32_t)slot_base(k + 1) + (uint32_t)carry_;
+    cudaStream_t st = ctx_.stream;
+    IngestState* state = B.state.as<IngestState>();
+    const uint8_t* ring = B.text.as<uint8_t>();
+    uint32_t* lines = B.lines.as<uint32_t>();
+    const int nblocks = (int)((end - slot0 + kBlockBytes - 1) / kBlockBytes);
+    const int out_slot = out_slot_;
+    out_slot_ ^= 1;
+    uint16_t* lens = B.lens[out_slot].as<uint16_t>();
+
+    SCG_CUDA_CHECK(cudaStreamWaitEvent(st, B.copied[s], 0));
+    count_newlines<<<nblocks, kBlockThreads, 0, st>>>(ring, slot0, end, state, B.block_counts.as<uint32_t>());
+    scan_blocks<<<1, 1024, 0, st>>>(B.block_counts.as<uint32_t>(), nblocks, state, (uint32_t)line_cap_);
+    scatter_newlines<<<nblocks, kBlockThreads, 0, st>>>(ring, slot0, end, state, B.block_counts.as<uint32_t>(), lines, (uint32_t)line_cap_);
+    // at most one record per 6 bytes ("@\n\n+\n\n"), and never more than the position buffer describes
+    const uint32_t max_rec = (uint32_t)std::min<size_t>(line_cap_ / 4, (end - slot0) / 6 + 1);
+    const int rec_blocks = (int)((max_rec + 255) / 256);
+    validate_records<<<rec_blocks, 256, 0, st>>>(ring, lines, state, B.seq_off.as<uint32_t>(), lens);
+    record_extent<<<rec_blocks, 256, 0, st>>>(lens, state);
+    finish_chunk<<<1, 1024, 0, st>>>(B.text.as<uint8_t>(), lines, state, end, final_chunk ? 1 : 0, next_data0, (uint32_t)carry_);
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ctx_.launches += 6;
+    SCG_CUDA_CHECK(cudaMemcpyAsync(B.meta.ptr, state, sizeof(IngestState), cudaMemcpyDeviceToHost, st));
+    SCG_CUDA_CHECK(cudaEventRecord(B.meta_ready, st));
+    {
+        const double t0 = now_s();
+        SCG_CUDA_CHECK(cudaEventSynchronize(B.meta_ready));
+        ctx_.timing.device_s += now_s() - t0;
+    }
+    const IngestState m = *B.meta.as<IngestState>();
+    ++parsed_;
+
+    const long long tail_off = (long long)(k * chunk_) + ((long long)m.tail - (long long)data0);
+    consumed_ = (size_t)std::min<long long>(std::max<long long>(tail_off, 0), (long long)size_);
+    if (m.nrec > 0) {
+        const int W = std::max(1, ceil_div((int)m.max_len, 32));
+        const size_t ntiles = ((size_t)m.nrec + TILE - 1) / TILE;
+        const size_t data_bytes = ntiles * tile_words(W) * sizeof(uint32_t);
+        B.packed[out_slot].reserve(data_bytes + READ_GUARD_BYTES);
+        pack_records_dev<<<(unsigned)((ntiles + 3) / 4), 128, 0, st>>>(ring, B.seq_off.as<uint32_t>(), lens, m.nrec, W,
+                                                                       B.packed[out_slot].as<uint32_t>());
+        SCG_CUDA_CHECK(cudaGetLastError());
+        ++ctx_.launches;
+        out.n = m.nrec;
+        out.reads.data = B.packed[out_slot].as<uint32_t>();
+        out.reads.W = W;
+        out.reads.n = m.nrec;
+        out.reads.uniform_len = (int)m.max_len;
+        out.reads.lens = (m.min_len == m.max_len) ? nullptr : lens;
+        records_ += m.nrec;
+    }
+    SCG_CUDA_CHECK(cudaEventRecord(B.released[s], st));
+    B.released_valid[s] = true;
+    if (m.status != 0) {
+        // on the last chunk a clean end (nothing left) has status 0; everything else goes to the host reader
+        stopped_ = true;
+        out.handover = true;
+        out.resume_offset = consumed_;
+        return true;
+    }
+    return parsed_ < nchunks() || out.n > 0;
+}
+
+} // namespace scg

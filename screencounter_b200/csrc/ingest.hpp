@@ -1,0 +1,91 @@
+// FASTQ ingestion on the device: the raw text goes to HBM in fixed chunks over the copy engine
+// (straight from the caller's buffer when it is page-locked, through a ring of pinned bounce buffers otherwise) and
+// kernels find the newlines, check the records and pack the bases -- the work kaori::FastqReader does one byte at a
+// time on the main thread (inst/include/kaori/FastqReader.hpp:42-110).
+//
+// The kernels accept exactly the FOUR-LINE records for which a line-oriented split provably equals the reference's
+// character-by-character parse (the proof is in ingest.cu); anything else -- wrapped sequences or qualities, a '+'
+// inside a sequence line, a malformed or truncated record, a record longer than the carry area -- stops the device
+// reader at the last record boundary it is sure of, and the host reader (fastq.cpp: the full grammar, the
+// reference's error texts and line numbers) resumes from that byte.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "engine.hpp"
+
+namespace scg {
+
+struct IngestState;   // device-side cursor shared by the kernels of consecutive chunks
+
+class DeviceIngest {
+public:
+    static constexpr size_t kChunk = 32u << 20;     // text bytes per H2D copy (SCG_INGEST_CHUNK overrides, for tests)
+    static constexpr size_t kCarry = 1u << 20;      // room in front of every chunk for the unfinished tail of the previous one (SCG_INGEST_CARRY)
+    static constexpr int kSlots = 3;                // chunks in flight (copying, being parsed, being consumed)
+
+    struct Result {
+        bool handover = false;      // the device reader stops here: resume the host reader at `resume_offset`
+        size_t resume_offset = 0;   // byte offset into the text of the first record not consumed
+        long long n = 0;            // records of this batch (0 with handover or at the end of the input)
+        ReadsDev reads;             // packed batch, valid until the next call's kernels are enqueued
+    };
+
+    DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads);
+    ~DeviceIngest();
+
+    // Parses the next chunk.  false = the text is exhausted (and `out.n` is 0).
+    bool next(Result& out);
+
+    long long records() const { return records_; }
+
+private:
+    void issue_copy(size_t chunk);
+    size_t nchunks() const { return (size_ + chunk_ - 1) / chunk_; }
+    size_t slot_base(size_t chunk) const { return (chunk % kSlots) * stride_; }
+
+    size_t chunk_ = kChunk, carry_ = kCarry;
+    size_t stride_ = 0;      // carry + chunk + 256 (room for an appended newline; keeps slot bases 16-byte aligned)
+    size_t line_cap_ = 0;    // newline positions kept per chunk
+
+    Context& ctx_;
+    const char* text_;
+    size_t size_;
+    int nthreads_;
+    bool pinned_source_ = false;
+    bool virtual_newline_ = false;   // the text does not end with '\n': one is appended on the device
+    size_t issued_ = 0;              // chunks whose copy has been enqueued
+    size_t parsed_ = 0;              // chunks handed out
+    size_t consumed_ = 0;            // text bytes consumed as complete records so far
+    long long records_ = 0;
+    bool stopped_ = false;
+    int out_slot_ = 0;
+};
+
+// Device-ingest resources owned by the context (kept across calls).
+struct IngestBuffers {
+    DeviceBuffer text;         // kSlots x (kCarry + kChunk) bytes
+    DeviceBuffer lines;        // newline positions of the chunk being parsed
+    DeviceBuffer block_counts; // newlines per block
+    DeviceBuffer seq_off, seq_len;
+    DeviceBuffer state;        // IngestState
+    DeviceBuffer packed[2], lens[2];
+    PinnedBuffer bounce[DeviceIngest::kSlots];
+    PinnedBuffer meta;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copied[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };     // chunk text is in HBM
+    cudaEvent_t bounced[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };    // bounce buffer may be refilled
+    cudaEvent_t released[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };   // the parse no longer needs the slot's text
+    cudaEvent_t meta_ready = nullptr;
+    bool released_valid[DeviceIngest::kSlots] = { false, false, false };
+    bool bounced_valid[DeviceIngest::kSlots] = { false, false, false };
+    ~IngestBuffers();
+    void ensure(size_t chunk, size_t carry, bool need_bounce);
+};
+
+// false when the device reader is switched off (environment SCG_HOST_PARSE=1): every input then takes the host parser.
+bool device_ingest_enabled();
+
+} // namespace scg

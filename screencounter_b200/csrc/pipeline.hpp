@@ -4,9 +4,11 @@
 
 #include <cuda_runtime.h>
 
+#include <memory>
 #include <vector>
 
 #include "engine.hpp"
+#include "ingest.hpp"
 
 namespace scg {
 
@@ -50,6 +52,9 @@ private:
     const Record* recs2_ = nullptr;
     size_t n1_ = 0, cur1_ = 0, n2_ = 0, cur2_ = 0;
     long long consumed_ = 0;
+    std::unique_ptr<DeviceIngest> ingest_;   // set while the device-side reader is feeding the batches
+    bool handover_pending_ = false;
+    size_t handover_offset_ = 0;
 };
 
 } // namespace scg

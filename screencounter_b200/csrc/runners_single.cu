@@ -587,6 +587,22 @@ int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out) {
     });
 }
 
+int scg_host_alloc(scg_ctx* ctx, size_t bytes, void** out) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        void* p = nullptr;
+        SCG_CUDA_CHECK(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocPortable));
+        *out = p;
+    });
+}
+
+int scg_host_free(scg_ctx* ctx, void* ptr) {
+    return guarded(ctx, [&] {
+        ctx->impl.ensure_ready();
+        if (ptr) SCG_CUDA_CHECK(cudaFreeHost(ptr));
+    });
+}
+
 int scg_device_free(scg_ctx* ctx, void* ptr) {
     return guarded(ctx, [&] {
         ctx->impl.ensure_ready();

@@ -71,6 +71,19 @@ class SynthSpec:
             raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
         return buf.raw[: used.value]
 
+    def fastq_pinned(self, first_read, n_reads, device=None):
+        """The same text written straight into page-locked host memory (rcpp.PinnedText)."""
+        from .rcpp import PinnedText
+        spec, keep = self._c(first_read, n_reads)
+        used = C.c_size_t()
+        if lib().scg_synth_fastq(C.byref(spec), None, C.c_size_t(0), C.byref(used)) != 0:
+            raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+        text = PinnedText(used.value, device)
+        if lib().scg_synth_fastq(C.byref(spec), text.ptr, C.c_size_t(used.value), C.byref(used)) != 0:
+            raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+        text.size = used.value
+        return text
+
     def on_device(self, first_read, n_reads, device=None):
         ctx = context(device)
         spec, keep = self._c(first_read, n_reads)

@@ -42,11 +42,50 @@ def _check(ctx, status):
         raise ScreenCounterError(lib().scg_last_error(ctx).decode("latin-1"))
 
 
+class PinnedText:
+    """FASTQ text in page-locked host memory (scg_host_alloc): the engine copies it to the device by DMA
+    straight from this buffer.  `array` is a writable uint8 view; fill `array[:n]` and pass the object as
+    the `path` argument of a counting function after setting `size = n`."""
+
+    def __init__(self, capacity, device=None):
+        self.ctx = context(device)
+        self.capacity = int(capacity)
+        self.size = self.capacity
+        p = C.c_void_p()
+        _check(self.ctx, lib().scg_host_alloc(self.ctx, C.c_size_t(max(self.capacity, 1)), C.byref(p)))
+        self.ptr = p
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(self.capacity, 1),))[: self.capacity]
+
+    @classmethod
+    def from_bytes(cls, data, device=None):
+        self = cls(len(data), device)
+        self.array[:] = np.frombuffer(data, dtype=np.uint8)
+        return self
+
+    def free(self):
+        if self.ptr is not None:
+            self.array = None
+            lib().scg_host_free(self.ctx, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class _Src:
     """Keeps the bytes alive for the duration of the call."""
 
     def __init__(self, fastq):
-        if isinstance(fastq, (bytes, bytearray, memoryview)):
+        if isinstance(fastq, PinnedText):
+            self.keep = fastq
+            self.struct = ScgSource(None, fastq.ptr, fastq.size)
+        elif isinstance(fastq, np.ndarray):
+            self.keep = np.ascontiguousarray(fastq, dtype=np.uint8)
+            self.struct = ScgSource(None, self.keep.ctypes.data_as(C.c_void_p), self.keep.size)
+        elif isinstance(fastq, (bytes, bytearray, memoryview)):
             self.keep = fastq if isinstance(fastq, bytes) else bytes(fastq)
             # a pointer INTO the bytes object: no copy of what can be gigabytes of text
             self.struct = ScgSource(None, C.cast(C.c_char_p(self.keep), C.c_void_p), len(self.keep))

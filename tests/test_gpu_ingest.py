@@ -1,0 +1,228 @@
+"""The device-side FASTQ reader (screencounter_b200/csrc/ingest.cu) against the reference's parser:
+four-line records split and packed by kernels, everything else handed to the host reader at the exact byte, with the
+reference's results, error texts and line numbers (FastqReader.hpp:42-110).  Small chunk sizes (SCG_INGEST_CHUNK /
+SCG_INGEST_CARRY) make texts of a few kilobytes cross many chunk boundaries."""
+import numpy as np
+import pytest
+
+from engines import GpuEngine
+from fastq_cases import GOOD, BAD
+from util import fastq, random_seq, dense_pool, distinct_pool, adversarial_reads
+from screencounter_b200 import rcpp
+
+pytestmark = pytest.mark.gpu
+
+TEMPLATE = "ACGTA" + "-" * 6 + "TGCAT"
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return GpuEngine()
+
+
+def _set(monkeypatch, chunk=None, carry=None, host=False):
+    for name, value in (("SCG_INGEST_CHUNK", chunk), ("SCG_INGEST_CARRY", carry), ("SCG_HOST_PARSE", "1" if host else None)):
+        if value is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, str(value))
+
+
+def _case(seed, n=4000, **kw):
+    rng = np.random.default_rng(seed)
+    pool = dense_pool(rng, 50, 6)
+    reads = adversarial_reads(rng, n, TEMPLATE, [pool], strand="both", **kw)
+    return pool, reads
+
+
+@pytest.mark.parametrize("chunk,carry", [(64, 1024), (256, 512), (4096, 4096), (100000, 4096), (None, None)])
+def test_many_chunks(gpu, kref, monkeypatch, chunk, carry):
+    """Ragged reads (0 .. ~130 bases) across many chunk boundaries: per-read outcomes equal the reference's."""
+    pool, reads = _case(7)
+    data = fastq(reads)
+    want = kref.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    _set(monkeypatch, chunk, carry)
+    got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    t = rcpp.timing()
+    assert t["reader"].startswith("device"), t
+    assert "then host" not in t["reader"], t
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+    assert t["reads"] == len(reads)
+
+
+@pytest.mark.parametrize("final_newline", [True, False])
+@pytest.mark.parametrize("crlf", [False, True])
+def test_line_endings(gpu, kref, monkeypatch, final_newline, crlf):
+    pool, reads = _case(8, n=700)
+    data = fastq(reads, crlf=crlf)
+    if not final_newline:
+        data = data[:-2] if crlf else data[:-1]
+    want = kref.trace_single(data, TEMPLATE, 2, pool, 1, True)
+    for chunk in (128, 3000, None):
+        _set(monkeypatch, chunk, 2048)
+        got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, True)
+        assert "then host" not in rcpp.timing()["reader"]
+        assert np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1], want[1])
+
+
+def test_uniform_and_ragged_lengths(gpu, kref, monkeypatch):
+    """Uniform 75-base reads take the no-length-array layout, one odd read switches the batch to per-read lengths."""
+    rng = np.random.default_rng(9)
+    pool = distinct_pool(rng, 300, 20)
+    template = "CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG"
+    reads = adversarial_reads(rng, 5000, template, [pool], strand="both", read_len=75, sub_rate=0.01, n_rate=0.001, lower_rate=0.01,
+                              double_frac=0.0, short_frac=0.0)
+    for extra in ([], ["ACGT"], ["A" * 300]):
+        data = fastq(reads[:2500] + extra + reads[2500:])
+        want = kref.trace_single(data, template, 2, pool, 1, True)
+        for chunk in (50000, None):
+            _set(monkeypatch, chunk, 4096)
+            got = gpu.trace_single(data, template, 2, pool, 1, True)
+            assert np.array_equal(got[0], want[0])
+            assert np.array_equal(got[1], want[1])
+
+
+def _irregular(kind, seq):
+    q = "I" * len(seq)
+    if kind == "wrapped_seq":
+        return "@w\n%s\n%s\n+\n%s\n" % (seq[:3], seq[3:], q)
+    if kind == "wrapped_qual":
+        return "@w\n%s\n+\n%s\n%s\n" % (seq, q[:2], q[2:])
+    if kind == "plus_in_seq":   # the sequence ends at the first '+' wherever it is (FastqReader.hpp:72)
+        return "@w\n%s+junk\n%s\n" % (seq, q)
+    if kind == "at_in_qual":
+        return "@w\n%s\n+\n@%s\n" % (seq, q[1:])
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["wrapped_seq", "wrapped_qual", "plus_in_seq", "at_in_qual"])
+@pytest.mark.parametrize("where", [0, 1, 777, -1])
+def test_handover_to_the_host_reader(gpu, kref, monkeypatch, kind, where):
+    """One record that is not a plain four-line record, anywhere in the text: the device reader stops in front of it,
+    the host reader resumes at that byte, and nothing is lost or read twice."""
+    pool, reads = _case(10, n=1500, short_frac=0.0)
+    recs = [fastq([r]).decode() for r in reads]
+    at = where if where >= 0 else len(recs)
+    recs.insert(at, _irregular(kind, reads[5]))
+    data = "".join(recs).encode()
+    want = kref.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    assert len(want[0]) == len(reads) + 1
+    for chunk in (200, 5000, None):
+        _set(monkeypatch, chunk, 1024)
+        got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, False)
+        t = rcpp.timing()
+        if kind != "at_in_qual":   # '@' as a quality character is still a four-line record
+            assert "then host from byte %d" % len("".join(recs[:at])) in t["reader"], t
+        else:
+            assert "then host" not in t["reader"], t
+        assert np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("name", sorted(GOOD))
+@pytest.mark.parametrize("chunk", [64, 80])
+def test_grammar_cases_small_chunks(gpu, kref, monkeypatch, name, chunk):
+    data = GOOD[name]
+    want = kref.trace_single(data, "AC--", 2, ["GT", "AC", "TT", "GG"], 1, False)
+    _set(monkeypatch, chunk, 32)   # a 32-byte carry area overflows on most of these: another way to hand over
+    got = gpu.trace_single(data, "AC--", 2, ["GT", "AC", "TT", "GG"], 1, False)
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+
+
+@pytest.mark.parametrize("name", sorted(BAD))
+@pytest.mark.parametrize("lead", [0, 3, 500])
+def test_errors_keep_their_line_numbers(gpu, monkeypatch, name, lead):
+    """A malformed record after `lead` good ones: the message names the line the reference would name."""
+    data, msg = BAD[name]
+    good = fastq(["ACGTAGG"] * lead)
+    import re
+    shifted = re.sub(r"line (\d+)", lambda m: "line %d" % (int(m.group(1)) + 4 * lead), msg)
+    for chunk in (96, None):
+        _set(monkeypatch, chunk, 64)
+        with pytest.raises(Exception) as err:
+            gpu.count_single(good + data, "AC--", 2, ["GT"], 0, True)
+        assert str(err.value) == shifted
+
+
+def test_record_longer_than_the_carry_area(gpu, kref, monkeypatch):
+    pool, reads = _case(11, n=300)
+    reads.insert(100, random_seq(np.random.default_rng(1), 5000))
+    data = fastq(reads)
+    want = kref.trace_single(data, TEMPLATE, 2, pool, 1, True)
+    _set(monkeypatch, 2048, 512)
+    got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, True)
+    assert "then host" in rcpp.timing()["reader"]
+    assert np.array_equal(got[0], want[0])
+    assert np.array_equal(got[1], want[1])
+
+
+def test_pinned_text_and_both_readers_agree(gpu, kref, monkeypatch):
+    """Text in page-locked memory (scg_host_alloc) is copied by DMA straight from the caller's buffer; the host reader
+    (SCG_HOST_PARSE=1) gives the same answer as both device routes."""
+    pool, reads = _case(12, n=20000)
+    data = fastq(reads)
+    want = kref.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    _set(monkeypatch, 1 << 20, 1 << 16)
+    pinned = rcpp.PinnedText.from_bytes(data)
+    got = gpu.trace_single(pinned, TEMPLATE, 2, pool, 1, False)
+    assert "page-locked" in rcpp.timing()["reader"]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    assert "bounce" in rcpp.timing()["reader"]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    _set(monkeypatch, host=True)
+    got = gpu.trace_single(data, TEMPLATE, 2, pool, 1, False)
+    assert rcpp.timing()["reader"] == "host"
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    pinned.free()
+
+
+def test_files_take_the_device_reader(gpu, kref, monkeypatch, tmp_path):
+    pool, reads = _case(13, n=30000)
+    data = fastq(reads)
+    path = tmp_path / "reads.fastq"
+    path.write_bytes(data)
+    want = kref.count_single(data, TEMPLATE, 2, pool, 1, True)
+    _set(monkeypatch, 1 << 18, 1 << 12)
+    got = gpu.count_single(str(path), TEMPLATE, 2, pool, 1, True, nthreads=4)
+    assert rcpp.timing()["reader"].startswith("device")
+    assert got[1] == want[1] and np.array_equal(got[0], want[0])
+
+
+def test_other_single_end_entry_points(gpu, kref, monkeypatch):
+    """Combinatorial and dual single-end counting read through the same pipeline."""
+    rng = np.random.default_rng(14)
+    p1, p2 = distinct_pool(rng, 30, 5), distinct_pool(rng, 30, 5)
+    template = "ACGT" + "-" * 5 + "GG" + "-" * 5 + "TGCA"
+    reads = adversarial_reads(rng, 5000, template, [p1, p2], strand="both")
+    data = fastq(reads)
+    _set(monkeypatch, 3000, 1024)
+    want = kref.count_combo_single(data, template, 2, p1, p2, 1, True)
+    got = gpu.count_combo_single(data, template, 2, p1, p2, 1, True)
+    assert rcpp.timing()["reader"].startswith("device")
+    assert got[2] == want[2] and np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    want = kref.count_dual_single_end(data, template, [p1, p2], 2, 1, True)
+    got = gpu.count_dual_single_end(data, template, [p1, p2], 2, 1, True)
+    assert got[1] == want[1] and np.array_equal(got[0], want[0])
+
+
+def test_two_full_size_chunks(gpu, kref, monkeypatch):
+    """Default chunk size (32 MiB): 330k reads of 75 bases cross one real chunk boundary."""
+    rng = np.random.default_rng(15)
+    pool = distinct_pool(rng, 1000, 20)
+    template = "CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG"
+    base = adversarial_reads(rng, 3000, template, [pool], strand="both", read_len=75, sub_rate=0.01, n_rate=0.001, lower_rate=0.0,
+                             double_frac=0.0, short_frac=0.0)
+    reads = base * 110
+    data = fastq(reads)
+    assert len(data) > (32 << 20)
+    _set(monkeypatch)
+    want = kref.count_single(data, template, 2, pool, 1, True)
+    got = gpu.count_single(data, template, 2, pool, 1, True, nthreads=8)
+    t = rcpp.timing()
+    assert t["reader"].startswith("device") and "then host" not in t["reader"]
+    assert got[1] == want[1] == len(reads)
+    assert np.array_equal(got[0], want[0])
