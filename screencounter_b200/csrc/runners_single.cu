@@ -136,25 +136,36 @@ void SingleMatcher::upload(Context& ctx) {
 
 // A matcher for these arguments, from the context's cache when an earlier call (another file of the same screen)
 // already built and uploaded it.  Only successful builds are cached, so validation errors are raised every time.
-std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const std::string& constant, int strand, const Pool& pool,
+// A matcher of a recent call with the same template, options and pool (compared by a 128-bit hash of the pool's raw
+// C strings, eight bytes at a time): a hit skips marshalling the pool altogether -- the same content went through
+// every validation when the entry was made.  A miss marshals the pool, validates, builds and uploads.
+std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* constant, int strand, const char* const* pool, int npool,
                                                      int mismatches, bool use_first) {
     unsigned long long k1 = 1469598103934665603ull, k2 = 0x9E3779B97F4A7C15ull;
-    auto feed = [&](const void* data, size_t n) {
-        const unsigned char* p = static_cast<const unsigned char*>(data);
-        for (size_t i = 0; i < n; ++i) {
-            k1 = (k1 ^ p[i]) * 1099511628211ull;
-            k2 = mix64(k2 + p[i] + 0x100 * (i & 0xFF));
+    auto feed = [&](const char* data, size_t n) {
+        k1 = mix64(k1 ^ n);
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            unsigned long long w;
+            std::memcpy(&w, data + i, 8);
+            k1 = mix64(k1 ^ w);
+            k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
         }
+        unsigned long long w = 0;
+        if (i < n) std::memcpy(&w, data + i, n - i);
+        k1 = mix64(k1 ^ w);
+        k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
     };
-    const int header[4] = { strand, mismatches, use_first ? 1 : 0, (int)pool.seqs.size() };
-    feed(header, sizeof header);
-    feed(constant.data(), constant.size() + 1);
-    for (const auto& s : pool.seqs) feed(s.data(), s.size() + 1);
+    const int header[4] = { strand, mismatches, use_first ? 1 : 0, npool };
+    feed(reinterpret_cast<const char*>(header), sizeof header);
+    feed(constant, std::strlen(constant));
+    for (int i = 0; i < npool; ++i) feed(pool[i], std::strlen(pool[i]));
     for (auto& e : ctx.single_cache) {
         if (e.key1 == k1 && e.key2 == k2) return e.matcher;
     }
+    const Pool p(pool, npool);
     auto m = std::make_shared<SingleMatcher>();
-    m->prepare(constant, strand, pool, mismatches, use_first, Duplicates::ERROR);  // all validation happens on the host
+    m->prepare(constant, strand, p, mismatches, use_first, Duplicates::ERROR);  // all validation happens on the host
     ctx.ensure_ready();
     m->upload(ctx);
     if (ctx.single_cache.size() >= 4) ctx.single_cache.erase(ctx.single_cache.begin());
@@ -303,9 +314,8 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         c.timing = Timing();
         // same order as the reference glue: open the file, marshal the pool, build the handler, then read
         Source source(src);
-        Pool p(pool, npool);
         const double t_setup = now_s();
-        const std::shared_ptr<SingleMatcher> matcher = cached_single_matcher(c, constant, strand, p, mismatches, use_first != 0);
+        const std::shared_ptr<SingleMatcher> matcher = cached_single_matcher(c, constant, strand, pool, npool, mismatches, use_first != 0);
         const SingleMatcher& m = *matcher;
         c.ensure_ready();
         c.timing.setup_s += now_s() - t_setup;

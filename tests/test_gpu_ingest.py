@@ -57,7 +57,7 @@ def test_line_endings(gpu, kref, monkeypatch, final_newline, crlf):
     pool, reads = _case(8, n=700)
     data = fastq(reads, crlf=crlf)
     if not final_newline:
-        data = data[:-2] if crlf else data[:-1]
+        data = data[:-1]   # CRLF files keep the '\r' (it is a base, and a quality character) and lose only the '\n'
     want = kref.trace_single(data, TEMPLATE, 2, pool, 1, True)
     for chunk in (128, 3000, None):
         _set(monkeypatch, chunk, 2048)
