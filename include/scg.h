@@ -187,6 +187,8 @@ int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, lo
  * present, loads it.  Returns 0 = compiled and loaded, 2 = compiled but no device to load it on,
  * 1 = failed; `message` receives the details.  Diagnostic only. */
 int scg_jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, char* message, size_t capacity);
+/* The same for the uniform-length variant of that kernel (every read `read_len` bases, 1 to 32 windows). */
+int scg_jit_selftest_uniform(const char* constant, int strand, int mismatches, int read_len, char* message, size_t capacity);
 
 /* Plain device-memory helpers so that a caller without a CUDA runtime of its own (R, ctypes)
  * can own buffers for scg_single_plan_run. */

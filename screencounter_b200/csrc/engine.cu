@@ -109,7 +109,7 @@ void Context::finish_timing() {
                   timing.launches, timing.reader.c_str());
     timing_json = buf;
     for (char ch : kernel_note) {
-        if (ch == '"' || ch == '\\' || ch == '\n') ch = ' ';
+        if (ch == '"' || ch == '\\' || (unsigned char)ch < 0x20) ch = ' ';
         timing_json.push_back(ch);
     }
     timing_json += "\"}";

@@ -96,7 +96,7 @@ std::map<std::string, Cached> g_cache;
 std::string SpecSingleConfig::key() const {
     std::ostringstream o;
     o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << nb << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
-      << fstart << '|' << rstart << '|' << keylen << '|' << dup_first;
+      << fstart << '|' << rstart << '|' << keylen << '|' << dup_first << '|' << ulen << '|' << info;
     for (uint32_t m : seed_masks) o << '|' << m;
     return o.str();
 }
@@ -150,7 +150,9 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     };
     const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
-    const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages);
+    const int group = env_int("SCG_SPEC_GROUP", 2, 1, 8);
+    const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages) + "#" +
+                            std::to_string(group);
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
@@ -193,6 +195,11 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_NAME spec_single_kernel\n"
         << "#define SPEC_MIN_BLOCKS " << min_blocks << "\n"
         << "#define SPEC_STAGES " << stages << "\n"
+        << "#define SPEC_ULEN " << cfg.ulen << "\n"
+        << "#define SPEC_NAME_U spec_single_kernel_u\n"
+        << "#define SPEC_GROUP " << group << "\n"
+        << "#define SPEC_INFO " << cfg.info << "\n"
+        << "#define SPEC_SKIP_GENERAL " << (cfg.ulen > 0 ? 1 : 0) << "\n"
         << "#include \"spec_single.cuh\"\n";
     const std::string program_text = src.str();
 
@@ -224,7 +231,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
 
     cudaError_t st = cudaLibraryLoadData(&entry.library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (st != cudaSuccess) return remember(std::string("cudaLibraryLoadData: ") + cudaGetErrorString(st));
-    st = cudaLibraryGetKernel(&entry.kernel, entry.library, "spec_single_kernel");
+    st = cudaLibraryGetKernel(&entry.kernel, entry.library, cfg.ulen > 0 ? "spec_single_kernel_u" : "spec_single_kernel");
     if (st != cudaSuccess) {
         entry.kernel = nullptr;
         return remember(std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(st));

@@ -219,6 +219,19 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
     cfg.rstart = P.spec.rstart[0];
     cfg.keylen = P.spec.rlen_f[0];
     spec_seeds(m, cfg);
+    // the uniform-length kernel: every read as long as the longest, 1 to 32 windows, a budget the pigeonhole filter is
+    // worth having for (at least four constant positions per group), indices that fit 32 bits
+    {
+        const int nwin = reads.uniform_len - m.tmpl.length + 1;
+        int nconst = 0;
+        for (char ch : m.tmpl.fwd_seq) nconst += ch != '-';
+        const bool want_u = !std::getenv("SCG_SPEC_NO_UNIFORM");
+        if (want_u && reads.lens == nullptr && nwin >= 1 && nwin <= 32 && P.spec.mm >= 0 && P.spec.mm <= 3 && nconst >= 4 * (P.spec.mm + 1) &&
+            cfg.T <= 128 && reads.W + 2 >= (cfg.T + 31) / 32 + 1 && reads.n <= 0x7FFFFFC0ll) {
+            cfg.ulen = reads.uniform_len;
+            cfg.info = d_info ? 1 : 0;
+        }
+    }
     std::string why;
     cudaKernel_t spec = (P.spec.mm >= 0 && cfg.T > 0) ? specialised_single_kernel(cfg, ctx.device, &why) : nullptr;
     if (spec) {
@@ -241,7 +254,7 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
         const int resident = specialised_blocks_per_sm(spec);
         const int spec_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * resident));
         SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
-        m.kernel_note = "specialised (NVRTC)";
+        m.kernel_note = cfg.ulen > 0 ? "specialised (NVRTC), uniform-length filter+verify" : "specialised (NVRTC)";
         ctx.kernel_note = m.kernel_note;
     } else {
         dispatch_cb(P.spec.cbits, [&](auto CB) {
@@ -490,7 +503,17 @@ void scg_plan_free(scg_plan* plan) { delete plan; }
 const char* scg_plan_kernel(const scg_plan* plan) { return plan ? plan->matcher.kernel_note.c_str() : ""; }
 
 // ---- run-time compiler check (no device needed for the compile step) --------------------------------------
+static int jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, int uniform_len, char* message, size_t capacity);
+
 int scg_jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, char* message, size_t capacity) {
+    return jit_selftest(constant, strand, mismatches, words_per_plane, 0, message, capacity);
+}
+
+int scg_jit_selftest_uniform(const char* constant, int strand, int mismatches, int read_len, char* message, size_t capacity) {
+    return jit_selftest(constant, strand, mismatches, std::max(1, (read_len + 31) / 32), read_len, message, capacity);
+}
+
+static int jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, int uniform_len, char* message, size_t capacity) {
     std::string msg;
     int status = 1;
     try {
@@ -521,6 +544,12 @@ int scg_jit_selftest(const char* constant, int strand, int mismatches, int words
                 for (int b = from; b < to; ++b) mask |= 1u << b;
                 cfg.seed_masks.push_back(mask);
             }
+        }
+        if (uniform_len > 0) {
+            const int nwin = uniform_len - t.length + 1;
+            if (nwin < 1 || nwin > 32) throw Error("the uniform-length kernel needs 1 to 32 windows per read");
+            cfg.ulen = uniform_len;
+            cfg.nb = 1;
         }
         std::string why;
         cudaKernel_t k = specialised_single_kernel(cfg, 0, &why);

@@ -75,6 +75,26 @@
 #ifndef SPEC_DUP_FIRST
 #define SPEC_DUP_FIRST 0
 #endif
+// Every read of the batch has this length (0 = lengths differ): enables the second kernel of this file,
+// `SPEC_NAME_U`, whose windows, masks and loop bounds are all compile-time constants.
+#ifndef SPEC_ULEN
+#ifdef SPEC_CUSTOM
+#define SPEC_ULEN 0
+#else
+#define SPEC_ULEN 75
+#endif
+#endif
+#ifndef SPEC_NAME_U
+#define SPEC_NAME_U spec_single_kernel_u_default
+#endif
+// tiles fetched by one bulk copy of the uniform-length kernel
+#ifndef SPEC_GROUP
+#define SPEC_GROUP 2
+#endif
+// whether the uniform-length kernel is ever asked for the per-read info word (traces)
+#ifndef SPEC_INFO
+#define SPEC_INFO 1
+#endif
 
 namespace scg {
 namespace spec {
@@ -418,6 +438,10 @@ __device__ __forceinline__ Hit seeded_search(const SpecTables& tb, bool rev, uin
 } // namespace spec
 } // namespace scg
 
+#ifndef SPEC_SKIP_GENERAL
+#define SPEC_SKIP_GENERAL 0
+#endif
+#if !SPEC_SKIP_GENERAL
 extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
     SPEC_NAME(const scg::ReadsDev reads, const scg::SpecTables tb, int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
               uint32_t* __restrict__ out_info) {
@@ -623,3 +647,348 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         tile += nwarps;
     }
 }
+#endif  // !SPEC_SKIP_GENERAL
+
+
+// =====================================================================================================================
+// Uniform-length variant.  Same per-read outcomes as the kernel above, for batches whose reads all have SPEC_ULEN
+// bases with at most 32 windows (the sequencing-run case: BASELINE configs[1] is 75-base reads, 44-base template,
+// exactly 32 windows).  What changes:
+//   * FILTER + VERIFY instead of counting every constant position in every window.  A window with at most MM
+//     constant mismatches is mismatch-free in at least one of MM + 1 groups of constant positions (pigeonhole), so
+//     the bit-sliced pass only ORs the mismatch planes of up to 8 sampled positions per group (one funnel shift and
+//     about half a LOP3 per sampled position) and keeps the windows where some group stayed clean.  Each lane then
+//     cuts its candidate window out of its registers (funnel shifts by the lane's own position) and counts the
+//     constant mismatches exactly with XOR / mask / POPC against the template's words, which are immediates; the
+//     variable region falls out of the same window words.  False candidates (about 0.2 % of random reads at 8
+//     sampled positions per group) cost another round of the verify loop for their warp.
+//   * several tiles per bulk copy, 32-bit read indices, no per-read length loads, no window-validity masks.
+// The exact-table probe carried across tiles, the deferred queue and the searches behind it are the ones above.
+// =====================================================================================================================
+#if SPEC_ULEN > 0
+
+namespace scg {
+namespace spec {
+
+constexpr int ULEN = SPEC_ULEN;
+constexpr int NWIN = ULEN - T + 1;
+static_assert(NWIN >= 1 && NWIN <= 32, "the uniform-length kernel handles reads with 1 to 32 windows");
+constexpr uint32_t WINMASK = NWIN >= 32 ? 0xFFFFFFFFu : ((1u << NWIN) - 1u);
+constexpr int TW = (T + 31) / 32;           // words per window
+constexpr int GROUP = SPEC_GROUP;           // tiles per bulk copy
+constexpr int NGROUPS = SPEC_MM + 1;        // pigeonhole groups of constant positions
+constexpr int SAMPLES = 8;                  // sampled positions per group
+static_assert(W + 2 >= TW + 1, "window words plus their funnel partner must exist");
+
+// constant positions [lo, hi) of a strand's group g
+template <bool REV, int G>
+struct Group {
+    static constexpr int NC = REV ? NCR : NCF;
+    static constexpr int lo = NC * G / NGROUPS, hi = NC * (G + 1) / NGROUPS, size = hi - lo;
+    static constexpr int S = size < SAMPLES ? size : SAMPLES;
+    // the K-th sampled constant position (index among the strand's constant positions), evenly spread
+    __host__ __device__ static constexpr int sample(int k) { return lo + (S > 0 ? k * size / S : 0); }
+};
+
+// OR of the mismatch planes of a group's sampled positions: bit p set = window p mismatches at a sampled position
+template <bool REV, int G, int K>
+__device__ __forceinline__ uint32_t group_any(const Planes& P) {
+    using Gr = Group<REV, G>;
+    if constexpr (K >= Gr::S) {
+        return 0u;
+    } else if constexpr (K + 3 <= Gr::S) {
+        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) | cplane<REV, Gr::sample(K + 2)>(P, 0) |
+               group_any<REV, G, K + 3>(P);
+    } else if constexpr (K + 2 <= Gr::S) {
+        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) | group_any<REV, G, K + 2>(P);
+    } else {
+        return cplane<REV, Gr::sample(K)>(P, 0) | group_any<REV, G, K + 1>(P);
+    }
+}
+
+// windows in which EVERY group shows a mismatch among its samples (those cannot be within the budget)
+template <bool REV, int G>
+__device__ __forceinline__ uint32_t all_groups_dirty(const Planes& P) {
+    if constexpr (G >= NGROUPS) {
+        return 0xFFFFFFFFu;
+    } else if constexpr (Group<REV, G>::S == 0) {
+        return 0u;   // an empty group is trivially clean: nothing can be excluded
+    } else {
+        return group_any<REV, G, 0>(P) & all_groups_dirty<REV, G + 1>(P);
+    }
+}
+
+template <bool REV>
+__device__ __forceinline__ uint32_t candidate_windows(const Planes& P, uint32_t live) {
+    return ~all_groups_dirty<REV, 0>(P) & live;
+}
+
+// word k of a strand's template: what = 0 constant-position mask, 1 high bits of the bases, 2 low bits
+__host__ __device__ constexpr uint32_t template_word(const char* s, int k, int what) {
+    uint32_t w = 0;
+    for (int j = 0; j < 32; ++j) {
+        const int pos = 32 * k + j;
+        if (pos >= T || s[pos] == '-') continue;
+        const char c = s[pos];
+        const uint32_t code = (c == 'A' || c == 'a') ? 0u : ((c == 'C' || c == 'c') ? 1u : ((c == 'G' || c == 'g') ? 2u : 3u));
+        const uint32_t bit = what == 0 ? 1u : (what == 1 ? (code >> 1) : (code & 1u));
+        w |= bit << j;
+    }
+    return w;
+}
+
+// Exact constant-mismatch count of window p on a strand; leaves the window's words in wh / wl / wn.
+template <int K>
+__device__ __forceinline__ int verify_words(const Words& R, int p, bool rev, uint32_t (&wh)[TW + 1], uint32_t (&wl)[TW + 1],
+                                            uint32_t (&wn)[TW + 1]) {
+    if constexpr (K >= TW) {
+        return 0;
+    } else {
+        constexpr uint32_t fth = template_word(FB, K, 1), ftl = template_word(FB, K, 2), fcm = template_word(FB, K, 0);
+        constexpr uint32_t rth = template_word(RB, K, 1), rtl = template_word(RB, K, 2), rcm = template_word(RB, K, 0);
+        wh[K] = __funnelshift_r(R.h[K], R.h[K + 1], p);
+        wl[K] = __funnelshift_r(R.l[K], R.l[K + 1], p);
+        wn[K] = __funnelshift_r(R.n[K], R.n[K + 1], p);
+        const uint32_t th = (SPEC_FWD && SPEC_REV) ? (rev ? rth : fth) : (SPEC_REV ? rth : fth);
+        const uint32_t tl = (SPEC_FWD && SPEC_REV) ? (rev ? rtl : ftl) : (SPEC_REV ? rtl : ftl);
+        const uint32_t cm = (SPEC_FWD && SPEC_REV) ? (rev ? rcm : fcm) : (SPEC_REV ? rcm : fcm);
+        return __popc(((wh[K] ^ th) | (wl[K] ^ tl) | wn[K]) & cm) + verify_words<K + 1>(R, p, rev, wh, wl, wn);
+    }
+}
+__device__ __forceinline__ int verify_window(const Words& R, int p, bool rev, uint32_t (&wh)[TW + 1], uint32_t (&wl)[TW + 1],
+                                             uint32_t (&wn)[TW + 1]) {
+    wh[TW] = wl[TW] = wn[TW] = 0;
+    return verify_words<0>(R, p, rev, wh, wl, wn);
+}
+
+// bits [START, START + KEYLEN) of a window given as words
+template <int START>
+__device__ __forceinline__ uint32_t window_key(const uint32_t (&w)[TW + 1]) {
+    constexpr int a = START >> 5, sh = START & 31;
+    const uint32_t lo = w[a], hi = a + 1 <= TW ? w[a + 1] : 0u;
+    return (sh == 0 ? lo : __funnelshift_r(lo, hi, sh)) & KEYMASK;
+}
+
+} // namespace spec
+} // namespace scg
+
+extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
+    SPEC_NAME_U(const scg::ReadsDev reads, const scg::SpecTables tb, int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
+                uint32_t* __restrict__ out_info) {
+    using namespace scg;
+    using namespace scg::spec;
+    static_assert(KEYLEN <= 32, "the specialised kernel handles variable regions of at most 32 bases");
+    constexpr uint32_t GROUP_BYTES = GROUP * TILE_BYTES;
+    __shared__ __align__(128) uint32_t stage_all[WARPS][STAGES][GROUP * TILE_WORDS];
+    __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
+    __shared__ uint32_t queue_all[WARPS][5][QCAP];
+    const int wib = threadIdx.x >> 5;
+    uint32_t(*queue)[QCAP] = queue_all[wib];
+    int waiting = 0;   // warp-uniform
+
+    const int lane = threadIdx.x & 31;
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    const uint32_t n = (uint32_t)reads.n;                       // the host sends at most 2^31 - 64 reads per launch
+    const int ntiles = (int)((n + TILE - 1) / TILE);
+    const int ngroups = (ntiles + GROUP - 1) / GROUP;
+
+    const uint32_t stage_base = smem_addr(&stage_all[wib][0][0]);
+    const uint32_t bar_base = smem_addr(&bar_all[wib][0]);
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar_base + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    // group g = tiles [GROUP * g, GROUP * g + GROUP) (the last group may be short): one bulk copy each
+    auto fetch = [&](int g, uint32_t stage) {
+        const int tiles = min(GROUP, ntiles - GROUP * g);
+        const uint32_t bytes = (uint32_t)tiles * TILE_BYTES;
+        const uint32_t bar = bar_base + 8u * stage;
+        const char* src = reinterpret_cast<const char*>(reads.data) + (size_t)g * GROUP_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         stage_base + stage * GROUP_BYTES),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            if (warp + s * nwarps < ngroups) fetch(warp + s * nwarps, (uint32_t)s);
+        }
+    }
+
+    Pending pend;
+    pend.meta = 0;
+    pend.a = pend.b = make_uint4(0, 0, 0, 0);
+    pend.kh = pend.kl = pend.i = 0;
+    uint32_t stage = 0, parity = 0;
+    int group = warp;
+    int tile_in_group = 0, tiles_here = 0;
+    bool have = group < ngroups;   // warp-uniform
+    if (have) {
+        mbar_wait(bar_base, 0);
+        tiles_here = min(GROUP, ntiles - GROUP * group);
+    }
+    for (;;) {
+        Words R;
+        uint32_t meta = 0, kh = 0, kl = 0, kn = 0;
+        if (have) {
+            const uint32_t* buf = stage_all[wib][stage] + tile_in_group * TILE_WORDS + lane;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                R.h[w] = buf[(PLANE_H * W + w) * TILE];
+                R.l[w] = buf[(PLANE_L * W + w) * TILE];
+                R.n[w] = buf[(PLANE_N * W + w) * TILE];
+            }
+            R.h[W] = R.l[W] = R.n[W] = 0;
+            R.h[W + 1] = R.l[W + 1] = R.n[W + 1] = 0;
+            const uint32_t i = (uint32_t)(group * GROUP + tile_in_group) * TILE + lane;
+            const bool inrange = i < n;
+            Planes P;
+            make_planes(R, P);
+
+            // ---- filter: windows that can still be within the budget ----
+            const uint32_t live = inrange ? WINMASK : 0u;
+            uint32_t cf = SPEC_FWD ? candidate_windows<false>(P, live) : 0u;
+            uint32_t cr = SPEC_REV ? candidate_windows<true>(P, live) : 0u;
+            // ---- verify: exact constant mismatches of each candidate, in the reference's order ----
+            int ncand = 0;
+            while (__any_sync(0xFFFFFFFFu, (cf | cr) != 0u)) {
+                const uint32_t any = cf | cr;
+                const bool some = any != 0u;
+                const int p = some ? __ffs(any) - 1 : 0;
+                const bool rev = SPEC_FWD ? !((cf >> p) & 1u) : true;
+                const uint32_t bit = some ? (1u << p) : 0u;
+                if (rev) {
+                    cr &= ~bit;
+                } else {
+                    cf &= ~bit;
+                }
+                uint32_t wh[TW + 1], wl[TW + 1], wn[TW + 1];
+                const int c = verify_window(R, p, rev, wh, wl, wn);
+                const bool ok = some && c <= SPEC_MM;
+                if (ok && ncand == 0) {
+                    meta = PM_CAND | (rev ? PM_REV : 0u) | ((uint32_t)c << 16) | (uint32_t)p;
+                    if (SPEC_FSTART == SPEC_RSTART || !SPEC_REV || !SPEC_FWD) {
+                        constexpr int START = (SPEC_FWD && SPEC_REV) ? SPEC_FSTART : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
+                        kh = window_key<START>(wh);
+                        kl = window_key<START>(wl);
+                        kn = window_key<START>(wn);
+                    } else {
+                        kh = rev ? window_key<SPEC_RSTART>(wh) : window_key<SPEC_FSTART>(wh);
+                        kl = rev ? window_key<SPEC_RSTART>(wl) : window_key<SPEC_FSTART>(wl);
+                        kn = rev ? window_key<SPEC_RSTART>(wn) : window_key<SPEC_FSTART>(wn);
+                    }
+                }
+                ncand += ok ? 1 : 0;
+            }
+            meta |= (inrange ? PM_INRANGE : 0u) | (ncand > 1 ? PM_MANY : 0u);
+
+            // the group's buffer goes back to the TMA once every lane has consumed its last tile
+            if (++tile_in_group == tiles_here) {
+                __syncwarp();
+                const int ahead = group + STAGES * nwarps;
+                if (lane == 0 && ahead < ngroups) fetch(ahead, stage);
+            }
+        }
+
+        // ---- settle the PREVIOUS tile: its table slots were requested one scan ago ----
+        if (__any_sync(0xFFFFFFFFu, pend.meta != 0)) {
+            const uint32_t m = pend.meta;
+            int index = -1;
+            if (m & PM_PROBED) {
+                const int ra = (pend.a.x == pend.kh && pend.a.y == pend.kl) ? (int)pend.a.z : -1;
+                const int rb = (pend.b.x == pend.kh && pend.b.y == pend.kl) ? (int)pend.b.z : -1;
+                index = max(ra, rb);
+            }
+            const int pfc = (int)((m >> 16) & 0xFFu), pfp = (int)(m & 0xFFFFu);
+            const bool found = index >= 0 && (SPEC_USE_FIRST || !(m & PM_MANY));
+            const bool defer = (m & PM_CAND) && !found && ((SPEC_MAXMM - pfc >= 1) || (m & PM_MANY));
+            if ((m & PM_INRANGE) && !defer) {
+                if (found) atomicAdd(counts + index, 1);
+                if (out_index) out_index[pend.i] = found ? index : -1;
+                if (SPEC_INFO && out_info) out_info[pend.i] = pack_info(found, (m & PM_REV) != 0, pfc, 0, pfp);
+            }
+            const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
+            if (dm) {
+                if (defer) {
+                    const int at = waiting + __popc(dm & lanes_below);
+                    queue[0][at] = pend.i;
+                    queue[1][at] = m;
+                    queue[2][at] = pend.kh;
+                    queue[3][at] = pend.kl;
+                    queue[4][at] = (m & PM_PROBED) ? 0u : pend.a.x;
+                }
+                waiting += __popc(dm);
+                __syncwarp();
+            }
+        }
+
+        // ---- this tile's first candidate: request the two slots of its variable region ----
+        pend.meta = meta;
+        if (have) {
+            pend.i = (uint32_t)(group * GROUP + tile_in_group - 1) * TILE + lane;
+            pend.kh = kh;
+            pend.kl = kl;
+            pend.a.x = kn;
+            if ((meta & PM_CAND) && kn == 0) {
+                const bool frev = (meta & PM_REV) != 0;
+                const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
+                const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
+                const uint32_t acc = hash_key(&kh, &kl, 1, 0);
+                pend.a = __ldg(slots + (acc & mask));
+                pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+                pend.meta |= PM_PROBED;
+            }
+        }
+
+        // ---- deferred reads: searched when a warp's worth is waiting, and whatever is left at the end ----
+        while (waiting >= 32 || (!have && waiting > 0)) {
+            const int take = waiting < 32 ? waiting : 32;
+            waiting -= take;
+            const bool active = lane < take;
+            const uint32_t qi = active ? queue[0][waiting + lane] : 0u;
+            const uint32_t qm = active ? queue[1][waiting + lane] : 0u;
+            const uint32_t qh = active ? queue[2][waiting + lane] : 0u;
+            const uint32_t ql = active ? queue[3][waiting + lane] : 0u;
+            const uint32_t qn = active ? queue[4][waiting + lane] : 0u;
+            __syncwarp();
+            const bool simple = active && NSEEDS > 0 && !(qm & PM_MANY);
+            if (NSEEDS > 0) {
+                const bool rev = (qm & PM_REV) != 0;
+                const int fc = (int)((qm >> 16) & 0xFFu);
+                const Hit h = seeded_search(tb, rev, qh, ql, qn, SPEC_MAXMM - fc, simple);
+                if (simple) {
+                    const bool found = h.index >= 0;
+                    if (found) atomicAdd(counts + h.index, 1);
+                    if (out_index) out_index[qi] = h.index;
+                    if (SPEC_INFO && out_info) out_info[qi] = pack_info(found, rev, fc + h.dist, h.dist, (int)(qm & 0xFFFFu));
+                }
+            }
+            if (__any_sync(0xFFFFFFFFu, active && !simple)) {
+                slow_single(reads, tb.libs, (long long)qi, active && !simple, counts, out_index, out_info);
+            }
+        }
+        if (!have) break;
+        // ---- next tile: the same group, or the warp's next group ----
+        if (tile_in_group == tiles_here) {
+            group += nwarps;
+            tile_in_group = 0;
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+            have = group < ngroups;
+            if (have) {
+                mbar_wait(bar_base + 8u * stage, parity);
+                tiles_here = min(GROUP, ntiles - GROUP * group);
+            }
+        }
+    }
+}
+
+#endif  // SPEC_ULEN > 0

@@ -174,6 +174,23 @@ def test_runtime_specialised_kernel_compiles(template, strand, mm, words):
     assert rc in (0, 2), buf.value.decode()
 
 
+@pytest.mark.parametrize("template,strand,mm,read_len", [
+    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 1, 75),
+    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 0, 60),
+    ("CAGCTACGTACGAA" + "-" * 20 + "CCAGCTCGAT", 2, 2, 50),      # asymmetric flanks: the strands' regions start apart
+    ("ACGTACGT" + "-" * 10 + "TGCATGCA", 0, 1, 40),
+    ("ACGTACGT" + "-" * 10 + "TGCATGCA", 1, 3, 26),
+    ("A" * 40 + "-" * 30 + "C" * 40, 2, 1, 120),
+])
+def test_uniform_length_kernel_compiles(template, strand, mm, read_len):
+    """The uniform-length (filter + verify) variant through NVRTC, without a device."""
+    import ctypes as C
+    from screencounter_b200._lib import lib
+    buf = C.create_string_buffer(16384)
+    rc = lib().scg_jit_selftest_uniform(template.encode(), strand, mm, read_len, buf, C.c_size_t(16384))
+    assert rc in (0, 2), buf.value.decode()
+
+
 def _tricky_fastq(rng, n, wrap_every=0, bad_at=None):
     """Records that defeat naive boundary guessing: qualities starting with '@' or '+', wrapped
     sequences and qualities, names holding '@' and '+', an occasional empty read."""
