@@ -97,6 +97,7 @@ struct Context {
         std::shared_ptr<SingleMatcher> matcher;
     };
     std::vector<CachedMatcher> single_cache;
+    DeviceBuffer slow_list, slow_count;      // reads the uniform-length kernel hands to its follow-up kernel (spec_single.cuh)
     std::shared_ptr<IngestBuffers> ingest;   // text ring, line tables and streams of the device-side FASTQ reader
     int device = 0;
     bool ready = false;

@@ -85,6 +85,7 @@ Nvrtc& nvrtc() {
 struct Cached {
     cudaLibrary_t library = nullptr;
     cudaKernel_t kernel = nullptr;
+    cudaKernel_t slow = nullptr;   // follow-up kernel of the uniform-length variant
     std::string problem;
 };
 
@@ -108,6 +109,12 @@ int specialised_blocks_per_sm(cudaKernel_t kernel) {
     auto it = cache.find(kernel);
     if (it != cache.end()) return it->second;
     int blocks = 0;
+    // the tile rings live in (static) shared memory: ask for the largest carve-out so that registers, not the default
+    // L1/shared split, decide how many blocks are resident
+    if (const char* v = std::getenv("SCG_SPEC_CARVEOUT")) {
+        cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(v));
+        cudaGetLastError();
+    }
     cudaError_t st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, reinterpret_cast<const void*>(kernel), 128, 0);
     if (st != cudaSuccess || blocks < 1) {
         cudaGetLastError();
@@ -125,7 +132,7 @@ std::string jit_status() {
     return "nvrtc " + std::to_string(major) + "." + std::to_string(minor) + " from " + n.where;
 }
 
-cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why) {
+cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why, cudaKernel_t* slow) {
     auto fail = [&](const std::string& msg) -> cudaKernel_t {
         if (why) *why = msg;
         return nullptr;
@@ -148,7 +155,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         int x = std::atoi(v);
         return x < lo ? lo : (x > hi ? hi : x);
     };
-    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", 4, 1, 16);
+    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? 8 : 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
     const int group = env_int("SCG_SPEC_GROUP", 2, 1, 8);
     const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages) + "#" +
@@ -157,6 +164,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
         if (!it->second.kernel && why) *why = it->second.problem;
+        if (slow) *slow = it->second.slow;
         return it->second.kernel;
     }
     Cached entry;
@@ -197,6 +205,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_STAGES " << stages << "\n"
         << "#define SPEC_ULEN " << cfg.ulen << "\n"
         << "#define SPEC_NAME_U spec_single_kernel_u\n"
+        << "#define SPEC_NAME_SLOW spec_single_kernel_slow\n"
         << "#define SPEC_GROUP " << group << "\n"
         << "#define SPEC_INFO " << cfg.info << "\n"
         << "#define SPEC_SKIP_GENERAL " << (cfg.ulen > 0 ? 1 : 0) << "\n"
@@ -236,7 +245,15 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         entry.kernel = nullptr;
         return remember(std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(st));
     }
+    if (cfg.ulen > 0) {
+        st = cudaLibraryGetKernel(&entry.slow, entry.library, "spec_single_kernel_slow");
+        if (st != cudaSuccess) {
+            entry.kernel = nullptr;
+            return remember(std::string("cudaLibraryGetKernel (slow): ") + cudaGetErrorString(st));
+        }
+    }
     g_cache[key] = entry;
+    if (slow) *slow = entry.slow;
     return entry.kernel;
 }
 

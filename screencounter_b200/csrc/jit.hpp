@@ -32,7 +32,9 @@ struct SpecSingleConfig {
 // Returns a launchable kernel for the configuration, or nullptr (with the reason in *why) when
 // run-time compilation is unavailable or disabled (SCG_NO_SPECIALIZE=1); callers then use the
 // generic kernel.  Thread-safe.
-cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why);
+// With cfg.ulen > 0 the module also holds the follow-up kernel for the reads the uniform-length kernel lists as needing
+// the full per-read search; *slow receives it.
+cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, std::string* why, cudaKernel_t* slow = nullptr);
 
 // Blocks of 128 threads of a specialised kernel that fit on one SM (occupancy query, cached per kernel).
 int specialised_blocks_per_sm(cudaKernel_t kernel);

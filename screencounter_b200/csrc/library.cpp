@@ -291,7 +291,9 @@ Library::Library(const std::vector<std::string>& sequences, int length, const Li
         for (int p : seed_positions[s]) seed_masks[(size_t)s * KW + (p >> 5)] |= 1u << (p & 31);
     }
     if (nseeds > 0) {
-        nbuckets = std::max<uint32_t>(16, next_pow2((uint32_t)std::min<size_t>(E * 2 + 1, 1u << 30)));
+        // four buckets per entry: a bucket holding an entry holds a third one 1 % of the time, so the device searches fetch
+        // two candidate rows per seed without looping (more buckets would push the tables out of L2)
+        nbuckets = std::max<uint32_t>(16, next_pow2((uint32_t)std::min<size_t>(E * 4 + 1, 1u << 22)));
         buckets.assign((size_t)nseeds * nbuckets, make_uint2(0, 0));
         cands.assign((size_t)nseeds * E, 0);
         std::vector<uint32_t> mh(KW), ml(KW), which(E);

@@ -233,7 +233,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
         }
     }
     std::string why;
-    cudaKernel_t spec = (P.spec.mm >= 0 && cfg.T > 0) ? specialised_single_kernel(cfg, ctx.device, &why) : nullptr;
+    cudaKernel_t slow = nullptr;
+    cudaKernel_t spec = (P.spec.mm >= 0 && cfg.T > 0) ? specialised_single_kernel(cfg, ctx.device, &why, &slow) : nullptr;
     if (spec) {
         ReadsDev reads_arg = reads;
         SpecTables tables;
@@ -249,12 +250,29 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             tables.nentries[s] = both[s]->dev.nentries;
         }
         tables.libs = P.libs;
-        void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info };
         // persistent warps: as many blocks as are resident at once, each warp strides over the tiles
         const int resident = specialised_blocks_per_sm(spec);
         const int spec_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * resident));
-        SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
-        m.kernel_note = cfg.ulen > 0 ? "specialised (NVRTC), uniform-length filter+verify" : "specialised (NVRTC)";
+        if (cfg.ulen > 0) {
+            // reads with several candidate windows are listed by the main kernel and finished by the follow-up kernel
+            ctx.slow_list.reserve((size_t)(ntiles * TILE) * sizeof(uint32_t));
+            ctx.slow_count.reserve(sizeof(uint32_t));
+            uint32_t* d_list = ctx.slow_list.as<uint32_t>();
+            uint32_t* d_count = ctx.slow_count.as<uint32_t>();
+            SCG_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), stream));
+            void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info, &d_list, &d_count };
+            SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
+            const LibDev* libs = P.libs;
+            void* slow_args[] = { &reads_arg, &libs, &d_list, &d_count, &d_counts, &d_index, &d_info };
+            const int slow_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * 2));
+            SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(slow), dim3(slow_grid), dim3(128), slow_args, 0, stream));
+            ++ctx.launches;
+        } else {
+            void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info };
+            SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
+        }
+        m.kernel_note = cfg.ulen > 0 ? "specialised (NVRTC), uniform-length filter+verify, " + std::to_string(resident) + " blocks/SM"
+                                     : "specialised (NVRTC)";
         ctx.kernel_note = m.kernel_note;
     } else {
         dispatch_cb(P.spec.cbits, [&](auto CB) {

@@ -87,6 +87,9 @@
 #ifndef SPEC_NAME_U
 #define SPEC_NAME_U spec_single_kernel_u_default
 #endif
+#ifndef SPEC_NAME_SLOW
+#define SPEC_NAME_SLOW spec_single_kernel_slow_default
+#endif
 // tiles fetched by one bulk copy of the uniform-length kernel
 #ifndef SPEC_GROUP
 #define SPEC_GROUP 2
@@ -415,18 +418,24 @@ __device__ __forceinline__ Hit seeded_search(const SpecTables& tb, bool rev, uin
             bk[sd] = __ldg(buckets + (size_t)sd * (bmask + 1) + b);
         }
     }
-    uint4 first[NSEEDS > 0 ? NSEEDS : 1];
+    // the first two candidate rows of every bucket go out together (a bucket with an entry holds a second one 7 % of
+    // the time, a third one almost never)
+    uint4 first[NSEEDS > 0 ? NSEEDS : 1], second[NSEEDS > 0 ? NSEEDS : 1];
 #pragma unroll
     for (int sd = 0; sd < NSEEDS; ++sd) {
-        first[sd] = make_uint4(0, 0, 0, 0);
+        first[sd] = second[sd] = make_uint4(0, 0, 0, 0);
         if (bk[sd].y > 0) first[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x);
+        if (bk[sd].y > 1) second[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x + 1);
     }
     Best best{ cap + 1, -1, false };
 #pragma unroll
-    for (int sd = 0; sd < NSEEDS; ++sd) best.consider(first[sd], kh, kl, kn, cap, bk[sd].y > 0);
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        best.consider(first[sd], kh, kl, kn, cap, bk[sd].y > 0);
+        best.consider(second[sd], kh, kl, kn, cap, bk[sd].y > 1);
+    }
 #pragma unroll
     for (int sd = 0; sd < NSEEDS; ++sd) {
-        for (uint32_t c = 1; c < bk[sd].y; ++c) best.consider(__ldg(rows + (size_t)sd * nent + bk[sd].x + c), kh, kl, kn, cap, true);
+        for (uint32_t c = 2; c < bk[sd].y; ++c) best.consider(__ldg(rows + (size_t)sd * nent + bk[sd].x + c), kh, kl, kn, cap, true);
     }
     if (best.index >= 0 && !best.ambiguous) {
         out.index = best.index;
@@ -769,12 +778,49 @@ __device__ __forceinline__ uint32_t window_key(const uint32_t (&w)[TW + 1]) {
     return (sh == 0 ? lo : __funnelshift_r(lo, hi, sh)) & KEYMASK;
 }
 
+// One warp's worth of deferred reads (lane < take holds one): the seeded search for reads with a single candidate
+// window.  Reads with several candidate windows need the full per-read search, whose register appetite would
+// halve this kernel's occupancy: their indices go to a list in global memory that `SPEC_NAME_SLOW` works off
+// right after this kernel, on the same stream.
+__device__ __forceinline__ void drain_deferred(const SpecTables& tb, const uint32_t (*queue)[QCAP], int at, int take, int lane,
+                                               int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
+                                               uint32_t* __restrict__ out_info, uint32_t* __restrict__ slow_list,
+                                               uint32_t* __restrict__ slow_count) {
+    const bool active = lane < take;
+    const uint32_t qi = active ? queue[0][at + lane] : 0u;
+    const uint32_t qm = active ? queue[1][at + lane] : 0u;
+    const uint32_t qh = active ? queue[2][at + lane] : 0u;
+    const uint32_t ql = active ? queue[3][at + lane] : 0u;
+    const uint32_t qn = active ? queue[4][at + lane] : 0u;
+    __syncwarp();
+    const bool simple = active && NSEEDS > 0 && !(qm & PM_MANY);
+    if (NSEEDS > 0) {
+        const bool rev = (qm & PM_REV) != 0;
+        const int fc = (int)((qm >> 16) & 0xFFu);
+        const Hit h = seeded_search(tb, rev, qh, ql, qn, SPEC_MAXMM - fc, simple);
+        if (simple) {
+            const bool found = h.index >= 0;
+            if (found) atomicAdd(counts + h.index, 1);
+            if (out_index) out_index[qi] = h.index;
+            if (SPEC_INFO && out_info) out_info[qi] = pack_info(found, rev, fc + h.dist, h.dist, (int)(qm & 0xFFFFu));
+        }
+    }
+    const uint32_t hard = __ballot_sync(0xFFFFFFFFu, active && !simple);
+    if (hard) {
+        const int leader = __ffs(hard) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(slow_count, (uint32_t)__popc(hard));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (active && !simple) slow_list[base + __popc(hard & ((1u << lane) - 1u))] = qi;
+    }
+}
+
 } // namespace spec
 } // namespace scg
 
 extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
     SPEC_NAME_U(const scg::ReadsDev reads, const scg::SpecTables tb, int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
-                uint32_t* __restrict__ out_info) {
+                uint32_t* __restrict__ out_info, uint32_t* __restrict__ slow_list, uint32_t* __restrict__ slow_count) {
     using namespace scg;
     using namespace scg::spec;
     static_assert(KEYLEN <= 32, "the specialised kernel handles variable regions of at most 32 bases");
@@ -803,22 +849,26 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
     }
     __syncwarp();
     // group g = tiles [GROUP * g, GROUP * g + GROUP) (the last group may be short): one bulk copy each
+    // The packed reads pass through L2 once: their lines are marked evict-first so that the tables stay resident.
+    uint64_t stream_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream_policy));
+    // one elected lane arms the barrier and issues the copy (called by the whole warp, converged)
     auto fetch = [&](int g, uint32_t stage) {
         const int tiles = min(GROUP, ntiles - GROUP * g);
         const uint32_t bytes = (uint32_t)tiles * TILE_BYTES;
         const uint32_t bar = bar_base + 8u * stage;
         const char* src = reinterpret_cast<const char*>(reads.data) + (size_t)g * GROUP_BYTES;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         stage_base + stage * GROUP_BYTES),
-                     "l"(src), "r"(bytes), "r"(bar)
-                     : "memory");
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "elect.sync _|p, 0xFFFFFFFF;\n\t"
+            "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+            "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%2], [%3], %1, [%0], %4;\n\t}"
+            ::"r"(bar), "r"(bytes), "r"(stage_base + stage * GROUP_BYTES), "l"(src), "l"(stream_policy)
+            : "memory");
     };
-    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            if (warp + s * nwarps < ngroups) fetch(warp + s * nwarps, (uint32_t)s);
-        }
+    for (int s = 0; s < STAGES; ++s) {
+        if (warp + s * nwarps < ngroups) fetch(warp + s * nwarps, (uint32_t)s);
     }
 
     Pending pend;
@@ -892,7 +942,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             if (++tile_in_group == tiles_here) {
                 __syncwarp();
                 const int ahead = group + STAGES * nwarps;
-                if (lane == 0 && ahead < ngroups) fetch(ahead, stage);
+                if (ahead < ngroups) fetch(ahead, stage);
             }
         }
 
@@ -910,8 +960,8 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             const bool defer = (m & PM_CAND) && !found && ((SPEC_MAXMM - pfc >= 1) || (m & PM_MANY));
             if ((m & PM_INRANGE) && !defer) {
                 if (found) atomicAdd(counts + index, 1);
-                if (out_index) out_index[pend.i] = found ? index : -1;
-                if (SPEC_INFO && out_info) out_info[pend.i] = pack_info(found, (m & PM_REV) != 0, pfc, 0, pfp);
+                if (out_index) __stcs(out_index + pend.i, found ? index : -1);
+                if (SPEC_INFO && out_info) __stcs(out_info + pend.i, pack_info(found, (m & PM_REV) != 0, pfc, 0, pfp));
             }
             const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
             if (dm) {
@@ -950,28 +1000,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         while (waiting >= 32 || (!have && waiting > 0)) {
             const int take = waiting < 32 ? waiting : 32;
             waiting -= take;
-            const bool active = lane < take;
-            const uint32_t qi = active ? queue[0][waiting + lane] : 0u;
-            const uint32_t qm = active ? queue[1][waiting + lane] : 0u;
-            const uint32_t qh = active ? queue[2][waiting + lane] : 0u;
-            const uint32_t ql = active ? queue[3][waiting + lane] : 0u;
-            const uint32_t qn = active ? queue[4][waiting + lane] : 0u;
-            __syncwarp();
-            const bool simple = active && NSEEDS > 0 && !(qm & PM_MANY);
-            if (NSEEDS > 0) {
-                const bool rev = (qm & PM_REV) != 0;
-                const int fc = (int)((qm >> 16) & 0xFFu);
-                const Hit h = seeded_search(tb, rev, qh, ql, qn, SPEC_MAXMM - fc, simple);
-                if (simple) {
-                    const bool found = h.index >= 0;
-                    if (found) atomicAdd(counts + h.index, 1);
-                    if (out_index) out_index[qi] = h.index;
-                    if (SPEC_INFO && out_info) out_info[qi] = pack_info(found, rev, fc + h.dist, h.dist, (int)(qm & 0xFFFFu));
-                }
-            }
-            if (__any_sync(0xFFFFFFFFu, active && !simple)) {
-                slow_single(reads, tb.libs, (long long)qi, active && !simple, counts, out_index, out_info);
-            }
+            drain_deferred(tb, queue, waiting, take, lane, counts, out_index, out_info, slow_list, slow_count);
         }
         if (!have) break;
         // ---- next tile: the same group, or the warp's next group ----
@@ -988,6 +1017,26 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                 tiles_here = min(GROUP, ntiles - GROUP * group);
             }
         }
+    }
+}
+
+
+// The reads the kernel above could not settle (several candidate windows): the full per-read search, one lane per
+// listed read, any grid.
+extern "C" __global__ void __launch_bounds__(128)
+    SPEC_NAME_SLOW(const scg::ReadsDev reads, const scg::LibDev* __restrict__ libs, const uint32_t* __restrict__ slow_list,
+                   const uint32_t* __restrict__ slow_count, int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
+                   uint32_t* __restrict__ out_info) {
+    using namespace scg;
+    using namespace scg::spec;
+    const uint32_t total = *slow_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps enter the search together (it votes); lanes past the end of the list idle through it
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < total; base += stride) {
+        const uint32_t k = base + (threadIdx.x & 31);
+        const bool active = k < total;
+        const uint32_t i = active ? slow_list[k] : 0u;
+        slow_single(reads, libs, (long long)i, active, counts, out_index, out_info);
     }
 }
 
