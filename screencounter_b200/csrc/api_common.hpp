@@ -127,6 +127,9 @@ struct CountTable {
     // live entries to the host
     void download(Context& ctx, std::vector<unsigned long long>& keys_lo, std::vector<unsigned long long>& keys_hi,
                   std::vector<uint32_t>& counts);
+    // narrow tables of random barcodes: live entries sorted in the text order of the barcodes (A < C < G < N < T), each
+    // key as three bits per base, first base most significant
+    void download_sorted(Context& ctx, int key_len, std::vector<unsigned long long>& order_keys, std::vector<uint32_t>& counts);
     long long upper_bound = 0;
 };
 

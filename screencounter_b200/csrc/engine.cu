@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "ingest.hpp"
 #include "pipeline.hpp"
@@ -18,12 +20,73 @@ double now_s() {
 // ---------------------------------------------------------------------------------------
 // buffers
 // ---------------------------------------------------------------------------------------
+// Device allocations are recycled through a small per-device cache: on the target boxes a cudaMalloc / cudaFree
+// pair costs anywhere between 0.3 and 20 ms, which is more than a whole counting call.  A released block goes to the
+// cache after a device-wide synchronise (what cudaFree would have implied); a request takes the smallest cached block
+// of at least its size and at most twice its size.
+namespace {
+struct BlockCache {
+    struct Block {
+        void* ptr;
+        size_t bytes;
+        int device;
+    };
+    std::mutex mutex;
+    std::vector<Block> blocks;
+    size_t held = 0;
+    static constexpr size_t kMaxHeld = 24ull << 30;
+    static constexpr size_t kMaxBlocks = 256;
+    ~BlockCache() {
+        // process exit: the driver reclaims device memory; calling into a torn-down runtime is not safe
+    }
+    void* take(size_t n, int device, size_t* got) {
+        std::lock_guard<std::mutex> lock(mutex);
+        size_t best = blocks.size();
+        const size_t limit = std::max<size_t>(2 * n, 1u << 16);
+        for (size_t k = 0; k < blocks.size(); ++k) {
+            const Block& b = blocks[k];
+            if (b.device != device || b.bytes < n || b.bytes > limit) continue;
+            if (best == blocks.size() || b.bytes < blocks[best].bytes) best = k;
+        }
+        if (best == blocks.size()) return nullptr;
+        void* p = blocks[best].ptr;
+        *got = blocks[best].bytes;
+        held -= blocks[best].bytes;
+        blocks.erase(blocks.begin() + (long)best);
+        return p;
+    }
+    bool give(void* p, size_t n, int device) {
+        std::lock_guard<std::mutex> lock(mutex);
+        if (blocks.size() >= kMaxBlocks || held + n > kMaxHeld) return false;
+        blocks.push_back(Block{ p, n, device });
+        held += n;
+        return true;
+    }
+};
+BlockCache& block_cache() {
+    static BlockCache* c = new BlockCache;   // intentionally leaked, see ~BlockCache
+    return *c;
+}
+} // namespace
+
 void DeviceBuffer::alloc(size_t n, bool zero) {
     release();
     if (n == 0) n = 16;
-    SCG_CUDA_CHECK(cudaMalloc(&ptr, n));
-    bytes = n;
-    if (zero) SCG_CUDA_CHECK(cudaMemset(ptr, 0, n));
+    int device = 0;
+    SCG_CUDA_CHECK(cudaGetDevice(&device));
+    size_t got = 0;
+    ptr = block_cache().take(n, device, &got);
+    if (ptr) {
+        bytes = got;
+    } else {
+        SCG_CUDA_CHECK(cudaMalloc(&ptr, n));
+        bytes = n;
+    }
+    if (zero) {
+        // the memset runs on the legacy stream, which the context's non-blocking stream does not wait for
+        SCG_CUDA_CHECK(cudaMemset(ptr, 0, n));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));
+    }
 }
 
 void DeviceBuffer::reserve(size_t n) {
@@ -36,7 +99,13 @@ void DeviceBuffer::upload(const void* host, size_t n, cudaStream_t stream) {
 }
 
 void DeviceBuffer::release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) {
+        int device = 0;
+        // whatever still uses the block must be done before somebody else gets it (cudaFree's implicit guarantee)
+        if (cudaGetDevice(&device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess || !block_cache().give(ptr, bytes, device)) {
+            cudaFree(ptr);
+        }
+    }
     ptr = nullptr;
     bytes = 0;
 }
@@ -103,9 +172,9 @@ int Context::grid_for(long long ntiles) const {
 void Context::finish_timing() {
     char buf[512];
     std::snprintf(buf, sizeof buf,
-                  "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"setup_s\": %.6f, \"total_s\": %.6f, "
+                  "{\"parse_s\": %.6f, \"pack_s\": %.6f, \"h2d_s\": %.6f, \"device_s\": %.6f, \"setup_s\": %.6f, \"harvest_s\": %.6f, \"total_s\": %.6f, "
                   "\"reads\": %lld, \"bytes_h2d\": %lld, \"launches\": %lld, \"reader\": \"%s\", \"kernel\": \"",
-                  timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.setup_s, timing.total_s, timing.reads, timing.bytes_h2d,
+                  timing.parse_s, timing.pack_s, timing.h2d_s, timing.device_s, timing.setup_s, timing.harvest_s, timing.total_s, timing.reads, timing.bytes_h2d,
                   timing.launches, timing.reader.c_str());
     timing_json = buf;
     for (char ch : kernel_note) {

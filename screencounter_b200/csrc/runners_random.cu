@@ -5,8 +5,11 @@
 #include <cstring>
 #include <map>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "api_common.hpp"
 #include "handlers.cuh"
+#include "hostpool.hpp"
 
 namespace scg {
 
@@ -158,6 +161,61 @@ void CountTable::download(Context& ctx, std::vector<unsigned long long>& keys_lo
     }
 }
 
+// Rank of every base in the byte order of its letter (A < C < G < N < T, what R's order() sees,
+// R/countRandomBarcodes.R:73), three bits per base, first base most significant: sorting these integers sorts the
+// barcodes as text.  Keys of up to 21 bases (random_kernel's narrow layout: H | L << 21 | N << 42).
+__global__ void text_order_kernel(const unsigned long long* __restrict__ keys, size_t n, int len, unsigned long long* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        const uint32_t H = (uint32_t)(k & 0x1FFFFFull), L = (uint32_t)((k >> 21) & 0x1FFFFFull), N = (uint32_t)((k >> 42) & 0x1FFFFFull);
+        unsigned long long s = 0;
+        for (int b = 0; b < len; ++b) {
+            const uint32_t code = (((H >> b) & 1u) << 1) | ((L >> b) & 1u);
+            const uint32_t rank = ((N >> b) & 1u) ? 3u : (code == 3u ? 4u : code);
+            s = (s << 3) | rank;
+        }
+        out[i] = s;
+    }
+}
+
+// Live entries of a narrow table as (text-order key, count), sorted by the key on the device.
+void CountTable::download_sorted(Context& ctx, int key_len, std::vector<unsigned long long>& order_keys, std::vector<uint32_t>& out_counts) {
+    DeviceBuffer d_keys, d_counts, d_cursor, d_order, d_order_sorted, d_counts_sorted, d_temp;
+    const size_t maxlive = (size_t)std::min<unsigned long long>(capacity, (unsigned long long)std::max<long long>(upper_bound, 1));
+    d_keys.alloc(maxlive * 8, false);
+    d_counts.alloc(maxlive * sizeof(uint32_t), false);
+    d_cursor.alloc(sizeof(unsigned long long), true);
+    const int grid = (int)std::min<size_t>((capacity + 255) / 256, (size_t)ctx.sm_count * 32);
+    compact64_kernel<<<grid, 256, 0, ctx.stream>>>(keys.as<unsigned long long>(), counts.as<uint32_t>(), capacity,
+                                                   d_keys.as<unsigned long long>(), d_counts.as<uint32_t>(), d_cursor.as<unsigned long long>());
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    unsigned long long live = 0;
+    SCG_CUDA_CHECK(cudaMemcpyAsync(&live, d_cursor.ptr, sizeof live, cudaMemcpyDeviceToHost, ctx.stream));
+    SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+    order_keys.resize(live);
+    out_counts.resize(live);
+    if (live == 0) return;
+    d_order.alloc(live * 8, false);
+    d_order_sorted.alloc(live * 8, false);
+    d_counts_sorted.alloc(live * sizeof(uint32_t), false);
+    text_order_kernel<<<(int)std::min<size_t>((live + 255) / 256, (size_t)ctx.sm_count * 32), 256, 0, ctx.stream>>>(
+        d_keys.as<unsigned long long>(), live, key_len, d_order.as<unsigned long long>());
+    SCG_CUDA_CHECK(cudaGetLastError());
+    size_t temp_bytes = 0;
+    SCG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_order.as<unsigned long long>(), d_order_sorted.as<unsigned long long>(),
+                                                   d_counts.as<uint32_t>(), d_counts_sorted.as<uint32_t>(), (long long)live, 0, 3 * key_len,
+                                                   ctx.stream));
+    d_temp.alloc(temp_bytes, false);
+    SCG_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.ptr, temp_bytes, d_order.as<unsigned long long>(), d_order_sorted.as<unsigned long long>(),
+                                                   d_counts.as<uint32_t>(), d_counts_sorted.as<uint32_t>(), (long long)live, 0, 3 * key_len,
+                                                   ctx.stream));
+    ctx.launches += 2;
+    SCG_CUDA_CHECK(cudaMemcpyAsync(order_keys.data(), d_order_sorted.ptr, live * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    SCG_CUDA_CHECK(cudaMemcpyAsync(out_counts.data(), d_counts_sorted.ptr, live * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx.stream));
+    SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+}
+
 // ---------------------------------------------------------------------------------------
 // ComboTally
 // ---------------------------------------------------------------------------------------
@@ -288,7 +346,11 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
         long long nreads = 0;
         std::vector<OddOutcome> odd_host;
         while (pipe.next(b)) {
-            tab.ensure(c, b.n);
+            {
+                const double t0 = now_s();
+                tab.ensure(c, b.n);
+                c.timing.setup_s += now_s() - t0;
+            }
             const auto& flags = pipe.odd_flags(b);
             long long nodd = 0;
             for (long long i = 0; i < b.n; ++i) nodd += flags[i];
@@ -354,19 +416,72 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
             }
             nreads += b.n;
         }
-        std::vector<unsigned long long> lo, hi;
-        std::vector<uint32_t> cnt;
-        tab.download(c, lo, hi, cnt);
-        std::map<std::string, int> merged(std::move(extra));
-        for (size_t i = 0; i < lo.size(); ++i) merged[decode_key(lo[i], wide ? hi[i] : 0ull, key_len, wide)] += (int)cnt[i];
+        const double t_harvest = now_s();
         auto* r = new scg_result;
         r->width = key_len;
-        r->strings.reserve(merged.size() * (size_t)key_len);
-        r->freq.reserve(merged.size());
-        for (const auto& kv : merged) {  // std::map iterates in byte order = R's order(sequences) for ACGTN text
-            r->strings.insert(r->strings.end(), kv.first.begin(), kv.first.end());
-            r->freq.push_back(kv.second);
+        if (!wide) {
+            // barcodes of up to 21 bases: sorted as text on the device (radix sort of rank-coded keys), rendered by the
+            // host threads, merged with the few keys that came from raw read text
+            std::vector<unsigned long long> order_keys;
+            std::vector<uint32_t> cnt;
+            tab.download_sorted(c, key_len, order_keys, cnt);
+            const size_t n = order_keys.size();
+            auto render = [&](unsigned long long k, char* out) {
+                for (int b = key_len - 1; b >= 0; --b) {
+                    out[b] = "ACGNT"[k & 7ull];
+                    k >>= 3;
+                }
+            };
+            if (extra.empty()) {
+                r->strings.resize(n * (size_t)key_len);
+                r->freq.resize(n);
+                const int pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, nthreads), n >> 16));
+                const size_t per = (n + pieces - 1) / pieces;
+                HostPool::instance().parallel_for(pieces, pieces, [&](int k) {
+                    const size_t b = (size_t)k * per, e = std::min(n, b + per);
+                    for (size_t i = b; i < e; ++i) {
+                        render(order_keys[i], &r->strings[i * (size_t)key_len]);
+                        r->freq[i] = (int32_t)cnt[i];
+                    }
+                });
+            } else {
+                r->strings.reserve((n + extra.size()) * (size_t)key_len);
+                r->freq.reserve(n + extra.size());
+                std::string cur(key_len, ' ');
+                auto it = extra.begin();
+                auto emit = [&](const std::string& k, int f) {
+                    r->strings.insert(r->strings.end(), k.begin(), k.end());
+                    r->freq.push_back(f);
+                };
+                for (size_t i = 0; i < n; ++i) {
+                    render(order_keys[i], &cur[0]);
+                    while (it != extra.end() && it->first < cur) {
+                        emit(it->first, it->second);
+                        ++it;
+                    }
+                    int f = (int)cnt[i];
+                    if (it != extra.end() && it->first == cur) {
+                        f += it->second;
+                        ++it;
+                    }
+                    emit(cur, f);
+                }
+                for (; it != extra.end(); ++it) emit(it->first, it->second);
+            }
+        } else {
+            std::vector<unsigned long long> lo, hi;
+            std::vector<uint32_t> cnt;
+            tab.download(c, lo, hi, cnt);
+            std::map<std::string, int> merged(std::move(extra));
+            for (size_t i = 0; i < lo.size(); ++i) merged[decode_key(lo[i], hi[i], key_len, wide)] += (int)cnt[i];
+            r->strings.reserve(merged.size() * (size_t)key_len);
+            r->freq.reserve(merged.size());
+            for (const auto& kv : merged) {  // std::map iterates in byte order = R's order(sequences) for ACGTN text
+                r->strings.insert(r->strings.end(), kv.first.begin(), kv.first.end());
+                r->freq.push_back(kv.second);
+            }
         }
+        c.timing.harvest_s = now_s() - t_harvest;
         *table = r;
         *total = (int32_t)nreads;
         c.timing.parse_s = source.reader->parse_seconds();

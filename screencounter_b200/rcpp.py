@@ -137,6 +137,11 @@ def _table(handle, kind):
     buf = C.create_string_buffer(max(n * w, 1))
     L.scg_result_copy_table(handle, None, buf, _ip(freq))
     raw = buf.raw[: n * w]
+    if n and w and b"\0" not in raw:
+        try:   # millions of barcodes: decode them in one vectorised step
+            return np.frombuffer(raw, dtype="S%d" % w).astype("U%d" % w).tolist(), freq
+        except UnicodeDecodeError:
+            pass
     return [raw[i * w:(i + 1) * w].decode("latin-1") for i in range(n)], freq
 
 
