@@ -132,7 +132,8 @@ Context::~Context() {
         if (slot.done) cudaEventDestroy(slot.done);
     }
     single_cache.clear();
-    ingest.reset();
+    ingest[0].reset();
+    ingest[1].reset();
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -231,13 +232,17 @@ ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int n
         if (!slots_[k].done) SCG_CUDA_CHECK(cudaEventCreateWithFlags(&slots_[k].done, cudaEventDisableTiming));
         slots_[k].in_flight = false;
     }
-    // Single-end text that is entirely in host memory is read on the device (ingest.hpp).  Paired input (the two
-    // mates' chunks would have to be cut at the same record) and callers that need the raw characters of a read back
-    // (random barcodes) keep the host reader.
-    const char* text = nullptr;
-    size_t size = 0;
-    if (r1_ && !r2_ && !want_odd_ && device_ingest_enabled() && r1_->memory_text(&text, &size) && size > 0) {
-        ingest_.reset(new DeviceIngest(ctx_, text, size, nthreads_));
+    // Text that is entirely in host memory (caller's buffer, mmap'd raw file) is read on the device (ingest.hpp); gzip
+    // streams keep the host reader.  Paired input needs both files in memory.
+    if (device_ingest_enabled() && r1_) {
+        const char *t1 = nullptr, *t2 = nullptr;
+        size_t n1 = 0, n2 = 0;
+        const bool ok1 = r1_->memory_text(&t1, &n1) && n1 > 0;
+        const bool ok2 = r2_ ? (r2_->memory_text(&t2, &n2) && n2 > 0) : true;
+        if (ok1 && ok2) {
+            ingest_[0].reset(new DeviceIngest(ctx_, t1, n1, nthreads_, 0, want_odd_));
+            if (r2_) ingest_[1].reset(new DeviceIngest(ctx_, t2, n2, nthreads_, 1, false));
+        }
     }
 }
 
@@ -287,33 +292,93 @@ void ReadPipeline::stage(Slot& slot, int mate, const Record* recs, size_t count,
     }
 }
 
-bool ReadPipeline::next(Batch& out) {
-    while (ingest_) {
+long long ReadPipeline::count_odd(const Batch& b) const {
+    if (!b.slot) return -1;
+    const auto& flags = static_cast<StagingSlot*>(b.slot)->mate[0].odd_host;
+    long long n = 0;
+    for (long long i = 0; i < b.n; ++i) n += flags[(size_t)i];
+    return n;
+}
+
+void ReadPipeline::raw_read(const Batch& b, long long index, std::string& seq) {
+    seq.clear();
+    if (!b.slot) {
+        const char* p = nullptr;
+        uint32_t len = 0;
+        ingest_[0]->raw_read(index, &p, &len);
+        seq.assign(p, len);
+        return;
+    }
+    const Record& r = b.recs1[index];
+    seq.reserve(r.len);
+    for (uint32_t k = 0; k < r.span; ++k) {
+        if (r.seq[k] != '\n') seq.push_back(r.seq[k]);
+    }
+}
+
+// One round of the device-side reader(s).  Returns true with a batch in `out`, or true with `ended` set at the clean end
+// of the input, or false once the host readers have been positioned to take over.
+bool ReadPipeline::next_device(Batch& out, bool& ended) {
+    ended = false;
+    const bool paired = ingest_[1] != nullptr;
+    for (;;) {
         if (handover_pending_) {
-            // the device reader met something that is not a four-line record: the host reader takes over at that byte
-            r1_->resume_at(handover_offset_, ingest_->records());
-            ingest_.reset();
+            // something that is not a four-line record (or a carry area that ran over): the host reader(s) take over at
+            // the byte where the device stopped, both mates having consumed the same number of records
+            r1_->resume_at(ingest_[0]->consumed(), ingest_[0]->records());
+            ctx_.timing.reader += ", then host from byte " + std::to_string(ingest_[0]->consumed());
+            if (paired) r2_->resume_at(ingest_[1]->consumed(), ingest_[1]->records());
+            ingest_[0].reset();
+            ingest_[1].reset();
             handover_pending_ = false;
-            ctx_.timing.reader += ", then host from byte " + std::to_string(handover_offset_);
-            break;
+            return false;
         }
-        DeviceIngest::Result res;
-        const bool more = ingest_->next(res);
-        if (res.handover) {
-            handover_pending_ = true;
-            handover_offset_ = res.resume_offset;
+        DeviceIngest::Result res1, res2;
+        bool more = false;
+        if (!paired) {
+            more = ingest_[0]->next(res1);
+        } else {
+            const bool s1 = ingest_[0]->stage(), s2 = ingest_[1]->stage();
+            if (!s1 && !s2) {
+                ended = true;   // both texts consumed to the last byte in the same round
+                return true;
+            }
+            if (!s1 || !s2) {
+                // one text has run out of chunks while the other has not: the host readers decide what that means
+                // (process_data.hpp:284-285 raises "different number of reads" unless the rest is empty)
+                handover_pending_ = true;
+                continue;
+            }
+            DeviceIngest::pair(ctx_, *ingest_[0], *ingest_[1]);
+            const bool m1 = ingest_[0]->complete(res1), m2 = ingest_[1]->complete(res2);
+            more = m1 || m2;
+            if (res1.n != res2.n) throw Error("internal error: the paired device readers disagree on the number of records");
+            if (res2.handover) res1.handover = true;
         }
-        if (res.n > 0) {
+        if (res1.handover) handover_pending_ = true;
+        if (res1.n > 0) {
             out = Batch();
             out.first_read = consumed_;
-            out.n = res.n;
-            out.reads1 = res.reads;
+            out.n = res1.n;
+            out.reads1 = res1.reads;
+            out.odd1 = res1.odd;
+            if (paired) out.reads2 = res2.reads;
             out.slot = nullptr;
-            consumed_ += res.n;
-            ctx_.timing.reads += res.n;
+            consumed_ += res1.n;
+            ctx_.timing.reads += res1.n;
             return true;
         }
-        if (!more && !handover_pending_) return false;
+        if (!more && !handover_pending_) {
+            ended = true;
+            return true;
+        }
+    }
+}
+
+bool ReadPipeline::next(Batch& out) {
+    if (ingest_[0]) {
+        bool ended = false;
+        if (next_device(out, ended)) return !ended;
     }
     // refill the record windows
     if (cur1_ >= n1_) {

@@ -99,7 +99,7 @@ struct Context {
     };
     std::vector<CachedMatcher> single_cache;
     DeviceBuffer slow_list, slow_count;      // reads the uniform-length kernel hands to its follow-up kernel (spec_single.cuh)
-    std::shared_ptr<IngestBuffers> ingest;   // text ring, line tables and streams of the device-side FASTQ reader
+    std::shared_ptr<IngestBuffers> ingest[2];   // text ring, line tables and streams of the device-side FASTQ reader, per mate
     int device = 0;
     bool ready = false;
     int sm_count = 0;

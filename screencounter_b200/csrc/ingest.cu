@@ -50,6 +50,7 @@ struct IngestState {
     uint32_t min_len, max_len;
     uint32_t status;     // ST_* flags: the device reader stops after this chunk
     uint32_t tail;       // ring position just past the last accepted record
+    uint32_t limit;      // paired input: records the other mate can match in this round (0xFFFFFFFF = no limit)
 };
 
 namespace {
@@ -63,6 +64,7 @@ __global__ void ingest_init(IngestState* st, uint32_t begin) {
     st->max_len = 0;
     st->status = 0;
     st->tail = begin;
+    st->limit = 0xFFFFFFFFu;
 }
 
 // newlines among the 16 bytes at ring position p that lie in [begin, end): bit j of the result = byte j is one
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(1024) scan_blocks(uint32_t* __restrict__ block
         st->min_len = 0xFFFFFFFFu;
         st->max_len = 0;
         st->status = status;
+        st->limit = 0xFFFFFFFFu;
     }
 }
 
@@ -221,6 +224,13 @@ __global__ void __launch_bounds__(256) record_extent(const uint16_t* __restrict_
     }
 }
 
+// paired input: both mates accept the same number of records in a round; what one has in excess stays in its carry
+__global__ void pair_limit(IngestState* a, IngestState* b) {
+    const uint32_t n = min(min(a->nrec, a->bad_rec), min(b->nrec, b->bad_rec));
+    a->limit = n;
+    b->limit = n;
+}
+
 // pass 6 (one block): settles what this chunk contributes, moves the unfinished tail in front of the next slot
 __global__ void __launch_bounds__(1024) finish_chunk(uint8_t* __restrict__ ring, const uint32_t* __restrict__ lines, IngestState* st, uint32_t end,
                                                      int final_chunk, uint32_t next_data0, uint32_t carry_room) {
@@ -232,9 +242,16 @@ __global__ void __launch_bounds__(1024) finish_chunk(uint8_t* __restrict__ ring,
             n = st->bad_rec;
             status |= ST_BADREC;
         }
+        if (st->limit < n) {
+            // the other mate has fewer records this round: the rest waits in the carry (not an irregularity, and a bad
+            // record beyond the limit is next round's business)
+            n = st->limit;
+            status &= ~(ST_BADREC | ST_LINECAP);
+        }
         const uint32_t tail = n ? lines[4 * n - 1] + 1 : st->begin;
         const uint32_t left = end - tail;
         if (final_chunk) {
+            // paired input may leave records for a round that will not come: the host readers sort that out
             if (left) status |= ST_REMAINDER;
         } else if (left > carry_room) {
             status |= ST_CARRY;
@@ -255,7 +272,8 @@ __global__ void __launch_bounds__(1024) finish_chunk(uint8_t* __restrict__ ring,
 
 // pass 7: bases -> tile-planar bit planes (layout.hpp); one warp per tile, one lane per record
 __global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restrict__ ring, const uint32_t* __restrict__ seq_off,
-                                                        uint16_t* __restrict__ seq_len, uint32_t nrec, int W, uint32_t* __restrict__ out) {
+                                                        uint16_t* __restrict__ seq_len, uint32_t nrec, int W, uint32_t* __restrict__ out,
+                                                        uint8_t* __restrict__ odd) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ntiles = (nrec + TILE - 1) / TILE;
@@ -270,6 +288,7 @@ __global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restric
         seq_len[r] = 0;   // the length array is padded to whole tiles like the host packer's
     }
     uint32_t* base = out + (size_t)warp * 3 * W * TILE + lane;
+    bool plain = true;   // only upper-case A, C, G, T, N (what the random-barcode handler can take from the packed form)
     for (int w = 0; w < W; ++w) {
         uint32_t hh = 0, ll = 0, nn = 0;
         const int first = 32 * w;
@@ -278,6 +297,7 @@ __global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restric
             const uint32_t c = s[first + j];
             const uint32_t u = c & 0xDFu;   // fold case: only X and x map to X
             const bool valid = u == 'A' || u == 'C' || u == 'G' || u == 'T';
+            plain = plain && ((valid && c == u) || c == 'N');
             // ASCII: bit 2 of A/C/G/T (either case) is 0/0/1/1 = plane H, bit 1 is 0/1/1/0, so L = bit 1 ^ bit 2
             const uint32_t hb = (c >> 2) & 1u, lb = ((c >> 1) ^ (c >> 2)) & 1u;
             hh |= (valid ? hb : 0u) << j;
@@ -288,6 +308,7 @@ __global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restric
         base[(size_t)(PLANE_L * W + w) * TILE] = ll;
         base[(size_t)(PLANE_N * W + w) * TILE] = nn;
     }
+    if (odd) odd[r] = plain ? 0 : 1;
 }
 
 } // namespace
@@ -326,15 +347,20 @@ void IngestBuffers::ensure(size_t chunk, size_t carry, bool need_bounce) {
     seq_off.reserve((line_cap / 4 + 1) * sizeof(uint32_t));
     state.reserve(sizeof(IngestState));
     meta.reserve(sizeof(IngestState));
-    for (int k = 0; k < 2; ++k) lens[k].reserve((line_cap / 4 + TILE) * sizeof(uint16_t));
+    for (int k = 0; k < 2; ++k) {
+        lens[k].reserve((line_cap / 4 + TILE) * sizeof(uint16_t));
+        odd[k].reserve(line_cap / 4 + TILE);
+    }
     if (need_bounce) {
         for (int k = 0; k < DeviceIngest::kSlots; ++k) bounce[k].reserve(chunk);
     }
     for (int k = 0; k < DeviceIngest::kSlots; ++k) released_valid[k] = bounced_valid[k] = false;
 }
 
-DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads)
-    : ctx_(ctx), text_(text), size_(size), nthreads_(std::max(1, nthreads)) {
+IngestBuffers& DeviceIngest::buffers() const { return *ctx_.ingest[mate_]; }
+
+DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads, int mate, bool want_odd)
+    : ctx_(ctx), text_(text), size_(size), nthreads_(std::max(1, nthreads)), mate_(mate ? 1 : 0), want_odd_(want_odd) {
     ctx_.ensure_ready();
     // a page-locked source (scg_host_alloc, cudaHostRegister) feeds the copy engine directly
     cudaPointerAttributes a0, a1;
@@ -354,8 +380,8 @@ DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthr
     carry_ = env_size("SCG_INGEST_CARRY", kCarry, 16, 64u << 20) / 16 * 16;
     stride_ = carry_ + chunk_ + 256;
     line_cap_ = (carry_ + chunk_) / 4;
-    if (!ctx_.ingest) ctx_.ingest.reset(new IngestBuffers);
-    IngestBuffers& B = *ctx_.ingest;
+    if (!ctx_.ingest[mate_]) ctx_.ingest[mate_].reset(new IngestBuffers);
+    IngestBuffers& B = buffers();
     B.ensure(chunk_, carry_, !pinned_source_);
     ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_));
     SCG_CUDA_CHECK(cudaGetLastError());
@@ -365,11 +391,11 @@ DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthr
 
 DeviceIngest::~DeviceIngest() {
     // copies still in flight read the caller's text (or the bounce buffers): let them finish
-    if (ctx_.ingest && ctx_.ingest->copy_stream) cudaStreamSynchronize(ctx_.ingest->copy_stream);
+    if (ctx_.ingest[mate_] && ctx_.ingest[mate_]->copy_stream) cudaStreamSynchronize(ctx_.ingest[mate_]->copy_stream);
 }
 
 void DeviceIngest::issue_copy(size_t chunk) {
-    IngestBuffers& B = *ctx_.ingest;
+    IngestBuffers& B = buffers();
     const int s = (int)(chunk % kSlots);
     const size_t off = chunk * chunk_;
     const size_t bytes = std::min(chunk_, size_ - off);
@@ -402,8 +428,13 @@ void DeviceIngest::issue_copy(size_t chunk) {
 
 bool DeviceIngest::next(Result& out) {
     out = Result();
-    if (stopped_ || parsed_ >= nchunks()) return false;
-    IngestBuffers& B = *ctx_.ingest;
+    if (!stage()) return false;
+    return complete(out);
+}
+
+bool DeviceIngest::stage() {
+    if (exhausted()) return false;
+    IngestBuffers& B = buffers();
     const size_t k = parsed_;
     // chunk k + kSlots - 1 reuses the slot of chunk k - 1, whose kernels (and `released` event) are already enqueued;
     // one further would need the slot this call is about to parse
@@ -415,17 +446,13 @@ bool DeviceIngest::next(Result& out) {
     const bool final_chunk = k + 1 == nchunks();
     const size_t bytes = std::min(chunk_, size_ - k * chunk_) + ((final_chunk && virtual_newline_) ? 1 : 0);
     const uint32_t slot0 = (uint32_t)slot_base(k);
-    const uint32_t data0 = slot0 + (uint32_t)carry_;
-    const uint32_t end = data0 + (uint32_t)bytes;
-    const uint32_t next_data0 = (uint32_t)slot_base(k + 1) + (uint32_t)carry_;
+    const uint32_t end = slot0 + (uint32_t)carry_ + (uint32_t)bytes;
     cudaStream_t st = ctx_.stream;
     IngestState* state = B.state.as<IngestState>();
     const uint8_t* ring = B.text.as<uint8_t>();
     uint32_t* lines = B.lines.as<uint32_t>();
     const int nblocks = (int)((end - slot0 + kBlockBytes - 1) / kBlockBytes);
-    const int out_slot = out_slot_;
-    out_slot_ ^= 1;
-    uint16_t* lens = B.lens[out_slot].as<uint16_t>();
+    uint16_t* lens = B.lens[out_slot_].as<uint16_t>();
 
     SCG_CUDA_CHECK(cudaStreamWaitEvent(st, B.copied[s], 0));
     count_newlines<<<nblocks, kBlockThreads, 0, st>>>(ring, slot0, end, state, B.block_counts.as<uint32_t>());
@@ -436,9 +463,41 @@ bool DeviceIngest::next(Result& out) {
     const int rec_blocks = (int)((max_rec + 255) / 256);
     validate_records<<<rec_blocks, 256, 0, st>>>(ring, lines, state, B.seq_off.as<uint32_t>(), lens);
     record_extent<<<rec_blocks, 256, 0, st>>>(lens, state);
-    finish_chunk<<<1, 1024, 0, st>>>(B.text.as<uint8_t>(), lines, state, end, final_chunk ? 1 : 0, next_data0, (uint32_t)carry_);
     SCG_CUDA_CHECK(cudaGetLastError());
-    ctx_.launches += 6;
+    ctx_.launches += 5;
+    staged_ = true;
+    return true;
+}
+
+void DeviceIngest::pair(Context& ctx, DeviceIngest& a, DeviceIngest& b) {
+    pair_limit<<<1, 1, 0, ctx.stream>>>(a.buffers().state.as<IngestState>(), b.buffers().state.as<IngestState>());
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+}
+
+bool DeviceIngest::complete(Result& out) {
+    out = Result();
+    if (!staged_) return false;
+    staged_ = false;
+    IngestBuffers& B = buffers();
+    const size_t k = parsed_;
+    const int s = (int)(k % kSlots);
+    const bool final_chunk = k + 1 == nchunks();
+    const size_t bytes = std::min(chunk_, size_ - k * chunk_) + ((final_chunk && virtual_newline_) ? 1 : 0);
+    const uint32_t slot0 = (uint32_t)slot_base(k);
+    const uint32_t data0 = slot0 + (uint32_t)carry_;
+    const uint32_t end = data0 + (uint32_t)bytes;
+    const uint32_t next_data0 = (uint32_t)slot_base(k + 1) + (uint32_t)carry_;
+    cudaStream_t st = ctx_.stream;
+    IngestState* state = B.state.as<IngestState>();
+    const uint8_t* ring = B.text.as<uint8_t>();
+    const int out_slot = out_slot_;
+    out_slot_ ^= 1;
+    uint16_t* lens = B.lens[out_slot].as<uint16_t>();
+
+    finish_chunk<<<1, 1024, 0, st>>>(B.text.as<uint8_t>(), B.lines.as<uint32_t>(), state, end, final_chunk ? 1 : 0, next_data0, (uint32_t)carry_);
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx_.launches;
     SCG_CUDA_CHECK(cudaMemcpyAsync(B.meta.ptr, state, sizeof(IngestState), cudaMemcpyDeviceToHost, st));
     SCG_CUDA_CHECK(cudaEventRecord(B.meta_ready, st));
     {
@@ -451,13 +510,15 @@ bool DeviceIngest::next(Result& out) {
 
     const long long tail_off = (long long)(k * chunk_) + ((long long)m.tail - (long long)data0);
     consumed_ = (size_t)std::min<long long>(std::max<long long>(tail_off, 0), (long long)size_);
+    last_n_ = 0;
     if (m.nrec > 0) {
         const int W = std::max(1, ceil_div((int)m.max_len, 32));
         const size_t ntiles = ((size_t)m.nrec + TILE - 1) / TILE;
         const size_t data_bytes = ntiles * tile_words(W) * sizeof(uint32_t);
         B.packed[out_slot].reserve(data_bytes + READ_GUARD_BYTES);
+        uint8_t* odd = want_odd_ ? B.odd[out_slot].as<uint8_t>() : nullptr;
         pack_records_dev<<<(unsigned)((ntiles + 3) / 4), 128, 0, st>>>(ring, B.seq_off.as<uint32_t>(), lens, m.nrec, W,
-                                                                       B.packed[out_slot].as<uint32_t>());
+                                                                       B.packed[out_slot].as<uint32_t>(), odd);
         SCG_CUDA_CHECK(cudaGetLastError());
         ++ctx_.launches;
         out.n = m.nrec;
@@ -466,7 +527,12 @@ bool DeviceIngest::next(Result& out) {
         out.reads.n = m.nrec;
         out.reads.uniform_len = (int)m.max_len;
         out.reads.lens = (m.min_len == m.max_len) ? nullptr : lens;
+        out.odd = odd;
         records_ += m.nrec;
+        last_n_ = m.nrec;
+        last_text_base_ = (long long)(k * chunk_) - (long long)data0;
+        last_out_slot_ = out_slot;
+        last_off_.clear();
     }
     SCG_CUDA_CHECK(cudaEventRecord(B.released[s], st));
     B.released_valid[s] = true;
@@ -478,6 +544,22 @@ bool DeviceIngest::next(Result& out) {
         return true;
     }
     return parsed_ < nchunks() || out.n > 0;
+}
+
+void DeviceIngest::raw_read(long long index, const char** seq, uint32_t* len) {
+    if (index < 0 || index >= last_n_) throw Error("raw_read: no such read in the current batch");
+    if (last_off_.empty()) {
+        // sequence offsets (ring positions) and lengths of the batch: still in place until the next chunk is staged
+        IngestBuffers& B = buffers();
+        last_off_.resize((size_t)last_n_);
+        last_len_.resize((size_t)last_n_);
+        SCG_CUDA_CHECK(cudaMemcpyAsync(last_off_.data(), B.seq_off.ptr, (size_t)last_n_ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx_.stream));
+        SCG_CUDA_CHECK(cudaMemcpyAsync(last_len_.data(), B.lens[last_out_slot_].ptr, (size_t)last_n_ * sizeof(uint16_t), cudaMemcpyDeviceToHost,
+                                       ctx_.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(ctx_.stream));
+    }
+    *seq = text_ + (last_text_base_ + (long long)last_off_[(size_t)index]);
+    *len = last_len_[(size_t)index];
 }
 
 } // namespace scg

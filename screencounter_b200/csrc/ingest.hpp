@@ -13,12 +13,15 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
 
 #include "engine.hpp"
 
 namespace scg {
 
 struct IngestState;   // device-side cursor shared by the kernels of consecutive chunks
+
+struct IngestBuffers;
 
 class DeviceIngest {
 public:
@@ -31,20 +34,34 @@ public:
         size_t resume_offset = 0;   // byte offset into the text of the first record not consumed
         long long n = 0;            // records of this batch (0 with handover or at the end of the input)
         ReadsDev reads;             // packed batch, valid until the next call's kernels are enqueued
+        const uint8_t* odd = nullptr;   // device flags (when asked for): the read holds characters other than ACGTN
     };
 
-    DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads);
+    // `mate` selects the context's buffer set (0, or 1 for the second file of paired input); `want_odd` makes the pack
+    // kernel flag reads that hold anything but upper-case A, C, G, T, N.
+    DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads, int mate, bool want_odd);
     ~DeviceIngest();
 
-    // Parses the next chunk.  false = the text is exhausted (and `out.n` is 0).
+    // Parses the next chunk.  false = the text is exhausted (and `out.n` is 0).  Same as stage() + complete().
     bool next(Result& out);
+    // The two halves, for paired input: stage() enqueues the line and record kernels of the next chunk (false = no chunk
+    // left), pair() makes two staged mates agree on the number of records of the round, complete() settles the chunk.
+    bool stage();
+    static void pair(Context& ctx, DeviceIngest& a, DeviceIngest& b);
+    bool complete(Result& out);
 
     long long records() const { return records_; }
+    size_t consumed() const { return consumed_; }
+    bool exhausted() const { return stopped_ || parsed_ >= nchunks(); }
+
+    // Raw text of read `index` of the batch handed out last (single-line records): pointer into the caller's text.
+    void raw_read(long long index, const char** seq, uint32_t* len);
 
 private:
     void issue_copy(size_t chunk);
     size_t nchunks() const { return (size_ + chunk_ - 1) / chunk_; }
     size_t slot_base(size_t chunk) const { return (chunk % kSlots) * stride_; }
+    IngestBuffers& buffers() const;
 
     size_t chunk_ = kChunk, carry_ = kCarry;
     size_t stride_ = 0;      // carry + chunk + 256 (room for an appended newline; keeps slot bases 16-byte aligned)
@@ -54,6 +71,8 @@ private:
     const char* text_;
     size_t size_;
     int nthreads_;
+    int mate_ = 0;
+    bool want_odd_ = false;
     bool pinned_source_ = false;
     bool virtual_newline_ = false;   // the text does not end with '\n': one is appended on the device
     size_t issued_ = 0;              // chunks whose copy has been enqueued
@@ -61,7 +80,14 @@ private:
     size_t consumed_ = 0;            // text bytes consumed as complete records so far
     long long records_ = 0;
     bool stopped_ = false;
+    bool staged_ = false;
     int out_slot_ = 0;
+    // the batch handed out last, for raw_read()
+    long long last_n_ = 0;
+    long long last_text_base_ = 0;   // text offset of ring position 0 of the batch's slot
+    std::vector<uint32_t> last_off_;
+    std::vector<uint16_t> last_len_;
+    int last_out_slot_ = 0;
 };
 
 // Device-ingest resources owned by the context (kept across calls).
@@ -71,7 +97,7 @@ struct IngestBuffers {
     DeviceBuffer block_counts; // newlines per block
     DeviceBuffer seq_off, seq_len;
     DeviceBuffer state;        // IngestState
-    DeviceBuffer packed[2], lens[2];
+    DeviceBuffer packed[2], lens[2], odd[2];
     PinnedBuffer bounce[DeviceIngest::kSlots];
     PinnedBuffer meta;
     cudaStream_t copy_stream = nullptr;

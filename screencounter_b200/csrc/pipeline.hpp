@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "engine.hpp"
@@ -31,7 +32,11 @@ public:
     // Call after the kernels that read the batch have been enqueued.
     void submitted(Batch& b);
 
-    const std::vector<uint8_t>& odd_flags(const Batch& b) const { return static_cast<StagingSlot*>(b.slot)->mate[0].odd_host; }
+    // Reads of the batch flagged as holding characters other than ACGTN (callers that asked for the flags), or -1 when only
+    // the device knows (batches of the device-side reader).
+    long long count_odd(const Batch& b) const;
+    // Raw characters of read `index` of the batch (mate 1), newlines of wrapped records removed.
+    void raw_read(const Batch& b, long long index, std::string& seq);
 
 private:
     static constexpr int kSlots = Context::kStagingSlots;
@@ -52,9 +57,9 @@ private:
     const Record* recs2_ = nullptr;
     size_t n1_ = 0, cur1_ = 0, n2_ = 0, cur2_ = 0;
     long long consumed_ = 0;
-    std::unique_ptr<DeviceIngest> ingest_;   // set while the device-side reader is feeding the batches
+    std::unique_ptr<DeviceIngest> ingest_[2];   // set while the device-side reader is feeding the batches (one per mate)
     bool handover_pending_ = false;
-    size_t handover_offset_ = 0;
+    bool next_device(Batch& out, bool& ended);   // false = the device readers have handed over to the host readers
 };
 
 } // namespace scg

@@ -351,9 +351,10 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
                 tab.ensure(c, b.n);
                 c.timing.setup_s += now_s() - t0;
             }
-            const auto& flags = pipe.odd_flags(b);
-            long long nodd = 0;
-            for (long long i = 0; i < b.n; ++i) nodd += flags[i];
+            // reads flagged odd get their outcome reported back; the device-side reader only knows on the device how many
+            // there are (count_odd < 0), so room is made for all
+            const long long nodd_host = pipe.count_odd(b);
+            const long long nodd = nodd_host < 0 ? b.n : nodd_host;
             d_odd_out.reserve((size_t)std::max<long long>(nodd, 1) * sizeof(OddOutcome));
             SCG_CUDA_CHECK(cudaMemsetAsync(d_odd_count.ptr, 0, sizeof(unsigned long long), c.stream));
             const long long ntiles = (b.n + TILE - 1) / TILE;
@@ -386,13 +387,9 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
                 }
                 std::sort(odd_host.begin(), odd_host.end(), [](const OddOutcome& x, const OddOutcome& y) { return x.read < y.read; });
                 std::string key(key_len, ' ');
+                std::string seq;
                 for (const auto& o : odd_host) {
-                    const Record& r = b.recs1[o.read];
-                    std::string seq;
-                    seq.reserve(r.len);
-                    for (uint32_t k = 0; k < r.span; ++k) {
-                        if (r.seq[k] != '\n') seq.push_back(r.seq[k]);
-                    }
+                    pipe.raw_read(b, (long long)o.read, seq);
                     const char* start = seq.data() + o.position + tmpl.fwd_regions[0].start;
                     if (!o.reverse) {  // forward_match: raw characters (handlers/RandomBarcodeSingleEnd.hpp:93-104)
                         key.assign(start, key_len);

@@ -134,11 +134,16 @@ def _table(handle, kind):
         keys = np.zeros((n, w), dtype=np.int32)
         L.scg_result_copy_table(handle, _ip(keys), None, _ip(freq))
         return keys, freq
+    if kind == "random_array":
+        # millions of barcodes: one fixed-width bytes array (dtype S<w>) instead of a Python string per barcode
+        arr = np.empty(n, dtype="S%d" % max(w, 1))
+        L.scg_result_copy_table(handle, None, _ip(arr), _ip(freq))
+        return arr, freq
     buf = C.create_string_buffer(max(n * w, 1))
     L.scg_result_copy_table(handle, None, buf, _ip(freq))
     raw = buf.raw[: n * w]
     if n and w and b"\0" not in raw:
-        try:   # millions of barcodes: decode them in one vectorised step
+        try:   # decode in one vectorised step
             return np.frombuffer(raw, dtype="S%d" % w).astype("U%d" % w).tolist(), freq
         except UnicodeDecodeError:
             pass
@@ -208,16 +213,17 @@ def kernel_launches(device=None):
     return int(lib().scg_kernel_launches(context(device)))
 
 
-def count_random_barcodes(path, constant, strand, mismatches, use_first, nthreads, device=None):
+def count_random_barcodes(path, constant, strand, mismatches, use_first, nthreads, device=None, as_array=False):
     """reference: src/count_random_barcodes.cpp:41-60 -> list(list(sequences, frequencies), total).
-    Sequences come back sorted (R sorts them anyway, R/countRandomBarcodes.R:73-74)."""
+    Sequences come back sorted (R sorts them anyway, R/countRandomBarcodes.R:73-74); with as_array they are one numpy
+    bytes array (dtype S<length>) instead of a list of str."""
     ctx = context(device)
     src = _Src(path)
     handle = C.c_void_p()
     total = C.c_int32()
     _check(ctx, lib().scg_count_random(ctx, src.ref(), constant.encode("latin-1"), int(strand), int(mismatches), int(bool(use_first)),
                                        int(nthreads), C.byref(handle), C.byref(total)))
-    seqs, freq = _table(handle, "random")
+    seqs, freq = _table(handle, "random_array" if as_array else "random")
     lib().scg_result_free(handle)
     return [[seqs, freq], total.value]
 

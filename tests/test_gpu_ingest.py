@@ -226,3 +226,99 @@ def test_two_full_size_chunks(gpu, kref, monkeypatch):
     assert t["reader"].startswith("device") and "then host" not in t["reader"]
     assert got[1] == want[1] == len(reads)
     assert np.array_equal(got[0], want[0])
+
+
+# ---- paired input: two device readers that must cut their chunks at the same record ----------------------------------
+def _paired_case(seed, n, len2_extra=0, dense=True):
+    rng = np.random.default_rng(seed)
+    p1, p2 = (dense_pool(rng, 40, 6), dense_pool(rng, 40, 6)) if dense else (distinct_pool(rng, 40, 6), distinct_pool(rng, 40, 6))
+    t1, t2 = "ACGTA" + "-" * 6 + "TGCAT", "GGATC" + "-" * 6 + "CCTAG"
+    r1 = adversarial_reads(rng, n, t1, [p1], strand="original", short_frac=0.01)
+    r2 = adversarial_reads(rng, n, t2, [p2], strand="original", short_frac=0.01)
+    if len2_extra:
+        r2 = [r + "A" * len2_extra for r in r2]
+    return (t1, p1, r1), (t2, p2, r2)
+
+
+@pytest.mark.parametrize("chunk,carry", [(300, 2048), (5000, 4096), (None, None)])
+@pytest.mark.parametrize("use_first", [True, False])
+def test_paired_chunks_stay_aligned(gpu, kref, monkeypatch, chunk, carry, use_first):
+    (t1, p1, r1), (t2, p2, r2) = _paired_case(21, 3000)
+    f1, f2 = fastq(r1), fastq(r2, names=["pair%d/2" % i for i in range(len(r2))])   # records of different sizes
+    want = kref.trace_dual(f1, t1, False, 1, p1, f2, t2, False, 1, p2, True, use_first)
+    _set(monkeypatch, chunk, carry)
+    got = gpu.trace_dual(f1, t1, False, 1, p1, f2, t2, False, 1, p2, True, use_first)
+    assert rcpp.timing()["reader"].startswith("device")
+    assert np.array_equal(np.asarray(got).ravel(), np.asarray(want).ravel())
+    # counts against the per-pair trace (the reference's own counts can depend on read order through its result cache,
+    # SURVEY 8.1 T20; the trace above is its fresh-state run)
+    gc = gpu.count_dual(f1, t1, False, 1, p1, f2, t2, False, 1, p2, True, use_first)
+    w = np.asarray(want).ravel()
+    assert gc[1] == len(r1) and np.array_equal(gc[0], np.bincount(w[w >= 0], minlength=len(p1)))
+
+
+def test_paired_mates_of_very_different_size(gpu, kref, monkeypatch):
+    """Mate 2 records are much longer: its reader falls behind, the carry area runs over, the host readers finish."""
+    (t1, p1, r1), (t2, p2, r2) = _paired_case(22, 2500, len2_extra=150)
+    f1, f2 = fastq(r1), fastq(r2)
+    want = kref.count_combo_paired(f1, t1, False, 1, p1, f2, t2, False, 1, p2, False, True)
+    for chunk, carry in ((2000, 512), (None, None)):
+        _set(monkeypatch, chunk, carry)
+        got = gpu.count_combo_paired(f1, t1, False, 1, p1, f2, t2, False, 1, p2, False, True)
+        assert got[2] == want[2] == len(r1)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        assert got[3] == want[3] and got[4] == want[4]
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_paired_files_of_different_length(gpu, monkeypatch, which):
+    (t1, p1, r1), (t2, p2, r2) = _paired_case(23, 1200)
+    if which == 1:
+        r1 = r1 + ["ACGTAGGGTTTTGCAT"]
+    else:
+        r2 = r2 + ["GGATCAAAAAACCTAG", "GGATCAAAAAACCTAG"]
+    f1, f2 = fastq(r1), fastq(r2)
+    for chunk in (700, None):
+        _set(monkeypatch, chunk, 1024)
+        with pytest.raises(Exception, match="different number of reads in paired FASTQ files"):
+            gpu.count_dual(f1, t1, False, 1, p1, f2, t2, False, 1, p2, False, True)
+
+
+def test_paired_irregular_record_in_one_mate(gpu, kref, monkeypatch):
+    (t1, p1, r1), (t2, p2, r2) = _paired_case(24, 2000, dense=False)
+    recs2 = [fastq([r]).decode() for r in r2]
+    recs2[1234] = _irregular("wrapped_seq", r2[1234] if len(r2[1234]) > 4 else "ACGTACGT")
+    f1, f2 = fastq(r1), "".join(recs2).encode()
+    want = kref.count_dual(f1, t1, False, 0, p1, f2, t2, False, 0, p2, False, False)
+    for chunk in (900, None):
+        _set(monkeypatch, chunk, 1024)
+        got = gpu.count_dual(f1, t1, False, 0, p1, f2, t2, False, 0, p2, False, False)
+        assert "then host" in rcpp.timing()["reader"]
+        assert got[1] == want[1] and np.array_equal(got[0], want[0])
+
+
+# ---- random barcodes: the device reader flags reads whose raw characters the host has to render -------------------------
+@pytest.mark.parametrize("chunk", [200, 4096, None])
+def test_random_barcodes_through_the_device_reader(gpu, kref, monkeypatch, chunk):
+    rng = np.random.default_rng(25)
+    template = "ACGTACGT" + "-" * 8 + "TTGCAGCA"
+    reads = []
+    for _ in range(3000):
+        core = "ACGTACGT" + random_seq(rng, 8) + "TTGCAGCA"
+        u = rng.random()
+        if u < 0.1:
+            core = core.lower()
+        elif u < 0.2:
+            core = core[:10] + "n" + core[11:]
+        elif u < 0.3:
+            core = core[:9] + "N" + core[10:]
+        reads.append(random_seq(rng, int(rng.integers(0, 9))) + core + random_seq(rng, int(rng.integers(0, 9))))
+    data = fastq(reads)
+    want = kref.count_random(data, template, 0, 1, True)
+    _set(monkeypatch, chunk, 1024)
+    got = gpu.count_random(data, template, 0, 1, True)
+    assert rcpp.timing()["reader"].startswith("device")
+    order = sorted(range(len(want[0])), key=lambda i: want[0][i])
+    assert list(got[0]) == [want[0][i] for i in order]
+    assert np.array_equal(got[1], np.asarray(want[1])[order])
+    assert got[2] == want[2]
