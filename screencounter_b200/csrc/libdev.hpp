@@ -45,7 +45,18 @@ struct SpecTables {
     uint32_t bucket_mask[2];
     int nentries[2];
     const LibDev* libs;         // the full descriptors, for the generic search of the rare complicated reads
+    // Compact exact table of BOTH strands for keys of up to 20 bases (uniform-length kernel): buckets of two 8-byte slots,
+    // one bucket (one 16-byte load, one L2 sector) per lookup.  Slot = lo word: H bits | low 12 L bits << 20;
+    // hi word: high 8 L bits | strand << 8 | valid << 9 | bucket-overflowed << 10 (first slot only) | pool index << 11.
+    // A key whose bucket was full is simply absent (its bucket carries the overflow flag; the generic tables have it).
+    const uint4* compact;
+    uint32_t compact_shift;     // bucket = hash >> compact_shift
 };
+
+// hash of a compact-table key (shared by the host builder and the kernel)
+SCG_HD uint32_t compact_hash(uint32_t key_lo, uint32_t key_hi) { return key_lo * 0x9E3779B1u + key_hi * 0x85EBCA6Bu; }
+constexpr int COMPACT_MAX_KEYLEN = 20;
+constexpr int COMPACT_MAX_POOL = (1 << 21) - 1;
 
 // Packed reads of one batch on the device.
 struct ReadsDev {

@@ -98,6 +98,10 @@
 #ifndef SPEC_INFO
 #define SPEC_INFO 1
 #endif
+// the compact exact table of both strands (libdev.hpp SpecTables::compact) is there: one 16-byte load per lookup
+#ifndef SPEC_COMPACT
+#define SPEC_COMPACT 0
+#endif
 
 namespace scg {
 namespace spec {
@@ -706,8 +710,8 @@ __device__ __forceinline__ uint32_t group_any(const Planes& P) {
     if constexpr (K >= Gr::S) {
         return 0u;
     } else if constexpr (K + 3 <= Gr::S) {
-        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) | cplane<REV, Gr::sample(K + 2)>(P, 0) |
-               group_any<REV, G, K + 3>(P);
+        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) |
+               cplane<REV, Gr::sample(K + 2)>(P, 0) | group_any<REV, G, K + 3>(P);
     } else if constexpr (K + 2 <= Gr::S) {
         return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) | group_any<REV, G, K + 2>(P);
     } else {
@@ -948,15 +952,25 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
 
         // ---- settle the PREVIOUS tile: its table slots were requested one scan ago ----
         if (__any_sync(0xFFFFFFFFu, pend.meta != 0)) {
-            const uint32_t m = pend.meta;
+            uint32_t m = pend.meta;
             int index = -1;
+            bool unresolved = false;   // compact table only: the key's bucket was full when the table was built
             if (m & PM_PROBED) {
+#if SPEC_COMPACT
+                const bool hit0 = pend.a.x == pend.kh && (pend.a.y & 0x3FFu) == pend.kl;
+                const bool hit1 = pend.a.z == pend.kh && (pend.a.w & 0x3FFu) == pend.kl;
+                index = hit0 ? (int)(pend.a.y >> 11) : (hit1 ? (int)(pend.a.w >> 11) : -1);
+                unresolved = index < 0 && ((pend.a.y >> 10) & 1u);
+#else
                 const int ra = (pend.a.x == pend.kh && pend.a.y == pend.kl) ? (int)pend.a.z : -1;
                 const int rb = (pend.b.x == pend.kh && pend.b.y == pend.kl) ? (int)pend.b.z : -1;
                 index = max(ra, rb);
+#endif
             }
             const int pfc = (int)((m >> 16) & 0xFFu), pfp = (int)(m & 0xFFFFu);
             const bool found = index >= 0 && (SPEC_USE_FIRST || !(m & PM_MANY));
+            // an unresolved exact lookup with no budget left for the seeded search goes the way of the multi-window reads
+            if (unresolved && SPEC_MAXMM - pfc < 1) m |= PM_MANY;
             const bool defer = (m & PM_CAND) && !found && ((SPEC_MAXMM - pfc >= 1) || (m & PM_MANY));
             if ((m & PM_INRANGE) && !defer) {
                 if (found) atomicAdd(counts + index, 1);
@@ -969,8 +983,13 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                     const int at = waiting + __popc(dm & lanes_below);
                     queue[0][at] = pend.i;
                     queue[1][at] = m;
+#if SPEC_COMPACT
+                    queue[2][at] = pend.kh & 0xFFFFFu;
+                    queue[3][at] = (pend.kh >> 20) | ((pend.kl & 0xFFu) << 12);
+#else
                     queue[2][at] = pend.kh;
                     queue[3][at] = pend.kl;
+#endif
                     queue[4][at] = (m & PM_PROBED) ? 0u : pend.a.x;
                 }
                 waiting += __popc(dm);
@@ -982,6 +1001,18 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         pend.meta = meta;
         if (have) {
             pend.i = (uint32_t)(group * GROUP + tile_in_group - 1) * TILE + lane;
+#if SPEC_COMPACT
+            // both strands share one table of 8-byte slots: the strand is a key bit, a lookup is one 16-byte bucket
+            const uint32_t klo = kh | (kl << 20);
+            const uint32_t khi = (kl >> 12) | ((meta & PM_REV) ? 0x300u : 0x200u);
+            pend.kh = klo;
+            pend.kl = khi;
+            pend.a.x = kn;
+            if ((meta & PM_CAND) && kn == 0) {
+                pend.a = __ldg(tb.compact + (compact_hash(klo, khi) >> tb.compact_shift));
+                pend.meta |= PM_PROBED;
+            }
+#else
             pend.kh = kh;
             pend.kl = kl;
             pend.a.x = kn;
@@ -994,6 +1025,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                 pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
                 pend.meta |= PM_PROBED;
             }
+#endif
         }
 
         // ---- deferred reads: searched when a warp's worth is waiting, and whatever is left at the end ----

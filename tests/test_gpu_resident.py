@@ -76,3 +76,23 @@ def test_many_tiles_per_warp(kref, use_first):
     want_index, _ = kref.trace_single(spec.fastq(0, n), TEMPLATE, 2, pool, 1, use_first)
     assert np.array_equal(got_index, want_index)
     assert np.array_equal(got_counts, np.bincount(want_index[want_index >= 0], minlength=len(pool)))
+
+
+@pytest.mark.parametrize("mm", [0, 1, 2])
+def test_compact_exact_table(kref, monkeypatch, mm):
+    """The opt-in one-load exact table of the uniform-length kernel (SCG_SPEC_COMPACT=1), all three budgets (a handful of
+    the 6,000 keys find their bucket full and take the "bucket was full" route)."""
+    from screencounter_b200.device import SynthSpec, SinglePlan, DeviceArray
+    monkeypatch.setenv("SCG_SPEC_COMPACT", "1")
+    rng = np.random.default_rng(6 + mm)
+    pool = distinct_pool(rng, 3000, 20)
+    spec = SynthSpec(TEMPLATE, [pool], seed=12, read_len=75, strand=2, sub_per_10k=200, n_per_10k=20)
+    n = 300_001
+    reads = spec.on_device(0, n)
+    plan = SinglePlan(TEMPLATE, 2, pool, mm, True)
+    counts = DeviceArray(4 * len(pool))
+    index = DeviceArray(4 * n)
+    plan.run(reads, counts.ptr, index.ptr)
+    want_index, _ = kref.trace_single(spec.fastq(0, n), TEMPLATE, 2, pool, mm, True)
+    assert np.array_equal(index.to_numpy(np.int32), want_index)
+    assert np.array_equal(counts.to_numpy(np.int32), np.bincount(want_index[want_index >= 0], minlength=len(pool)))
