@@ -190,6 +190,13 @@ int scg_jit_selftest(const char* constant, int strand, int mismatches, int words
 /* The same for the uniform-length variant of that kernel (every read `read_len` bases, 1 to 32 windows). */
 int scg_jit_selftest_uniform(const char* constant, int strand, int mismatches, int read_len, char* message, size_t capacity);
 
+/* The segmented search behind countDualBarcodes on its own (SegmentedBarcodeSearch<2>::search,
+ * inst/include/kaori/BarcodeSearch.hpp:478-487, without its result cache): `caps` holds two budgets per
+ * query (first, second segment); index is 0-based, -1 = no match.  Diagnostic, used by the tests. */
+int scg_search_segmented(scg_ctx* ctx, const char* const* sequences, int nsequences, const int32_t* caps,
+                         const char* const* choices, int nchoices, int len1, int len2, int max1, int max2,
+                         int32_t* index, int32_t* mismatches);
+
 /* Plain device-memory helpers so that a caller without a CUDA runtime of its own (R, ctypes)
  * can own buffers for scg_single_plan_run. */
 int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out);   /* zero-initialised */

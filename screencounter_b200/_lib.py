@@ -86,5 +86,5 @@ EXPORTS = [
     "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",
     "scg_host_pack_roundtrip", "scg_jit_selftest", "scg_jit_selftest_uniform",
     "scg_device_alloc", "scg_device_free", "scg_device_zero", "scg_device_to_host", "scg_synchronize",
-    "scg_host_alloc", "scg_host_free",
+    "scg_host_alloc", "scg_host_free", "scg_search_segmented",
 ]

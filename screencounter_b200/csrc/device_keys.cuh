@@ -339,12 +339,175 @@ __device__ __forceinline__ Hit lookup_any(const LibDev* __restrict__ lib, const 
     return lookup_seeded<KW>(lib, q, min(cap, lib->L), 0, -1);
 }
 
+// SegmentedMismatches<2>::search (MismatchTrie.hpp:577-660) walked over the reference's own trie, frame by frame: the exact
+// child first, whose result becomes `best` by plain assignment (:624-627 -- this is where the phantom "missing, total + 1"
+// of a dead end enters), then the alternates in A, C, G, T order while the shared mismatch cap (lowered by every hit, :602)
+// still allows them, merged with replace_best_with_chosen (:266-299).  Only the caps the table search cannot reproduce come
+// here ([>= 2, 0]); it is correct for any caps, which is how the tests check it.  One lane, iterative, frames in local memory.
+constexpr int TRIE_MAX_LEN = 64;
+template <int KW>
+__device__ __noinline__ Hit trie_search_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
+    const int32_t* __restrict__ ptr = libp->trie;
+    const int L = libp->L, seg1 = libp->seg1;
+    constexpr int MISSING = -1, AMBIGUOUS = -2;
+    int cap = c1 + c2;
+    int node[TRIE_MAX_LEN], tot[TRIE_MAX_LEN], bidx[TRIE_MAX_LEN], btot[TRIE_MAX_LEN];
+    signed char m0[TRIE_MAX_LEN], m1[TRIE_MAX_LEN], sh[TRIE_MAX_LEN], snext[TRIE_MAX_LEN], phase[TRIE_MAX_LEN], alts_ok[TRIE_MAX_LEN];
+    int d = 0, ret_idx = MISSING, ret_tot = 0;
+    bool entering = true;
+    node[0] = 0;
+    tot[0] = 0;
+    m0[0] = m1[0] = 0;
+    auto base_at = [&](int pos) -> int {
+        const int w = pos >> 5, bit = pos & 31;
+        uint32_t h = 0, l = 0, n = 0;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            if (k == w) {
+                h = q.h[k];
+                l = q.l[k];
+                n = q.n[k];
+            }
+        }
+        if ((n >> bit) & 1u) return -1;
+        return (int)((((h >> bit) & 1u) << 1) | ((l >> bit) & 1u));
+    };
+    while (d >= 0) {
+        const int seg = d < seg1 ? 0 : 1;
+        const int segcap = seg == 0 ? c1 : c2;
+        if (entering) {
+            const int shift = base_at(d);
+            const int current = shift >= 0 ? ptr[node[d] + shift] : MISSING;
+            if (d + 1 == L) {
+                // the last position (:595-613)
+                if (current >= 0 || current == AMBIGUOUS) {
+                    cap = tot[d];
+                    ret_idx = current;
+                    ret_tot = tot[d];
+                } else {
+                    int idx = MISSING;
+                    const int t = tot[d] + 1;
+                    const int segmm = (seg == 0 ? m0[d] : m1[d]) + 1;
+                    if (t <= cap && segmm <= segcap) {
+                        // scan_final_position_with_mismatch (:302-343)
+                        bool found = false;
+                        for (int s = 0; s < 4; ++s) {
+                            if (s == shift) continue;
+                            const int cand = ptr[node[d] + s];
+                            if (cand >= 0) {
+                                if (found) {
+                                    if (cand != idx) {
+                                        if (libp->dup_first) {
+                                            if (idx > cand) idx = cand;
+                                        } else {
+                                            idx = AMBIGUOUS;
+                                            break;
+                                        }
+                                    }
+                                } else {
+                                    idx = cand;
+                                    cap = t;
+                                    found = true;
+                                }
+                            } else if (cand == AMBIGUOUS) {
+                                idx = AMBIGUOUS;
+                                cap = t;
+                                break;
+                            }
+                        }
+                    }
+                    ret_idx = idx;
+                    ret_tot = t;
+                }
+                entering = false;
+                --d;
+                continue;
+            }
+            sh[d] = (signed char)shift;
+            bidx[d] = MISSING;
+            btot[d] = cap + 1;
+            if (current >= 0) {
+                phase[d] = 1;
+                node[d + 1] = current;
+                tot[d + 1] = tot[d];
+                m0[d + 1] = m0[d];
+                m1[d + 1] = m1[d];
+                ++d;
+                continue;   // entering the exact child
+            }
+            phase[d] = 2;
+            const int t = tot[d] + 1, segmm = (seg == 0 ? m0[d] : m1[d]) + 1;
+            alts_ok[d] = (t <= cap && segmm <= segcap) ? 1 : 0;
+            snext[d] = 0;
+        } else if (phase[d] == 1) {
+            // back from the exact child: its result IS best (:624-627)
+            bidx[d] = ret_idx;
+            btot[d] = ret_tot;
+            phase[d] = 2;
+            const int t = tot[d] + 1, segmm = (seg == 0 ? m0[d] : m1[d]) + 1;
+            alts_ok[d] = (t <= cap && segmm <= segcap) ? 1 : 0;
+            snext[d] = 0;
+        } else {
+            // back from an alternate: replace_best_with_chosen (:266-299)
+            if (ret_idx >= 0) {
+                if (ret_tot < btot[d]) {
+                    bidx[d] = ret_idx;
+                    btot[d] = ret_tot;
+                } else if (ret_tot == btot[d] && ret_idx != bidx[d]) {
+                    if (libp->dup_first) {
+                        if (ret_idx < bidx[d]) bidx[d] = ret_idx;
+                    } else {
+                        bidx[d] = AMBIGUOUS;
+                    }
+                }
+            } else if (ret_idx == AMBIGUOUS) {
+                if (ret_tot < btot[d]) {
+                    bidx[d] = ret_idx;
+                    btot[d] = ret_tot;
+                } else if (ret_tot == btot[d]) {
+                    bidx[d] = AMBIGUOUS;
+                }
+            }
+        }
+        // the alternates of frame d (:633-650)
+        entering = false;
+        if (alts_ok[d]) {
+            const int t = tot[d] + 1;
+            while (snext[d] < 4) {
+                const int s = snext[d]++;
+                if (s == sh[d]) continue;
+                const int alt = ptr[node[d] + s];
+                if (alt < 0) continue;
+                if (t <= cap) {
+                    node[d + 1] = alt;
+                    tot[d + 1] = t;
+                    m0[d + 1] = (signed char)(m0[d] + (seg == 0 ? 1 : 0));
+                    m1[d + 1] = (signed char)(m1[d] + (seg == 1 ? 1 : 0));
+                    ++d;
+                    entering = true;
+                    break;
+                }
+            }
+        }
+        if (entering) continue;
+        ret_idx = bidx[d];
+        ret_tot = btot[d];
+        --d;
+    }
+    Hit out{ -1, 0 };
+    if (ret_idx >= 0) {
+        out.index = ret_idx;
+        out.dist = ret_tot;
+    }
+    return out;
+}
+
 // Best-unique search with one cap per segment (SegmentedMismatches<2>::search,
 // MismatchTrie.hpp:577-660), cache-free semantics, including the phantom result of :608-617
 // when the second segment's cap is 0 ("Quirk A"):
 //   c2 == 0, c1 == 1 : if the query minus its last base is free of N and is a prefix of a library
 //                      row, the search reports no match ("root rule");
-//   c2 == 0, c1 >= 2 : not handled here -- the host refuses such budgets (runners_paired.cu).
+//   c2 == 0, c1 >= 2 : the reference's own walk over its trie (trie_search_segmented above).
 template <int KW>
 __device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
     Hit out{ -1, 0 };
@@ -358,6 +521,8 @@ __device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp,
         }
     }
     if ((c1 <= 0 && c2 <= 0) || lib.nseeds == 0) return out;
+    // caps [>= 2, 0]: only the reference's own walk over its trie gives the reference's answer
+    if (c2 == 0 && c1 >= 2 && lib.trie != nullptr) return trie_search_segmented<KW>(libp, q, c1, 0);
     if (c2 == 0 && c1 >= 1) {
         // root rule: the exact chain down to the last base exists -> the phantom (MISSING, 1) ties or beats every hit
         uint32_t ph[KW], pl[KW], pn = 0;

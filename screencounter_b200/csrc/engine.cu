@@ -198,6 +198,7 @@ void DeviceLibrary::upload(Context& ctx) {
     cands.upload(host.cands.data(), host.cands.size() * sizeof(int32_t), st);
     cand_rows.upload(host.cand_rows.data(), host.cand_rows.size() * sizeof(uint32_t), st);
     prefix_slots.upload(host.prefix_slots.data(), host.prefix_slots.size() * sizeof(uint32_t), st);
+    trie.upload(host.trie.data(), host.trie.size() * sizeof(int32_t), st);
     SCG_CUDA_CHECK(cudaStreamSynchronize(st));
     std::memset(&dev, 0, sizeof dev);
     dev.L = host.L;
@@ -218,6 +219,7 @@ void DeviceLibrary::upload(Context& ctx) {
     dev.seg1 = host.opt.segmented ? host.opt.seg1 : 0;
     dev.prefix_slots = prefix_slots.as<uint32_t>();
     dev.prefix_mask = host.prefix_mask;
+    dev.trie = host.trie.empty() ? nullptr : trie.as<int32_t>();
 }
 
 // ---------------------------------------------------------------------------------------

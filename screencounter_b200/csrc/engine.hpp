@@ -61,7 +61,7 @@ struct Timing {
 // A library resident on the device.
 struct DeviceLibrary {
     Library host;
-    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots;
+    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots, trie;
     LibDev dev;
     void upload(struct Context& ctx);
 };

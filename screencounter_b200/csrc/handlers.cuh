@@ -608,4 +608,22 @@ __global__ void match_kernel(const uint32_t* __restrict__ qkeys /* n * 3KW: h, l
     mm[i] = h.index >= 0 ? h.dist : -1;
 }
 
+// the segmented search on its own, one thread per query, caps per query (tests)
+template <int KW>
+__global__ void segmented_probe_kernel(const uint32_t* __restrict__ qkeys /* n * 3KW: h, l, n */, int nq, const LibDev* lib,
+                                       const int32_t* __restrict__ caps, int32_t* __restrict__ index, int32_t* __restrict__ mm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    Key<KW> q;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        q.h[w] = qkeys[(size_t)i * 3 * KW + w];
+        q.l[w] = qkeys[(size_t)i * 3 * KW + KW + w];
+        q.n[w] = qkeys[(size_t)i * 3 * KW + 2 * KW + w];
+    }
+    const Hit h = lookup_segmented<KW>(lib, q, caps[2 * i], caps[2 * i + 1]);
+    index[i] = h.index;
+    mm[i] = h.index >= 0 ? h.dist : -1;
+}
+
 } // namespace scg

@@ -33,6 +33,8 @@ struct LibDev {
     // table of library rows with their last base dropped (SURVEY 8.1 T8 root rule)
     const uint32_t* prefix_slots;
     uint32_t prefix_mask;
+    // the reference's flat trie (library.hpp), nullptr unless the first segment may take 2 or more mismatches
+    const int32_t* trie;
 };
 
 // What the specialised single-barcode kernel (spec_single.cuh) needs of the two strands' libraries, passed by

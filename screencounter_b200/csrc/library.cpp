@@ -350,6 +350,29 @@ Library::Library(const std::vector<std::string>& sequences, int length, const Li
         prefix_slots.swap(t.slots);
         prefix_mask = t.n - 1;
     }
+
+    // The reference's trie, node for node (MismatchTrie::next / end, MismatchTrie.hpp:66-105), from the concrete rows in
+    // insertion order; duplicates were settled by the builder above, so a leaf is a pool index or missing.
+    if (options.segmented && options.max_mismatches1 >= 2 && L > 0) {
+        trie.assign(4, -1);
+        for (size_t e = 0; e < E; ++e) {
+            const std::string& row = b.concrete[e];
+            int position = 0;
+            for (int i = 0; i < L; ++i) {
+                const int shift = base_code(row[i]);
+                if (i + 1 == L) {
+                    if (trie[position + shift] < 0) trie[position + shift] = ent_idx[e];
+                } else if (trie[position + shift] < 0) {
+                    const int fresh = (int)trie.size();
+                    trie[position + shift] = fresh;
+                    trie.resize(trie.size() + 4, -1);
+                    position = fresh;
+                } else {
+                    position = trie[position + shift];
+                }
+            }
+        }
+    }
 }
 
 } // namespace scg

@@ -49,6 +49,10 @@ struct Library {
     std::vector<uint32_t> cand_rows;    // KW == 1: 4 words (h, l, pool index, 0) per (seed, candidate), in `cands` order
     std::vector<uint32_t> prefix_slots; // same layout, rows with the last base dropped
     uint32_t prefix_mask = 0;
+    // kaori's flat 4-ary trie of the concrete rows (MismatchTrie.hpp:93-205: node = 4 child pointers, -1 = none, leaves hold pool
+    // indices), built for segmented libraries whose first segment may take 2 or more mismatches: the search with caps [>= 2, 0]
+    // can only be reproduced by walking it like the reference does
+    std::vector<int32_t> trie;
 
     // `sequences` are the library rows as they must match the read (i.e. already
     // reverse-complemented by the caller when the reverse strand is searched).

@@ -91,11 +91,12 @@ struct DualPEMatcher {
             combined.push_back((rev1 ? reverse_complement_iupac(p1.seqs[i]) : p1.seqs[i]) +
                                (rev2 ? reverse_complement_iupac(p2.seqs[i]) : p2.seqs[i]));
         }
-        // The reference's segmented trie search has a phantom result when the second cap is 0.
-        // The device search reproduces it for first-segment caps 0 and 1; larger budgets on read 1 need the
-        // trie-walk emulation, which this engine does not carry yet -- refuse rather than risk different counts.
-        if (mm1 >= 2) {
-            throw Error("countDualBarcodes with 2 or more substitutions on the first read is not supported by this engine yet");
+        // The reference's segmented trie search has a phantom result when the second cap is 0.  The
+        // table search reproduces it for first-segment caps 0 and 1; with 2 or more substitutions on read 1 the library also
+        // carries the reference's trie and caps [>= 2, 0] are answered by walking it (device_keys.cuh trie_search_segmented).
+        if (mm1 >= 2 && len1 + len2 > TRIE_MAX_LEN) {
+            throw Error("countDualBarcodes with 2 or more substitutions on the first read needs variable regions of at most " +
+                        std::to_string(TRIE_MAX_LEN) + " bp in total in this engine");
         }
         LibraryOptions opt;
         opt.segmented = true;
@@ -282,6 +283,56 @@ int scg_count_dual(scg_ctx* ctx, const scg_source* src1, const char* constant1, 
         c.timing.parse_s = s1.reader->parse_seconds() + s2.reader->parse_seconds();
         c.timing.total_s = now_s() - t_start;
         c.finish_timing();
+    });
+}
+
+
+// Raw SegmentedBarcodeSearch<2>::search with per-query caps (reference BarcodeSearch.hpp:478-487, cache-free): the device
+// search behind countDualBarcodes, exposed for the tests.  caps: two per query.
+int scg_search_segmented(scg_ctx* ctx, const char* const* sequences, int nsequences, const int32_t* caps, const char* const* choices,
+                         int nchoices, int len1, int len2, int max1, int max2, int32_t* index, int32_t* mismatches) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Pool pool(choices, nchoices);
+        if (pool.length != len1 + len2) throw Error("choices should be len1 + len2 bases long");
+        if (max1 >= 2 && len1 + len2 > TRIE_MAX_LEN) throw Error("segments too long for the trie walk");
+        LibraryOptions opt;
+        opt.segmented = true;
+        opt.seg1 = len1;
+        opt.max_mismatches1 = max1;
+        opt.max_mismatches2 = max2;
+        opt.duplicates = Duplicates::ERROR;
+        DeviceLibrary lib;
+        lib.host = Library(pool.seqs, len1 + len2, opt);
+        Pool queries(sequences, nsequences);
+        if (nsequences == 0) return;
+        if (queries.length < len1 + len2) throw Error("sequences are shorter than the choices");
+        c.ensure_ready();
+        lib.upload(c);
+        const int KW = lib.host.KW;
+        DeviceBuffer d_lib, d_q, d_caps, d_idx, d_mm;
+        const LibDev* libp = upload_lib_array(c, std::vector<LibDev>{ lib.dev }, d_lib);
+        d_caps.upload(caps, (size_t)nsequences * 2 * sizeof(int32_t), c.stream);
+        d_idx.alloc((size_t)nsequences * sizeof(int32_t), false);
+        d_mm.alloc((size_t)nsequences * sizeof(int32_t), false);
+        const int grid = (nsequences + 127) / 128;
+        dispatch_kw(KW, [&](auto KWC) {
+            constexpr int K = decltype(KWC)::value;
+            std::vector<uint32_t> qk((size_t)nsequences * 3 * K, 0);
+            for (int i = 0; i < nsequences; ++i) {
+                uint32_t* base = &qk[(size_t)i * 3 * K];
+                pack_key(queries.seqs[i].data(), len1 + len2, base, base + K, base + 2 * K);
+            }
+            d_q.upload(qk.data(), qk.size() * sizeof(uint32_t), c.stream);
+            SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            segmented_probe_kernel<K><<<grid, 128, 0, c.stream>>>(d_q.as<uint32_t>(), nsequences, libp, d_caps.as<int32_t>(), d_idx.as<int32_t>(),
+                                                                  d_mm.as<int32_t>());
+        });
+        SCG_CUDA_CHECK(cudaGetLastError());
+        ++c.launches;
+        SCG_CUDA_CHECK(cudaMemcpyAsync(index, d_idx.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaMemcpyAsync(mismatches, d_mm.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
     });
 }
 

@@ -204,6 +204,19 @@ def match_barcodes(sequences, choices, substitutions, reverse, device=None):
     return [[int(i) + 1 if i >= 0 else None for i in index], [int(m) if i >= 0 else None for i, m in zip(index, mm)]]
 
 
+def search_segmented(sequences, caps, choices, len1, len2, max1, max2, device=None):
+    """The two-segment search behind countDualBarcodes on its own (tests): per-query caps, 0-based index or -1."""
+    ctx = context(device)
+    qs, kq = _strs(sequences)
+    cs, kc = _strs(choices)
+    caps = np.ascontiguousarray(caps, dtype=np.int32).reshape(-1, 2)
+    index = np.zeros(len(sequences), dtype=np.int32)
+    mm = np.zeros(len(sequences), dtype=np.int32)
+    _check(ctx, lib().scg_search_segmented(ctx, qs, len(sequences), _ip(caps), cs, len(choices), int(len1), int(len2), int(max1),
+                                           int(max2), _ip(index), _ip(mm)))
+    return index, mm
+
+
 def timing(device=None):
     import json
     return json.loads(lib().scg_timing_json(context(device)).decode())

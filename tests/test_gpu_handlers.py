@@ -186,9 +186,13 @@ def test_dual_paired_against_reference(gpu, kref, diagnostics, randomized, use_f
 
 
 def test_dual_paired_unsupported_budget(gpu):
+    """2+ substitutions on read 1 walk the reference's trie on the device, which holds keys of up to 64 bases in total."""
     f = fastq(["ACGTAAAATG"])
-    with pytest.raises(Exception, match="2 or more substitutions on the first read"):
-        gpu.count_dual(f, "ACGT----TG", False, 2, ["AAAA"], f, "ACGT----TG", False, 0, ["AAAA"], False, True)
+    counts, total = gpu.count_dual(f, "ACGT----TG", False, 2, ["AAAA"], f, "ACGT----TG", False, 0, ["AAAA"], False, True)
+    assert total == 1 and counts.tolist() == [1]
+    long1, long2 = "A" * 40, "C" * 40
+    with pytest.raises(Exception, match="at most 64 bp in total"):
+        gpu.count_dual(f, "ACGT" + "-" * 40 + "TG", False, 2, [long1], f, "ACGT" + "-" * 40 + "TG", False, 0, [long2], False, True)
 
 
 def test_paired_read_count_mismatch(gpu):
