@@ -2,6 +2,8 @@
 // template-instantiation dispatch.
 #pragma once
 
+#include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -80,6 +82,49 @@ void dispatch_kw(int kw, F&& f) {
     } else {
         f(IntC<16>());
     }
+}
+
+// 128-bit key over everything that defines a matcher (handler kind, templates, options, the pools' sequences): calls that
+// repeat it (one call per FASTQ file of a screen, R/countDualBarcodes.R matrixOf* loops) find the tables already on the
+// device.  Only successfully built matchers are cached, so validation errors are raised every time.
+struct CacheKey {
+    unsigned long long k1 = 1469598103934665603ull, k2 = 0x9E3779B97F4A7C15ull;
+    void feed(const void* data, size_t n) {
+        const char* p = static_cast<const char*>(data);
+        k1 = mix64(k1 ^ n);
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            unsigned long long w;
+            std::memcpy(&w, p + i, 8);
+            k1 = mix64(k1 ^ w);
+            k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
+        }
+        unsigned long long w = 0;
+        if (i < n) std::memcpy(&w, p + i, n - i);
+        k1 = mix64(k1 ^ w);
+        k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
+    }
+    void feed(int v) { feed(&v, sizeof v); }
+    void feed(const std::string& s) { feed(s.data(), s.size()); }
+    void feed(const Pool& p) {
+        feed((int)p.seqs.size());
+        for (const auto& s : p.seqs) feed(s);
+    }
+};
+
+template <class M, class Build>
+std::shared_ptr<M> cached_matcher(Context& ctx, const CacheKey& key, Build&& build) {
+    for (auto& e : ctx.matcher_cache) {
+        if (e.key1 == key.k1 && e.key2 == key.k2) return std::static_pointer_cast<M>(e.object);
+    }
+    std::shared_ptr<M> m = build();
+    if (ctx.matcher_cache.size() >= 6) ctx.matcher_cache.erase(ctx.matcher_cache.begin());
+    Context::CachedObject entry;
+    entry.key1 = key.k1;
+    entry.key2 = key.k2;
+    entry.object = m;
+    ctx.matcher_cache.push_back(entry);
+    return m;
 }
 
 // Device scratch for per-read outputs of one batch, copied back after each batch when tracing.

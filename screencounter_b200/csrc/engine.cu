@@ -132,6 +132,7 @@ Context::~Context() {
         if (slot.done) cudaEventDestroy(slot.done);
     }
     single_cache.clear();
+    matcher_cache.clear();
     ingest[0].reset();
     ingest[1].reset();
     if (stream) cudaStreamDestroy(stream);

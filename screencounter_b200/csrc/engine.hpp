@@ -98,6 +98,12 @@ struct Context {
         std::shared_ptr<SingleMatcher> matcher;
     };
     std::vector<CachedMatcher> single_cache;
+    // matchers of the other handlers (any type behind the pointer; the key's first word names it), most recent last
+    struct CachedObject {
+        unsigned long long key1 = 0, key2 = 0;
+        std::shared_ptr<void> object;
+    };
+    std::vector<CachedObject> matcher_cache;
     DeviceBuffer slow_list, slow_count;      // reads the uniform-length kernel hands to its follow-up kernel (spec_single.cuh)
     std::shared_ptr<IngestBuffers> ingest[2];   // text ring, line tables and streams of the device-side FASTQ reader, per mate
     int device = 0;

@@ -149,10 +149,23 @@ int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* cons
         c.timing = Timing();
         Source source(src);
         Pool p1(pool1, npool1), p2(pool2, npool2);
-        ComboMatcher m;
-        m.prepare(constant, strand, p1, p2, mismatches, use_first != 0, Duplicates::ERROR);
+        CacheKey key;
+        {
+            const int header[5] = { /* combo single */ 3, strand, mismatches, use_first, 0 };
+            key.feed(header, sizeof header);
+            key.feed(std::string(constant));
+            key.feed(p1);
+            key.feed(p2);
+        }
+        const std::shared_ptr<ComboMatcher> mp = cached_matcher<ComboMatcher>(c, key, [&] {
+            auto built = std::make_shared<ComboMatcher>();
+            built->prepare(constant, strand, p1, p2, mismatches, use_first != 0, Duplicates::ERROR);
+            c.ensure_ready();
+            built->upload(c);
+            return built;
+        });
+        ComboMatcher& m = *mp;
         c.ensure_ready();
-        m.upload(c);
         ComboTally tally;
         tally.init(c, npool1, npool2);
         TraceSink trace;
@@ -193,22 +206,39 @@ int scg_count_dual_single_end(scg_ctx* ctx, const scg_source* src, const char* c
         Source source(src);
         std::vector<Pool> pools;
         for (int p = 0; p < npools; ++p) pools.emplace_back(pools_flat + (size_t)p * nchoices, nchoices);
-        DualSEMatcher m;
-        m.prepare(constant, pools, nchoices, strand, mismatches, use_first != 0);
-        ComboMatcher combo;
+        auto key_for = [&](int kind, int dup) {
+            CacheKey k;
+            const int header[6] = { kind, strand, mismatches, use_first, dup, npools };
+            k.feed(header, sizeof header);
+            k.feed(std::string(constant));
+            for (const auto& p : pools) k.feed(p);
+            return k;
+        };
+        const std::shared_ptr<DualSEMatcher> mp = cached_matcher<DualSEMatcher>(c, key_for(/* dual single-end */ 4, 0), [&] {
+            auto built = std::make_shared<DualSEMatcher>();
+            built->prepare(constant, pools, nchoices, strand, mismatches, use_first != 0);
+            if (diagnostics && npools != 2) throw Error("expected 2 variable regions in the constant template");
+            c.ensure_ready();
+            built->upload(c);
+            return built;
+        });
+        DualSEMatcher& m = *mp;
+        std::shared_ptr<ComboMatcher> combop;
         if (diagnostics) {
             // DualBarcodesSingleEndWithDiagnostics<_, 2> (reference handlers/DualBarcodesSingleEndWithDiagnostics.hpp:44-58):
             // two variable regions, each pool searched on its own with DuplicateAction::FIRST
             if (npools != 2) throw Error("expected 2 variable regions in the constant template");
-            combo.prepare(constant, strand, pools[0], pools[1], mismatches, use_first != 0, Duplicates::FIRST);
+            combop = cached_matcher<ComboMatcher>(c, key_for(/* combo single */ 3, 1), [&] {
+                auto built = std::make_shared<ComboMatcher>();
+                built->prepare(constant, strand, pools[0], pools[1], mismatches, use_first != 0, Duplicates::FIRST);
+                c.ensure_ready();
+                built->upload(c);
+                return built;
+            });
         }
         c.ensure_ready();
-        m.upload(c);
         ComboTally tally;
-        if (diagnostics) {
-            combo.upload(c);
-            tally.init(c, nchoices, nchoices);
-        }
+        if (diagnostics) tally.init(c, nchoices, nchoices);
         DeviceBuffer d_counts, d_index;
         d_counts.alloc((size_t)std::max(nchoices, 1) * sizeof(int32_t), true);
         const bool need_index = diagnostics || want_trace;
@@ -232,7 +262,7 @@ int scg_count_dual_single_end(scg_ctx* ctx, const scg_source* src, const char* c
             ++c.timing.launches;
             if (diagnostics) {
                 // only reads without a valid pair are tabulated (:99-104)
-                launch_combo(c, b.reads1, combo.params, tally.sink(c, b.n), d_index.as<int32_t>(), nullptr);
+                launch_combo(c, b.reads1, combop->params, tally.sink(c, b.n), d_index.as<int32_t>(), nullptr);
             }
             pipe.submitted(b);
             if (want_trace) {

@@ -146,11 +146,26 @@ int scg_count_combo_paired(scg_ctx* ctx, const scg_source* src1, const char* con
         Pool p1(pool1, npool1);
         Source s2(src2);
         Pool p2(pool2, npool2);
-        ComboPEMatcher m;
-        m.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0,
-                  Duplicates::ERROR);
+        auto key_for = [&](int kind, int dup) {
+            CacheKey k;
+            const int header[8] = { kind, reverse1, mismatches1, reverse2, mismatches2, randomized, use_first, dup };
+            k.feed(header, sizeof header);
+            k.feed(std::string(constant1));
+            k.feed(std::string(constant2));
+            k.feed(p1);
+            k.feed(p2);
+            return k;
+        };
+        const std::shared_ptr<ComboPEMatcher> mp = cached_matcher<ComboPEMatcher>(c, key_for(/* combo paired */ 2, 0), [&] {
+            auto built = std::make_shared<ComboPEMatcher>();
+            built->prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0,
+                           use_first != 0, Duplicates::ERROR);
+            c.ensure_ready();
+            built->upload(c);
+            return built;
+        });
+        ComboPEMatcher& m = *mp;
         c.ensure_ready();
-        m.upload(c);
         ComboTally tally;
         tally.init(c, npool1, npool2);
         DeviceBuffer d_counters, d_pairs, d_code;
@@ -210,24 +225,42 @@ int scg_count_dual(scg_ctx* ctx, const scg_source* src1, const char* constant1, 
         Pool p1(pool1, npool1);
         Source s2(src2);
         Pool p2(pool2, npool2);
-        DualPEMatcher m;
-        m.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0);
-        ComboPEMatcher combo;
+        auto key_for = [&](int kind, int dup) {
+            CacheKey k;
+            const int header[8] = { kind, reverse1, mismatches1, reverse2, mismatches2, randomized, use_first, dup };
+            k.feed(header, sizeof header);
+            k.feed(std::string(constant1));
+            k.feed(std::string(constant2));
+            k.feed(p1);
+            k.feed(p2);
+            return k;
+        };
+        const std::shared_ptr<DualPEMatcher> mp = cached_matcher<DualPEMatcher>(c, key_for(/* dual paired */ 1, 0), [&] {
+            auto built = std::make_shared<DualPEMatcher>();
+            built->prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0);
+            c.ensure_ready();
+            built->upload(c);
+            return built;
+        });
+        DualPEMatcher& m = *mp;
+        std::shared_ptr<ComboPEMatcher> combop;
         if (diagnostics) {
             // DualBarcodesPairedEndWithDiagnostics (reference handlers/DualBarcodesPairedEndWithDiagnostics.hpp:53-72):
             // the combinatorial sub-handler allows duplicated single barcodes (DuplicateAction::FIRST)
-            combo.prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0,
-                          use_first != 0, Duplicates::FIRST);
+            combop = cached_matcher<ComboPEMatcher>(c, key_for(/* combo paired */ 2, 1), [&] {
+                auto built = std::make_shared<ComboPEMatcher>();
+                built->prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0,
+                               use_first != 0, Duplicates::FIRST);
+                c.ensure_ready();
+                built->upload(c);
+                return built;
+            });
         }
         c.ensure_ready();
-        m.upload(c);
         ComboTally tally;
         DeviceBuffer d_counters;
         d_counters.alloc(2 * sizeof(int32_t), true);
-        if (diagnostics) {
-            combo.upload(c);
-            tally.init(c, npool1, npool2);
-        }
+        if (diagnostics) tally.init(c, npool1, npool2);
         DeviceBuffer d_counts, d_index;
         d_counts.alloc((size_t)std::max(npool1, 1) * sizeof(int32_t), true);
         const bool need_index = diagnostics || want_trace;
@@ -252,7 +285,7 @@ int scg_count_dual(scg_ctx* ctx, const scg_source* src1, const char* constant1, 
             ++c.timing.launches;
             if (diagnostics) {
                 // pairs without a valid combination go to the combinatorial handler (:115-120)
-                launch_combo_pe(c, b.reads1, b.reads2, combo.params, tally.sink(c, b.n), d_counters.as<int32_t>(), d_index.as<int32_t>(),
+                launch_combo_pe(c, b.reads1, b.reads2, combop->params, tally.sink(c, b.n), d_counters.as<int32_t>(), d_index.as<int32_t>(),
                                 nullptr, nullptr);
             }
             pipe.submitted(b);
