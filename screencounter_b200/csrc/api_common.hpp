@@ -146,8 +146,8 @@ struct SingleMatcher {
     TemplateSpec tmpl;
     DeviceLibrary lib_f, lib_r;
     DeviceBuffer libs_dev;   // LibDev[2] on the device: forward, reverse
-    DeviceBuffer compact;    // compact exact table of both strands (libdev.hpp SpecTables::compact), keys of up to 20 bases
-    uint32_t compact_shift = 0;
+    DeviceBuffer joint;      // exact table of both strands (libdev.hpp SpecTables::joint), keys of up to 31 bases
+    uint32_t joint_shift = 0;
     SingleParams params;
     int npool = 0;
     mutable std::string kernel_note;   // which kernel the last launch used, and why

@@ -26,7 +26,8 @@ struct SpecSingleConfig {
     // scan, several tiles per bulk copy) is compiled instead of the general one
     int ulen = 0;
     int info = 1;                 // the per-read info word may be asked for
-    int compact = 0;              // the compact exact table of both strands is there (keys of up to 20 bases)
+    int joint = 0;                // the joint exact table of both strands is there (keys of up to 31 bases)
+    int has_index = 1;            // the per-read index is asked for
     std::string key() const;
 };
 

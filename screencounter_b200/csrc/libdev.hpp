@@ -47,18 +47,18 @@ struct SpecTables {
     uint32_t bucket_mask[2];
     int nentries[2];
     const LibDev* libs;         // the full descriptors, for the generic search of the rare complicated reads
-    // Compact exact table of BOTH strands for keys of up to 20 bases (uniform-length kernel): buckets of two 8-byte slots,
-    // one bucket (one 16-byte load, one L2 sector) per lookup.  Slot = lo word: H bits | low 12 L bits << 20;
-    // hi word: high 8 L bits | strand << 8 | valid << 9 | bucket-overflowed << 10 (first slot only) | pool index << 11.
-    // A key whose bucket was full is simply absent (its bucket carries the overflow flag; the generic tables have it).
-    const uint4* compact;
-    uint32_t compact_shift;     // bucket = hash >> compact_shift
+    // Exact table of BOTH strands for keys of up to 31 bases (uniform-length kernel): a two-table cuckoo hash like the
+    // per-strand ones (16-byte slots: H word, L word, pool index, 0; empty = index -1) with the strand as bit 31 of the H
+    // word, so that the table's address and size are the same for every lane, and with a hash of three multiply-adds.
+    // Table 1 holds n = 1 << (32 - joint_shift) slots, table 2 the next n.
+    const uint4* joint;
+    uint32_t joint_shift;
 };
 
-// hash of a compact-table key (shared by the host builder and the kernel)
-SCG_HD uint32_t compact_hash(uint32_t key_lo, uint32_t key_hi) { return key_lo * 0x9E3779B1u + key_hi * 0x85EBCA6Bu; }
-constexpr int COMPACT_MAX_KEYLEN = 20;
-constexpr int COMPACT_MAX_POOL = (1 << 21) - 1;
+// the two homes of a key in the joint table (host builder and kernel alike): top bits of a multiplicative hash
+SCG_HD uint32_t joint_hash(uint32_t kh_tagged, uint32_t kl) { return kh_tagged * 0x9E3779B1u + kl * 0x85EBCA6Bu; }
+SCG_HD uint32_t joint_hash2(uint32_t x) { return x * 0xC2B2AE35u; }
+constexpr int JOINT_MAX_KEYLEN = 31;
 
 // Packed reads of one batch on the device.
 struct ReadsDev {

@@ -133,45 +133,77 @@ void SingleMatcher::upload(Context& ctx) {
     }
     params.libs = upload_lib_array(ctx, libs, libs_dev);
 
-    // Compact exact table (libdev.hpp): filled from the strands' cuckoo tables, so an exact lookup answers exactly what they
-    // answer; a key that finds its bucket full is left out and the bucket flagged.
-    compact.release();
-    compact_shift = 0;
+    // Joint exact table of both strands (libdev.hpp): filled from the strands' own cuckoo tables, so a lookup answers exactly
+    // what they answer.
+    joint.release();
+    joint_shift = 0;
     const Library* both[2] = { tmpl.fwd ? &lib_f.host : nullptr, tmpl.rev ? &lib_r.host : nullptr };
     const Library* any = both[0] ? both[0] : both[1];
-    if (any && any->KW == 1 && any->L <= COMPACT_MAX_KEYLEN && npool <= COMPACT_MAX_POOL) {
-        size_t total = 0;
-        for (const Library* lib : both) total += lib ? lib->nentries() : 0;
-        uint32_t bits = 4;
-        while ((1ull << bits) < 3ull * total + 1 && bits < 28) ++bits;
-        const size_t nb = (size_t)1 << bits;
-        std::vector<uint32_t> table(nb * 4, 0);
+    if (any && any->KW == 1 && any->L <= JOINT_MAX_KEYLEN) {
+        struct Entry {
+            uint32_t kh, kl;
+            int32_t value;
+        };
+        std::vector<Entry> entries;
         for (int strand = 0; strand < 2; ++strand) {
             const Library* lib = both[strand];
             if (!lib) continue;
             const size_t nslots = lib->slots.size() / lib->slot_words;
             for (size_t k = 0; k < nslots; ++k) {
                 const uint32_t* slot = &lib->slots[k * lib->slot_words];
-                const int32_t value = (int32_t)slot[2];
-                if (value < 0) continue;   // empty
-                const uint32_t kh = slot[0], kl = slot[1];
-                const uint32_t lo = kh | (kl << 20);
-                const uint32_t hi = (kl >> 12) | ((uint32_t)strand << 8) | (1u << 9);
-                uint32_t* bucket = &table[(size_t)(compact_hash(lo, hi) >> (32 - bits)) * 4];
-                if (!(bucket[1] & (1u << 9))) {
-                    bucket[0] = lo;
-                    bucket[1] = hi | ((uint32_t)value << 11);
-                } else if (!(bucket[3] & (1u << 9))) {
-                    bucket[2] = lo;
-                    bucket[3] = hi | ((uint32_t)value << 11);
-                } else {
-                    bucket[1] |= 1u << 10;
-                }
+                if ((int32_t)slot[2] < 0) continue;   // empty
+                entries.push_back(Entry{ slot[0] | ((uint32_t)strand << 31), slot[1], (int32_t)slot[2] });
             }
         }
-        compact.upload(table.data(), table.size() * sizeof(uint32_t), ctx.stream);
+        uint32_t bits = 4;
+        while ((1ull << bits) < entries.size() + 1 && bits < 28) ++bits;
+        std::vector<uint32_t> table;
+        for (;; ++bits) {
+            if (bits > 29) throw Error("could not build the joint barcode hash table");
+            const size_t n = (size_t)1 << bits;
+            table.assign(2 * n * 4, 0);
+            for (size_t k = 0; k < 2 * n; ++k) table[4 * k + 2] = 0xFFFFFFFFu;
+            auto home = [&](const Entry& e, int t) {
+                const uint32_t x = joint_hash(e.kh, e.kl);
+                return (size_t)t * n + ((t == 0 ? x : joint_hash2(x)) >> (32 - bits));
+            };
+            bool ok = true;
+            for (size_t i = 0; i < entries.size() && ok; ++i) {
+                Entry cur = entries[i];
+                int t = 0;
+                ok = false;
+                for (int kicks = 0; kicks < 2000; ++kicks) {
+                    uint32_t* slot = &table[4 * home(cur, t)];
+                    if ((int32_t)slot[2] < 0) {
+                        slot[0] = cur.kh;
+                        slot[1] = cur.kl;
+                        slot[2] = (uint32_t)cur.value;
+                        ok = true;
+                        break;
+                    }
+                    if (kicks == 0) {   // try the other home before evicting anyone
+                        uint32_t* other = &table[4 * home(cur, 1)];
+                        if ((int32_t)other[2] < 0) {
+                            other[0] = cur.kh;
+                            other[1] = cur.kl;
+                            other[2] = (uint32_t)cur.value;
+                            ok = true;
+                            break;
+                        }
+                    }
+                    const Entry evicted{ slot[0], slot[1], (int32_t)slot[2] };
+                    slot[0] = cur.kh;
+                    slot[1] = cur.kl;
+                    slot[2] = (uint32_t)cur.value;
+                    cur = evicted;
+                    t ^= 1;
+                }
+            }
+            if (ok) break;
+        }
+        joint.upload(table.data(), table.size() * sizeof(uint32_t), ctx.stream);
         SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
-        compact_shift = 32 - bits;
+        joint_shift = 32 - bits;
     }
 }
 
@@ -271,10 +303,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             cfg.T <= 128 && reads.W + 2 >= (cfg.T + 31) / 32 + 1 && reads.n <= 0x7FFFFFC0ll) {
             cfg.ulen = reads.uniform_len;
             cfg.info = d_info ? 1 : 0;
-            // the compact table halves the probe traffic (one L2 sector per read instead of two) but costs a few more ALU
-            // instructions per read; on the benchmark the kernel is ALU-bound and 2.4 % slower with it, so it is opt-in
-            const char* want_compact = std::getenv("SCG_SPEC_COMPACT");
-            cfg.compact = (m.compact.ptr != nullptr && m.compact_shift != 0 && want_compact && *want_compact == '1') ? 1 : 0;
+            cfg.joint = (m.joint.ptr != nullptr && m.joint_shift != 0 && !std::getenv("SCG_SPEC_NO_JOINT")) ? 1 : 0;
+            cfg.has_index = d_index ? 1 : 0;
         }
     }
     std::string why;
@@ -295,8 +325,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             tables.nentries[s] = both[s]->dev.nentries;
         }
         tables.libs = P.libs;
-        tables.compact = m.compact.as<uint4>();
-        tables.compact_shift = m.compact_shift;
+        tables.joint = m.joint.as<uint4>();
+        tables.joint_shift = m.joint_shift;
         // persistent warps: as many blocks as are resident at once, each warp strides over the tiles
         const int resident = specialised_blocks_per_sm(spec);
         const int spec_grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * resident));

@@ -98,9 +98,13 @@
 #ifndef SPEC_INFO
 #define SPEC_INFO 1
 #endif
-// the compact exact table of both strands (libdev.hpp SpecTables::compact) is there: one 16-byte load per lookup
-#ifndef SPEC_COMPACT
-#define SPEC_COMPACT 0
+// the joint exact table of both strands (libdev.hpp SpecTables::joint) is there: same table for every lane, cheap hash
+#ifndef SPEC_JOINT
+#define SPEC_JOINT 0
+#endif
+// the caller asks for the per-read index (always, in practice; without it the stores and their null checks go away)
+#ifndef SPEC_HAS_INDEX
+#define SPEC_HAS_INDEX 1
 #endif
 
 namespace scg {
@@ -875,6 +879,14 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         if (warp + s * nwarps < ngroups) fetch(warp + s * nwarps, (uint32_t)s);
     }
 
+    // What a lane carries from one tile to the next: the slots of its candidate's variable region (requested after the scan,
+    // looked at one tile later), the region itself, and the flags below.
+    //   PM_CAND     a window passed the verify         PM_PROBED  the slots were requested (no N in the region)
+    //   PM_MANY     more than one verified window      PM_REV     the first one is on the reverse strand
+    //   PM_INRANGE  the lane holds a real read
+    //   PU_MISS_DEFERS  (bit 25) if the probe misses, the read is deferred (budget left for the seeded search, or other windows)
+    //   PU_ALWAYS_DEFERS (bit 24) deferred whatever the probe says (best mode with several windows)
+    constexpr uint32_t PU_MISS_DEFERS = 1u << 25, PU_ALWAYS_DEFERS = 1u << 24;
     Pending pend;
     pend.meta = 0;
     pend.a = pend.b = make_uint4(0, 0, 0, 0);
@@ -888,9 +900,9 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         tiles_here = min(GROUP, ntiles - GROUP * group);
     }
     for (;;) {
-        Words R;
-        uint32_t meta = 0, kh = 0, kl = 0, kn = 0;
+        uint32_t meta = 0, kh = 0, kl = 0, kn = 0, i = 0;
         if (have) {
+            Words R;
             const uint32_t* buf = stage_all[wib][stage] + tile_in_group * TILE_WORDS + lane;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
@@ -900,7 +912,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             }
             R.h[W] = R.l[W] = R.n[W] = 0;
             R.h[W + 1] = R.l[W + 1] = R.n[W + 1] = 0;
-            const uint32_t i = (uint32_t)(group * GROUP + tile_in_group) * TILE + lane;
+            i = (uint32_t)(group * GROUP + tile_in_group) * TILE + lane;
             const bool inrange = i < n;
             Planes P;
             make_planes(R, P);
@@ -909,24 +921,25 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             const uint32_t live = inrange ? WINMASK : 0u;
             uint32_t cf = SPEC_FWD ? candidate_windows<false>(P, live) : 0u;
             uint32_t cr = SPEC_REV ? candidate_windows<true>(P, live) : 0u;
-            // ---- verify: exact constant mismatches of each candidate, in the reference's order ----
+            // ---- verify: exact constant mismatches of each candidate, in the reference's order (positions ascending, forward
+            // before reverse).  The first round runs unconditionally (nine reads in ten have a candidate); further rounds only
+            // while some lane still has one. ----
             int ncand = 0;
-            while (__any_sync(0xFFFFFFFFu, (cf | cr) != 0u)) {
+            do {
                 const uint32_t any = cf | cr;
-                const bool some = any != 0u;
-                const int p = some ? __ffs(any) - 1 : 0;
-                const bool rev = SPEC_FWD ? !((cf >> p) & 1u) : true;
-                const uint32_t bit = some ? (1u << p) : 0u;
+                const uint32_t lowest = any & (0u - any);   // 0 when the lane has no candidate left
+                const int p = 31 - __clz(lowest | 1u);
+                const bool rev = SPEC_FWD ? !(cf & lowest) : true;
                 if (rev) {
-                    cr &= ~bit;
+                    cr &= ~lowest;
                 } else {
-                    cf &= ~bit;
+                    cf &= ~lowest;
                 }
                 uint32_t wh[TW + 1], wl[TW + 1], wn[TW + 1];
                 const int c = verify_window(R, p, rev, wh, wl, wn);
-                const bool ok = some && c <= SPEC_MM;
+                const bool ok = lowest != 0u && c <= SPEC_MM;
                 if (ok && ncand == 0) {
-                    meta = PM_CAND | (rev ? PM_REV : 0u) | ((uint32_t)c << 16) | (uint32_t)p;
+                    meta = PM_CAND + (rev ? PM_REV : 0u) + ((uint32_t)c << 16) + (uint32_t)p;
                     if (SPEC_FSTART == SPEC_RSTART || !SPEC_REV || !SPEC_FWD) {
                         constexpr int START = (SPEC_FWD && SPEC_REV) ? SPEC_FSTART : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
                         kh = window_key<START>(wh);
@@ -939,8 +952,17 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                     }
                 }
                 ncand += ok ? 1 : 0;
+            } while (__any_sync(0xFFFFFFFFu, (cf | cr) != 0u));
+            // what the settle step will need to know, decided here once
+            {
+                const bool many = ncand > 1;
+                const int fc = (int)((meta >> 16) & 0xFFu);
+                const bool cand = (meta & PM_CAND) != 0;
+                const bool miss_defers = cand && ((SPEC_MAXMM - fc >= 1) || many);
+                const bool always_defers = cand && many && !SPEC_USE_FIRST;
+                meta += (inrange ? PM_INRANGE : 0u) + (many ? PM_MANY : 0u) + (miss_defers ? PU_MISS_DEFERS : 0u) +
+                        (always_defers ? PU_ALWAYS_DEFERS : 0u);
             }
-            meta |= (inrange ? PM_INRANGE : 0u) | (ncand > 1 ? PM_MANY : 0u);
 
             // the group's buffer goes back to the TMA once every lane has consumed its last tile
             if (++tile_in_group == tiles_here) {
@@ -951,31 +973,21 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         }
 
         // ---- settle the PREVIOUS tile: its table slots were requested one scan ago ----
-        if (__any_sync(0xFFFFFFFFu, pend.meta != 0)) {
-            uint32_t m = pend.meta;
+        {
+            const uint32_t m = pend.meta;
             int index = -1;
-            bool unresolved = false;   // compact table only: the key's bucket was full when the table was built
             if (m & PM_PROBED) {
-#if SPEC_COMPACT
-                const bool hit0 = pend.a.x == pend.kh && (pend.a.y & 0x3FFu) == pend.kl;
-                const bool hit1 = pend.a.z == pend.kh && (pend.a.w & 0x3FFu) == pend.kl;
-                index = hit0 ? (int)(pend.a.y >> 11) : (hit1 ? (int)(pend.a.w >> 11) : -1);
-                unresolved = index < 0 && ((pend.a.y >> 10) & 1u);
-#else
                 const int ra = (pend.a.x == pend.kh && pend.a.y == pend.kl) ? (int)pend.a.z : -1;
                 const int rb = (pend.b.x == pend.kh && pend.b.y == pend.kl) ? (int)pend.b.z : -1;
                 index = max(ra, rb);
-#endif
             }
-            const int pfc = (int)((m >> 16) & 0xFFu), pfp = (int)(m & 0xFFFFu);
-            const bool found = index >= 0 && (SPEC_USE_FIRST || !(m & PM_MANY));
-            // an unresolved exact lookup with no budget left for the seeded search goes the way of the multi-window reads
-            if (unresolved && SPEC_MAXMM - pfc < 1) m |= PM_MANY;
-            const bool defer = (m & PM_CAND) && !found && ((SPEC_MAXMM - pfc >= 1) || (m & PM_MANY));
+            const bool defer = (m & PU_ALWAYS_DEFERS) || ((m & PU_MISS_DEFERS) && index < 0);
             if ((m & PM_INRANGE) && !defer) {
-                if (found) atomicAdd(counts + index, 1);
-                if (out_index) __stcs(out_index + pend.i, found ? index : -1);
-                if (SPEC_INFO && out_info) __stcs(out_info + pend.i, pack_info(found, (m & PM_REV) != 0, pfc, 0, pfp));
+                if (index >= 0) atomicAdd(counts + index, 1);
+                if (SPEC_HAS_INDEX) __stcs(out_index + pend.i, index);
+                if (SPEC_INFO && out_info) {
+                    __stcs(out_info + pend.i, pack_info(index >= 0, (m & PM_REV) != 0, (int)((m >> 16) & 0xFFu), 0, (int)(m & 0xFFFFu)));
+                }
             }
             const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
             if (dm) {
@@ -983,13 +995,12 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                     const int at = waiting + __popc(dm & lanes_below);
                     queue[0][at] = pend.i;
                     queue[1][at] = m;
-#if SPEC_COMPACT
-                    queue[2][at] = pend.kh & 0xFFFFFu;
-                    queue[3][at] = (pend.kh >> 20) | ((pend.kl & 0xFFu) << 12);
+#if SPEC_JOINT
+                    queue[2][at] = pend.kh & 0x7FFFFFFFu;
 #else
                     queue[2][at] = pend.kh;
-                    queue[3][at] = pend.kl;
 #endif
+                    queue[3][at] = pend.kl;
                     queue[4][at] = (m & PM_PROBED) ? 0u : pend.a.x;
                 }
                 waiting += __popc(dm);
@@ -999,34 +1010,31 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
 
         // ---- this tile's first candidate: request the two slots of its variable region ----
         pend.meta = meta;
-        if (have) {
-            pend.i = (uint32_t)(group * GROUP + tile_in_group - 1) * TILE + lane;
-#if SPEC_COMPACT
-            // both strands share one table of 8-byte slots: the strand is a key bit, a lookup is one 16-byte bucket
-            const uint32_t klo = kh | (kl << 20);
-            const uint32_t khi = (kl >> 12) | ((meta & PM_REV) ? 0x300u : 0x200u);
-            pend.kh = klo;
-            pend.kl = khi;
-            pend.a.x = kn;
-            if ((meta & PM_CAND) && kn == 0) {
-                pend.a = __ldg(tb.compact + (compact_hash(klo, khi) >> tb.compact_shift));
-                pend.meta |= PM_PROBED;
-            }
-#else
-            pend.kh = kh;
-            pend.kl = kl;
-            pend.a.x = kn;
-            if ((meta & PM_CAND) && kn == 0) {
-                const bool frev = (meta & PM_REV) != 0;
-                const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
-                const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
-                const uint32_t acc = hash_key(&kh, &kl, 1, 0);
-                pend.a = __ldg(slots + (acc & mask));
-                pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
-                pend.meta |= PM_PROBED;
-            }
-#endif
+        pend.i = i;
+        pend.kl = kl;
+        pend.a.x = kn;
+#if SPEC_JOINT
+        // one table for both strands: the strand is bit 31 of the H word, the homes are the top bits of two multiply-adds
+        pend.kh = kh + ((meta & PM_REV) ? 0x80000000u : 0u);
+        if ((meta & PM_CAND) && kn == 0) {
+            const uint32_t x = joint_hash(pend.kh, kl);
+            const uint32_t second = (1u << (32 - tb.joint_shift)) + (joint_hash2(x) >> tb.joint_shift);
+            pend.a = __ldg(tb.joint + (x >> tb.joint_shift));
+            pend.b = __ldg(tb.joint + second);
+            pend.meta = meta + PM_PROBED;
         }
+#else
+        pend.kh = kh;
+        if ((meta & PM_CAND) && kn == 0) {
+            const bool frev = (meta & PM_REV) != 0;
+            const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
+            const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
+            const uint32_t acc = hash_key(&kh, &kl, 1, 0);
+            pend.a = __ldg(slots + (acc & mask));
+            pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+            pend.meta = meta + PM_PROBED;
+        }
+#endif
 
         // ---- deferred reads: searched when a warp's worth is waiting, and whatever is left at the end ----
         while (waiting >= 32 || (!have && waiting > 0)) {
@@ -1051,7 +1059,6 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         }
     }
 }
-
 
 // The reads the kernel above could not settle (several candidate windows): the full per-read search, one lane per
 // listed read, any grid.

@@ -79,11 +79,13 @@ def test_many_tiles_per_warp(kref, use_first):
 
 
 @pytest.mark.parametrize("mm", [0, 1, 2])
-def test_compact_exact_table(kref, monkeypatch, mm):
-    """The opt-in one-load exact table of the uniform-length kernel (SCG_SPEC_COMPACT=1), all three budgets (a handful of
-    the 6,000 keys find their bucket full and take the "bucket was full" route)."""
+@pytest.mark.parametrize("joint", [True, False])
+def test_exact_table_variants(kref, monkeypatch, mm, joint):
+    """The uniform-length kernel with the joint exact table of both strands (default) and with the per-strand tables
+    (SCG_SPEC_NO_JOINT=1), all three budgets."""
     from screencounter_b200.device import SynthSpec, SinglePlan, DeviceArray
-    monkeypatch.setenv("SCG_SPEC_COMPACT", "1")
+    if not joint:
+        monkeypatch.setenv("SCG_SPEC_NO_JOINT", "1")
     rng = np.random.default_rng(6 + mm)
     pool = distinct_pool(rng, 3000, 20)
     spec = SynthSpec(TEMPLATE, [pool], seed=12, read_len=75, strand=2, sub_per_10k=200, n_per_10k=20)
