@@ -1019,8 +1019,9 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         if ((meta & PM_CAND) && kn == 0) {
             const uint32_t x = joint_hash(pend.kh, kl);
             const uint32_t second = (1u << (32 - tb.joint_shift)) + (joint_hash2(x) >> tb.joint_shift);
-            pend.a = __ldg(tb.joint + (x >> tb.joint_shift));
-            pend.b = __ldg(tb.joint + second);
+            // scattered 16-byte loads that never hit L1: .cg keeps them out of it (measured + 1.7 %)
+            pend.a = __ldcg(tb.joint + (x >> tb.joint_shift));
+            pend.b = __ldcg(tb.joint + second);
             pend.meta = meta + PM_PROBED;
         }
 #else
@@ -1030,8 +1031,8 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
             const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
             const uint32_t acc = hash_key(&kh, &kl, 1, 0);
-            pend.a = __ldg(slots + (acc & mask));
-            pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+            pend.a = __ldcg(slots + (acc & mask));
+            pend.b = __ldcg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
             pend.meta = meta + PM_PROBED;
         }
 #endif
