@@ -51,11 +51,23 @@ Nvrtc& nvrtc() {
                                   "libnvrtc.so.13", "libnvrtc.so" }) {
             candidates.push_back(name);
         }
-        for (const auto& c : candidates) {
-            n.handle = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
-            if (n.handle) {
-                n.where = c;
-                break;
+        // An explicit path wins; otherwise the NEWEST of the candidates: a host process may already carry an older NVRTC
+        // under the bare soname (PyTorch bundles one), and the kernels are written against the toolkit's PTX version.
+        int best_version = -1;
+        for (size_t k = 0; k < candidates.size(); ++k) {
+            void* h = dlopen(candidates[k].c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (!h) continue;
+            int major = 0, minor = 0;
+            auto version = reinterpret_cast<nvrtcResult (*)(int*, int*)>(dlsym(h, "nvrtcVersion"));
+            if (version) version(&major, &minor);
+            const int v = (k == 0 && std::getenv("SCG_NVRTC_PATH")) ? (1 << 30) : major * 1000 + minor;
+            if (v > best_version) {
+                if (n.handle) dlclose(n.handle);
+                n.handle = h;
+                n.where = candidates[k];
+                best_version = v;
+            } else {
+                dlclose(h);
             }
         }
         if (!n.handle) {
