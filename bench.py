@@ -111,6 +111,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this rank's threads (and, by first touch, its page-locked FASTQ text) on the CPU cores that
+    are local to its GPU's PCIe root, like a numactl line in a launch script would.  Best effort; returns what it did."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        domain, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (domain[-4:], rest)
+        with open(path) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d cores local to %s" % (len(cpus), bus)
+    except Exception:
+        return None
+
+
 def reference_arm(args, library):
     """The reference's own CPU implementation of the path (kaori compiled from /root/reference in
     oracle/_ref, else the C restatement) on all host cores, on a bounded sample of the workload."""
@@ -170,6 +195,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_near_gpu(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -244,7 +270,7 @@ def main():
     # the device (157 B/read over PCIe), splits and packs the records there, counts, and reads the count vector back.
     e2e_reads = args.e2e_reads
     text = spec.fastq_pinned(first, e2e_reads, device=local_rank)
-    nthreads = os.cpu_count() or 1
+    nthreads = len(os.sched_getaffinity(0)) or 1
     for _ in range(2):
         rcpp.count_single_barcodes(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
     barrier()
@@ -312,7 +338,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
                 "d2h_bytes_per_step": 4 * len(library), "reads_per_step": e2e_reads, "host_threads": nthreads,
                 "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "total_s")},
-                "reader": stage.get("reader"),
+                "reader": stage.get("reader"), "cpu_binding": binding,
                 "note": "FASTQ text in page-locked host memory -> scg_count_single: text H2D in 32 MiB chunks, records split + packed "
                         "by kernels (ingest.cu), scan/lookup/count kernel per chunk, counts D2H; wall clock around the calls"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
