@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "api_common.hpp"
+#include "hostpool.hpp"
 #include "handlers.cuh"
 #include "jit.hpp"
 
@@ -214,25 +215,46 @@ void SingleMatcher::upload(Context& ctx) {
 // every validation when the entry was made.  A miss marshals the pool, validates, builds and uploads.
 std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* constant, int strand, const char* const* pool, int npool,
                                                      int mismatches, bool use_first) {
-    unsigned long long k1 = 1469598103934665603ull, k2 = 0x9E3779B97F4A7C15ull;
-    auto feed = [&](const char* data, size_t n) {
-        k1 = mix64(k1 ^ n);
+    // The pool's strings are separate allocations (one cache miss each): pieces of the pool are hashed on the host threads,
+    // every piece into its own pair of words, and the pairs are folded in order.
+    struct Pair {
+        unsigned long long k1, k2;
+    };
+    auto feed = [](Pair& h, const char* data, size_t n) {
+        h.k1 = mix64(h.k1 ^ n);
         size_t i = 0;
         for (; i + 8 <= n; i += 8) {
             unsigned long long w;
             std::memcpy(&w, data + i, 8);
-            k1 = mix64(k1 ^ w);
-            k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
+            h.k1 = mix64(h.k1 ^ w);
+            h.k2 = (h.k2 ^ w) * 1099511628211ull + (h.k2 >> 29);
         }
         unsigned long long w = 0;
         if (i < n) std::memcpy(&w, data + i, n - i);
-        k1 = mix64(k1 ^ w);
-        k2 = (k2 ^ w) * 1099511628211ull + (k2 >> 29);
+        h.k1 = mix64(h.k1 ^ w);
+        h.k2 = (h.k2 ^ w) * 1099511628211ull + (h.k2 >> 29);
     };
+    Pair total{ 1469598103934665603ull, 0x9E3779B97F4A7C15ull };
     const int header[4] = { strand, mismatches, use_first ? 1 : 0, npool };
-    feed(reinterpret_cast<const char*>(header), sizeof header);
-    feed(constant, std::strlen(constant));
-    for (int i = 0; i < npool; ++i) feed(pool[i], std::strlen(pool[i]));
+    feed(total, reinterpret_cast<const char*>(header), sizeof header);
+    feed(total, constant, std::strlen(constant));
+    {
+        const int pieces = npool >= 4096 ? 16 : 1;
+        std::vector<Pair> part((size_t)pieces);
+        auto work = [&](int k) {
+            Pair h{ 1469598103934665603ull + (unsigned long long)k, 0x9E3779B97F4A7C15ull };
+            const int b = (int)((long long)npool * k / pieces), e = (int)((long long)npool * (k + 1) / pieces);
+            for (int i = b; i < e; ++i) feed(h, pool[i], std::strlen(pool[i]));
+            part[(size_t)k] = h;
+        };
+        if (pieces > 1) {
+            HostPool::instance().parallel_for(pieces, pieces, work);
+        } else {
+            work(0);
+        }
+        for (const Pair& h : part) feed(total, reinterpret_cast<const char*>(&h), sizeof h);
+    }
+    const unsigned long long k1 = total.k1, k2 = total.k2;
     for (auto& e : ctx.single_cache) {
         if (e.key1 == k1 && e.key2 == k2) return e.matcher;
     }
