@@ -36,6 +36,8 @@ public:
         (void)size;
         return false;
     }
+    // Host threads the input may use for its own work (block-gzip inflates its blocks in parallel).
+    virtual void set_threads(int n) { (void)n; }
 };
 
 namespace {
@@ -121,6 +123,133 @@ private:
     bool eof_ = false;
 };
 
+// Block gzip (BGZF: what bgzip and Illumina's bcl-convert / bcl2fastq write): a chain of gzip members of at most 64 KiB,
+// each announcing its compressed size in a 'BC' extra field, so the members can be found without inflating and inflated
+// independently -- here on the host thread pool, where kaori (byteme::GzipFileReader over gzread, one thread) goes member
+// by member.  The text is the same; plain gzip streams keep GzInput.
+class BgzfInput : public FastqInput {
+public:
+    // nullptr when the file is not a complete chain of BGZF members
+    static std::unique_ptr<FastqInput> open(int fd, size_t size) {
+        if (size < 28) return nullptr;
+        void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (map == MAP_FAILED) return nullptr;
+        std::unique_ptr<BgzfInput> in(new BgzfInput(fd, map, size));
+        if (!in->index()) {
+            in->fd_ = -1;   // the caller keeps the descriptor
+            return nullptr;
+        }
+        madvise(map, size, MADV_SEQUENTIAL);
+        return std::unique_ptr<FastqInput>(in.release());
+    }
+    ~BgzfInput() override {
+        if (map_) munmap(map_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    void set_threads(int n) override { threads_ = n < 1 ? 1 : n; }
+    void window(size_t keep_from, const char** base, size_t* avail, bool* final) override {
+        const size_t tail = filled_ - keep_from;
+        if (keep_from > 0 && tail > 0) std::memmove(buf_.data(), buf_.data() + keep_from, tail);
+        filled_ = tail;
+        if (next_ < blocks_.size()) {
+            // the next batch of members: about kBatch bytes of text
+            size_t last = next_, bytes = 0;
+            while (last < blocks_.size() && (bytes == 0 || bytes + blocks_[last].isize <= kBatch)) bytes += blocks_[last++].isize;
+            if (buf_.size() < filled_ + bytes) buf_.resize(filled_ + bytes);
+            std::vector<size_t> at(last - next_ + 1, filled_);
+            for (size_t k = next_; k < last; ++k) at[k - next_ + 1] = at[k - next_] + blocks_[k].isize;
+            const int nblocks = (int)(last - next_);
+            const int pieces = std::max(1, std::min(nblocks, threads_ * 4));
+            std::vector<int> failed((size_t)pieces, 0);
+            char* out = buf_.data();
+            const unsigned char* file = static_cast<const unsigned char*>(map_);
+            const size_t first = next_;
+            HostPool::instance().parallel_for(pieces, std::min(pieces, threads_), [&](int p) {
+                const int b = (int)((long long)nblocks * p / pieces), e = (int)((long long)nblocks * (p + 1) / pieces);
+                z_stream z;
+                std::memset(&z, 0, sizeof z);
+                if (inflateInit2(&z, -15) != Z_OK) {
+                    failed[(size_t)p] = 1;
+                    return;
+                }
+                for (int k = b; k < e; ++k) {
+                    const Block& blk = blocks_[first + (size_t)k];
+                    inflateReset(&z);
+                    z.next_in = const_cast<unsigned char*>(file + blk.data);
+                    z.avail_in = blk.csize;
+                    z.next_out = reinterpret_cast<unsigned char*>(out + at[(size_t)k]);
+                    z.avail_out = blk.isize;
+                    const int rc = blk.isize == 0 && blk.csize == 2 ? Z_STREAM_END : inflate(&z, Z_FINISH);
+                    const bool empty = blk.isize == 0;
+                    if (!empty && (rc != Z_STREAM_END || z.avail_out != 0 ||
+                                   crc32(0L, reinterpret_cast<const unsigned char*>(out + at[(size_t)k]), blk.isize) != blk.crc)) {
+                        failed[(size_t)p] = 1;
+                        break;
+                    }
+                }
+                inflateEnd(&z);
+            });
+            for (int f : failed) {
+                if (f) throw Error("failed to inflate the block-gzip file (corrupt member)");
+            }
+            filled_ = at.back();
+            next_ = last;
+        }
+        *base = buf_.data();
+        *avail = filled_;
+        *final = next_ >= blocks_.size();
+    }
+
+private:
+    struct Block {
+        size_t data;       // offset of the raw deflate stream
+        uint32_t csize;    // its length
+        uint32_t isize;    // text bytes
+        uint32_t crc;
+    };
+    static constexpr size_t kBatch = 64u << 20;
+
+    BgzfInput(int fd, void* map, size_t size) : fd_(fd), map_(map), size_(size) {}
+
+    // walks the member chain; false unless every byte of the file belongs to a well-formed BGZF member
+    bool index() {
+        const unsigned char* f = static_cast<const unsigned char*>(map_);
+        size_t p = 0;
+        while (p < size_) {
+            if (size_ - p < 18) return false;
+            if (f[p] != 0x1f || f[p + 1] != 0x8b || f[p + 2] != 8 || f[p + 3] != 4) return false;   // FLG = FEXTRA only
+            const size_t xlen = f[p + 10] | ((size_t)f[p + 11] << 8);
+            if (size_ - p < 12 + xlen + 8) return false;
+            size_t bsize = 0;
+            for (size_t q = p + 12; q + 4 <= p + 12 + xlen;) {
+                const size_t slen = f[q + 2] | ((size_t)f[q + 3] << 8);
+                if (f[q] == 'B' && f[q + 1] == 'C' && slen == 2 && q + 6 <= p + 12 + xlen) bsize = (f[q + 4] | ((size_t)f[q + 5] << 8)) + 1;
+                q += 4 + slen;
+            }
+            if (bsize < 12 + xlen + 8 || bsize > size_ - p) return false;
+            Block b;
+            b.data = p + 12 + xlen;
+            b.csize = (uint32_t)(bsize - 12 - xlen - 8);
+            const unsigned char* t = f + p + bsize - 8;
+            b.crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            b.isize = t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (b.isize > (1u << 16)) return false;   // BGZF members hold at most 64 KiB of text
+            blocks_.push_back(b);
+            p += bsize;
+        }
+        return !blocks_.empty();
+    }
+
+    int fd_;
+    void* map_;
+    size_t size_;
+    int threads_ = 1;
+    std::vector<Block> blocks_;
+    size_t next_ = 0;
+    std::vector<char> buf_;
+    size_t filled_ = 0;
+};
+
 std::unique_ptr<FastqInput> open_input(const char* path, const char* data, size_t size) {
     if (!path) return std::unique_ptr<FastqInput>(new MemoryInput(data, size));
     // byteme::SomeFileReader (inst/include/byteme/SomeFileReader.hpp:31-44): sniff the gzip magic.
@@ -129,6 +258,11 @@ std::unique_ptr<FastqInput> open_input(const char* path, const char* data, size_
     unsigned char header[2];
     ssize_t got = read(fd, header, 2);
     if (got == 2 && header[0] == 0x1f && header[1] == 0x8b) {
+        struct stat gst;
+        if (fstat(fd, &gst) == 0 && gst.st_size > 0 && !std::getenv("SCG_NO_BGZF")) {
+            std::unique_ptr<FastqInput> bgzf = BgzfInput::open(fd, (size_t)gst.st_size);
+            if (bgzf) return bgzf;   // owns the descriptor now
+        }
         close(fd);
         return std::unique_ptr<FastqInput>(new GzInput(path));
     }
@@ -163,6 +297,11 @@ double now_s() {
 FastqReader::FastqReader(const char* path, const char* data, size_t size) : in_(open_input(path, data, size)) {}
 
 FastqReader::~FastqReader() {}
+
+void FastqReader::set_threads(int n) {
+    threads_ = n < 1 ? 1 : n;
+    in_->set_threads(threads_);
+}
 
 bool FastqReader::memory_text(const char** data, size_t* size) const {
     return !started_ && in_->memory(data, size);

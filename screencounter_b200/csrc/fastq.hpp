@@ -42,7 +42,7 @@ public:
     const std::vector<Record>& next(size_t max_records);
 
     // Threads the record splitter may use on inputs that are entirely in memory (caller's buffer, mmap'd file).
-    void set_threads(int n) { threads_ = n < 1 ? 1 : n; }
+    void set_threads(int n);
 
     // shortest / longest read of the batch returned by the last next()
     uint32_t batch_min_len() const { return batch_min_len_; }

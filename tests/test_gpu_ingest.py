@@ -192,6 +192,22 @@ def test_files_take_the_device_reader(gpu, kref, monkeypatch, tmp_path):
     assert got[1] == want[1] and np.array_equal(got[0], want[0])
 
 
+def test_block_gzip_file(gpu, kref, monkeypatch, tmp_path):
+    """A BGZF file is inflated member-parallel on the host and parsed there; a plain gzip file goes member by member."""
+    import gzip
+    from util import bgzf
+    pool, reads = _case(16, n=30000)
+    data = fastq(reads)
+    want = kref.count_single(data, TEMPLATE, 2, pool, 1, True)
+    _set(monkeypatch)
+    for name, blob in (("b.fastq.gz", bgzf(data, 20000)), ("p.fastq.gz", gzip.compress(data, 1))):
+        path = tmp_path / name
+        path.write_bytes(blob)
+        got = gpu.count_single(str(path), TEMPLATE, 2, pool, 1, True, nthreads=6)
+        assert rcpp.timing()["reader"] == "host"
+        assert got[1] == want[1] and np.array_equal(got[0], want[0])
+
+
 def test_other_single_end_entry_points(gpu, kref, monkeypatch):
     """Combinatorial and dual single-end counting read through the same pipeline."""
     rng = np.random.default_rng(14)

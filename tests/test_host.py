@@ -236,3 +236,47 @@ def test_parallel_splitter_reports_the_serial_error(kref):
     with pytest.raises(Exception) as err:
         kref.parse(data)
     assert msgs[0] in str(err.value)
+
+
+@pytest.mark.parametrize("block", [200, 4096, 65280])
+@pytest.mark.parametrize("threads", [1, 8])
+def test_block_gzip_is_inflated_in_parallel_and_reads_the_same(kref, tmp_path, block, threads):
+    """BGZF members are found from their headers and inflated on the thread pool; the text, and so every record, is
+    what zlib's member-by-member gzread gives the reference.  Records straddle members at every block size."""
+    import gzip
+    from util import bgzf
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(block + threads)
+    data = _tricky_fastq(rng, 20000, wrap_every=40)
+    path = tmp_path / "reads.fastq.gz"
+    path.write_bytes(bgzf(data, block))
+    assert gzip.decompress(path.read_bytes()) == data          # a valid multi-member gzip file
+    want = kref.parse(str(path))
+    got = rcpp.host_pack_roundtrip(str(path), threads)
+    plain = rcpp.host_pack_roundtrip(data, threads)
+    assert got == plain
+    assert len(got) == len(want) == 20000
+    norm = lambda r: "".join(c if c in "ACGT" else "N" for c in r.upper())
+    assert got[:50] == [norm(r) for r in want[:50]]
+
+
+def test_block_gzip_edge_cases(tmp_path, monkeypatch):
+    from util import bgzf
+    from screencounter_b200 import rcpp
+    empty = tmp_path / "empty.fastq.gz"
+    empty.write_bytes(bgzf(b""))
+    assert rcpp.host_pack_roundtrip(str(empty), 4) == []
+    good = fastq(["ACGT", "GGTTAA"])
+    rng = np.random.default_rng(77)
+    noisy = fastq([random_seq(rng, 60) for _ in range(3000)])   # text that does not compress to nothing
+    broken = bytearray(bgzf(noisy, 3000))
+    broken[18 + 40] ^= 0x5A                                      # a flipped byte inside the first member's deflate stream
+    bad = tmp_path / "bad.fastq.gz"
+    bad.write_bytes(bytes(broken))
+    with pytest.raises(Exception):
+        rcpp.host_pack_roundtrip(str(bad), 4)
+    # a plain gzip member after BGZF members: not a BGZF chain, the serial gzip reader takes the file
+    import gzip
+    mixed = tmp_path / "mixed.fastq.gz"
+    mixed.write_bytes(bgzf(good)[:-28] + gzip.compress(good))
+    assert len(rcpp.host_pack_roundtrip(str(mixed), 4)) == 4

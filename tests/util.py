@@ -156,3 +156,19 @@ def adversarial_reads(rng, n, template, pools, strand="both", read_len=None,
             r = (r + random_seq(rng, read_len))[:read_len]
         reads.append(r)
     return reads
+
+
+def bgzf(data, block=65280, level=6):
+    """Block gzip (BGZF, as written by bgzip / bcl-convert): gzip members of at most 64 KiB with a 'BC' extra field
+    giving the member's size, closed by the standard empty member."""
+    import struct
+    import zlib
+    out = []
+    for at in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if at is None else data[at:at + block]
+        comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = comp.compress(chunk) + comp.flush()
+        bsize = 12 + 6 + len(raw) + 8
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) + raw +
+                   struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
