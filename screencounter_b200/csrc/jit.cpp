@@ -170,8 +170,9 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? 8 : 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
     const int group = env_int("SCG_SPEC_GROUP", 2, 1, 8);
+    const int samples = env_int("SCG_SPEC_SAMPLES", 8, 1, 32);
     const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages) + "#" +
-                            std::to_string(group);
+                            std::to_string(group) + "#" + std::to_string(samples);
     std::lock_guard<std::mutex> lock(g_mutex);
     auto it = g_cache.find(key);
     if (it != g_cache.end()) {
@@ -219,6 +220,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_NAME_U spec_single_kernel_u\n"
         << "#define SPEC_NAME_SLOW spec_single_kernel_slow\n"
         << "#define SPEC_GROUP " << group << "\n"
+        << "#define SPEC_SAMPLES " << samples << "\n"
         << "#define SPEC_INFO " << cfg.info << "\n"
         << "#define SPEC_JOINT " << cfg.joint << "\n"
         << "#define SPEC_HAS_INDEX " << cfg.has_index << "\n"

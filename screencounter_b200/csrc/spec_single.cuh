@@ -694,7 +694,10 @@ constexpr uint32_t WINMASK = NWIN >= 32 ? 0xFFFFFFFFu : ((1u << NWIN) - 1u);
 constexpr int TW = (T + 31) / 32;           // words per window
 constexpr int GROUP = SPEC_GROUP;           // tiles per bulk copy
 constexpr int NGROUPS = SPEC_MM + 1;        // pigeonhole groups of constant positions
-constexpr int SAMPLES = 8;                  // sampled positions per group
+#ifndef SPEC_SAMPLES
+#define SPEC_SAMPLES 8
+#endif
+constexpr int SAMPLES = SPEC_SAMPLES;       // sampled positions per group
 static_assert(W + 2 >= TW + 1, "window words plus their funnel partner must exist");
 
 // constant positions [lo, hi) of a strand's group g
