@@ -458,8 +458,9 @@ bool DeviceIngest::stage() {
     count_newlines<<<nblocks, kBlockThreads, 0, st>>>(ring, slot0, end, state, B.block_counts.as<uint32_t>());
     scan_blocks<<<1, 1024, 0, st>>>(B.block_counts.as<uint32_t>(), nblocks, state, (uint32_t)line_cap_);
     scatter_newlines<<<nblocks, kBlockThreads, 0, st>>>(ring, slot0, end, state, B.block_counts.as<uint32_t>(), lines, (uint32_t)line_cap_);
-    // at most one record per 6 bytes ("@\n\n+\n\n"), and never more than the position buffer describes
-    const uint32_t max_rec = (uint32_t)std::min<size_t>(line_cap_ / 4, (end - slot0) / 6 + 1);
+    // every group of four lines is looked at, also the ones that are no records (four newlines are four bytes); never more
+    // groups than the position buffer describes
+    const uint32_t max_rec = (uint32_t)std::min<size_t>(line_cap_ / 4, (end - slot0) / 4 + 1);
     const int rec_blocks = (int)((max_rec + 255) / 256);
     validate_records<<<rec_blocks, 256, 0, st>>>(ring, lines, state, B.seq_off.as<uint32_t>(), lens);
     record_extent<<<rec_blocks, 256, 0, st>>>(lens, state);

@@ -147,6 +147,28 @@ def test_errors_keep_their_line_numbers(gpu, monkeypatch, name, lead):
         assert str(err.value) == shifted
 
 
+@pytest.mark.parametrize("junk", [b"\n" * 5000, b"\n\n\n\n" * 300 + b"@r\nACGTAGGGTTTTGCAT\n+\nIIIIIIIIIIIIIIII\n", b"+\n" * 999, b"@\n" * 4001])
+def test_texts_that_are_mostly_newlines(gpu, kref, monkeypatch, junk):
+    """Every group of four lines is validated, however short the lines: blank-line floods are the host reader's to reject,
+    with the reference's message."""
+    good = fastq(["ACGTAGGGTTTTGCAT"] * 50)
+    for data in (junk, good + junk):
+        try:
+            want = kref.count_single(data, TEMPLATE, 2, ["GGGTTT"], 0, True)
+            err = None
+        except Exception as e:
+            want, err = None, str(e)
+        for chunk in (4096, None):
+            _set(monkeypatch, chunk, 1024)
+            if err is None:
+                got = gpu.count_single(data, TEMPLATE, 2, ["GGGTTT"], 0, True)
+                assert got[1] == want[1] and np.array_equal(got[0], want[0])
+            else:
+                with pytest.raises(Exception) as raised:
+                    gpu.count_single(data, TEMPLATE, 2, ["GGGTTT"], 0, True)
+                assert str(raised.value) == err
+
+
 def test_record_longer_than_the_carry_area(gpu, kref, monkeypatch):
     pool, reads = _case(11, n=300)
     reads.insert(100, random_seq(np.random.default_rng(1), 5000))
