@@ -122,6 +122,13 @@ int scg_count_combo_paired(scg_ctx* ctx,
                            int randomized, int use_first, int nthreads, int want_trace,
                            scg_result** table, int32_t* total, int32_t* barcode1_only, int32_t* barcode2_only);
 
+/* kaori's SingleBarcodePairedEnd handler (inst/include/kaori/handlers/SingleBarcodePairedEnd.hpp:27-170): one barcode per
+ * read PAIR, searched on read 1 and on read 2 with the same template, pool and options.  screenCounter exports no R
+ * function for this handler; the entry point is here for callers of kaori that use it.  trace: per-pair pool index. */
+int scg_count_single_paired(scg_ctx* ctx, const scg_source* src1, const scg_source* src2, const char* constant, int strand,
+                            const char* const* pool, int npool, int mismatches, int use_first, int nthreads,
+                            int32_t* counts, int32_t* total, scg_result** trace);
+
 /* replaces match_barcodes, src/match_barcodes.cpp:7-37.  index is 0-based with -1 where the
  * reference returns NA_INTEGER (the shim adds 1); mismatches is -1 for NA. */
 int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequences,

@@ -124,6 +124,18 @@ class OracleBinding:
         return counts, total.value
 
 
+    def count_single_paired(self, fastq1, fastq2, template, strand, pool, mismatches, use_first, nthreads=1):
+        """SingleBarcodePairedEnd (compiled reference only)."""
+        p1, d1, s1 = _src(fastq1)
+        p2, d2, s2 = _src(fastq2)
+        arr, keep = _strs(pool)
+        counts = np.zeros(len(pool), dtype=np.int32)
+        total = C.c_int()
+        self._check(self._f("count_single_paired")(p1, d1, C.c_size_t(s1), p2, d2, C.c_size_t(s2), template.encode("latin-1"), int(strand),
+                                                   arr, len(pool), int(mismatches), int(bool(use_first)), int(nthreads), _ip(counts),
+                                                   C.byref(total)))
+        return counts, total.value
+
     def trace_single(self, fastq, template, strand, pool, mismatches, use_first):
         n, _ = self.count_reads(fastq)
         p, d, s = _src(fastq)

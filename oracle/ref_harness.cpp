@@ -665,4 +665,28 @@ int kref_search_segmented2(const char* const* seqs, int nseqs, const int* caps /
     });
 }
 
+
+// SingleBarcodePairedEnd (handlers/SingleBarcodePairedEnd.hpp:93-124): the single-barcode search on both mates.
+int kref_count_single_paired(const char* path1, const char* data1, size_t size1, const char* path2, const char* data2, size_t size2,
+                             const char* tmpl, int strand, const char* const* pool, int npool, int mismatches, int use_first,
+                             int nthreads, int* counts, int* total) {
+    return guarded([&] {
+        Source src1(path1, data1, size1);
+        Source src2(path2, data2, size2);
+        auto bp = make_pool(pool, npool);
+        std::string constant(tmpl);
+        dispatch(constant.size(), [&](auto N) {
+            typename kaori::SingleBarcodePairedEnd<N.value>::Options opt;
+            opt.strand = to_strand_int(strand);
+            opt.max_mismatches = mismatches;
+            opt.use_first = use_first;
+            kaori::SingleBarcodePairedEnd<N.value> handler(constant.c_str(), constant.size(), bp, opt);
+            kaori::process_paired_end_data(src1.get(), src2.get(), handler, nthreads);
+            const auto& c = handler.get_counts();
+            std::copy(c.begin(), c.end(), counts);
+            *total = handler.get_total();
+        });
+    });
+}
+
 } // extern "C"

@@ -80,7 +80,7 @@ EXPORTS = [
     "scg_result_rows", "scg_result_width", "scg_result_reads", "scg_result_copy_table", "scg_result_trace_width",
     "scg_result_copy_trace", "scg_result_free",
     "scg_count_single", "scg_count_random", "scg_count_combo_single", "scg_count_dual_single_end", "scg_count_dual",
-    "scg_count_combo_paired", "scg_match_barcodes",
+    "scg_count_combo_paired", "scg_count_single_paired", "scg_match_barcodes",
     "scg_reads_from_source", "scg_reads_count", "scg_reads_device_bytes", "scg_reads_free",
     "scg_reads_synthesize", "scg_synth_fastq",
     "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",

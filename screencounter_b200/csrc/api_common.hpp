@@ -157,6 +157,10 @@ struct SingleMatcher {
     void upload(Context& ctx);
 };
 
+// A matcher for these arguments from the context's cache, built and uploaded on a miss (runners_single.cu).
+std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* constant, int strand, const char* const* pool, int npool,
+                                                     int mismatches, bool use_first);
+
 // Runs the single-barcode kernel over one batch: the run-time specialised kernel (jit.hpp) when it
 // can be had, the generic one otherwise.
 void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, int32_t* d_counts, int32_t* d_index,

@@ -123,6 +123,36 @@ struct DualPEMatcher {
     }
 };
 
+// SingleBarcodePairedEnd::process (reference handlers/SingleBarcodePairedEnd.hpp:93-124) from the two mates' single-barcode
+// outcomes: first mode takes read 1's match, else read 2's; best mode takes the match with fewer mismatches, and on equal
+// mismatches only when both reads name the same barcode.
+__global__ void single_paired_combine(const int32_t* __restrict__ idx1, const uint32_t* __restrict__ info1, const int32_t* __restrict__ idx2,
+                                      const uint32_t* __restrict__ info2, long long n, int use_first, int32_t* __restrict__ counts,
+                                      int32_t* __restrict__ out_index) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = idx1[i], b = idx2[i];
+    int chosen = -1;
+    if (use_first) {
+        chosen = a >= 0 ? a : b;
+    } else if (a >= 0 && b < 0) {
+        chosen = a;
+    } else if (a < 0 && b >= 0) {
+        chosen = b;
+    } else if (a >= 0 && b >= 0) {
+        const uint32_t m1 = (info1[i] >> 20) & 31u, m2 = (info2[i] >> 20) & 31u;
+        if (m1 < m2) {
+            chosen = a;
+        } else if (m1 > m2) {
+            chosen = b;
+        } else if (a == b) {
+            chosen = a;
+        }
+    }
+    if (chosen >= 0) atomicAdd(counts + chosen, 1);
+    if (out_index) out_index[i] = chosen;
+}
+
 struct PairedSources {
     Source s1, s2;
     PairedSources(const scg_source* a, const scg_source* b) : s1(a), s2(b) {}
@@ -366,6 +396,68 @@ int scg_search_segmented(scg_ctx* ctx, const char* const* sequences, int nsequen
         SCG_CUDA_CHECK(cudaMemcpyAsync(index, d_idx.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         SCG_CUDA_CHECK(cudaMemcpyAsync(mismatches, d_mm.ptr, (size_t)nsequences * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    });
+}
+
+
+// SingleBarcodePairedEnd (reference handlers/SingleBarcodePairedEnd.hpp:27-170): one barcode per PAIR, looked for on read 1
+// and on read 2 with the same template and pool.  kaori has the handler; screenCounter exports no R function for it.
+int scg_count_single_paired(scg_ctx* ctx, const scg_source* src1, const scg_source* src2, const char* constant, int strand,
+                            const char* const* pool, int npool, int mismatches, int use_first, int nthreads, int32_t* counts,
+                            int32_t* total, scg_result** trace) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        const double t_start = now_s();
+        c.timing = Timing();
+        if (mismatches > 31) throw Error("SingleBarcodePairedEnd with more than 31 mismatches is not supported by this engine");
+        Source s1(src1);
+        Source s2(src2);
+        const std::shared_ptr<SingleMatcher> matcher = cached_single_matcher(c, constant, strand, pool, npool, mismatches, use_first != 0);
+        c.ensure_ready();
+        DeviceBuffer d_counts, d_scratch, d_idx1, d_idx2, d_info1, d_info2, d_out;
+        d_counts.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);
+        d_scratch.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);   // the per-mate kernels count here; not reported
+        std::vector<int32_t> trace_index;
+
+        ReadPipeline pipe(c, s1.reader.get(), s2.reader.get(), nthreads, false);
+        ReadPipeline::Batch b;
+        long long npairs = 0;
+        while (pipe.next(b)) {
+            const size_t n = (size_t)b.n;
+            d_idx1.reserve(n * sizeof(int32_t));
+            d_idx2.reserve(n * sizeof(int32_t));
+            d_info1.reserve(n * sizeof(uint32_t));
+            d_info2.reserve(n * sizeof(uint32_t));
+            if (trace) d_out.reserve(n * sizeof(int32_t));
+            launch_single(c, b.reads1, *matcher, d_scratch.as<int32_t>(), d_idx1.as<int32_t>(), d_info1.as<uint32_t>(), c.stream);
+            launch_single(c, b.reads2, *matcher, d_scratch.as<int32_t>(), d_idx2.as<int32_t>(), d_info2.as<uint32_t>(), c.stream);
+            single_paired_combine<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_idx1.as<int32_t>(), d_info1.as<uint32_t>(), d_idx2.as<int32_t>(),
+                                                                                     d_info2.as<uint32_t>(), b.n, use_first ? 1 : 0,
+                                                                                     d_counts.as<int32_t>(), trace ? d_out.as<int32_t>() : nullptr);
+            SCG_CUDA_CHECK(cudaGetLastError());
+            ++c.launches;
+            pipe.submitted(b);
+            if (trace) {
+                const size_t at = trace_index.size();
+                trace_index.resize(at + n);
+                SCG_CUDA_CHECK(cudaMemcpyAsync(trace_index.data() + at, d_out.ptr, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            }
+            npairs += b.n;
+        }
+        SCG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts.ptr, (size_t)npool * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        *total = (int32_t)npairs;
+        if (trace) {
+            auto* r = new scg_result;
+            r->trace_width = 1;
+            r->trace_index.swap(trace_index);
+            r->trace_info.assign(r->trace_index.size(), 0u);
+            *trace = r;
+        }
+        c.timing.parse_s = s1.reader->parse_seconds() + s2.reader->parse_seconds();
+        c.timing.total_s = now_s() - t_start;
+        c.finish_timing();
     });
 }
 

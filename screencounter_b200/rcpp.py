@@ -192,6 +192,24 @@ def count_single_barcodes(path, constant, strand, pool, mismatches, use_first, n
     return out
 
 
+def count_single_barcodes_paired(path1, path2, constant, strand, pool, mismatches, use_first, nthreads, trace=False, device=None):
+    """kaori's SingleBarcodePairedEnd handler (no R entry point in screenCounter): list(counts, total[, per-pair index])."""
+    ctx = context(device)
+    s1, s2 = _Src(path1), _Src(path2)
+    arr, keep = _strs(pool)
+    counts = np.zeros(len(pool), dtype=np.int32)
+    total = C.c_int32()
+    handle = C.c_void_p()
+    _check(ctx, lib().scg_count_single_paired(ctx, s1.ref(), s2.ref(), constant.encode("latin-1"), int(strand), arr, len(pool),
+                                              int(mismatches), int(bool(use_first)), int(nthreads), _ip(counts), C.byref(total),
+                                              C.byref(handle) if trace else None))
+    out = [counts, total.value]
+    if trace:
+        out.append(_trace(handle)[0][:, 0])
+        lib().scg_result_free(handle)
+    return out
+
+
 def match_barcodes(sequences, choices, substitutions, reverse, device=None):
     """reference: src/match_barcodes.cpp:7-37 -> list(index (1-based, None = NA), mismatches (None = NA))."""
     ctx = context(device)

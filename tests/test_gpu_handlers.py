@@ -220,3 +220,36 @@ def test_combo_paired(gpu, kref, rev, mms, use_first, randomized):
     a = kref.trace_combo_paired(f1, t1, rev[0], mms[0], g1, f2, t2, rev[1], mms[1], g2, randomized, use_first)
     b = gpu.trace_combo_paired(f1, t1, rev[0], mms[0], g1, f2, t2, rev[1], mms[1], g2, randomized, use_first)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# ---- SingleBarcodePairedEnd (kaori handler without an R entry point) --------------------------------------------------
+@pytest.mark.parametrize("strand", ["original", "both"])
+@pytest.mark.parametrize("mm", [0, 1, 2])
+@pytest.mark.parametrize("use_first", [True, False])
+def test_single_barcode_paired_end(kref, strand, mm, use_first):
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(50 + mm + 7 * STRANDS[strand])
+    pool = dense_pool(rng, 60, 7)
+    template = "ACGTA" + "-" * 7 + "TGCAT"
+    # the barcode may sit on read 1, on read 2, on both (same or different barcodes, cleaner or noisier), or on neither
+    r1 = adversarial_reads(rng, 4000, template, [pool], strand=strand, junk_frac=0.35)
+    r2 = adversarial_reads(rng, 4000, template, [pool], strand=strand, junk_frac=0.35)
+    same = rng.random(4000) < 0.3
+    r2 = [a if s else b for a, b, s in zip(r1, r2, same)]
+    f1, f2 = fastq(r1), fastq(r2)
+    want_counts, want_total = kref.count_single_paired(f1, f2, template, STRANDS[strand], pool, mm, use_first)
+    counts, total, index = rcpp.count_single_barcodes_paired(f1, f2, template, STRANDS[strand], pool, mm, use_first, 4, trace=True)
+    assert total == want_total == 4000
+    assert np.array_equal(counts, want_counts)
+    assert np.array_equal(counts, np.bincount(index[index >= 0], minlength=len(pool)))
+    # per pair against the single-barcode traces of the reference and the handler's rule
+    i1, n1 = kref.trace_single(f1, template, STRANDS[strand], pool, mm, use_first)
+    i2, n2 = kref.trace_single(f2, template, STRANDS[strand], pool, mm, use_first)
+    if use_first:
+        expect = np.where(i1 >= 0, i1, i2)
+    else:
+        m1, m2 = n1[:, 2], n2[:, 2]
+        both = (i1 >= 0) & (i2 >= 0)
+        expect = np.where(both, np.where(m1 < m2, i1, np.where(m1 > m2, i2, np.where(i1 == i2, i1, -1))), np.where(i1 >= 0, i1, i2))
+    assert np.array_equal(index, expect)
+    assert counts.sum() > 1000
