@@ -148,6 +148,8 @@ struct SingleMatcher {
     DeviceBuffer libs_dev;   // LibDev[2] on the device: forward, reverse
     DeviceBuffer joint;      // exact table of both strands (libdev.hpp SpecTables::joint), keys of up to 31 bases
     uint32_t joint_shift = 0;
+    DeviceBuffer ibuckets[2]; // seed buckets with the first candidate inline, per strand (SpecTables::ibuckets)
+    bool have_ibuckets = false;
     SingleParams params;
     int npool = 0;
     mutable std::string kernel_note;   // which kernel the last launch used, and why

@@ -28,6 +28,7 @@ struct SpecSingleConfig {
     int info = 1;                 // the per-read info word may be asked for
     int joint = 0;                // the joint exact table of both strands is there (keys of up to 31 bases)
     int has_index = 1;            // the per-read index is asked for
+    int ibuckets = 0;             // seed buckets with the first candidate inline are there
     std::string key() const;
 };
 

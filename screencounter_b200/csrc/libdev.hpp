@@ -53,6 +53,9 @@ struct SpecTables {
     // Table 1 holds n = 1 << (32 - joint_shift) slots, table 2 the next n.
     const uint4* joint;
     uint32_t joint_shift;
+    // Seed buckets with their first candidate inline: (H word, L word, pool index, start | count << 24) per bucket, same
+    // indexing as `buckets`.  Nine in ten non-empty buckets hold one candidate: one load instead of bucket -> row.
+    const uint4* ibuckets[2];
 };
 
 // the two homes of a key in the joint table (host builder and kernel alike): top bits of a multiplicative hash

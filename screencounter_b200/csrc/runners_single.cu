@@ -134,6 +134,42 @@ void SingleMatcher::upload(Context& ctx) {
     }
     params.libs = upload_lib_array(ctx, libs, libs_dev);
 
+    // Seed buckets with the first candidate inline (uniform-length kernel's seeded search)
+    have_ibuckets = false;
+    {
+        const Library* strands[2] = { tmpl.fwd ? &lib_f.host : nullptr, tmpl.rev ? &lib_r.host : nullptr };
+        bool ok = true;
+        for (const Library* lib : strands) {
+            if (!lib) continue;
+            if (lib->KW != 1 || lib->nseeds < 1 || lib->cand_rows.empty() || lib->nentries() >= (1u << 24)) ok = false;
+            if (ok) {
+                for (const uint2& b : lib->buckets) ok = ok && b.y < 255;
+            }
+        }
+        if (ok && (strands[0] || strands[1])) {
+            for (int k = 0; k < 2; ++k) {
+                ibuckets[k].release();
+                const Library* lib = strands[k];
+                if (!lib) continue;
+                std::vector<uint32_t> rows(lib->buckets.size() * 4, 0);
+                const size_t per_seed = lib->nbuckets, E = lib->nentries();
+                for (size_t b = 0; b < lib->buckets.size(); ++b) {
+                    const uint2 bk = lib->buckets[b];
+                    if (bk.y == 0) continue;
+                    const size_t sd = b / per_seed;
+                    const uint32_t* first = &lib->cand_rows[4 * (sd * E + bk.x)];
+                    rows[4 * b + 0] = first[0];
+                    rows[4 * b + 1] = first[1];
+                    rows[4 * b + 2] = first[2];
+                    rows[4 * b + 3] = bk.x | (bk.y << 24);
+                }
+                ibuckets[k].upload(rows.data(), rows.size() * sizeof(uint32_t), ctx.stream);
+            }
+            SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+            have_ibuckets = true;
+        }
+    }
+
     // Joint exact table of both strands (libdev.hpp): filled from the strands' own cuckoo tables, so a lookup answers exactly
     // what they answer.
     joint.release();
@@ -327,6 +363,7 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             cfg.info = d_info ? 1 : 0;
             cfg.joint = (m.joint.ptr != nullptr && m.joint_shift != 0 && !std::getenv("SCG_SPEC_NO_JOINT")) ? 1 : 0;
             cfg.has_index = d_index ? 1 : 0;
+            cfg.ibuckets = (m.have_ibuckets && !std::getenv("SCG_SPEC_NO_IBUCKETS")) ? 1 : 0;
         }
     }
     std::string why;
@@ -348,6 +385,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
         }
         tables.libs = P.libs;
         tables.joint = m.joint.as<uint4>();
+        tables.ibuckets[0] = m.ibuckets[0].as<uint4>();
+        tables.ibuckets[1] = m.ibuckets[1].as<uint4>();
         tables.joint_shift = m.joint_shift;
         // persistent warps: as many blocks as are resident at once, each warp strides over the tiles
         const int resident = specialised_blocks_per_sm(spec);

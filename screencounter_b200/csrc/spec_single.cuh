@@ -106,6 +106,10 @@
 #ifndef SPEC_HAS_INDEX
 #define SPEC_HAS_INDEX 1
 #endif
+// the seed buckets with their first candidate inline (libdev.hpp SpecTables::ibuckets) are there
+#ifndef SPEC_IBUCKETS
+#define SPEC_IBUCKETS 0
+#endif
 
 namespace scg {
 namespace spec {
@@ -415,6 +419,28 @@ __device__ __forceinline__ Hit seeded_search(const SpecTables& tb, bool rev, uin
     const uint32_t bmask = rev ? tb.bucket_mask[1] : tb.bucket_mask[0];
     const int nent = rev ? tb.nentries[1] : tb.nentries[0];
     uint2 bk[NSEEDS > 0 ? NSEEDS : 1];
+    uint4 first[NSEEDS > 0 ? NSEEDS : 1], second[NSEEDS > 0 ? NSEEDS : 1];
+#if SPEC_IBUCKETS
+    // buckets that carry their first candidate: one round of loads settles nine deferred reads in ten
+    const uint4* __restrict__ ibuckets = rev ? tb.ibuckets[1] : tb.ibuckets[0];
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        const uint32_t m = seed_mask(sd);
+        const uint32_t mh = kh & m, ml = kl & m;
+        first[sd] = make_uint4(0, 0, 0, 0);
+        // an N inside the seed: no barcode agrees with the region there
+        if (active && !(kn & m)) {
+            const uint32_t b = hash_key(&mh, &ml, 1, 0x5EED0000u + sd) & bmask;
+            first[sd] = __ldg(ibuckets + (size_t)sd * (bmask + 1) + b);
+        }
+        bk[sd] = make_uint2(first[sd].w & 0xFFFFFFu, first[sd].w >> 24);
+    }
+#pragma unroll
+    for (int sd = 0; sd < NSEEDS; ++sd) {
+        second[sd] = make_uint4(0, 0, 0, 0);
+        if (bk[sd].y > 1) second[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x + 1);
+    }
+#else
 #pragma unroll
     for (int sd = 0; sd < NSEEDS; ++sd) {
         const uint32_t m = seed_mask(sd);
@@ -428,13 +454,13 @@ __device__ __forceinline__ Hit seeded_search(const SpecTables& tb, bool rev, uin
     }
     // the first two candidate rows of every bucket go out together (a bucket with an entry holds a second one 7 % of
     // the time, a third one almost never)
-    uint4 first[NSEEDS > 0 ? NSEEDS : 1], second[NSEEDS > 0 ? NSEEDS : 1];
 #pragma unroll
     for (int sd = 0; sd < NSEEDS; ++sd) {
         first[sd] = second[sd] = make_uint4(0, 0, 0, 0);
         if (bk[sd].y > 0) first[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x);
         if (bk[sd].y > 1) second[sd] = __ldg(rows + (size_t)sd * nent + bk[sd].x + 1);
     }
+#endif
     Best best{ cap + 1, -1, false };
 #pragma unroll
     for (int sd = 0; sd < NSEEDS; ++sd) {
