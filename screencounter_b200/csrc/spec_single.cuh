@@ -650,8 +650,9 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
                     const uint4* __restrict__ slots = frev ? tb.slots[1] : tb.slots[0];
                     const uint32_t mask = frev ? tb.slot_mask[1] : tb.slot_mask[0];
                     const uint32_t acc = hash_key(&kh, &kl, 1, 0);
-                    pend.a = __ldg(slots + (acc & mask));
-                    pend.b = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+                    // scattered 16-byte loads that never hit L1: .cg keeps them out of it
+                    pend.a = __ldcg(slots + (acc & mask));
+                    pend.b = __ldcg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
                     pend.meta |= PM_PROBED;
                 }
             }
