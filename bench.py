@@ -238,7 +238,7 @@ def main():
     launches_per_step = (rcpp.kernel_launches(local_rank) - launches_before) // args.steps
     # the uniform-length kernel is followed by a (microseconds-long) kernel for its rare multi-window reads: the pair is
     # one pass over the launch's reads
-    passes_per_step = launches_per_step // 2 if "uniform-length" in plan.kernel else launches_per_step
+    passes_per_step = launches_per_step // 2 if "filter+verify" in plan.kernel else launches_per_step
     kernel_ms_per_step = k0.elapsed_time(k1) / args.steps
     matched_per_step = int(counts.sum().item()) // args.steps
     assert int((index >= 0).sum().item()) == matched_per_step, "per-read outcomes and counts disagree"

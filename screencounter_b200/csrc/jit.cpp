@@ -109,7 +109,7 @@ std::map<std::string, Cached> g_cache;
 std::string SpecSingleConfig::key() const {
     std::ostringstream o;
     o << fbases << '|' << rbases << '|' << T << '|' << fwd << rev << '|' << W << '|' << nb << '|' << cb << '|' << mm << '|' << maxmm << '|' << use_first << '|'
-      << fstart << '|' << rstart << '|' << keylen << '|' << dup_first << '|' << ulen << '|' << info << '|' << joint << '|' << has_index << '|' << ibuckets;
+      << fstart << '|' << rstart << '|' << keylen << '|' << dup_first << '|' << ulen << '|' << info << '|' << joint << '|' << has_index << '|' << ibuckets << '|' << ragged;
     for (uint32_t m : seed_masks) o << '|' << m;
     return o.str();
 }
@@ -225,6 +225,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_JOINT " << cfg.joint << "\n"
         << "#define SPEC_HAS_INDEX " << cfg.has_index << "\n"
         << "#define SPEC_IBUCKETS " << cfg.ibuckets << "\n"
+        << "#define SPEC_RAGGED " << cfg.ragged << "\n"
         << "#define SPEC_SKIP_GENERAL " << (cfg.ulen > 0 ? 1 : 0) << "\n"
         << "#include \"spec_single.cuh\"\n";
     const std::string program_text = src.str();

@@ -29,6 +29,7 @@ struct SpecSingleConfig {
     int joint = 0;                // the joint exact table of both strands is there (keys of up to 31 bases)
     int has_index = 1;            // the per-read index is asked for
     int ibuckets = 0;             // seed buckets with the first candidate inline are there
+    int ragged = 0;               // the batch carries per-read lengths (ulen is then the longest read)
     std::string key() const;
 };
 

@@ -357,9 +357,10 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
         int nconst = 0;
         for (char ch : m.tmpl.fwd_seq) nconst += ch != '-';
         const bool want_u = !std::getenv("SCG_SPEC_NO_UNIFORM");
-        if (want_u && reads.lens == nullptr && nwin >= 1 && nwin <= 32 && P.spec.mm >= 0 && P.spec.mm <= 3 && nconst >= 4 * (P.spec.mm + 1) &&
+        if (want_u && nwin >= 1 && nwin <= 32 && P.spec.mm >= 0 && P.spec.mm <= 3 && nconst >= 4 * (P.spec.mm + 1) &&
             cfg.T <= 128 && reads.W + 2 >= (cfg.T + 31) / 32 + 1 && reads.n <= 0x7FFFFFC0ll) {
             cfg.ulen = reads.uniform_len;
+            cfg.ragged = reads.lens != nullptr ? 1 : 0;   // trimmed reads: per-lane window masks
             cfg.info = d_info ? 1 : 0;
             cfg.joint = (m.joint.ptr != nullptr && m.joint_shift != 0 && !std::getenv("SCG_SPEC_NO_JOINT")) ? 1 : 0;
             cfg.has_index = d_index ? 1 : 0;
@@ -409,7 +410,8 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info };
             SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
         }
-        m.kernel_note = cfg.ulen > 0 ? "specialised (NVRTC), uniform-length filter+verify, " + std::to_string(resident) + " blocks/SM"
+        m.kernel_note = cfg.ulen > 0 ? std::string("specialised (NVRTC), ") + (cfg.ragged ? "at most 32 windows, " : "uniform-length ") +
+                                           "filter+verify, " + std::to_string(resident) + " blocks/SM"
                                      : "specialised (NVRTC)";
         ctx.kernel_note = m.kernel_note;
     } else {

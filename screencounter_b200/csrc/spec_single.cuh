@@ -110,6 +110,11 @@
 #ifndef SPEC_IBUCKETS
 #define SPEC_IBUCKETS 0
 #endif
+// the batch of the "uniform-length" kernel has per-read lengths after all (trimmed reads): SPEC_ULEN is then the longest read,
+// still with at most 32 windows, and every lane masks the windows its own read does not have
+#ifndef SPEC_RAGGED
+#define SPEC_RAGGED 0
+#endif
 
 namespace scg {
 namespace spec {
@@ -948,7 +953,13 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             make_planes(R, P);
 
             // ---- filter: windows that can still be within the budget ----
+#if SPEC_RAGGED
+            // windows p with p + T <= this read's length (ScanTemplate.hpp:153,168-170: a read shorter than the template has none)
+            const int npos = inrange ? (int)reads.lens[i] - T + 1 : 0;
+            const uint32_t live = npos <= 0 ? 0u : (npos >= 32 ? 0xFFFFFFFFu : ((1u << npos) - 1u));
+#else
             const uint32_t live = inrange ? WINMASK : 0u;
+#endif
             uint32_t cf = SPEC_FWD ? candidate_windows<false>(P, live) : 0u;
             uint32_t cr = SPEC_REV ? candidate_windows<true>(P, live) : 0u;
             // ---- verify: exact constant mismatches of each candidate, in the reference's order (positions ascending, forward

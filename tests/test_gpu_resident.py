@@ -98,3 +98,29 @@ def test_exact_table_variants(kref, monkeypatch, mm, joint):
     want_index, _ = kref.trace_single(spec.fastq(0, n), TEMPLATE, 2, pool, mm, True)
     assert np.array_equal(index.to_numpy(np.int32), want_index)
     assert np.array_equal(counts.to_numpy(np.int32), np.bincount(want_index[want_index >= 0], minlength=len(pool)))
+
+
+@pytest.mark.parametrize("mm", [0, 1, 2])
+@pytest.mark.parametrize("use_first", [True, False])
+def test_trimmed_reads_take_the_filter_verify_kernel(kref, mm, use_first):
+    """Reads of different lengths with at most 32 windows (adapter-trimmed data): the filter + verify kernel with per-lane
+    window masks; reads shorter than the template have no window at all (ScanTemplate.hpp:153,168-170)."""
+    from screencounter_b200 import rcpp
+    from util import adversarial_reads, fastq
+    rng = np.random.default_rng(40 + mm)
+    pool = distinct_pool(rng, 400, 20)
+    T = len(TEMPLATE)
+    reads = adversarial_reads(rng, 30000, TEMPLATE, [pool], strand="both", sub_rate=0.02, n_rate=0.005, lower_rate=0.01,
+                              double_frac=0.0, short_frac=0.05, edge_frac=0.3)
+    reads = [r[: T + 31] for r in reads]            # at most 32 windows each
+    reads[7] = ""                                     # and the odd empty or tiny read
+    reads[8] = "ACGT"
+    assert len({len(r) for r in reads}) > 20
+    data = fastq(reads)
+    want_index, want_info = kref.trace_single(data, TEMPLATE, 2, pool, mm, use_first)
+    counts, total, (index, info) = rcpp.count_single_barcodes(data, TEMPLATE, 2, pool, mm, use_first, 4, trace=True)
+    assert "at most 32 windows" in rcpp.timing()["kernel"], rcpp.timing()
+    assert total == len(reads)
+    assert np.array_equal(index[:, 0] if index.ndim > 1 else index, want_index)
+    assert np.array_equal(info, want_info)
+    assert (want_index >= 0).mean() > 0.2
