@@ -167,7 +167,9 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         int x = std::atoi(v);
         return x < lo ? lo : (x > hi ? hi : x);
     };
-    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? 8 : 4, 1, 16);
+    // the uniform-length kernel keeps a read's words and mismatch planes in registers: 8 blocks of 128 threads fit up to
+    // 96-base reads at 64 registers, longer reads trade occupancy for registers
+    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? (cfg.W <= 3 ? 8 : (cfg.W == 4 ? 6 : 4)) : 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
     const int group = env_int("SCG_SPEC_GROUP", 2, 1, 8);
     const int samples = env_int("SCG_SPEC_SAMPLES", 8, 1, 32);

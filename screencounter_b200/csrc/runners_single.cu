@@ -350,14 +350,14 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
     cfg.rstart = P.spec.rstart[0];
     cfg.keylen = P.spec.rlen_f[0];
     spec_seeds(m, cfg);
-    // the uniform-length kernel: every read as long as the longest, 1 to 32 windows, a budget the pigeonhole filter is
-    // worth having for (at least four constant positions per group), indices that fit 32 bits
+    // the uniform-length kernel: reads no longer than 192 bases with at least one window, a budget the pigeonhole filter
+    // is worth having for (at least four constant positions per group), indices that fit 32 bits
     {
         const int nwin = reads.uniform_len - m.tmpl.length + 1;
         int nconst = 0;
         for (char ch : m.tmpl.fwd_seq) nconst += ch != '-';
         const bool want_u = !std::getenv("SCG_SPEC_NO_UNIFORM");
-        if (want_u && nwin >= 1 && nwin <= 32 && P.spec.mm >= 0 && P.spec.mm <= 3 && nconst >= 4 * (P.spec.mm + 1) &&
+        if (want_u && nwin >= 1 && P.spec.mm >= 0 && P.spec.mm <= 3 && nconst >= 4 * (P.spec.mm + 1) &&
             cfg.T <= 128 && reads.W + 2 >= (cfg.T + 31) / 32 + 1 && reads.n <= 0x7FFFFFC0ll) {
             cfg.ulen = reads.uniform_len;
             cfg.ragged = reads.lens != nullptr ? 1 : 0;   // trimmed reads: per-lane window masks
@@ -410,7 +410,7 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             void* args[] = { &reads_arg, &tables, &d_counts, &d_index, &d_info };
             SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(spec), dim3(spec_grid), dim3(128), args, 0, stream));
         }
-        m.kernel_note = cfg.ulen > 0 ? std::string("specialised (NVRTC), ") + (cfg.ragged ? "at most 32 windows, " : "uniform-length ") +
+        m.kernel_note = cfg.ulen > 0 ? std::string("specialised (NVRTC), ") + (cfg.ragged ? "trimmed reads, " : "uniform-length ") +
                                            "filter+verify, " + std::to_string(resident) + " blocks/SM"
                                      : "specialised (NVRTC)";
         ctx.kernel_note = m.kernel_note;
@@ -705,8 +705,9 @@ static int jit_selftest(const char* constant, int strand, int mismatches, int wo
         }
         if (uniform_len > 0) {
             const int nwin = uniform_len - t.length + 1;
-            if (nwin < 1 || nwin > 32) throw Error("the uniform-length kernel needs 1 to 32 windows per read");
+            if (nwin < 1) throw Error("the uniform-length kernel needs reads at least as long as the template");
             cfg.ulen = uniform_len;
+            cfg.W = std::max(cfg.W, (uniform_len + 31) / 32);
             cfg.nb = 1;
         }
         std::string why;

@@ -721,8 +721,13 @@ namespace spec {
 
 constexpr int ULEN = SPEC_ULEN;
 constexpr int NWIN = ULEN - T + 1;
-static_assert(NWIN >= 1 && NWIN <= 32, "the uniform-length kernel handles reads with 1 to 32 windows");
-constexpr uint32_t WINMASK = NWIN >= 32 ? 0xFFFFFFFFu : ((1u << NWIN) - 1u);
+static_assert(NWIN >= 1, "the uniform-length kernel needs reads at least as long as the template");
+constexpr int NBLOCKS = (NWIN + 31) / 32;   // window blocks: block b holds windows [32 b, 32 b + 32)
+// windows of block PB that exist in a read of ULEN bases
+template <int PB>
+__host__ __device__ constexpr uint32_t block_mask() {
+    return NWIN - 32 * PB >= 32 ? 0xFFFFFFFFu : ((1u << (NWIN - 32 * PB)) - 1u);
+}
 constexpr int TW = (T + 31) / 32;           // words per window
 constexpr int GROUP = SPEC_GROUP;           // tiles per bulk copy
 constexpr int NGROUPS = SPEC_MM + 1;        // pigeonhole groups of constant positions
@@ -731,6 +736,7 @@ constexpr int NGROUPS = SPEC_MM + 1;        // pigeonhole groups of constant pos
 #endif
 constexpr int SAMPLES = SPEC_SAMPLES;       // sampled positions per group
 static_assert(W + 2 >= TW + 1, "window words plus their funnel partner must exist");
+static_assert(NBLOCKS - 1 + TW <= W, "the last block's window words and their funnel partners lie within the guarded words");
 
 // constant positions [lo, hi) of a strand's group g
 template <bool REV, int G>
@@ -743,36 +749,37 @@ struct Group {
 };
 
 // OR of the mismatch planes of a group's sampled positions: bit p set = window p mismatches at a sampled position
-template <bool REV, int G, int K>
+template <bool REV, int PB, int G, int K>
 __device__ __forceinline__ uint32_t group_any(const Planes& P) {
     using Gr = Group<REV, G>;
     if constexpr (K >= Gr::S) {
         return 0u;
     } else if constexpr (K + 3 <= Gr::S) {
-        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) |
-               cplane<REV, Gr::sample(K + 2)>(P, 0) | group_any<REV, G, K + 3>(P);
+        return cplane<REV, Gr::sample(K)>(P, PB) | cplane<REV, Gr::sample(K + 1)>(P, PB) |
+               cplane<REV, Gr::sample(K + 2)>(P, PB) | group_any<REV, PB, G, K + 3>(P);
     } else if constexpr (K + 2 <= Gr::S) {
-        return cplane<REV, Gr::sample(K)>(P, 0) | cplane<REV, Gr::sample(K + 1)>(P, 0) | group_any<REV, G, K + 2>(P);
+        return cplane<REV, Gr::sample(K)>(P, PB) | cplane<REV, Gr::sample(K + 1)>(P, PB) | group_any<REV, PB, G, K + 2>(P);
     } else {
-        return cplane<REV, Gr::sample(K)>(P, 0) | group_any<REV, G, K + 1>(P);
+        return cplane<REV, Gr::sample(K)>(P, PB) | group_any<REV, PB, G, K + 1>(P);
     }
 }
 
 // windows in which EVERY group shows a mismatch among its samples (those cannot be within the budget)
-template <bool REV, int G>
+template <bool REV, int PB, int G>
 __device__ __forceinline__ uint32_t all_groups_dirty(const Planes& P) {
     if constexpr (G >= NGROUPS) {
         return 0xFFFFFFFFu;
     } else if constexpr (Group<REV, G>::S == 0) {
         return 0u;   // an empty group is trivially clean: nothing can be excluded
     } else {
-        return group_any<REV, G, 0>(P) & all_groups_dirty<REV, G + 1>(P);
+        return group_any<REV, PB, G, 0>(P) & all_groups_dirty<REV, PB, G + 1>(P);
     }
 }
 
-template <bool REV>
+// candidate windows of block PB
+template <bool REV, int PB>
 __device__ __forceinline__ uint32_t candidate_windows(const Planes& P, uint32_t live) {
-    return ~all_groups_dirty<REV, 0>(P) & live;
+    return ~all_groups_dirty<REV, PB, 0>(P) & live;
 }
 
 // word k of a strand's template: what = 0 constant-position mask, 1 high bits of the bases, 2 low bits
@@ -789,8 +796,8 @@ __host__ __device__ constexpr uint32_t template_word(const char* s, int k, int w
     return w;
 }
 
-// Exact constant-mismatch count of window p on a strand; leaves the window's words in wh / wl / wn.
-template <int K>
+// Exact constant-mismatch count of window 32 PB + p on a strand; leaves the window's words in wh / wl / wn.
+template <int K, int PB>
 __device__ __forceinline__ int verify_words(const Words& R, int p, bool rev, uint32_t (&wh)[TW + 1], uint32_t (&wl)[TW + 1],
                                             uint32_t (&wn)[TW + 1]) {
     if constexpr (K >= TW) {
@@ -798,19 +805,20 @@ __device__ __forceinline__ int verify_words(const Words& R, int p, bool rev, uin
     } else {
         constexpr uint32_t fth = template_word(FB, K, 1), ftl = template_word(FB, K, 2), fcm = template_word(FB, K, 0);
         constexpr uint32_t rth = template_word(RB, K, 1), rtl = template_word(RB, K, 2), rcm = template_word(RB, K, 0);
-        wh[K] = __funnelshift_r(R.h[K], R.h[K + 1], p);
-        wl[K] = __funnelshift_r(R.l[K], R.l[K + 1], p);
-        wn[K] = __funnelshift_r(R.n[K], R.n[K + 1], p);
+        wh[K] = __funnelshift_r(R.h[PB + K], R.h[PB + K + 1], p);
+        wl[K] = __funnelshift_r(R.l[PB + K], R.l[PB + K + 1], p);
+        wn[K] = __funnelshift_r(R.n[PB + K], R.n[PB + K + 1], p);
         const uint32_t th = (SPEC_FWD && SPEC_REV) ? (rev ? rth : fth) : (SPEC_REV ? rth : fth);
         const uint32_t tl = (SPEC_FWD && SPEC_REV) ? (rev ? rtl : ftl) : (SPEC_REV ? rtl : ftl);
         const uint32_t cm = (SPEC_FWD && SPEC_REV) ? (rev ? rcm : fcm) : (SPEC_REV ? rcm : fcm);
-        return __popc(((wh[K] ^ th) | (wl[K] ^ tl) | wn[K]) & cm) + verify_words<K + 1>(R, p, rev, wh, wl, wn);
+        return __popc(((wh[K] ^ th) | (wl[K] ^ tl) | wn[K]) & cm) + verify_words<K + 1, PB>(R, p, rev, wh, wl, wn);
     }
 }
+template <int PB>
 __device__ __forceinline__ int verify_window(const Words& R, int p, bool rev, uint32_t (&wh)[TW + 1], uint32_t (&wl)[TW + 1],
                                              uint32_t (&wn)[TW + 1]) {
     wh[TW] = wl[TW] = wn[TW] = 0;
-    return verify_words<0>(R, p, rev, wh, wl, wn);
+    return verify_words<0, PB>(R, p, rev, wh, wl, wn);
 }
 
 // bits [START, START + KEYLEN) of a window given as words
@@ -819,6 +827,56 @@ __device__ __forceinline__ uint32_t window_key(const uint32_t (&w)[TW + 1]) {
     constexpr int a = START >> 5, sh = START & 31;
     const uint32_t lo = w[a], hi = a + 1 <= TW ? w[a + 1] : 0u;
     return (sh == 0 ? lo : __funnelshift_r(lo, hi, sh)) & KEYMASK;
+}
+
+// Filter + verify of window block PB (and, recursively, the blocks after it): exact constant mismatches of each candidate, in
+// the reference's order (positions ascending, forward before reverse at a position).  `npos` is the lane's number of windows.
+// The first block's first round runs unconditionally (nine reads in ten have a candidate); further rounds only while some lane
+// still has one.  The first verified window's strand, mismatches, position and variable region go to meta / kh / kl / kn.
+template <int PB>
+__device__ __forceinline__ void scan_blocks(const Words& R, const Planes& P, int npos, int& ncand, uint32_t& meta, uint32_t& kh,
+                                            uint32_t& kl, uint32_t& kn) {
+    if constexpr (PB < NBLOCKS) {
+#if SPEC_RAGGED
+        const int left = npos - 32 * PB;
+        const uint32_t live = left <= 0 ? 0u : (left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u));
+#else
+        const uint32_t live = npos > 0 ? block_mask<PB>() : 0u;
+#endif
+        uint32_t cf = SPEC_FWD ? candidate_windows<false, PB>(P, live) : 0u;
+        uint32_t cr = SPEC_REV ? candidate_windows<true, PB>(P, live) : 0u;
+        bool more = PB == 0 ? true : __any_sync(0xFFFFFFFFu, (cf | cr) != 0u);
+        while (more) {
+            const uint32_t any = cf | cr;
+            const uint32_t lowest = any & (0u - any);   // 0 when the lane has no candidate left
+            const int p = 31 - __clz(lowest | 1u);
+            const bool rev = SPEC_FWD ? !(cf & lowest) : true;
+            if (rev) {
+                cr &= ~lowest;
+            } else {
+                cf &= ~lowest;
+            }
+            uint32_t wh[TW + 1], wl[TW + 1], wn[TW + 1];
+            const int c = verify_window<PB>(R, p, rev, wh, wl, wn);
+            const bool ok = lowest != 0u && c <= SPEC_MM;
+            if (ok && ncand == 0) {
+                meta = PM_CAND + (rev ? PM_REV : 0u) + ((uint32_t)c << 16) + (uint32_t)(32 * PB + p);
+                if (SPEC_FSTART == SPEC_RSTART || !SPEC_REV || !SPEC_FWD) {
+                    constexpr int START = (SPEC_FWD && SPEC_REV) ? SPEC_FSTART : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
+                    kh = window_key<START>(wh);
+                    kl = window_key<START>(wl);
+                    kn = window_key<START>(wn);
+                } else {
+                    kh = rev ? window_key<SPEC_RSTART>(wh) : window_key<SPEC_FSTART>(wh);
+                    kl = rev ? window_key<SPEC_RSTART>(wl) : window_key<SPEC_FSTART>(wl);
+                    kn = rev ? window_key<SPEC_RSTART>(wn) : window_key<SPEC_FSTART>(wn);
+                }
+            }
+            ncand += ok ? 1 : 0;
+            more = __any_sync(0xFFFFFFFFu, (cf | cr) != 0u);
+        }
+        scan_blocks<PB + 1>(R, P, npos, ncand, meta, kh, kl, kn);
+    }
 }
 
 // One warp's worth of deferred reads (lane < take holds one): the seeded search for reads with a single candidate
@@ -952,48 +1010,15 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             Planes P;
             make_planes(R, P);
 
-            // ---- filter: windows that can still be within the budget ----
+            // ---- filter + verify, window block by window block ----
 #if SPEC_RAGGED
             // windows p with p + T <= this read's length (ScanTemplate.hpp:153,168-170: a read shorter than the template has none)
             const int npos = inrange ? (int)reads.lens[i] - T + 1 : 0;
-            const uint32_t live = npos <= 0 ? 0u : (npos >= 32 ? 0xFFFFFFFFu : ((1u << npos) - 1u));
 #else
-            const uint32_t live = inrange ? WINMASK : 0u;
+            const int npos = inrange ? NWIN : 0;
 #endif
-            uint32_t cf = SPEC_FWD ? candidate_windows<false>(P, live) : 0u;
-            uint32_t cr = SPEC_REV ? candidate_windows<true>(P, live) : 0u;
-            // ---- verify: exact constant mismatches of each candidate, in the reference's order (positions ascending, forward
-            // before reverse).  The first round runs unconditionally (nine reads in ten have a candidate); further rounds only
-            // while some lane still has one. ----
             int ncand = 0;
-            do {
-                const uint32_t any = cf | cr;
-                const uint32_t lowest = any & (0u - any);   // 0 when the lane has no candidate left
-                const int p = 31 - __clz(lowest | 1u);
-                const bool rev = SPEC_FWD ? !(cf & lowest) : true;
-                if (rev) {
-                    cr &= ~lowest;
-                } else {
-                    cf &= ~lowest;
-                }
-                uint32_t wh[TW + 1], wl[TW + 1], wn[TW + 1];
-                const int c = verify_window(R, p, rev, wh, wl, wn);
-                const bool ok = lowest != 0u && c <= SPEC_MM;
-                if (ok && ncand == 0) {
-                    meta = PM_CAND + (rev ? PM_REV : 0u) + ((uint32_t)c << 16) + (uint32_t)p;
-                    if (SPEC_FSTART == SPEC_RSTART || !SPEC_REV || !SPEC_FWD) {
-                        constexpr int START = (SPEC_FWD && SPEC_REV) ? SPEC_FSTART : (SPEC_FWD ? SPEC_FSTART : SPEC_RSTART);
-                        kh = window_key<START>(wh);
-                        kl = window_key<START>(wl);
-                        kn = window_key<START>(wn);
-                    } else {
-                        kh = rev ? window_key<SPEC_RSTART>(wh) : window_key<SPEC_FSTART>(wh);
-                        kl = rev ? window_key<SPEC_RSTART>(wl) : window_key<SPEC_FSTART>(wl);
-                        kn = rev ? window_key<SPEC_RSTART>(wn) : window_key<SPEC_FSTART>(wn);
-                    }
-                }
-                ncand += ok ? 1 : 0;
-            } while (__any_sync(0xFFFFFFFFu, (cf | cr) != 0u));
+            scan_blocks<0>(R, P, npos, ncand, meta, kh, kl, kn);
             // what the settle step will need to know, decided here once
             {
                 const bool many = ncand > 1;

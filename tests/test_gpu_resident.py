@@ -103,7 +103,7 @@ def test_exact_table_variants(kref, monkeypatch, mm, joint):
 @pytest.mark.parametrize("mm", [0, 1, 2])
 @pytest.mark.parametrize("use_first", [True, False])
 def test_trimmed_reads_take_the_filter_verify_kernel(kref, mm, use_first):
-    """Reads of different lengths with at most 32 windows (adapter-trimmed data): the filter + verify kernel with per-lane
+    """Reads of different lengths (adapter-trimmed data), here at most 32 windows each: the filter + verify kernel with per-lane
     window masks; reads shorter than the template have no window at all (ScanTemplate.hpp:153,168-170)."""
     from screencounter_b200 import rcpp
     from util import adversarial_reads, fastq
@@ -119,7 +119,59 @@ def test_trimmed_reads_take_the_filter_verify_kernel(kref, mm, use_first):
     data = fastq(reads)
     want_index, want_info = kref.trace_single(data, TEMPLATE, 2, pool, mm, use_first)
     counts, total, (index, info) = rcpp.count_single_barcodes(data, TEMPLATE, 2, pool, mm, use_first, 4, trace=True)
-    assert "at most 32 windows" in rcpp.timing()["kernel"], rcpp.timing()
+    assert "trimmed reads, filter+verify" in rcpp.timing()["kernel"], rcpp.timing()
+    assert total == len(reads)
+    assert np.array_equal(index[:, 0] if index.ndim > 1 else index, want_index)
+    assert np.array_equal(info, want_info)
+    assert (want_index >= 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("read_len", [76, 100, 108, 150, 192])
+@pytest.mark.parametrize("mm,use_first", [(0, True), (1, True), (1, False), (2, False)])
+def test_long_reads_scan_several_window_blocks(kref, read_len, mm, use_first):
+    """Reads with more than 32 windows: the filter + verify kernel goes through the window blocks in turn.  Constructs at
+    every offset (first window, last window, block boundaries), two constructs in one read (first-versus-best, ties across
+    blocks), per-read outcomes (index, strand, mismatches, position) equal to the reference's."""
+    from screencounter_b200 import rcpp
+    from util import adversarial_reads, fastq, random_seq, fill_template
+    rng = np.random.default_rng(1000 + read_len + mm)
+    pool = distinct_pool(rng, 500, 20)
+    T = len(TEMPLATE)
+    reads = adversarial_reads(rng, 20000, TEMPLATE, [pool], strand="both", read_len=read_len, sub_rate=0.02, n_rate=0.004,
+                              lower_rate=0.01, double_frac=0.3, short_frac=0.0, edge_frac=0.3)
+    reads = [(r + random_seq(rng, read_len))[:read_len] for r in reads]     # the junk reads come back shorter
+    # a clean construct at every possible offset
+    for off in range(read_len - T + 1):
+        c = fill_template(TEMPLATE, pool[off % len(pool)])
+        reads.append((random_seq(rng, off) + c + random_seq(rng, read_len))[:read_len])
+    assert {len(r) for r in reads} == {read_len}
+    data = fastq(reads)
+    want_index, want_info = kref.trace_single(data, TEMPLATE, 2, pool, mm, use_first)
+    counts, total, (index, info) = rcpp.count_single_barcodes(data, TEMPLATE, 2, pool, mm, use_first, 4, trace=True)
+    assert "uniform-length filter+verify" in rcpp.timing()["kernel"], rcpp.timing()
+    assert total == len(reads)
+    assert np.array_equal(index[:, 0] if index.ndim > 1 else index, want_index)
+    assert np.array_equal(info, want_info)
+    assert np.array_equal(counts, np.bincount(want_index[want_index >= 0], minlength=len(pool)))
+    assert (want_index >= 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("mm,use_first", [(1, True), (1, False)])
+def test_long_trimmed_reads(kref, mm, use_first):
+    """Ragged batch whose longest read has 149 windows: every lane masks, block by block, the windows its own read lacks."""
+    from screencounter_b200 import rcpp
+    from util import adversarial_reads, fastq
+    rng = np.random.default_rng(77 + mm)
+    pool = distinct_pool(rng, 500, 20)
+    reads = adversarial_reads(rng, 30000, TEMPLATE, [pool], strand="both", sub_rate=0.02, n_rate=0.004, lower_rate=0.01,
+                              double_frac=0.3, short_frac=0.05, edge_frac=0.3)
+    reads = [(r + "ACGT" * 48)[: int(rng.integers(0, 193))] if k % 3 == 0 else r for k, r in enumerate(reads)]
+    reads[5] = ""
+    assert max(len(r) for r in reads) > 150
+    data = fastq(reads)
+    want_index, want_info = kref.trace_single(data, TEMPLATE, 2, pool, mm, use_first)
+    counts, total, (index, info) = rcpp.count_single_barcodes(data, TEMPLATE, 2, pool, mm, use_first, 4, trace=True)
+    assert "trimmed reads, filter+verify" in rcpp.timing()["kernel"], rcpp.timing()
     assert total == len(reads)
     assert np.array_equal(index[:, 0] if index.ndim > 1 else index, want_index)
     assert np.array_equal(info, want_info)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs the resident single-barcode path a few times on the bench workload (for ncu captures and knob sweeps).
-usage: profile_single.py [n_reads] [launches]"""
+usage: profile_single.py [n_reads] [launches] [read_len]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,8 +10,9 @@ from screencounter_b200.device import SynthSpec, SinglePlan
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 launches = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+read_len = int(sys.argv[3]) if len(sys.argv) > 3 else 75
 lib = bench.make_library()
-spec = SynthSpec(bench.TEMPLATE, [lib], seed=42, read_len=75, strand=2)
+spec = SynthSpec(bench.TEMPLATE, [lib], seed=42, read_len=read_len, strand=2)
 reads = spec.on_device(0, n, device=0)
 plan = SinglePlan(bench.TEMPLATE, 2, lib, 1, True, device=0)
 counts = torch.zeros(len(lib), dtype=torch.int32, device="cuda")
