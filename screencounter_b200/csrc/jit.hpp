@@ -22,7 +22,7 @@ struct SpecSingleConfig {
     int fstart = 0, rstart = 0, keylen = 0;
     std::vector<uint32_t> seed_masks;   // pigeonhole seeds of the libraries (empty = deferred reads take the generic search)
     int dup_first = 0;
-    // > 0: every read of the batch has this length and at most 32 windows: the uniform-length kernel (filter + verify
+    // > 0: every read of the batch has this length (or, with `ragged`, at most this length): the uniform-length kernel (filter + verify
     // scan, several tiles per bulk copy) is compiled instead of the general one
     int ulen = 0;
     int info = 1;                 // the per-read info word may be asked for

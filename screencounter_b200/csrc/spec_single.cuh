@@ -111,7 +111,7 @@
 #define SPEC_IBUCKETS 0
 #endif
 // the batch of the "uniform-length" kernel has per-read lengths after all (trimmed reads): SPEC_ULEN is then the longest read,
-// still with at most 32 windows, and every lane masks the windows its own read does not have
+// and every lane masks, block by block, the windows its own read does not have
 #ifndef SPEC_RAGGED
 #define SPEC_RAGGED 0
 #endif
@@ -701,8 +701,8 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
 
 // =====================================================================================================================
 // Uniform-length variant.  Same per-read outcomes as the kernel above, for batches whose reads all have SPEC_ULEN
-// bases with at most 32 windows (the sequencing-run case: BASELINE configs[1] is 75-base reads, 44-base template,
-// exactly 32 windows).  What changes:
+// bases (the sequencing-run case: BASELINE configs[1] is 75-base reads, 44-base template, exactly 32 windows = one
+// window block; longer reads go through their blocks of 32 windows in turn).  What changes:
 //   * FILTER + VERIFY instead of counting every constant position in every window.  A window with at most MM
 //     constant mismatches is mismatch-free in at least one of MM + 1 groups of constant positions (pigeonhole), so
 //     the bit-sliced pass only ORs the mismatch planes of up to 8 sampled positions per group (one funnel shift and
