@@ -152,8 +152,11 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     if (const char* env = std::getenv("SCG_NO_SPECIALIZE")) {
         if (env[0] && env[0] != '0') return fail("disabled by SCG_NO_SPECIALIZE");
     }
-    // register budget: 4 mismatch planes of W + 2 words must stay in registers
-    if (cfg.W > 6) return fail("reads longer than 192 bases use the generic kernel");
+    // register budget: 4 mismatch planes of W + 2 words must stay in registers (the uniform-length kernel, which does not keep
+    // bit-sliced counters beside them, affords 10 words at 4 blocks/SM without spilling)
+    if (cfg.W > (cfg.ulen > 0 ? 10 : 6)) {
+        return fail(cfg.ulen > 0 ? "reads longer than 320 bases use the generic kernel" : "reads longer than 192 bases use the generic kernel");
+    }
     if (cfg.T > 128) return fail("templates longer than 128 bases use the generic kernel");
     if (cfg.cb > 3) return fail("mismatch budgets above 7 use the generic kernel");
     if (cfg.keylen > 32) return fail("variable regions longer than 32 bases use the generic kernel");
@@ -171,7 +174,8 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
     // 96-base reads at 64 registers, longer reads trade occupancy for registers
     const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? (cfg.W <= 3 ? 8 : (cfg.W == 4 ? 6 : 4)) : 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
-    const int group = env_int("SCG_SPEC_GROUP", 2, 1, 8);
+    // tiles per bulk copy: two, or one where two rings of long reads would not fit the static shared memory
+    const int group = env_int("SCG_SPEC_GROUP", (cfg.ulen > 0 && cfg.W >= 7) ? 1 : 2, 1, 8);
     const int samples = env_int("SCG_SPEC_SAMPLES", 8, 1, 32);
     const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages) + "#" +
                             std::to_string(group) + "#" + std::to_string(samples);

@@ -350,7 +350,7 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
     cfg.rstart = P.spec.rstart[0];
     cfg.keylen = P.spec.rlen_f[0];
     spec_seeds(m, cfg);
-    // the uniform-length kernel: reads no longer than 192 bases with at least one window, a budget the pigeonhole filter
+    // the uniform-length kernel: reads no longer than 320 bases with at least one window, a budget the pigeonhole filter
     // is worth having for (at least four constant positions per group), indices that fit 32 bits
     {
         const int nwin = reads.uniform_len - m.tmpl.length + 1;

@@ -126,7 +126,7 @@ def test_trimmed_reads_take_the_filter_verify_kernel(kref, mm, use_first):
     assert (want_index >= 0).mean() > 0.2
 
 
-@pytest.mark.parametrize("read_len", [76, 100, 108, 150, 192])
+@pytest.mark.parametrize("read_len", [76, 100, 108, 150, 192, 250, 320])
 @pytest.mark.parametrize("mm,use_first", [(0, True), (1, True), (1, False), (2, False)])
 def test_long_reads_scan_several_window_blocks(kref, read_len, mm, use_first):
     """Reads with more than 32 windows: the filter + verify kernel goes through the window blocks in turn.  Constructs at
@@ -156,16 +156,17 @@ def test_long_reads_scan_several_window_blocks(kref, read_len, mm, use_first):
     assert (want_index >= 0).mean() > 0.2
 
 
+@pytest.mark.parametrize("maxlen", [192, 320])
 @pytest.mark.parametrize("mm,use_first", [(1, True), (1, False)])
-def test_long_trimmed_reads(kref, mm, use_first):
-    """Ragged batch whose longest read has 149 windows: every lane masks, block by block, the windows its own read lacks."""
+def test_long_trimmed_reads(kref, mm, use_first, maxlen):
+    """Ragged batch whose longest read has 149 (277) windows: every lane masks, block by block, the windows its own read lacks."""
     from screencounter_b200 import rcpp
     from util import adversarial_reads, fastq
     rng = np.random.default_rng(77 + mm)
     pool = distinct_pool(rng, 500, 20)
     reads = adversarial_reads(rng, 30000, TEMPLATE, [pool], strand="both", sub_rate=0.02, n_rate=0.004, lower_rate=0.01,
                               double_frac=0.3, short_frac=0.05, edge_frac=0.3)
-    reads = [(r + "ACGT" * 48)[: int(rng.integers(0, 193))] if k % 3 == 0 else r for k, r in enumerate(reads)]
+    reads = [(r + "ACGT" * 80)[: int(rng.integers(0, maxlen + 1))] if k % 3 == 0 else r for k, r in enumerate(reads)]
     reads[5] = ""
     assert max(len(r) for r in reads) > 150
     data = fastq(reads)

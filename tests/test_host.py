@@ -182,7 +182,8 @@ def test_runtime_specialised_kernel_compiles(template, strand, mm, words):
     ("ACGTACGT" + "-" * 10 + "TGCATGCA", 1, 3, 26),
     ("A" * 40 + "-" * 30 + "C" * 40, 2, 1, 120),
     ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 1, 150),     # four window blocks
-    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 2, 192),     # five, the longest reads the kernel takes
+    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 2, 192),     # five
+    ("CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG", 2, 1, 320),     # nine, the longest reads the kernel takes
     ("ACGTACGT" + "-" * 10 + "TGCATGCA", 0, 0, 101),
 ])
 def test_uniform_length_kernel_compiles(template, strand, mm, read_len):
