@@ -167,7 +167,30 @@ def reference_arm(args, library):
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+    box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the run and the result line goes to the original."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -180,6 +203,7 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host FASTQ text)")
     ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-baseline sample")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     library = make_library()
@@ -349,7 +373,7 @@ def main():
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
