@@ -171,11 +171,12 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         return x < lo ? lo : (x > hi ? hi : x);
     };
     // the uniform-length kernel keeps a read's words and mismatch planes in registers: 8 blocks of 128 threads fit up to
-    // 96-base reads at 64 registers, longer reads trade occupancy for registers
-    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? (cfg.W <= 3 ? 8 : (cfg.W == 4 ? 6 : 4)) : 4, 1, 16);
+    // 96-base reads at 64 registers, longer reads trade occupancy for registers (the ALU pipe bounds those, and the sweeps in
+    // profiles/r1_v10_long_reads_perf.txt are flat within 3 % between 4 and 8 blocks)
+    const int min_blocks = env_int("SCG_SPEC_MIN_BLOCKS", cfg.ulen > 0 ? (cfg.W <= 3 ? 8 : (cfg.W <= 6 ? 6 : 4)) : 4, 1, 16);
     const int stages = env_int("SCG_SPEC_STAGES", 2, 1, 8);
-    // tiles per bulk copy: two, or one where two rings of long reads would not fit the static shared memory
-    const int group = env_int("SCG_SPEC_GROUP", (cfg.ulen > 0 && cfg.W >= 7) ? 1 : 2, 1, 8);
+    // tiles per bulk copy: two, or one where two would not fit the static shared memory (or would cost resident blocks: 192-base reads)
+    const int group = env_int("SCG_SPEC_GROUP", (cfg.ulen > 0 && cfg.W >= 6) ? 1 : 2, 1, 8);
     const int samples = env_int("SCG_SPEC_SAMPLES", 8, 1, 32);
     const std::string key = std::to_string(device) + "#" + cfg.key() + "#" + std::to_string(min_blocks) + "#" + std::to_string(stages) + "#" +
                             std::to_string(group) + "#" + std::to_string(samples);
