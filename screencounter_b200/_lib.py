@@ -74,7 +74,7 @@ def lib():
     return _lib
 
 
-# every symbol include/scg.h declares (checked by tests/test_abi.py)
+# every symbol include/scg.h declares (checked by tests/test_host.py::test_abi_exports_every_declared_symbol)
 EXPORTS = [
     "scg_ctx_create", "scg_ctx_destroy", "scg_last_error", "scg_version", "scg_timing_json", "scg_kernel_launches",
     "scg_result_rows", "scg_result_width", "scg_result_reads", "scg_result_copy_table", "scg_result_trace_width",

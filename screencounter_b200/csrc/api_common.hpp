@@ -89,9 +89,12 @@ void dispatch_kw(int kw, F&& f) {
 // device.  Only successfully built matchers are cached, so validation errors are raised every time.
 struct CacheKey {
     unsigned long long k1 = 1469598103934665603ull, k2 = 0x9E3779B97F4A7C15ull;
+    unsigned long long fed = 0;   // bytes fed so far (kept beside the hash as a cheap secondary check of a cache hit)
     void feed(const void* data, size_t n) {
         const char* p = static_cast<const char*>(data);
+        fed += n;
         k1 = mix64(k1 ^ n);
+        k2 = (k2 ^ (0xA24BAED4963EE407ull + n)) * 1099511628211ull + (k2 >> 29);   // the length goes into both words
         size_t i = 0;
         for (; i + 8 <= n; i += 8) {
             unsigned long long w;
@@ -115,13 +118,14 @@ struct CacheKey {
 template <class M, class Build>
 std::shared_ptr<M> cached_matcher(Context& ctx, const CacheKey& key, Build&& build) {
     for (auto& e : ctx.matcher_cache) {
-        if (e.key1 == key.k1 && e.key2 == key.k2) return std::static_pointer_cast<M>(e.object);
+        if (e.key1 == key.k1 && e.key2 == key.k2 && e.fed_bytes == key.fed) return std::static_pointer_cast<M>(e.object);
     }
     std::shared_ptr<M> m = build();
     if (ctx.matcher_cache.size() >= 6) ctx.matcher_cache.erase(ctx.matcher_cache.begin());
     Context::CachedObject entry;
     entry.key1 = key.k1;
     entry.key2 = key.k2;
+    entry.fed_bytes = key.fed;
     entry.object = m;
     ctx.matcher_cache.push_back(entry);
     return m;

@@ -55,6 +55,24 @@ struct BlockCache {
         blocks.erase(blocks.begin() + (long)best);
         return p;
     }
+    // frees every cached block of `device` (called on out-of-memory)
+    void trim(int device) {
+        std::vector<void*> doomed;
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            for (size_t k = 0; k < blocks.size();) {
+                if (blocks[k].device == device) {
+                    doomed.push_back(blocks[k].ptr);
+                    held -= blocks[k].bytes;
+                    blocks.erase(blocks.begin() + (long)k);
+                } else {
+                    ++k;
+                }
+            }
+        }
+        if (!doomed.empty()) cudaDeviceSynchronize();
+        for (void* p : doomed) cudaFree(p);
+    }
     bool give(void* p, size_t n, int device) {
         std::lock_guard<std::mutex> lock(mutex);
         if (blocks.size() >= kMaxBlocks || held + n > kMaxHeld) return false;
@@ -72,16 +90,28 @@ BlockCache& block_cache() {
 void DeviceBuffer::alloc(size_t n, bool zero) {
     release();
     if (n == 0) n = 16;
-    int device = 0;
-    SCG_CUDA_CHECK(cudaGetDevice(&device));
+    int current = 0;
+    SCG_CUDA_CHECK(cudaGetDevice(&current));
     size_t got = 0;
-    ptr = block_cache().take(n, device, &got);
+    ptr = block_cache().take(n, current, &got);
     if (ptr) {
         bytes = got;
     } else {
-        SCG_CUDA_CHECK(cudaMalloc(&ptr, n));
+        cudaError_t st = cudaMalloc(&ptr, n);
+        if (st == cudaErrorMemoryAllocation) {
+            // the cache may be sitting on the memory that is asked for (it holds up to 24 GB): give this device's cached
+            // blocks back and try once more before reporting out-of-memory
+            cudaGetLastError();
+            block_cache().trim(current);
+            st = cudaMalloc(&ptr, n);
+        }
+        if (st != cudaSuccess) {
+            ptr = nullptr;
+            SCG_CUDA_CHECK(st);
+        }
         bytes = n;
     }
+    device = current;
     if (zero) {
         // the memset runs on the legacy stream, which the context's non-blocking stream does not wait for
         SCG_CUDA_CHECK(cudaMemset(ptr, 0, n));
@@ -100,11 +130,20 @@ void DeviceBuffer::upload(const void* host, size_t n, cudaStream_t stream) {
 
 void DeviceBuffer::release() {
     if (ptr) {
-        int device = 0;
-        // whatever still uses the block must be done before somebody else gets it (cudaFree's implicit guarantee)
-        if (cudaGetDevice(&device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess || !block_cache().give(ptr, bytes, device)) {
+        // The block goes back to the cache of the device it was allocated on, whatever device is current now (handles are
+        // freed from Python's garbage collector, R finalisers, other contexts' calls).  Whatever still uses the block on
+        // THAT device must be done before somebody else gets it (cudaFree's implicit guarantee).
+        int current = -1;
+        const bool have_current = cudaGetDevice(&current) == cudaSuccess;
+        bool cached = false;
+        if (cudaSetDevice(device) == cudaSuccess) {
+            cached = cudaDeviceSynchronize() == cudaSuccess && block_cache().give(ptr, bytes, device);
+            if (!cached) cudaFree(ptr);
+        } else {
+            cudaGetLastError();
             cudaFree(ptr);
         }
+        if (have_current && current != device) cudaSetDevice(current);
     }
     ptr = nullptr;
     bytes = 0;

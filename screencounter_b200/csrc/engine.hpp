@@ -20,15 +20,17 @@ namespace scg {
 struct DeviceBuffer {
     void* ptr = nullptr;
     size_t bytes = 0;
+    int device = 0;   // the CUDA device the block was allocated on (release() returns it there)
     DeviceBuffer() {}
     DeviceBuffer(const DeviceBuffer&) = delete;
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
-    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), bytes(o.bytes) { o.ptr = nullptr; o.bytes = 0; }
+    DeviceBuffer(DeviceBuffer&& o) noexcept : ptr(o.ptr), bytes(o.bytes), device(o.device) { o.ptr = nullptr; o.bytes = 0; }
     DeviceBuffer& operator=(DeviceBuffer&& o) noexcept {
         if (this != &o) {
             release();
             ptr = o.ptr;
             bytes = o.bytes;
+            device = o.device;
             o.ptr = nullptr;
             o.bytes = 0;
         }
@@ -95,12 +97,15 @@ struct Context {
     // 128-bit hash of everything that defines them
     struct CachedMatcher {
         unsigned long long key1 = 0, key2 = 0;
+        int npool = 0;                               // secondary check of a cache hit, beside the 128-bit hash
+        std::string constant, first_seq, last_seq;
         std::shared_ptr<SingleMatcher> matcher;
     };
     std::vector<CachedMatcher> single_cache;
     // matchers of the other handlers (any type behind the pointer; the key's first word names it), most recent last
     struct CachedObject {
         unsigned long long key1 = 0, key2 = 0;
+        unsigned long long fed_bytes = 0;            // secondary check: total bytes hashed into the key
         std::shared_ptr<void> object;
     };
     std::vector<CachedObject> matcher_cache;

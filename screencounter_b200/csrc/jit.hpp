@@ -30,8 +30,32 @@ struct SpecSingleConfig {
     int has_index = 1;            // the per-read index is asked for
     int ibuckets = 0;             // seed buckets with the first candidate inline are there
     int ragged = 0;               // the batch carries per-read lengths (ulen is then the longest read)
+    int hist = 0;                 // > 0: counters privatised in shared memory, this many (pool size rounded up), flushed at the end
     std::string key() const;
 };
+
+// One run-time compiled module: program text (a few #defines + an #include of an embedded header) and the kernels wanted
+// from it.  Modules are cached per process (by device and text) and ON DISK (SCG_CACHE_DIR, else $XDG_CACHE_HOME or
+// ~/.cache/screencounter_b200; SCG_NO_DISK_CACHE=1 turns it off), keyed by the program text, a hash of the embedded headers,
+// the NVRTC version and the target, so that a fresh process pays a file read instead of a compilation.
+struct JitProgram {
+    std::string name;                  // file name shown in diagnostics
+    std::string text;
+    std::vector<std::string> kernels;  // extern "C" kernel names
+};
+struct JitModule {
+    cudaLibrary_t library = nullptr;
+    std::vector<cudaKernel_t> kernels; // in the order asked for
+    std::string problem;
+    bool from_disk = false;
+    double build_s = 0;                // compile (or disk read) + load
+};
+// nullptr (reason in *why) when run-time compilation is unavailable, disabled (SCG_NO_SPECIALIZE=1) or fails.  Thread-safe.
+const JitModule* jit_module(const JitProgram& prog, int device, std::string* why);
+// seconds this process has spent building or loading modules so far (reported as part of setup_s)
+double jit_seconds_total();
+// integer tuning knob from the environment, clamped to [lo, hi]
+int jit_env_int(const char* name, int fallback, int lo, int hi);
 
 // Returns a launchable kernel for the configuration, or nullptr (with the reason in *why) when
 // run-time compilation is unavailable or disabled (SCG_NO_SPECIALIZE=1); callers then use the

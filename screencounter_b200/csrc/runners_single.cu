@@ -258,6 +258,7 @@ std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* c
     };
     auto feed = [](Pair& h, const char* data, size_t n) {
         h.k1 = mix64(h.k1 ^ n);
+        h.k2 = (h.k2 ^ (0xA24BAED4963EE407ull + n)) * 1099511628211ull + (h.k2 >> 29);   // the length goes into both words
         size_t i = 0;
         for (; i + 8 <= n; i += 8) {
             unsigned long long w;
@@ -291,8 +292,13 @@ std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* c
         for (const Pair& h : part) feed(total, reinterpret_cast<const char*>(&h), sizeof h);
     }
     const unsigned long long k1 = total.k1, k2 = total.k2;
+    // a hit also has to agree on what can be compared without marshalling the pool: its size, the template, and the first
+    // and last sequences (a 128-bit collision between two real libraries would otherwise return the wrong tables silently)
+    const std::string first_seq = npool > 0 ? pool[0] : "", last_seq = npool > 0 ? pool[npool - 1] : "";
     for (auto& e : ctx.single_cache) {
-        if (e.key1 == k1 && e.key2 == k2) return e.matcher;
+        if (e.key1 == k1 && e.key2 == k2 && e.npool == npool && e.constant == constant && e.first_seq == first_seq && e.last_seq == last_seq) {
+            return e.matcher;
+        }
     }
     const Pool p(pool, npool);
     auto m = std::make_shared<SingleMatcher>();
@@ -303,6 +309,10 @@ std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* c
     Context::CachedMatcher entry;
     entry.key1 = k1;
     entry.key2 = k2;
+    entry.npool = npool;
+    entry.constant = constant;
+    entry.first_seq = first_seq;
+    entry.last_seq = last_seq;
     entry.matcher = m;
     ctx.single_cache.push_back(entry);
     return m;
@@ -365,6 +375,10 @@ void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, 
             cfg.joint = (m.joint.ptr != nullptr && m.joint_shift != 0 && !std::getenv("SCG_SPEC_NO_JOINT")) ? 1 : 0;
             cfg.has_index = d_index ? 1 : 0;
             cfg.ibuckets = (m.have_ibuckets && !std::getenv("SCG_SPEC_NO_IBUCKETS")) ? 1 : 0;
+            // small pools: counters privatised in shared memory (4 bytes per barcode and block; up to 1024 barcodes keep the
+            // kernel's 8 blocks per SM resident)
+            const int hist_max = jit_env_int("SCG_SPEC_HIST_MAX", 1024, 0, 8192);
+            if (m.npool > 0 && m.npool <= hist_max) cfg.hist = (m.npool + 31) / 32 * 32;
         }
     }
     std::string why;
@@ -780,7 +794,10 @@ int scg_device_alloc(scg_ctx* ctx, size_t bytes, void** out) {
         ctx->impl.ensure_ready();
         void* p = nullptr;
         SCG_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-        SCG_CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(bytes, 16)));
+        // zeroed on the context's stream and waited for: the context's stream is non-blocking, so a memset on the legacy
+        // stream would not be ordered before a following scg_*_plan_run on SCG_STREAM_OWN
+        SCG_CUDA_CHECK(cudaMemsetAsync(p, 0, std::max<size_t>(bytes, 16), ctx->impl.stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(ctx->impl.stream));
         *out = p;
     });
 }

@@ -115,6 +115,12 @@
 #ifndef SPEC_RAGGED
 #define SPEC_RAGGED 0
 #endif
+// > 0: the pool is small enough for the counters to be PRIVATISED IN SHARED MEMORY (one histogram of SPEC_HIST ints per block,
+// shared-memory atomics per matched read, one global atomic per non-zero counter and block at the end) -- the reference's
+// per-thread counter + reduce() of handlers/SingleBarcodeSingleEnd.hpp:93-104,119-125.  Uniform-length kernel only.
+#ifndef SPEC_HIST
+#define SPEC_HIST 0
+#endif
 
 namespace scg {
 namespace spec {
@@ -199,6 +205,15 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0x96>(a, b, c); }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xE8>(a, b, c); }
 __device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xFE>(a, b, c); }
+
+// counts[index]++ : a shared-memory reduction into the block's private histogram when there is one, else a global one
+__device__ __forceinline__ void count_hit(int32_t* __restrict__ counts, uint32_t hist_saddr, int index) {
+#if SPEC_HIST
+    asm volatile("red.shared.add.s32 [%0], 1;" ::"r"(hist_saddr + 4u * (uint32_t)index) : "memory");
+#else
+    atomicAdd(counts + index, 1);
+#endif
+}
 
 // ---- TMA (1-D bulk copy global -> shared) signalled on an mbarrier ----
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -884,7 +899,7 @@ __device__ __forceinline__ void scan_blocks(const Words& R, const Planes& P, int
 // halve this kernel's occupancy: their indices go to a list in global memory that `SPEC_NAME_SLOW` works off
 // right after this kernel, on the same stream.
 __device__ __forceinline__ void drain_deferred(const SpecTables& tb, const uint32_t (*queue)[QCAP], int at, int take, int lane,
-                                               int32_t* __restrict__ counts, int32_t* __restrict__ out_index,
+                                               int32_t* __restrict__ counts, uint32_t hist_saddr, int32_t* __restrict__ out_index,
                                                uint32_t* __restrict__ out_info, uint32_t* __restrict__ slow_list,
                                                uint32_t* __restrict__ slow_count) {
     const bool active = lane < take;
@@ -901,7 +916,7 @@ __device__ __forceinline__ void drain_deferred(const SpecTables& tb, const uint3
         const Hit h = seeded_search(tb, rev, qh, ql, qn, SPEC_MAXMM - fc, simple);
         if (simple) {
             const bool found = h.index >= 0;
-            if (found) atomicAdd(counts + h.index, 1);
+            if (found) count_hit(counts, hist_saddr, h.index);
             if (out_index) out_index[qi] = h.index;
             if (SPEC_INFO && out_info) out_info[qi] = pack_info(found, rev, fc + h.dist, h.dist, (int)(qm & 0xFFFFu));
         }
@@ -929,6 +944,14 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
     __shared__ __align__(128) uint32_t stage_all[WARPS][STAGES][GROUP * TILE_WORDS];
     __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
     __shared__ uint32_t queue_all[WARPS][5][QCAP];
+#if SPEC_HIST
+    __shared__ int32_t hist[SPEC_HIST];
+    for (int k = threadIdx.x; k < SPEC_HIST; k += SPEC_BLOCK) hist[k] = 0;
+    __syncthreads();
+    const uint32_t hist_saddr = smem_addr(hist);
+#else
+    const uint32_t hist_saddr = 0;
+#endif
     const int wib = threadIdx.x >> 5;
     uint32_t(*queue)[QCAP] = queue_all[wib];
     int waiting = 0;   // warp-uniform
@@ -1049,7 +1072,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             }
             const bool defer = (m & PU_ALWAYS_DEFERS) || ((m & PU_MISS_DEFERS) && index < 0);
             if ((m & PM_INRANGE) && !defer) {
-                if (index >= 0) atomicAdd(counts + index, 1);
+                if (index >= 0) count_hit(counts, hist_saddr, index);
                 if (SPEC_HAS_INDEX) __stcs(out_index + pend.i, index);
                 if (SPEC_INFO && out_info) {
                     __stcs(out_info + pend.i, pack_info(index >= 0, (m & PM_REV) != 0, (int)((m >> 16) & 0xFFu), 0, (int)(m & 0xFFFFu)));
@@ -1107,7 +1130,7 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
         while (waiting >= 32 || (!have && waiting > 0)) {
             const int take = waiting < 32 ? waiting : 32;
             waiting -= take;
-            drain_deferred(tb, queue, waiting, take, lane, counts, out_index, out_info, slow_list, slow_count);
+            drain_deferred(tb, queue, waiting, take, lane, counts, hist_saddr, out_index, out_info, slow_list, slow_count);
         }
         if (!have) break;
         // ---- next tile: the same group, or the warp's next group ----
@@ -1125,6 +1148,14 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
             }
         }
     }
+#if SPEC_HIST
+    // flush the block's private histogram: one global atomic per counter that was hit
+    __syncthreads();
+    for (int k = threadIdx.x; k < SPEC_HIST; k += SPEC_BLOCK) {
+        const int32_t v = hist[k];
+        if (v) atomicAdd(counts + k, v);
+    }
+#endif
 }
 
 // The reads the kernel above could not settle (several candidate windows): the full per-read search, one lane per
