@@ -179,9 +179,33 @@ int scg_single_plan_create(scg_ctx* ctx, const char* constant, int strand,
 int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_counts, int32_t* d_index,
                         void* cuda_stream);
 void scg_plan_free(scg_plan* plan);
-/* Which kernel variant the plan's last run used: "specialised (NVRTC)" = the template compiled into the
- * kernel at run time, or "generic (<why>)". */
+/* Which kernel variant the plan's last run used: "specialised (NVRTC) ..." = the template compiled into the
+ * kernel at run time, or "generic ... (<why>)". */
 const char* scg_plan_kernel(const scg_plan* plan);
+
+/* Compiled handlers of the other designs over resident reads: the kernels behind scg_count_dual (not randomized designs take
+ * the run-time specialised kernel), scg_count_combo_single and scg_count_random, without the FASTQ reader in front.  A
+ * context serves one stream at a time (the kernels share per-context scratch).
+ *   dual    d_counts (device, npool int32) is ACCUMULATED into; d_index (device, nullable) receives the pool row per pair.
+ *   combo   the plan owns the tally of combinations; d_pairs (device, nullable, 2 int32 per read) receives (first, second).
+ *   random  the plan owns the count table.  expected_distinct > 0 sizes it once for that many distinct barcodes (a run never
+ *           synchronises; a table that overflows is reported by scg_plan_harvest); 0 lets it grow like the reference's map.
+ *           d_index (device, nullable): 2 * window position + strand of the counted window, or -1.
+ * scg_plan_reset empties the plan's tally (asynchronously, on the stream); scg_plan_harvest synchronises the device and
+ * returns the table exactly as the file-level call would (sorted; rows stay on the device until scg_result_copy_table). */
+int scg_dual_plan_create(scg_ctx* ctx, const char* constant1, int reverse1, int mismatches1, const char* const* pool1, int npool1,
+                         const char* constant2, int reverse2, int mismatches2, const char* const* pool2, int npool2,
+                         int randomized, int use_first, scg_plan** out);
+int scg_dual_plan_run(scg_plan* plan, const scg_reads* reads1, const scg_reads* reads2, int32_t* d_counts, int32_t* d_index,
+                      void* cuda_stream);
+int scg_combo_plan_create(scg_ctx* ctx, const char* constant, int strand, const char* const* pool1, int npool1,
+                          const char* const* pool2, int npool2, int mismatches, int use_first, scg_plan** out);
+int scg_combo_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_pairs, void* cuda_stream);
+int scg_random_plan_create(scg_ctx* ctx, const char* constant, int strand, int mismatches, int use_first,
+                           long long expected_distinct, scg_plan** out);
+int scg_random_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_index, void* cuda_stream);
+int scg_plan_reset(scg_plan* plan, void* cuda_stream);
+int scg_plan_harvest(scg_plan* plan, scg_result** table);
 
 /* Host-only check of the FASTQ reader + packer (no device needed): parses `src`, packs every read into
  * the tile-planar 2-bit + N-mask layout and unpacks it again.  bases receives the concatenated
@@ -196,6 +220,11 @@ int scg_host_pack_roundtrip(const scg_source* src, int nthreads, char* bases, lo
 int scg_jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, char* message, size_t capacity);
 /* The same for the uniform-length variant of that kernel (every read `read_len` bases, 1 to 32 windows). */
 int scg_jit_selftest_uniform(const char* constant, int strand, int mismatches, int read_len, char* message, size_t capacity);
+
+/* The same for the specialised kernels of the other handlers (spec_handlers.cuh): kind 1 = dual paired-end (templates a and
+ * b, `strand_*` = 0 original / 1 reverse), 2 = combinatorial single-end, 3 = random barcodes (template a only). */
+int scg_jit_selftest_handler(int kind, const char* constant_a, int strand_a, int mismatches_a, const char* constant_b, int strand_b,
+                             int mismatches_b, int read_len, int use_first, char* message, size_t capacity);
 
 /* The segmented search behind countDualBarcodes on its own (SegmentedBarcodeSearch<2>::search,
  * inst/include/kaori/BarcodeSearch.hpp:478-487, without its result cache): `caps` holds two budgets per

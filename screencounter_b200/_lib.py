@@ -84,7 +84,9 @@ EXPORTS = [
     "scg_reads_from_source", "scg_reads_count", "scg_reads_device_bytes", "scg_reads_free",
     "scg_reads_synthesize", "scg_synth_fastq",
     "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",
-    "scg_host_pack_roundtrip", "scg_jit_selftest", "scg_jit_selftest_uniform",
+    "scg_dual_plan_create", "scg_dual_plan_run", "scg_combo_plan_create", "scg_combo_plan_run",
+    "scg_random_plan_create", "scg_random_plan_run", "scg_plan_reset", "scg_plan_harvest",
+    "scg_host_pack_roundtrip", "scg_jit_selftest", "scg_jit_selftest_uniform", "scg_jit_selftest_handler",
     "scg_device_alloc", "scg_device_free", "scg_device_zero", "scg_device_to_host", "scg_synchronize",
     "scg_host_alloc", "scg_host_free", "scg_search_segmented",
 ]

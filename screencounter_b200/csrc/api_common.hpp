@@ -172,23 +172,46 @@ std::shared_ptr<SingleMatcher> cached_single_matcher(Context& ctx, const char* c
 void launch_single(Context& ctx, const ReadsDev& reads, const SingleMatcher& m, int32_t* d_counts, int32_t* d_index,
                    uint32_t* d_info, cudaStream_t stream);
 
-// Device count table (64- or 128-bit keys) that grows with the number of reads seen.
+// A sparse result resident on the device, sorted: what scg_result hands out on demand (scg_result_copy_table) and what the
+// multi-GPU merge exchanges.  keys: one 64-bit word per row, ascending -- combinations as first << 32 | second, random
+// barcodes as three bits per base in text order (A < C < G < N < T), first base most significant.
+struct SortedTable {
+    DeviceBuffer keys, counts;   // unsigned long long[rows], uint32_t[rows]
+    size_t rows = 0;
+    int key_len = 0;             // > 0: random barcodes of this length; 0: combinations
+};
+
+// Device count table (libdev.hpp: 16-byte slots for 64-bit keys, separate arrays for 128-bit keys).  Sized for a load
+// factor of at most 1/2 of the keys it may hold; how many distinct keys it holds is tracked ON THE DEVICE (a counter bumped
+// by every first insert), so the table follows the number of distinct keys, not the number of reads.
 struct CountTable {
     bool wide = false;
-    DeviceBuffer keys, counts;
+    DeviceBuffer slots;    // narrow: CountSlot[capacity]; wide: ulonglong2[capacity]
+    DeviceBuffer counts;   // wide only: uint32_t[capacity]
+    DeviceBuffer live;     // device: [0] distinct keys inserted, [1] overflow flag
     size_t capacity = 0;
+    long long live_known = 0;   // distinct keys at the last read-back
+    long long pending = 0;      // inserts launched since (each may be a new key)
+    bool fixed = false;         // sized by the caller (resident plans): ensure() never grows it
     void init(Context& ctx, bool wide128, size_t initial);
-    void ensure(Context& ctx, long long upcoming_inserts);   // keeps load factor <= 1/2
+    void reset(Context& ctx, cudaStream_t stream);            // empties the table, asynchronously
+    void ensure(Context& ctx, long long upcoming_inserts);    // keeps (distinct keys + upcoming) <= capacity / 2; may synchronise
+    void check_overflow(Context& ctx);                        // throws when inserts were dropped (synchronises)
     CountTable64 view64() const;
     CountTable128 view128() const;
-    // live entries to the host
+    // live entries to the host, unsorted (wide tables)
     void download(Context& ctx, std::vector<unsigned long long>& keys_lo, std::vector<unsigned long long>& keys_hi,
                   std::vector<uint32_t>& counts);
-    // narrow tables of random barcodes: live entries sorted in the text order of the barcodes (A < C < G < N < T), each
-    // key as three bits per base, first base most significant
-    void download_sorted(Context& ctx, int key_len, std::vector<unsigned long long>& order_keys, std::vector<uint32_t>& counts);
-    long long upper_bound = 0;
+    // narrow tables: live entries sorted on the device.  key_len > 0: keys are random barcodes (random_key64), re-coded to
+    // text order before the sort; key_len == 0: sorted as they are (combinations).
+    void sorted(Context& ctx, int key_len, SortedTable& out);
 };
+
+// device-side helpers on sorted tables (runners_random.cu)
+void render_barcodes(Context& ctx, const SortedTable& t, DeviceBuffer& strings, DeviceBuffer& freq);   // rows * key_len chars, int32 freq
+void render_combinations(Context& ctx, const SortedTable& t, DeviceBuffer& keys, DeviceBuffer& freq);  // rows * 2 int32 (first, second), int32 freq
+// c = sorted merge of a and b with the counts of equal keys added (a and b sorted ascending, keys unique within each)
+void merge_sorted_tables(Context& ctx, const SortedTable& a, const SortedTable& b, SortedTable& c);
 
 // Tally of (i, j) combinations: dense matrix when small, count table otherwise.
 struct ComboTally {
@@ -198,13 +221,9 @@ struct ComboTally {
     CountTable table;
     void init(Context& ctx, int n1, int n2);
     ComboSink sink(Context& ctx, long long upcoming);
+    void reset(Context& ctx, cudaStream_t stream);
     void harvest(Context& ctx, scg_result& out);   // sorted (i, j) rows + freq (reference src/utils.h:14-45)
+    void sorted(Context& ctx, SortedTable& out);   // the same on the device, keys = first << 32 | second
 };
 
 } // namespace scg
-
-struct scg_plan {
-    scg_ctx* owner = nullptr;
-    int npool = 0;
-    scg::SingleMatcher matcher;
-};

@@ -508,18 +508,12 @@ __device__ __noinline__ Hit trie_search_segmented(const LibDev* __restrict__ lib
 //   c2 == 0, c1 == 1 : if the query minus its last base is free of N and is a prefix of a library
 //                      row, the search reports no match ("root rule");
 //   c2 == 0, c1 >= 2 : the reference's own walk over its trie (trie_search_segmented above).
+// the part of the search that follows a missed (or impossible) exact probe
 template <int KW>
-__device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
+__device__ __forceinline__ Hit lookup_segmented_inexact(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
     Hit out{ -1, 0 };
     const LibDev lib = *libp;
     const int kw = KW == 1 ? 1 : lib.KW;
-    if (!key_has_n(q)) {
-        const int v = probe_table<KW>(lib.slots, lib.slot_mask, lib.slot_words, kw, q.h, q.l);
-        if (v >= 0) {
-            out.index = v;
-            return out;
-        }
-    }
     if ((c1 <= 0 && c2 <= 0) || lib.nseeds == 0) return out;
     // caps [>= 2, 0]: only the reference's own walk over its trie gives the reference's answer
     if (c2 == 0 && c1 >= 2 && lib.trie != nullptr) return trie_search_segmented<KW>(libp, q, c1, 0);
@@ -543,6 +537,16 @@ __device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp,
         if (!pn && probe_table<KW>(lib.prefix_slots, lib.prefix_mask, lib.slot_words, kw, ph, pl) >= 0) return out;
     }
     return lookup_seeded<KW>(libp, q, min(c1, lib.seg1), min(c2, lib.L - lib.seg1), lib.seg1);
+}
+
+template <int KW>
+__device__ __forceinline__ Hit lookup_segmented(const LibDev* __restrict__ libp, const Key<KW>& q, int c1, int c2) {
+    if (!key_has_n(q)) {
+        const int kw = KW == 1 ? 1 : libp->KW;
+        const int v = probe_table<KW>(libp->slots, libp->slot_mask, libp->slot_words, kw, q.h, q.l);
+        if (v >= 0) return Hit{ v, 0 };
+    }
+    return lookup_segmented_inexact<KW>(libp, q, c1, c2);
 }
 
 } // namespace scg

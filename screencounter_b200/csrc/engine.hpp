@@ -109,7 +109,9 @@ struct Context {
         std::shared_ptr<void> object;
     };
     std::vector<CachedObject> matcher_cache;
-    DeviceBuffer slow_list, slow_count;      // reads the uniform-length kernel hands to its follow-up kernel (spec_single.cuh)
+    // Scratch of the specialised kernels, shared by every launch on this context: a context serves ONE stream at a time.
+    DeviceBuffer slow_list, slow_count;      // reads a specialised kernel hands to its full-search follow-up (spec_single.cuh, spec_handlers.cuh)
+    DeviceBuffer defer_words, defer_counts;  // per-warp regions of deferred lookups (libdev.hpp DeferredList)
     std::shared_ptr<IngestBuffers> ingest[2];   // text ring, line tables and streams of the device-side FASTQ reader, per mate
     int device = 0;
     bool ready = false;
@@ -151,5 +153,11 @@ struct scg_result {
     int trace_width = 0;
     std::vector<int32_t> trace_index;
     std::vector<uint32_t> trace_info;
-    size_t rows() const { return freq.size(); }
+    // A table may instead stay ON THE DEVICE, sorted and rendered in its final form, until scg_result_copy_table copies it
+    // straight into the caller's arrays: one device-to-host copy, no intermediate host image.
+    bool on_device = false;
+    int device = 0;
+    size_t d_rows = 0;
+    scg::DeviceBuffer d_keys, d_strings, d_freq;
+    size_t rows() const { return on_device ? d_rows : freq.size(); }
 };

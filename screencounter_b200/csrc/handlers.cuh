@@ -11,11 +11,38 @@
 //   dual (PE)    DualBarcodesPairedEnd::process                       handlers/DualBarcodesPairedEnd.hpp:229-381
 #pragma once
 
+#include "count_table.cuh"
 #include "device_scan.cuh"
 #include "handlers_params.hpp"
 
 namespace scg {
 
+// Which reads a kernel visits: every read of the batch (list == nullptr), or the reads whose indices a specialised
+// kernel listed as needing the full per-read search (spec_handlers.cuh; *list_count entries).
+struct ReadList {
+    const uint32_t* list;
+    const uint32_t* list_count;
+};
+__device__ __forceinline__ long long visit_rounds(const ReadList& v, long long n) {
+    const long long items = v.list ? (long long)*v.list_count : n;
+    return (items + TILE - 1) / TILE;
+}
+// the read (pair) index this lane handles in round t, or -1
+__device__ __forceinline__ long long visit_index(const ReadList& v, long long n, long long t, int lane) {
+    const long long k = t * TILE + lane;
+    if (v.list) return k < (long long)*v.list_count ? (long long)v.list[k] : -1;
+    return k < n ? k : -1;
+}
+__device__ __forceinline__ ReadView read_view_at(const ReadsDev& r, long long i) {
+    if (i < 0) {
+        ReadView v;
+        v.ptr = r.data;
+        v.W = r.W;
+        v.len = 0;
+        return v;
+    }
+    return read_view(r, i / TILE, (int)(i % TILE));
+}
 
 // -------------------------------------------------------------------------------------------
 // single barcode (also the building block of the paired combinatorial design)
@@ -100,53 +127,6 @@ __global__ void __launch_bounds__(128) single_kernel(ReadsDev reads, SingleParam
 }
 
 // -------------------------------------------------------------------------------------------
-// device hash of 64-/128-bit keys -> count (random barcodes, sparse combinations)
-// -------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ void count_insert64(const CountTable64& t, unsigned long long key, uint32_t add) {
-    unsigned long long pos = mix64(key) & t.mask;
-    for (;;) {
-        const unsigned long long seen = t.keys[pos];
-        if (seen == key) break;
-        if (seen == ~0ull) {
-            const unsigned long long old = atomicCAS(t.keys + pos, ~0ull, key);
-            if (old == ~0ull || old == key) break;
-        }
-        pos = (pos + 1) & t.mask;
-    }
-    atomicAdd(t.counts + pos, add);
-}
-
-
-// 128-bit compare-and-swap (atom.cas.b128, sm_90+).
-__device__ __forceinline__ ulonglong2 cas128(ulonglong2* addr, ulonglong2 expected, ulonglong2 desired) {
-    ulonglong2 old;
-    asm volatile(
-        "{\n\t"
-        ".reg .b128 e, d, o;\n\t"
-        "mov.b128 e, {%2, %3};\n\t"
-        "mov.b128 d, {%4, %5};\n\t"
-        "atom.cas.b128 o, [%6], e, d;\n\t"
-        "mov.b128 {%0, %1}, o;\n\t"
-        "}"
-        : "=l"(old.x), "=l"(old.y)
-        : "l"(expected.x), "l"(expected.y), "l"(desired.x), "l"(desired.y), "l"(addr)
-        : "memory");
-    return old;
-}
-
-__device__ __forceinline__ void count_insert128(const CountTable128& t, ulonglong2 key, uint32_t add) {
-    unsigned long long pos = mix64(key.x ^ mix64(key.y)) & t.mask;
-    const ulonglong2 empty = make_ulonglong2(~0ull, ~0ull);
-    for (;;) {
-        const ulonglong2 old = cas128(t.keys + pos, empty, key);
-        if ((old.x == ~0ull && old.y == ~0ull) || (old.x == key.x && old.y == key.y)) break;
-        pos = (pos + 1) & t.mask;
-    }
-    atomicAdd(t.counts + pos, add);
-}
-
-// -------------------------------------------------------------------------------------------
 // random barcodes
 // -------------------------------------------------------------------------------------------
 
@@ -155,15 +135,15 @@ template <int CB, int KW>
 __global__ void __launch_bounds__(128) random_kernel(ReadsDev reads, RandomParams P, CountTable64 t64, CountTable128 t128,
                                                      const uint8_t* __restrict__ odd, long long read_offset,
                                                      OddOutcome* __restrict__ odd_out, unsigned long long* __restrict__ odd_count,
-                                                     int32_t* __restrict__ out_index) {
+                                                     int32_t* __restrict__ out_index, ReadList visit) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long ntiles = (reads.n + TILE - 1) / TILE;
+    const long long ntiles = visit_rounds(visit, reads.n);
     const ScanSpec& s = P.spec;
     for (long long tile = warp; tile < ntiles; tile += nwarps) {
-        const long long i = tile * TILE + lane;
-        const ReadView rd = read_view(reads, tile, lane);
+        const long long i = visit_index(visit, reads.n, tile, lane);
+        const ReadView rd = read_view_at(reads, i);
         int best = P.max_mm + 1, best_pos = 0;
         bool best_rev = false, tied = false, have = false;
         const int nblocks = window_blocks(rd.len, s.T);
@@ -201,7 +181,7 @@ __global__ void __launch_bounds__(128) random_kernel(ReadsDev reads, RandomParam
             }
         }
         const bool counted = P.use_first ? have : (!tied && best <= P.max_mm);
-        if (i < reads.n) {
+        if (i >= 0) {
             if (out_index) out_index[i] = counted ? (best_pos * 2 + (best_rev ? 1 : 0)) : -1;
             if (counted) {
                 if (odd && odd[i]) {
@@ -213,9 +193,7 @@ __global__ void __launch_bounds__(128) random_kernel(ReadsDev reads, RandomParam
                     extract_region<KW>(rd, best_pos + s.fstart[0], P.key_len, key);
                     if (best_rev) key_revcomp<KW>(key, P.key_len);
                     if (KW == 1 && P.key_len <= 21) {
-                        const unsigned long long k = (unsigned long long)key.h[0] | ((unsigned long long)key.l[0] << 21) |
-                                                     ((unsigned long long)key.n[0] << 42);
-                        count_insert64(t64, k, 1u);
+                        count_insert64(t64, random_key64(key.h[0], key.l[0], key.n[0]), 1u);
                     } else {
                         // up to 42 bases: H, L, N in 42-bit fields of a 128-bit word
                         unsigned long long H = key.h[0], L = key.l[0], N = key.n[0];
@@ -306,29 +284,21 @@ __device__ __forceinline__ ComboOut combo_search(const ReadView& rd, const Combo
     return out;
 }
 
-__device__ __forceinline__ void combo_count(const ComboSink& k, int id0, int id1) {
-    if (k.dense) {
-        atomicAdd(k.dense + (size_t)id0 * k.n2 + id1, 1);
-    } else {
-        count_insert64(k.sparse, ((unsigned long long)(uint32_t)id0 << 32) | (uint32_t)id1, 1u);
-    }
-}
-
 template <int CB, int KW>
 __global__ void __launch_bounds__(128) combo_kernel(ReadsDev reads, ComboParams P, ComboSink sink,
-                                                    const int32_t* __restrict__ skip_if_found, int32_t* __restrict__ out_pairs) {
+                                                    const int32_t* __restrict__ skip_if_found, int32_t* __restrict__ out_pairs, ReadList visit) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long ntiles = (reads.n + TILE - 1) / TILE;
+    const long long ntiles = visit_rounds(visit, reads.n);
     for (long long tile = warp; tile < ntiles; tile += nwarps) {
-        const long long i = tile * TILE + lane;
-        ReadView rd = read_view(reads, tile, lane);
+        const long long i = visit_index(visit, reads.n, tile, lane);
+        ReadView rd = read_view_at(reads, i);
         // diagnostics: only reads the dual handler failed on are tabulated
         // (handlers/DualBarcodesSingleEndWithDiagnostics.hpp:99-104)
-        if (skip_if_found && i < reads.n && skip_if_found[i] >= 0) rd.len = 0;
+        if (skip_if_found && i >= 0 && skip_if_found[i] >= 0) rd.len = 0;
         const ComboOut o = combo_search<CB, KW>(rd, P);
-        if (i < reads.n) {
+        if (i >= 0) {
             if (o.found) combo_count(sink, o.id0, o.id1);
             if (out_pairs) {
                 out_pairs[2 * i] = o.found ? o.id0 : -1;
@@ -557,15 +527,15 @@ __device__ __forceinline__ DualOut dual_pe_search(const ReadView& ra, const Read
 
 template <int CB, int KW>
 __global__ void __launch_bounds__(128) dual_pe_kernel(ReadsDev reads1, ReadsDev reads2, DualPEParams P,
-                                                      int32_t* __restrict__ counts, int32_t* __restrict__ out_index) {
+                                                      int32_t* __restrict__ counts, int32_t* __restrict__ out_index, ReadList visit) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long ntiles = (reads1.n + TILE - 1) / TILE;
+    const long long ntiles = visit_rounds(visit, reads1.n);
     for (long long tile = warp; tile < ntiles; tile += nwarps) {
-        const long long i = tile * TILE + lane;
-        const ReadView r1 = read_view(reads1, tile, lane);
-        const ReadView r2 = read_view(reads2, tile, lane);
+        const long long i = visit_index(visit, reads1.n, tile, lane);
+        const ReadView r1 = read_view_at(reads1, i);
+        const ReadView r2 = read_view_at(reads2, i);
         DualOut best = dual_pe_search<CB, KW>(r1, r2, P);  // process, :353-381
         if (P.randomized) {
             if (P.use_first) {
@@ -579,7 +549,7 @@ __global__ void __launch_bounds__(128) dual_pe_kernel(ReadsDev reads1, ReadsDev 
                 }
             }
         }
-        if (i < reads1.n) {
+        if (i >= 0) {
             if (best.index >= 0) atomicAdd(counts + best.index, 1);
             if (out_index) out_index[i] = best.index;
         }

@@ -21,31 +21,14 @@ struct SingleParams {
     int use_first;
 };
 
-struct CountTable64 {
-    unsigned long long* keys;  // EMPTY = ~0
-    uint32_t* counts;
-    unsigned long long mask;   // capacity - 1
-};
-
-struct CountTable128 {
-    ulonglong2* keys;  // EMPTY = (~0, ~0); 16-byte aligned
-    uint32_t* counts;
-    unsigned long long mask;
-};
+// CountSlot / CountTable64 / CountTable128 (the device count tables) live in libdev.hpp: the run-time compiled kernels
+// use them too.
 
 struct RandomParams {
     ScanSpec spec;
     int max_mm;
     int use_first;
     int key_len;   // length of the first variable region
-};
-
-// Outcome for reads the packed representation cannot render as text (lower case, symbols other
-// than N): the host formats those keys from the raw read (handlers/RandomBarcodeSingleEnd.hpp:93-120).
-struct OddOutcome {
-    long long read;
-    int position;
-    int reverse;
 };
 
 struct ComboParams {
@@ -56,13 +39,6 @@ struct ComboParams {
     int max_mm;
     int use_first;
     int n1, n2;                  // pool sizes
-};
-
-// Where combinations are tallied: a dense n1 x n2 matrix when it is small, else the 64-bit hash.
-struct ComboSink {
-    int32_t* dense;        // n1 * n2 counters or nullptr
-    CountTable64 sparse;
-    int n2;
 };
 
 struct DualSEParams {

@@ -63,6 +63,86 @@ SCG_HD uint32_t joint_hash(uint32_t kh_tagged, uint32_t kl) { return kh_tagged *
 SCG_HD uint32_t joint_hash2(uint32_t x) { return x * 0xC2B2AE35u; }
 constexpr int JOINT_MAX_KEYLEN = 31;
 
+// Device count table of 64-bit keys (random barcodes of up to 21 bases, sparse combinations): open addressing with linear
+// probing over 16-byte slots (key, count, padding), so that finding or inserting a key touches ONE 32-byte sector -- the
+// device-side counterpart of the reference's unordered_map<string, int> (handlers/RandomBarcodeSingleEnd.hpp:93-104).
+struct CountSlot {
+    unsigned long long key;   // ~0 = empty
+    uint32_t count;
+    uint32_t pad;
+};
+struct CountTable64 {
+    CountSlot* slots;
+    unsigned long long mask;       // capacity - 1
+    unsigned long long* live;      // [0] distinct keys inserted so far, [1] != 0: the table overflowed and inserts were dropped
+};
+// 128-bit keys (random barcodes of 22 to 42 bases): keys and counts in separate arrays
+struct CountTable128 {
+    ulonglong2* keys;  // EMPTY = (~0, ~0); 16-byte aligned
+    uint32_t* counts;
+    unsigned long long mask;
+    unsigned long long* live;
+};
+// slot of a key: one 64-bit multiply, the halves folded (the low half alone only mixes upwards)
+SCG_HD unsigned long long count_hash(unsigned long long key) {
+    const unsigned long long x = key * 0x9E3779B97F4A7C15ull;
+    return x ^ (x >> 32);
+}
+
+// Outcome for reads the packed representation cannot render as text (lower case, symbols other
+// than N): the host formats those keys from the raw read (handlers/RandomBarcodeSingleEnd.hpp:93-120).
+struct OddOutcome {
+    long long read;
+    int position;
+    int reverse;
+};
+
+// Where combinations are tallied: a dense n1 x n2 matrix when it is small, else the 64-bit hash.
+struct ComboSink {
+    int32_t* dense;        // n1 * n2 counters or nullptr
+    CountTable64 sparse;
+    int n2;
+};
+
+// ---- arguments of the run-time compiled handler kernels (spec_handlers.cuh) ----
+
+// Reads a specialised kernel cannot settle on the spot wait, with everything the search behind them needs, in regions of a
+// global list -- ONE REGION PER WARP of the kernel that fills it (a persistent warp visits at most `per_warp / 32` tiles), so
+// that appending costs no atomic.  Entries are structures of arrays: word k of entry e is words[k * stride + e]; region w
+// holds entries [w * per_warp, w * per_warp + warp_counts[w]).  A follow-up kernel works the regions off.
+struct DeferredList {
+    uint32_t* words;
+    unsigned long long stride;   // entries per word plane (= regions * per_warp)
+    uint32_t per_warp;
+    uint32_t regions;
+    uint32_t* warp_counts;
+};
+// Reads that need the full per-read search (several candidate windows): their indices, appended with one atomic per warp
+// batch; the generic kernel of the handler visits them (handlers.cuh ReadList).
+struct SlowList {
+    uint32_t* list;
+    uint32_t* count;
+};
+// Exact table of the dual paired-end design for keys of up to 48 bases (both variable regions concatenated): a two-table
+// cuckoo hash of 16-byte slots (H bits 0..31, L bits 0..31, H bits 32..47 | L bits 32..47 << 16, pool row; empty = row -1).
+// Table 1 holds 1 << (32 - shift) slots, table 2 the next as many.
+struct DualTables {
+    const uint4* exact;
+    uint32_t shift;
+};
+SCG_HD uint32_t dual_hash(uint32_t x, uint32_t y, uint32_t z) { return x * 0x9E3779B1u + y * 0x85EBCA6Bu + z * 0xC2B2AE35u; }
+SCG_HD uint32_t dual_hash2(uint32_t h) { return h * 0x27D4EB2Fu + 0x165667B1u; }
+constexpr int DUAL_MAX_KEYLEN = 48;
+// Exact tables of the four libraries of the single-end combinatorial design, [2 * reverse + region in read order]: the
+// libraries' own cuckoo tables (library.cpp CuckooTable, keys of one word per plane, 16-byte slots).
+struct ComboTables {
+    const uint4* slots[4];
+    uint32_t mask[4];
+};
+// words per deferred entry
+constexpr int DUAL_DEFER_WORDS = 6;    // pair index, H lo, L lo, H hi | L hi << 16, N lo, N hi | cap1 << 16 | cap2 << 24
+constexpr int COMBO_DEFER_WORDS = 8;   // read index, reverse << 8 | constant mismatches, (H, L, N) of region 0, (H, L, N) of region 1
+
 // Packed reads of one batch on the device.
 struct ReadsDev {
     const uint32_t* data;   // tile-planar words

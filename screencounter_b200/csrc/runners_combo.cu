@@ -6,133 +6,14 @@
 
 #include "api_common.hpp"
 #include "handlers.cuh"
+#include "launchers.hpp"
+#include "matchers.hpp"
 
 namespace scg {
 
 static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-
-// CombinatorialBarcodesSingleEnd<_, 2> (reference handlers/CombinatorialBarcodesSingleEnd.hpp:66-119).
-struct ComboMatcher {
-    TemplateSpec tmpl;
-    DeviceLibrary lib[4];   // [2 * reverse + region]
-    DeviceBuffer libs_dev;
-    ComboParams params;
-
-    void prepare(const std::string& constant, int strand, const Pool& p1, const Pool& p2, int mismatches, bool use_first, Duplicates dup) {
-        tmpl = TemplateSpec(constant, strand);
-        const Pool* pools[2] = { &p1, &p2 };
-        if (tmpl.fwd_regions.size() != 2) throw Error("expected 2 variable regions in the constant template");
-        for (int i = 0; i < 2; ++i) {
-            const int rlen = tmpl.fwd_regions[i].end - tmpl.fwd_regions[i].start;
-            if (pools[i]->length != rlen) {
-                throw Error("length of variable region " + std::to_string(i + 1) + " (" + std::to_string(rlen) +
-                            ") should be the same as its sequences (" + std::to_string(pools[i]->length) + ")");
-            }
-        }
-        LibraryOptions opt;
-        opt.max_mismatches = mismatches;
-        opt.duplicates = dup;
-        if (tmpl.fwd) {
-            for (int r = 0; r < 2; ++r) lib[r].host = Library(pools[r]->seqs, pools[r]->length, opt);
-        }
-        if (tmpl.rev) {  // reversed pool order on the reverse strand (:111-116)
-            for (int r = 0; r < 2; ++r) lib[2 + r].host = Library(pools[1 - r]->reverse_complemented(), pools[1 - r]->length, opt);
-        }
-        std::memset(&params, 0, sizeof params);
-        params.spec = tmpl.scan_spec(mismatches);
-        params.max_mm = mismatches;
-        params.use_first = use_first ? 1 : 0;
-        params.n1 = (int)p1.seqs.size();
-        params.n2 = (int)p2.seqs.size();
-    }
-
-    void upload(Context& ctx) {
-        std::vector<LibDev> libs(4);
-        std::memset(libs.data(), 0, 4 * sizeof(LibDev));
-        params.kw = 1;
-        for (int k = 0; k < 4; ++k) {
-            const bool used = k < 2 ? tmpl.fwd : tmpl.rev;
-            if (!used) continue;
-            lib[k].upload(ctx);
-            libs[k] = lib[k].dev;
-            params.kw = std::max(params.kw, lib[k].dev.KW);
-        }
-        params.libs = upload_lib_array(ctx, libs, libs_dev);
-    }
-};
-
-static void launch_combo(Context& ctx, const ReadsDev& reads, const ComboParams& P, const ComboSink& sink, const int32_t* skip_if_found,
-                         int32_t* out_pairs) {
-    if (reads.n <= 0) return;
-    const long long ntiles = (reads.n + TILE - 1) / TILE;
-    const int grid = ctx.grid_for(ntiles);
-    dispatch_cb(P.spec.cbits, [&](auto CB) {
-        dispatch_kw(P.kw, [&](auto KW) {
-            combo_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, ctx.stream>>>(reads, P, sink, skip_if_found, out_pairs);
-        });
-    });
-    SCG_CUDA_CHECK(cudaGetLastError());
-    ++ctx.launches;
-    ++ctx.timing.launches;
-}
-
-// DualBarcodesSingleEnd (reference handlers/DualBarcodesSingleEnd.hpp:64-124).
-struct DualSEMatcher {
-    TemplateSpec tmpl;
-    DeviceLibrary lib[2];
-    DeviceBuffer libs_dev;
-    DualSEParams params;
-    int nchoices = 0;
-
-    void prepare(const std::string& constant, const std::vector<Pool>& pools, int nchoices_, int strand, int mismatches, bool use_first) {
-        tmpl = TemplateSpec(constant, strand);
-        nchoices = nchoices_;
-        if (pools.size() != tmpl.fwd_regions.size()) throw Error("length of 'barcode_pools' should equal the number of variable regions");
-        int klen = 0;
-        for (size_t i = 0; i < pools.size(); ++i) {
-            const int rlen = tmpl.fwd_regions[i].end - tmpl.fwd_regions[i].start;
-            if (pools[i].length != rlen) {
-                throw Error("length of variable region " + std::to_string(i + 1) + " (" + std::to_string(rlen) +
-                            ") should be the same as its sequences (" + std::to_string(pools[i].length) + ")");
-            }
-            klen += rlen;
-        }
-        std::vector<std::string> combined(nchoices);  // rows concatenated across the pools (:99-108)
-        for (const auto& p : pools) {
-            for (int c = 0; c < nchoices; ++c) combined[c] += p.seqs[c];
-        }
-        LibraryOptions opt;
-        opt.max_mismatches = mismatches;
-        opt.duplicates = Duplicates::ERROR;
-        if (tmpl.fwd) lib[0].host = Library(combined, klen, opt);
-        if (tmpl.rev) {  // reverse complement of the whole row (:117-120)
-            std::vector<std::string> rc;
-            rc.reserve(combined.size());
-            for (const auto& s : combined) rc.push_back(reverse_complement_iupac(s));
-            lib[1].host = Library(rc, klen, opt);
-        }
-        std::memset(&params, 0, sizeof params);
-        params.spec = tmpl.scan_spec(mismatches);
-        params.max_mm = mismatches;
-        params.use_first = use_first ? 1 : 0;
-    }
-
-    void upload(Context& ctx) {
-        std::vector<LibDev> libs(2);
-        std::memset(libs.data(), 0, 2 * sizeof(LibDev));
-        params.kw = 1;
-        for (int k = 0; k < 2; ++k) {
-            const bool used = k == 0 ? tmpl.fwd : tmpl.rev;
-            if (!used) continue;
-            lib[k].upload(ctx);
-            libs[k] = lib[k].dev;
-            params.kw = std::max(params.kw, lib[k].dev.KW);
-        }
-        params.libs = upload_lib_array(ctx, libs, libs_dev);
-    }
-};
 
 } // namespace scg
 
@@ -177,7 +58,7 @@ int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* cons
         long long nreads = 0;
         while (pipe.next(b)) {
             trace.prepare(b.n, false);
-            launch_combo(c, b.reads1, m.params, tally.sink(c, b.n), nullptr, trace.enabled ? trace.d_index.as<int32_t>() : nullptr);
+            launch_combo(c, b.reads1, m, tally.sink(c, b.n), nullptr, trace.enabled ? trace.d_index.as<int32_t>() : nullptr, c.stream);
             pipe.submitted(b);
             trace.collect(c, b.n, false);
             nreads += b.n;
@@ -260,9 +141,11 @@ int scg_count_dual_single_end(scg_ctx* ctx, const scg_source* src, const char* c
             SCG_CUDA_CHECK(cudaGetLastError());
             ++c.launches;
             ++c.timing.launches;
+            c.kernel_note = "generic dual_se_kernel (all variable regions concatenated, one any-mismatch search)";
             if (diagnostics) {
                 // only reads without a valid pair are tabulated (:99-104)
-                launch_combo(c, b.reads1, combop->params, tally.sink(c, b.n), d_index.as<int32_t>(), nullptr);
+                launch_combo(c, b.reads1, *combop, tally.sink(c, b.n), d_index.as<int32_t>(), nullptr, c.stream);
+                c.kernel_note = "generic dual_se_kernel; diagnostics: " + c.kernel_note;
             }
             pipe.submitted(b);
             if (want_trace) {

@@ -6,38 +6,14 @@
 
 #include "api_common.hpp"
 #include "handlers.cuh"
+#include "launchers.hpp"
+#include "matchers.hpp"
 
 namespace scg {
 
 static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-
-// CombinatorialBarcodesPairedEnd (reference handlers/CombinatorialBarcodesPairedEnd.hpp:58-98): two
-// independent single-barcode matchers, each on its own configured strand.
-struct ComboPEMatcher {
-    SingleMatcher m1, m2;
-    ComboPEParams params;
-
-    void prepare(const std::string& c1, bool rev1, int mm1, const Pool& p1, const std::string& c2, bool rev2, int mm2, const Pool& p2,
-                 bool randomized, bool use_first, Duplicates dup) {
-        if (std::max(c1.size(), c2.size()) > (size_t)MAX_TEMPLATE) {
-            throw Error("lacking compile-time support for constant regions longer than 256 bp");
-        }
-        m1.prepare(c1, rev1 ? 1 : 0, p1, mm1, use_first, dup);
-        m2.prepare(c2, rev2 ? 1 : 0, p2, mm2, use_first, dup);
-        std::memset(&params, 0, sizeof params);
-        params.randomized = randomized ? 1 : 0;
-        params.use_first = use_first ? 1 : 0;
-    }
-
-    void upload(Context& ctx) {
-        m1.upload(ctx);
-        m2.upload(ctx);
-        params.m1 = m1.params;
-        params.m2 = m2.params;
-    }
-};
 
 static void launch_combo_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const ComboPEParams& P, const ComboSink& sink,
                             int32_t* counters, const int32_t* skip_if_found, int32_t* out_pairs, int32_t* out_code) {
@@ -55,73 +31,8 @@ static void launch_combo_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2
     SCG_CUDA_CHECK(cudaGetLastError());
     ++ctx.launches;
     ++ctx.timing.launches;
+    ctx.kernel_note = "generic combo_pe_kernel (two single-barcode searches per pair)";
 }
-
-// DualBarcodesPairedEnd (reference handlers/DualBarcodesPairedEnd.hpp:92-179).
-struct DualPEMatcher {
-    TemplateSpec t1, t2;
-    DeviceLibrary lib;
-    DeviceBuffer lib_dev;
-    DualPEParams params;
-
-    void prepare(const std::string& c1, bool rev1, int mm1, const Pool& p1, const std::string& c2, bool rev2, int mm2, const Pool& p2,
-                 bool randomized, bool use_first) {
-        if (std::max(c1.size(), c2.size()) > (size_t)MAX_TEMPLATE) {
-            throw Error("lacking compile-time support for constant regions longer than 256 bp");
-        }
-        t1 = TemplateSpec(c1, rev1 ? 1 : 0);
-        t2 = TemplateSpec(c2, rev2 ? 1 : 0);
-        if (p1.seqs.size() != p2.seqs.size()) throw Error("both barcode pools should be of the same length");
-        if (t1.fwd_regions.size() != 1) throw Error("expected one variable region in the first constant template");
-        const int len1 = t1.fwd_regions[0].end - t1.fwd_regions[0].start;
-        if (len1 != p1.length) {
-            throw Error("length of variable sequences (" + std::to_string(p1.length) + ") should be the same as the variable region (" +
-                        std::to_string(len1) + ")");
-        }
-        if (t2.fwd_regions.size() != 1) throw Error("expected one variable region in the second constant template");
-        const int len2 = t2.fwd_regions[0].end - t2.fwd_regions[0].start;
-        if (len2 != p2.length) {
-            throw Error("length of variable sequences (" + std::to_string(p2.length) + ") should be the same as the variable region (" +
-                        std::to_string(len2) + ")");
-        }
-        // rows = each half reverse-complemented on its own when its strand is reverse (:139-164)
-        std::vector<std::string> combined;
-        combined.reserve(p1.seqs.size());
-        for (size_t i = 0; i < p1.seqs.size(); ++i) {
-            combined.push_back((rev1 ? reverse_complement_iupac(p1.seqs[i]) : p1.seqs[i]) +
-                               (rev2 ? reverse_complement_iupac(p2.seqs[i]) : p2.seqs[i]));
-        }
-        // The reference's segmented trie search has a phantom result when the second cap is 0.  The
-        // table search reproduces it for first-segment caps 0 and 1; with 2 or more substitutions on read 1 the library also
-        // carries the reference's trie and caps [>= 2, 0] are answered by walking it (device_keys.cuh trie_search_segmented).
-        if (mm1 >= 2 && len1 + len2 > TRIE_MAX_LEN) {
-            throw Error("countDualBarcodes with 2 or more substitutions on the first read needs variable regions of at most " +
-                        std::to_string(TRIE_MAX_LEN) + " bp in total in this engine");
-        }
-        LibraryOptions opt;
-        opt.segmented = true;
-        opt.seg1 = len1;
-        opt.max_mismatches1 = mm1;
-        opt.max_mismatches2 = mm2;
-        opt.duplicates = Duplicates::ERROR;
-        lib.host = Library(combined, len1 + len2, opt);
-        std::memset(&params, 0, sizeof params);
-        params.spec1 = t1.scan_spec(mm1);
-        params.spec2 = t2.scan_spec(mm2);
-        params.mm1 = mm1;
-        params.mm2 = mm2;
-        params.randomized = randomized ? 1 : 0;
-        params.use_first = use_first ? 1 : 0;
-        params.len1 = len1;
-        params.len2 = len2;
-    }
-
-    void upload(Context& ctx) {
-        lib.upload(ctx);
-        params.lib = upload_lib_array(ctx, std::vector<LibDev>{ lib.dev }, lib_dev);
-        params.kw = lib.dev.KW;
-    }
-};
 
 // SingleBarcodePairedEnd::process (reference handlers/SingleBarcodePairedEnd.hpp:93-124) from the two mates' single-barcode
 // outcomes: first mode takes read 1's match, else read 2's; best mode takes the match with fewer mismatches, and on equal
@@ -301,22 +212,13 @@ int scg_count_dual(scg_ctx* ctx, const scg_source* src1, const char* constant1, 
         long long npairs = 0;
         while (pipe.next(b)) {
             if (need_index) d_index.reserve((size_t)b.n * sizeof(int32_t));
-            const long long ntiles = (b.n + TILE - 1) / TILE;
-            const int grid = c.grid_for(ntiles);
-            const int cb = std::max(m.params.spec1.cbits, m.params.spec2.cbits);
-            dispatch_cb(cb, [&](auto CB) {
-                dispatch_kw(m.params.kw, [&](auto KW) {
-                    dual_pe_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, c.stream>>>(
-                        b.reads1, b.reads2, m.params, d_counts.as<int32_t>(), need_index ? d_index.as<int32_t>() : nullptr);
-                });
-            });
-            SCG_CUDA_CHECK(cudaGetLastError());
-            ++c.launches;
-            ++c.timing.launches;
+            launch_dual_pe(c, b.reads1, b.reads2, m, d_counts.as<int32_t>(), need_index ? d_index.as<int32_t>() : nullptr, c.stream);
+            const std::string dual_note = c.kernel_note;
             if (diagnostics) {
                 // pairs without a valid combination go to the combinatorial handler (:115-120)
                 launch_combo_pe(c, b.reads1, b.reads2, combop->params, tally.sink(c, b.n), d_counters.as<int32_t>(), d_index.as<int32_t>(),
                                 nullptr, nullptr);
+                c.kernel_note = dual_note + "; diagnostics: " + c.kernel_note;
             }
             pipe.submitted(b);
             if (want_trace) {

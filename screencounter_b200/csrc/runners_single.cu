@@ -10,6 +10,7 @@
 #include "hostpool.hpp"
 #include "handlers.cuh"
 #include "jit.hpp"
+#include "matchers.hpp"
 
 namespace scg {
 
@@ -475,6 +476,22 @@ int scg_result_trace_width(const scg_result* r) { return r ? r->trace_width : 0;
 
 int scg_result_copy_table(const scg_result* r, int32_t* keys, char* strings, int32_t* freq) {
     if (!r) return 1;
+    if (r->on_device) {
+        // the table was sorted and rendered on the device and waits there: straight into the caller's arrays
+        int current = -1;
+        cudaGetDevice(&current);
+        bool ok = cudaSetDevice(r->device) == cudaSuccess;
+        const size_t n = r->d_rows;
+        if (ok && n && keys && r->d_keys.ptr) ok = cudaMemcpy(keys, r->d_keys.ptr, n * (size_t)r->width * sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && n && strings && r->d_strings.ptr) ok = cudaMemcpy(strings, r->d_strings.ptr, n * (size_t)r->width, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && n && freq && r->d_freq.ptr) ok = cudaMemcpy(freq, r->d_freq.ptr, n * sizeof(int32_t), cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (current >= 0 && current != r->device) cudaSetDevice(current);
+        if (!ok) {
+            cudaGetLastError();
+            return 1;
+        }
+        return 0;
+    }
     if (keys && !r->keys.empty()) std::memcpy(keys, r->keys.data(), r->keys.size() * sizeof(int32_t));
     if (strings && !r->strings.empty()) std::memcpy(strings, r->strings.data(), r->strings.size());
     if (freq && !r->freq.empty()) std::memcpy(freq, r->freq.data(), r->freq.size() * sizeof(int32_t));
@@ -660,6 +677,7 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
     if (!plan || !reads) return 1;
     return guarded(plan->owner, [&] {
         Context& c = plan->owner->impl;
+        if (plan->kind != scg_plan::SINGLE) throw Error("not a single-barcode plan");
         SCG_CUDA_CHECK(cudaSetDevice(c.device));
         cudaStream_t st = cuda_stream == SCG_STREAM_OWN ? c.stream : static_cast<cudaStream_t>(cuda_stream);
         long long at = 0;
@@ -672,7 +690,10 @@ int scg_single_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_count
 
 void scg_plan_free(scg_plan* plan) { delete plan; }
 
-const char* scg_plan_kernel(const scg_plan* plan) { return plan ? plan->matcher.kernel_note.c_str() : ""; }
+const char* scg_plan_kernel(const scg_plan* plan) {
+    if (!plan) return "";
+    return plan->kind == scg_plan::SINGLE ? plan->matcher.kernel_note.c_str() : plan->kernel_note.c_str();
+}
 
 // ---- run-time compiler check (no device needed for the compile step) --------------------------------------
 static int jit_selftest(const char* constant, int strand, int mismatches, int words_per_plane, int uniform_len, char* message, size_t capacity);
@@ -738,8 +759,7 @@ static int jit_selftest(const char* constant, int strand, int mismatches, int wo
         msg = e.what();
     }
     if (message && capacity) {
-        std::strncpy(message, msg.c_str(), capacity - 1);
-        message[capacity - 1] = 0;
+        std::snprintf(message, capacity, "%s", msg.c_str());   // (strncpy would zero-fill the whole buffer)
     }
     return status;
 }

@@ -1,0 +1,640 @@
+// Launchers of the dual / combinatorial / random-barcode kernels -- the run-time specialised ones of spec_handlers.cuh
+// with their follow-up kernels where the batch allows, the generic ones of handlers.cuh otherwise -- and the resident
+// plans of include/scg.h built on them (scg_dual_plan_*, scg_combo_plan_*, scg_random_plan_*).
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+#include "api_common.hpp"
+#include "handlers.cuh"
+#include "jit.hpp"
+#include "launchers.hpp"
+#include "matchers.hpp"
+
+namespace scg {
+
+// ---------------------------------------------------------------------------------------
+// follow-up kernels of the specialised handlers: LOOKUPS ONLY, on the keys the main kernel left in its deferred list
+// ---------------------------------------------------------------------------------------
+
+// countDualBarcodes: the segmented mismatch-tolerant search (SegmentedBarcodeSearch<2>::search after its exact probe,
+// BarcodeSearch.hpp:478-487) for pairs whose concatenated key missed the exact table or holds an N.
+template <int KW>
+__global__ void __launch_bounds__(128) dual_deferred_kernel(DeferredList def, const LibDev* __restrict__ lib, int32_t* __restrict__ counts,
+                                                            int32_t* __restrict__ out_index) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < def.regions; r += nwarps) {
+        const uint32_t cnt = def.warp_counts[r];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= cnt) continue;
+            const unsigned long long at = (unsigned long long)r * def.per_warp + e;
+            const uint32_t i = def.words[at], x = def.words[def.stride + at], y = def.words[2 * def.stride + at],
+                           z = def.words[3 * def.stride + at], n_lo = def.words[4 * def.stride + at], w = def.words[5 * def.stride + at];
+            Key<KW> q;
+            q.h[0] = x;
+            q.l[0] = y;
+            q.n[0] = n_lo;
+            if (KW > 1) {
+                q.h[KW - 1] = z & 0xFFFFu;
+                q.l[KW - 1] = z >> 16;
+                q.n[KW - 1] = w & 0xFFFFu;
+            }
+            const Hit h = lookup_segmented_inexact<KW>(lib, q, (int)((w >> 16) & 0xFFu), (int)(w >> 24));
+            if (h.index >= 0) atomicAdd(counts + h.index, 1);
+            if (out_index) out_index[i] = h.index;
+        }
+    }
+}
+
+// countComboBarcodes: both regions of the read's one verified window through the mismatch-tolerant lookups, in read
+// order with the shared budget (find_match, handlers/CombinatorialBarcodesSingleEnd.hpp:149-186).
+__global__ void __launch_bounds__(128) combo_deferred_kernel(DeferredList def, ComboParams P, ComboSink sink, int32_t* __restrict__ out_pairs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < def.regions; r += nwarps) {
+        const uint32_t cnt = def.warp_counts[r];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= cnt) continue;
+            const unsigned long long at = (unsigned long long)r * def.per_warp + e;
+            const uint32_t i = def.words[at], m = def.words[def.stride + at];
+            const bool rev = (m & 0x100u) != 0;
+            int obs = (int)(m & 0xFFu);
+            int ids[2] = { -1, -1 };
+            bool ok = true;
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                if (!ok) continue;
+                Key<1> key;
+                key.h[0] = def.words[(2 + 3 * reg) * def.stride + at];
+                key.l[0] = def.words[(3 + 3 * reg) * def.stride + at];
+                key.n[0] = def.words[(4 + 3 * reg) * def.stride + at];
+                const Hit h = lookup_any<1>(P.libs + (rev ? 2 : 0) + reg, key, P.max_mm - obs);
+                if (h.index < 0) {
+                    ok = false;
+                } else {
+                    obs += h.dist;
+                    ids[rev ? 1 - reg : reg] = h.index;
+                }
+            }
+            if (ok) combo_count(sink, ids[0], ids[1]);
+            if (out_pairs) {
+                out_pairs[2 * (size_t)i] = ok ? ids[0] : -1;
+                out_pairs[2 * (size_t)i + 1] = ok ? ids[1] : -1;
+            }
+        }
+    }
+}
+
+namespace {
+
+// ---- program text of a specialised handler kernel ----
+bool template_fits(const TemplateSpec& t, const ScanSpec& s, const ReadsDev& reads, std::string* why) {
+    auto no = [&](const char* msg) {
+        if (why) *why = msg;
+        return false;
+    };
+    if (reads.lens != nullptr) return no("reads of different lengths use the generic kernel");
+    if (reads.n > 0x7FFFFFC0ll) return no("batch too large for 32-bit read indices");
+    const int nwin = reads.uniform_len - t.length + 1;
+    if (nwin < 1) return no("reads shorter than the template use the generic kernel");
+    if (reads.W > 5) return no("reads longer than 160 bases use the generic kernel");
+    if (t.length > 128) return no("templates longer than 128 bases use the generic kernel");
+    if (reads.W + 2 < (t.length + 31) / 32 + 1) return no("template too long for the read");
+    int nconst = 0;
+    for (char ch : t.fwd_seq) nconst += ch != '-';
+    if (s.mm < 0 || s.mm > 3 || nconst < 4 * (s.mm + 1)) return no("mismatch budget too large for the pigeonhole filter");
+    return true;
+}
+
+void template_macros(std::ostringstream& o, const char* P, const TemplateSpec& t, const ScanSpec& s, int maxmm, const ReadsDev& reads) {
+    const std::string rb = t.rev ? t.rev_seq : std::string(t.length, '-');
+    const std::string fb = t.fwd ? t.fwd_seq : std::string(t.length, '-');
+    o << "#define SPH_" << P << "_T " << t.length << "\n"
+      << "#define SPH_" << P << "_FB \"" << fb << "\"\n"
+      << "#define SPH_" << P << "_RB \"" << rb << "\"\n"
+      << "#define SPH_" << P << "_FWD " << (t.fwd ? 1 : 0) << "\n"
+      << "#define SPH_" << P << "_REV " << (t.rev ? 1 : 0) << "\n"
+      << "#define SPH_" << P << "_MM " << s.mm << "\n"
+      << "#define SPH_" << P << "_MAXMM " << maxmm << "\n"
+      << "#define SPH_" << P << "_ULEN " << reads.uniform_len << "\n"
+      << "#define SPH_" << P << "_W " << reads.W << "\n";
+    for (int r = 0; r < s.nreg && r < 2; ++r) {
+        o << "#define SPH_" << P << "_FSTART" << r << " " << s.fstart[r] << "\n"
+          << "#define SPH_" << P << "_FLEN" << r << " " << s.rlen_f[r] << "\n"
+          << "#define SPH_" << P << "_RSTART" << r << " " << s.rstart[r] << "\n"
+          << "#define SPH_" << P << "_RLEN" << r << " " << s.rlen_r[r] << "\n";
+    }
+}
+
+void common_macros(std::ostringstream& o, int kind, int min_blocks, int group, int use_first, int has_index) {
+    o << "#define SPH_KIND " << kind << "\n"
+      << "#define SPH_MIN_BLOCKS " << jit_env_int("SCG_SPH_MIN_BLOCKS", min_blocks, 1, 16) << "\n"
+      << "#define SPH_STAGES " << jit_env_int("SCG_SPH_STAGES", 2, 1, 8) << "\n"
+      << "#define SPH_GROUP " << jit_env_int("SCG_SPH_GROUP", group, 1, 8) << "\n"
+      << "#define SPH_SAMPLES " << jit_env_int("SCG_SPEC_SAMPLES", 8, 1, 32) << "\n"
+      << "#define SPH_USE_FIRST " << use_first << "\n"
+      << "#define SPH_HAS_INDEX " << has_index << "\n";
+}
+
+JitProgram dual_program(const TemplateSpec& t1, const ScanSpec& s1, int mm1, const ReadsDev& r1, const TemplateSpec& t2, const ScanSpec& s2,
+                        int mm2, const ReadsDev& r2, int use_first, int has_index) {
+    std::ostringstream src;
+    common_macros(src, 1, 8, 1, use_first, has_index);
+    template_macros(src, "A", t1, s1, mm1, r1);
+    template_macros(src, "B", t2, s2, mm2, r2);
+    src << "#include \"spec_handlers.cuh\"\n";
+    JitProgram prog;
+    prog.name = "spec_dual_pe_jit.cu";
+    prog.text = src.str();
+    prog.kernels = { "spec_dual_pe_kernel" };
+    return prog;
+}
+
+JitProgram combo_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index) {
+    std::ostringstream src;
+    common_macros(src, 2, 8, 2, use_first, has_index);
+    template_macros(src, "A", t, s, mm, r);
+    src << "#include \"spec_handlers.cuh\"\n";
+    JitProgram prog;
+    prog.name = "spec_combo_jit.cu";
+    prog.text = src.str();
+    prog.kernels = { "spec_combo_kernel" };
+    return prog;
+}
+
+JitProgram random_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index) {
+    std::ostringstream src;
+    common_macros(src, 3, 8, 2, use_first, has_index);
+    template_macros(src, "A", t, s, mm, r);
+    src << "#include \"spec_handlers.cuh\"\n";
+    JitProgram prog;
+    prog.name = "spec_random_jit.cu";
+    prog.text = src.str();
+    prog.kernels = { "spec_random_kernel" };
+    return prog;
+}
+
+bool spec_disabled() {
+    const char* env = std::getenv("SCG_NO_SPEC_HANDLERS");
+    return env && env[0] && env[0] != '0';
+}
+
+// Per-context scratch of the specialised handlers: one region of deferred entries per warp of the launch, the slow list.
+struct Scratch {
+    DeferredList def;
+    SlowList slow;
+};
+Scratch prepare_scratch(Context& ctx, long long n, int grid, int group, int nwords, cudaStream_t stream) {
+    const long long ntiles = (n + TILE - 1) / TILE;
+    const long long ngroups = (ntiles + group - 1) / group;
+    const long long nwarps = (long long)grid * 4;
+    const long long groups_per_warp = (ngroups + nwarps - 1) / nwarps;
+    Scratch s;
+    s.def.per_warp = (uint32_t)(groups_per_warp * group * TILE);
+    s.def.regions = (uint32_t)nwarps;
+    s.def.stride = (unsigned long long)nwarps * s.def.per_warp;
+    ctx.defer_words.reserve(std::max<size_t>((size_t)nwords * s.def.stride * sizeof(uint32_t), 16));
+    ctx.defer_counts.reserve((size_t)nwarps * sizeof(uint32_t));
+    ctx.slow_list.reserve((size_t)(ntiles * TILE) * sizeof(uint32_t));
+    ctx.slow_count.reserve(sizeof(uint32_t));
+    s.def.words = ctx.defer_words.as<uint32_t>();
+    s.def.warp_counts = ctx.defer_counts.as<uint32_t>();
+    s.slow.list = ctx.slow_list.as<uint32_t>();
+    s.slow.count = ctx.slow_count.as<uint32_t>();
+    // regions of warps that end up without work keep a count of zero
+    SCG_CUDA_CHECK(cudaMemsetAsync(s.def.warp_counts, 0, (size_t)nwarps * sizeof(uint32_t), stream));
+    SCG_CUDA_CHECK(cudaMemsetAsync(s.slow.count, 0, sizeof(uint32_t), stream));
+    return s;
+}
+
+int spec_grid(Context& ctx, cudaKernel_t k, long long n, int group) {
+    const long long ntiles = (n + TILE - 1) / TILE;
+    const long long ngroups = (ntiles + group - 1) / group;
+    const int resident = specialised_blocks_per_sm(k);
+    return (int)std::max<long long>(1, std::min<long long>((ngroups + 3) / 4, (long long)ctx.sm_count * resident));
+}
+
+int followup_grid(Context& ctx, long long n) {
+    const long long ntiles = (n + TILE - 1) / TILE;
+    return (int)std::max<long long>(1, std::min<long long>((ntiles + 3) / 4, (long long)ctx.sm_count * 8));
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// countDualBarcodes, paired-end
+// ---------------------------------------------------------------------------------------
+static void launch_dual_pe_generic(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const DualPEMatcher& m, int32_t* d_counts,
+                                   int32_t* d_index, ReadList visit, int grid, cudaStream_t stream) {
+    const int cb = std::max(m.params.spec1.cbits, m.params.spec2.cbits);
+    dispatch_cb(cb, [&](auto CB) {
+        dispatch_kw(m.params.kw, [&](auto KW) {
+            dual_pe_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(r1, r2, m.params, d_counts, d_index, visit);
+        });
+    });
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    ++ctx.timing.launches;
+}
+
+void launch_dual_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const DualPEMatcher& m, int32_t* d_counts, int32_t* d_index,
+                    cudaStream_t stream) {
+    if (r1.n <= 0) return;
+    const long long ntiles = (r1.n + TILE - 1) / TILE;
+    std::string why;
+    const JitModule* mod = nullptr;
+    int group = 1;
+    if (spec_disabled()) {
+        why = "disabled by SCG_NO_SPEC_HANDLERS";
+    } else if (m.params.randomized) {
+        why = "randomized designs use the generic kernel";
+    } else if (!m.exact16.ptr || m.exact16_shift == 0) {
+        why = "variable regions of more than 48 bases in total use the generic kernel";
+    } else if (m.params.len1 > 32 || m.params.len2 > 32) {
+        why = "variable regions longer than 32 bases use the generic kernel";
+    } else if (template_fits(m.t1, m.params.spec1, r1, &why) && template_fits(m.t2, m.params.spec2, r2, &why)) {
+        group = jit_env_int("SCG_SPH_GROUP", 1, 1, 8);
+        mod = jit_module(dual_program(m.t1, m.params.spec1, m.params.mm1, r1, m.t2, m.params.spec2, m.params.mm2, r2, m.params.use_first,
+                                      d_index ? 1 : 0),
+                         ctx.device, &why);
+    }
+    if (!mod) {
+        launch_dual_pe_generic(ctx, r1, r2, m, d_counts, d_index, ReadList{ nullptr, nullptr }, ctx.grid_for(ntiles), stream);
+        ctx.kernel_note = "generic dual_pe_kernel (" + why + ")";
+        return;
+    }
+    cudaKernel_t k = mod->kernels[0];
+    const int grid = spec_grid(ctx, k, r1.n, group);
+    Scratch sc = prepare_scratch(ctx, r1.n, grid, group, DUAL_DEFER_WORDS, stream);
+    ReadsDev a1 = r1, a2 = r2;
+    DualTables tb{ m.exact16.as<uint4>(), m.exact16_shift };
+    void* args[] = { &a1, &a2, &tb, &d_counts, &d_index, &sc.def, &sc.slow };
+    SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
+    const int fgrid = followup_grid(ctx, r1.n);
+    if (m.params.kw <= 1) {
+        dual_deferred_kernel<1><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+    } else {
+        dual_deferred_kernel<2><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+    }
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ctx.launches += 2;
+    ctx.timing.launches += 2;
+    // pairs with several verified windows: the full per-pair search of the generic kernel on exactly those
+    launch_dual_pe_generic(ctx, r1, r2, m, d_counts, d_index, ReadList{ sc.slow.list, sc.slow.count }, ctx.sm_count * 2, stream);
+    ctx.kernel_note = "specialised (NVRTC) spec_dual_pe_kernel, filter+verify on both mates, " + std::to_string(specialised_blocks_per_sm(k)) +
+                      " blocks/SM; + dual_deferred_kernel (mismatch lookups) + dual_pe_kernel on the multi-window pairs";
+}
+
+// ---------------------------------------------------------------------------------------
+// countComboBarcodes, single-end
+// ---------------------------------------------------------------------------------------
+static void launch_combo_generic(Context& ctx, const ReadsDev& reads, const ComboParams& P, const ComboSink& sink, const int32_t* skip_if_found,
+                                 int32_t* out_pairs, ReadList visit, int grid, cudaStream_t stream) {
+    dispatch_cb(P.spec.cbits, [&](auto CB) {
+        dispatch_kw(P.kw, [&](auto KW) {
+            combo_kernel<decltype(CB)::value, decltype(KW)::value><<<grid, 128, 0, stream>>>(reads, P, sink, skip_if_found, out_pairs, visit);
+        });
+    });
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    ++ctx.timing.launches;
+}
+
+void launch_combo(Context& ctx, const ReadsDev& reads, const ComboMatcher& m, const ComboSink& sink, const int32_t* skip_if_found,
+                  int32_t* out_pairs, cudaStream_t stream) {
+    if (reads.n <= 0) return;
+    const long long ntiles = (reads.n + TILE - 1) / TILE;
+    const ComboParams& P = m.params;
+    std::string why;
+    const JitModule* mod = nullptr;
+    int group = 2;
+    bool ok = !spec_disabled();
+    if (!ok) why = "disabled by SCG_NO_SPEC_HANDLERS";
+    if (ok && skip_if_found) {
+        ok = false;
+        why = "the diagnostics pass uses the generic kernel";
+    }
+    if (ok && P.kw > 1) {
+        ok = false;
+        why = "variable regions longer than 32 bases use the generic kernel";
+    }
+    if (ok) ok = template_fits(m.tmpl, P.spec, reads, &why);
+    if (ok) {
+        group = jit_env_int("SCG_SPH_GROUP", 2, 1, 8);
+        mod = jit_module(combo_program(m.tmpl, P.spec, P.max_mm, reads, P.use_first, out_pairs ? 1 : 0), ctx.device, &why);
+    }
+    if (!mod) {
+        launch_combo_generic(ctx, reads, P, sink, skip_if_found, out_pairs, ReadList{ nullptr, nullptr }, ctx.grid_for(ntiles), stream);
+        ctx.kernel_note = "generic combo_kernel (" + why + ")";
+        return;
+    }
+    cudaKernel_t k = mod->kernels[0];
+    const int grid = spec_grid(ctx, k, reads.n, group);
+    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, COMBO_DEFER_WORDS, stream);
+    ReadsDev a = reads;
+    ComboTables tb;
+    std::memset(&tb, 0, sizeof tb);
+    for (int l = 0; l < 4; ++l) {
+        const bool used = l < 2 ? m.tmpl.fwd : m.tmpl.rev;
+        if (!used) continue;
+        tb.slots[l] = reinterpret_cast<const uint4*>(m.lib[l].dev.slots);
+        tb.mask[l] = m.lib[l].dev.slot_mask;
+    }
+    ComboSink sk = sink;
+    void* args[] = { &a, &tb, &sk, &out_pairs, &sc.def, &sc.slow };
+    SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
+    ++ctx.launches;
+    ++ctx.timing.launches;
+    if (P.max_mm > 0) {
+        combo_deferred_kernel<<<followup_grid(ctx, reads.n), 128, 0, stream>>>(sc.def, P, sink, out_pairs);
+        SCG_CUDA_CHECK(cudaGetLastError());
+        ++ctx.launches;
+        ++ctx.timing.launches;
+    }
+    launch_combo_generic(ctx, reads, P, sink, nullptr, out_pairs, ReadList{ sc.slow.list, sc.slow.count }, ctx.sm_count * 2, stream);
+    ctx.kernel_note = "specialised (NVRTC) spec_combo_kernel, filter+verify, " + std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM" +
+                      (P.max_mm > 0 ? "; + combo_deferred_kernel (mismatch lookups)" : "") + " + combo_kernel on the multi-window reads";
+}
+
+// ---------------------------------------------------------------------------------------
+// countRandomBarcodes
+// ---------------------------------------------------------------------------------------
+static void launch_random_generic(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, CountTable& tab, const uint8_t* odd,
+                                  OddOutcome* odd_out, unsigned long long* odd_count, int32_t* out_index, ReadList visit, int grid,
+                                  cudaStream_t stream) {
+    const RandomParams& P = m.params;
+    CountTable64 t64 = m.wide ? CountTable64{ nullptr, 0, nullptr } : tab.view64();
+    CountTable128 t128 = m.wide ? tab.view128() : CountTable128{ nullptr, nullptr, 0, nullptr };
+    dispatch_cb(P.spec.cbits, [&](auto CB) {
+        if (m.key_len <= 32) {
+            random_kernel<decltype(CB)::value, 1><<<grid, 128, 0, stream>>>(reads, P, t64, t128, odd, 0, odd_out, odd_count, out_index, visit);
+        } else {
+            random_kernel<decltype(CB)::value, 2><<<grid, 128, 0, stream>>>(reads, P, t64, t128, odd, 0, odd_out, odd_count, out_index, visit);
+        }
+    });
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+    ++ctx.timing.launches;
+}
+
+void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, CountTable& tab, const uint8_t* odd, OddOutcome* odd_out,
+                   unsigned long long* odd_count, int32_t* out_index, cudaStream_t stream) {
+    if (reads.n <= 0) return;
+    const long long ntiles = (reads.n + TILE - 1) / TILE;
+    std::string why;
+    const JitModule* mod = nullptr;
+    int group = 2;
+    bool ok = !spec_disabled();
+    if (!ok) why = "disabled by SCG_NO_SPEC_HANDLERS";
+    if (ok && m.wide) {
+        ok = false;
+        why = "barcodes longer than 21 bases use the generic kernel";
+    }
+    if (ok) ok = template_fits(m.tmpl, m.params.spec, reads, &why);
+    if (ok) {
+        group = jit_env_int("SCG_SPH_GROUP", 2, 1, 8);
+        mod = jit_module(random_program(m.tmpl, m.params.spec, m.params.max_mm, reads, m.params.use_first, out_index ? 1 : 0), ctx.device, &why);
+    }
+    if (!mod) {
+        launch_random_generic(ctx, reads, m, tab, odd, odd_out, odd_count, out_index, ReadList{ nullptr, nullptr }, ctx.grid_for(ntiles), stream);
+        ctx.kernel_note = "generic random_kernel (" + why + ")";
+        return;
+    }
+    cudaKernel_t k = mod->kernels[0];
+    const int grid = spec_grid(ctx, k, reads.n, group);
+    ctx.slow_list.reserve((size_t)(ntiles * TILE) * sizeof(uint32_t));
+    ctx.slow_count.reserve(sizeof(uint32_t));
+    SlowList slow{ ctx.slow_list.as<uint32_t>(), ctx.slow_count.as<uint32_t>() };
+    SCG_CUDA_CHECK(cudaMemsetAsync(slow.count, 0, sizeof(uint32_t), stream));
+    ReadsDev a = reads;
+    CountTable64 t64 = tab.view64();
+    long long read_offset = 0;
+    void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &slow };
+    SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
+    ++ctx.launches;
+    ++ctx.timing.launches;
+    if (!m.params.use_first) {
+        // best mode: reads with several verified windows take the full scan (the minimum must be attained once)
+        launch_random_generic(ctx, reads, m, tab, odd, odd_out, odd_count, out_index, ReadList{ slow.list, slow.count }, ctx.sm_count * 2, stream);
+    }
+    ctx.kernel_note = "specialised (NVRTC) spec_random_kernel, filter+verify + 16-byte-slot count table, " +
+                      std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM" + (m.params.use_first ? "" : " + random_kernel on the multi-window reads");
+}
+
+} // namespace scg
+
+// ---------------------------------------------------------------------------------------
+// resident plans (include/scg.h)
+// ---------------------------------------------------------------------------------------
+using namespace scg;
+
+namespace {
+cudaStream_t plan_stream(Context& c, void* cuda_stream) {
+    return cuda_stream == SCG_STREAM_OWN ? c.stream : static_cast<cudaStream_t>(cuda_stream);
+}
+} // namespace
+
+extern "C" {
+
+// Compiles the run-time specialised kernel of a handler (NVRTC) for a template and read length; no device needed for the
+// compile step.  kind: 1 dual paired-end (both templates), 2 combinatorial single-end, 3 random barcodes.
+// Returns 0 = compiled and loaded, 2 = compiled but no device to load it on, 1 = failed; `message` has the details.
+int scg_jit_selftest_handler(int kind, const char* constant_a, int strand_a, int mismatches_a, const char* constant_b, int strand_b,
+                             int mismatches_b, int read_len, int use_first, char* message, size_t capacity) {
+    std::string msg;
+    int status = 1;
+    try {
+        ReadsDev fake;
+        std::memset(&fake, 0, sizeof fake);
+        fake.uniform_len = read_len;
+        fake.W = std::max(1, (read_len + 31) / 32);
+        fake.n = 1;
+        TemplateSpec ta(constant_a, strand_a);
+        const ScanSpec sa = ta.scan_spec(mismatches_a);
+        std::string why;
+        if (!template_fits(ta, sa, fake, &why)) throw Error(why);
+        JitProgram prog;
+        if (kind == 1) {
+            TemplateSpec tb(constant_b, strand_b);
+            const ScanSpec sb = tb.scan_spec(mismatches_b);
+            if (!template_fits(tb, sb, fake, &why)) throw Error(why);
+            prog = dual_program(ta, sa, mismatches_a, fake, tb, sb, mismatches_b, fake, use_first, 1);
+        } else if (kind == 2) {
+            if (ta.fwd_regions.size() != 2) throw Error("expected 2 variable regions in the constant template");
+            prog = combo_program(ta, sa, mismatches_a, fake, use_first, 1);
+        } else if (kind == 3) {
+            if (ta.fwd_regions.empty()) throw Error("expected at least one variable region in the constant template");
+            prog = random_program(ta, sa, mismatches_a, fake, use_first, 1);
+        } else {
+            throw Error("unknown handler kind");
+        }
+        const JitModule* mod = jit_module(prog, 0, &why);
+        if (mod) {
+            msg = "ok: " + jit_status();
+            status = 0;
+        } else {
+            msg = why + " [" + jit_status() + "]";
+            status = why.rfind("cudaLibraryLoadData", 0) == 0 ? 2 : 1;
+        }
+    } catch (const std::exception& e) {
+        msg = e.what();
+    }
+    if (message && capacity) {
+        std::snprintf(message, capacity, "%s", msg.c_str());   // (strncpy would zero-fill the whole buffer)
+    }
+    return status;
+}
+
+int scg_dual_plan_create(scg_ctx* ctx, const char* constant1, int reverse1, int mismatches1, const char* const* pool1, int npool1,
+                         const char* constant2, int reverse2, int mismatches2, const char* const* pool2, int npool2, int randomized,
+                         int use_first, scg_plan** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Pool p1(pool1, npool1), p2(pool2, npool2);
+        std::unique_ptr<scg_plan> plan(new scg_plan);
+        plan->owner = ctx;
+        plan->kind = scg_plan::DUAL;
+        plan->npool = npool1;
+        plan->dual = std::make_shared<DualPEMatcher>();
+        plan->dual->prepare(constant1, reverse1 != 0, mismatches1, p1, constant2, reverse2 != 0, mismatches2, p2, randomized != 0, use_first != 0);
+        c.ensure_ready();
+        plan->dual->upload(c);
+        *out = plan.release();
+    });
+}
+
+int scg_dual_plan_run(scg_plan* plan, const scg_reads* reads1, const scg_reads* reads2, int32_t* d_counts, int32_t* d_index, void* cuda_stream) {
+    if (!plan || !reads1 || !reads2) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        if (plan->kind != scg_plan::DUAL) throw Error("not a dual-barcode plan");
+        if (reads1->n != reads2->n || reads1->batches.size() != reads2->batches.size()) {
+            throw Error("different number of reads in paired FASTQ files");   // process_data.hpp:284-285
+        }
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaStream_t st = plan_stream(c, cuda_stream);
+        long long at = 0;
+        for (size_t k = 0; k < reads1->batches.size(); ++k) {
+            const ReadsDev& a = reads1->batches[k].view;
+            const ReadsDev& b = reads2->batches[k].view;
+            if (a.n != b.n) throw Error("the two mates' resident batches differ in size");
+            launch_dual_pe(c, a, b, *plan->dual, d_counts, d_index ? d_index + at : nullptr, st);
+            at += a.n;
+        }
+        plan->kernel_note = c.kernel_note;
+    });
+}
+
+int scg_combo_plan_create(scg_ctx* ctx, const char* constant, int strand, const char* const* pool1, int npool1, const char* const* pool2,
+                          int npool2, int mismatches, int use_first, scg_plan** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        Pool p1(pool1, npool1), p2(pool2, npool2);
+        std::unique_ptr<scg_plan> plan(new scg_plan);
+        plan->owner = ctx;
+        plan->kind = scg_plan::COMBO;
+        plan->combo = std::make_shared<ComboMatcher>();
+        plan->combo->prepare(constant, strand, p1, p2, mismatches, use_first != 0, Duplicates::ERROR);
+        c.ensure_ready();
+        plan->combo->upload(c);
+        plan->tally.init(c, npool1, npool2);
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        *out = plan.release();
+    });
+}
+
+int scg_combo_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_pairs, void* cuda_stream) {
+    if (!plan || !reads) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        if (plan->kind != scg_plan::COMBO) throw Error("not a combinatorial-barcode plan");
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaStream_t st = plan_stream(c, cuda_stream);
+        long long at = 0;
+        for (const auto& b : reads->batches) {
+            launch_combo(c, b.view, *plan->combo, plan->tally.sink(c, b.view.n), nullptr, d_pairs ? d_pairs + 2 * at : nullptr, st);
+            at += b.view.n;
+        }
+        plan->kernel_note = c.kernel_note;
+    });
+}
+
+int scg_random_plan_create(scg_ctx* ctx, const char* constant, int strand, int mismatches, int use_first, long long expected_distinct,
+                           scg_plan** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        std::unique_ptr<scg_plan> plan(new scg_plan);
+        plan->owner = ctx;
+        plan->kind = scg_plan::RANDOM;
+        plan->random = std::make_shared<RandomMatcher>();
+        plan->random->prepare(constant, strand, mismatches, use_first != 0);
+        c.ensure_ready();
+        // sized once for the distinct barcodes the caller expects (load factor <= 1/2); 0 = grow as the reference's map does
+        plan->table.init(c, plan->random->wide, expected_distinct > 0 ? (size_t)(2 * expected_distinct) : (size_t)1 << 20);
+        plan->table.fixed = expected_distinct > 0;
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        *out = plan.release();
+    });
+}
+
+int scg_random_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_index, void* cuda_stream) {
+    if (!plan || !reads) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        if (plan->kind != scg_plan::RANDOM) throw Error("not a random-barcode plan");
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaStream_t st = plan_stream(c, cuda_stream);
+        long long at = 0;
+        for (const auto& b : reads->batches) {
+            plan->table.ensure(c, b.view.n);
+            // resident reads are packed bases: no read needs its raw text
+            launch_random(c, b.view, *plan->random, plan->table, nullptr, nullptr, nullptr, d_index ? d_index + at : nullptr, st);
+            at += b.view.n;
+        }
+        plan->kernel_note = c.kernel_note;
+    });
+}
+
+int scg_plan_reset(scg_plan* plan, void* cuda_stream) {
+    if (!plan) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        cudaStream_t st = plan_stream(c, cuda_stream);
+        if (plan->kind == scg_plan::COMBO) plan->tally.reset(c, st);
+        if (plan->kind == scg_plan::RANDOM) plan->table.reset(c, st);
+    });
+}
+
+int scg_plan_harvest(scg_plan* plan, scg_result** table) {
+    if (!plan || !table) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        SCG_CUDA_CHECK(cudaDeviceSynchronize());   // the runs may have been enqueued on the caller's stream
+        std::unique_ptr<scg_result> r(new scg_result);
+        if (plan->kind == scg_plan::COMBO) {
+            plan->tally.harvest(c, *r);
+        } else if (plan->kind == scg_plan::RANDOM) {
+            if (plan->random->wide) throw Error("plans of random barcodes longer than 21 bases cannot be harvested on the device");
+            SortedTable sorted;
+            plan->table.sorted(c, plan->random->key_len, sorted);
+            r->width = plan->random->key_len;
+            render_barcodes(c, sorted, r->d_strings, r->d_freq);
+            SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            r->on_device = true;
+            r->device = c.device;
+            r->d_rows = sorted.rows;
+        } else {
+            throw Error("only combinatorial and random-barcode plans hold a table");
+        }
+        *table = r.release();
+    });
+}
+
+} // extern "C"

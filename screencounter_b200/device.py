@@ -159,6 +159,90 @@ class SinglePlan:
             pass
 
 
+class _Plan:
+    """Common part of the compiled handlers: the C handle, which kernel ran, release."""
+
+    handle = None
+
+    @property
+    def kernel(self):
+        return lib().scg_plan_kernel(self.handle).decode()
+
+    def reset(self, stream=None):
+        """Empties the plan's own tally (combinations, random barcodes); asynchronous."""
+        _check(self.ctx, lib().scg_plan_reset(self.handle, _stream(stream)))
+
+    def harvest(self, as_array=True):
+        """The plan's table exactly as the file-level call returns it (synchronises the device)."""
+        from .rcpp import _table
+        h = C.c_void_p()
+        _check(self.ctx, lib().scg_plan_harvest(self.handle, C.byref(h)))
+        try:
+            return _table(h, self._table_kind if as_array or self._table_kind == "combo" else "random")
+        finally:
+            lib().scg_result_free(h)
+
+    def free(self):
+        if self.handle:
+            lib().scg_plan_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DualPlan(_Plan):
+    """countDualBarcodes (paired-end) with both templates and the library of pairs compiled onto the device once."""
+
+    def __init__(self, constant1, reverse1, mismatches1, pool1, constant2, reverse2, mismatches2, pool2, randomized, use_first, device=None):
+        self.ctx = context(device)
+        self.npool = len(pool1)
+        a1, k1 = _strs(pool1)
+        a2, k2 = _strs(pool2)
+        self.handle = C.c_void_p()
+        _check(self.ctx, lib().scg_dual_plan_create(self.ctx, constant1.encode("latin-1"), int(bool(reverse1)), int(mismatches1), a1, len(pool1),
+                                                    constant2.encode("latin-1"), int(bool(reverse2)), int(mismatches2), a2, len(pool2),
+                                                    int(bool(randomized)), int(bool(use_first)), C.byref(self.handle)))
+
+    def run(self, reads1, reads2, counts_ptr, index_ptr=None, stream=None):
+        """One pass over the pairs; counts (device int32[npool]) are accumulated into.  Asynchronous."""
+        _check(self.ctx, lib().scg_dual_plan_run(self.handle, reads1.handle, reads2.handle, C.c_void_p(counts_ptr),
+                                                 C.c_void_p(index_ptr) if index_ptr else None, _stream(stream)))
+
+
+class ComboPlan(_Plan):
+    """countComboBarcodes (single-end, two variable regions); the plan owns the tally of combinations."""
+    _table_kind = "combo"
+
+    def __init__(self, constant, strand, pool1, pool2, mismatches, use_first, device=None):
+        self.ctx = context(device)
+        a1, k1 = _strs(pool1)
+        a2, k2 = _strs(pool2)
+        self.handle = C.c_void_p()
+        _check(self.ctx, lib().scg_combo_plan_create(self.ctx, constant.encode("latin-1"), int(strand), a1, len(pool1), a2, len(pool2),
+                                                     int(mismatches), int(bool(use_first)), C.byref(self.handle)))
+
+    def run(self, reads, pairs_ptr=None, stream=None):
+        _check(self.ctx, lib().scg_combo_plan_run(self.handle, reads.handle, C.c_void_p(pairs_ptr) if pairs_ptr else None, _stream(stream)))
+
+
+class RandomPlan(_Plan):
+    """countRandomBarcodes; the plan owns the device count table (sized once when expected_distinct > 0)."""
+    _table_kind = "random_array"
+
+    def __init__(self, constant, strand, mismatches, use_first, expected_distinct=0, device=None):
+        self.ctx = context(device)
+        self.handle = C.c_void_p()
+        _check(self.ctx, lib().scg_random_plan_create(self.ctx, constant.encode("latin-1"), int(strand), int(mismatches), int(bool(use_first)),
+                                                      C.c_longlong(int(expected_distinct)), C.byref(self.handle)))
+
+    def run(self, reads, index_ptr=None, stream=None):
+        _check(self.ctx, lib().scg_random_plan_run(self.handle, reads.handle, C.c_void_p(index_ptr) if index_ptr else None, _stream(stream)))
+
+
 class DeviceArray:
     """A zero-initialised device buffer owned through the C ABI (for callers without torch)."""
 

@@ -129,9 +129,9 @@ def _table(handle, kind):
     L = lib()
     n = L.scg_result_rows(handle)
     w = L.scg_result_width(handle)
-    freq = np.zeros(n, dtype=np.int32)
+    freq = np.empty(n, dtype=np.int32)
     if kind == "combo":
-        keys = np.zeros((n, w), dtype=np.int32)
+        keys = np.empty((n, w), dtype=np.int32)
         L.scg_result_copy_table(handle, _ip(keys), None, _ip(freq))
         return keys, freq
     if kind == "random_array":
@@ -244,10 +244,10 @@ def kernel_launches(device=None):
     return int(lib().scg_kernel_launches(context(device)))
 
 
-def count_random_barcodes(path, constant, strand, mismatches, use_first, nthreads, device=None, as_array=False):
+def count_random_barcodes(path, constant, strand, mismatches, use_first, nthreads, device=None, as_array=True):
     """reference: src/count_random_barcodes.cpp:41-60 -> list(list(sequences, frequencies), total).
-    Sequences come back sorted (R sorts them anyway, R/countRandomBarcodes.R:73-74); with as_array they are one numpy
-    bytes array (dtype S<length>) instead of a list of str."""
+    Sequences come back sorted (R sorts them anyway, R/countRandomBarcodes.R:73-74) as ONE numpy bytes array (dtype
+    S<length>: the table is copied from the device straight into it); as_array=False gives a list of str instead."""
     ctx = context(device)
     src = _Src(path)
     handle = C.c_void_p()

@@ -23,7 +23,7 @@ class GpuEngine:
         return index, mms
 
     def count_random(self, fastq, template, strand, mismatches, use_first, nthreads=1):
-        (seqs, freq), total = rcpp.count_random_barcodes(fastq, template, strand, mismatches, use_first, nthreads)
+        (seqs, freq), total = rcpp.count_random_barcodes(fastq, template, strand, mismatches, use_first, nthreads, as_array=False)
         return seqs, freq, total
 
     def count_combo_single(self, fastq, template, strand, pool1, pool2, mismatches, use_first, nthreads=1):

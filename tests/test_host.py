@@ -195,6 +195,32 @@ def test_uniform_length_kernel_compiles(template, strand, mm, read_len):
     assert rc in (0, 2), buf.value.decode()
 
 
+F12, R12 = "CAGCTACGTACG", "CCAGCTCGATCG"
+
+
+@pytest.mark.parametrize("kind,a,strand_a,mm_a,b,strand_b,mm_b,read_len,use_first", [
+    (1, F12 + "-" * 20 + R12, 0, 1, "GATTACAGGCTA" + "-" * 20 + "TTGACCGTAGCA", 0, 1, 75, 1),   # BASELINE configs[2]
+    (1, F12 + "-" * 20 + R12, 1, 1, "GATTACAGGCTA" + "-" * 20 + "TTGACCGTAGCA", 1, 0, 75, 0),   # reverse strands, best mode
+    (1, F12 + "-" * 8 + R12, 0, 2, "GATTACAGGCTA" + "-" * 30 + "TTGACCGTAGCA", 0, 0, 100, 1),   # uneven regions, key of 38 bases
+    (1, "ACGTACGT" + "-" * 32 + "TGCATGCA", 0, 1, "GATTACAG" + "-" * 16 + "TTGACCGT", 1, 1, 60, 1),   # 32 + 16 = 48 bases
+    (2, "CAGCTACG" + "-" * 20 + "GGTACCTT" + "-" * 20 + "CGATCGAG", 2, 1, "", 0, 0, 75, 1),     # BASELINE configs[3]
+    (2, "CAGCTACG" + "-" * 20 + "GGTACCTT" + "-" * 10 + "CGATCGAG", 0, 0, "", 0, 0, 75, 0),
+    (2, "CAGCTACG" + "-" * 6 + "GGTACCTT" + "-" * 9 + "CGATCGAGAA", 1, 2, "", 0, 0, 150, 1),
+    (3, F12 + "-" * 16 + R12, 2, 1, "", 0, 0, 75, 1),                                           # BASELINE configs[4]
+    (3, F12 + "-" * 16 + "CCAGCTCG", 2, 1, "", 0, 0, 75, 0),                                    # asymmetric flanks (Quirk B), best mode
+    (3, F12 + "-" * 21 + R12, 0, 0, "", 0, 0, 101, 1),
+])
+def test_handler_kernels_compile(kind, a, strand_a, mm_a, b, strand_b, mm_b, read_len, use_first):
+    """The specialised dual / combinatorial / random-barcode kernels (spec_handlers.cuh) through NVRTC, without a device."""
+    import ctypes as C
+    from screencounter_b200._lib import lib
+    buf = C.create_string_buffer(16384)
+    f = lib().scg_jit_selftest_handler
+    f.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    rc = f(kind, a.encode(), strand_a, mm_a, b.encode(), strand_b, mm_b, read_len, use_first, buf, 16384)
+    assert rc in (0, 2), buf.value.decode()
+
+
 def _tricky_fastq(rng, n, wrap_every=0, bad_at=None):
     """Records that defeat naive boundary guessing: qualities starting with '@' or '+', wrapped
     sequences and qualities, names holding '@' and '+', an occasional empty read."""

@@ -130,7 +130,7 @@ def config5():
     t0 = time.perf_counter()
     wseqs, wfreq, wtotal = kref.count_random(sample, template, 2, 1, True, THREADS)
     ref_s = time.perf_counter() - t0
-    (gseqs, gfreq), gtotal = rcpp.count_random_barcodes(sample, template, 2, 1, True, THREADS)
+    (gseqs, gfreq), gtotal = rcpp.count_random_barcodes(sample, template, 2, 1, True, THREADS, as_array=False)
     order = np.argsort(np.array(wseqs, dtype=object), kind="stable") if len(wseqs) else []
     assert gtotal == wtotal and list(gseqs) == [wseqs[i] for i in order] and np.array_equal(gfreq, np.asarray(wfreq)[order])
     report("5: countRandomBarcodes 16-bp random barcodes, both strands, 1 mismatch in the flanks", n, gpu_s, ref_s, int(wtotal),
