@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: countSingleBarcodes, BASELINE.json configs[1]
-(Brunello-sized 77,441-guide library, 1 mismatch, both strands, 75-bp synthetic reads).
+"""Benchmark of the hot path on the BASELINE.json configs (default: configs[1], the headline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
-  python bench.py --impl reference [...]                        the reference's own CPU path on the host cores
+  python bench.py [--config N] [--gpus N] [--steps K] [--warmup W] [--scaling weak|strong]     our arm (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                                                      the reference's own CPU path on the host cores
 
-One step = one pass of the hot path (template scan -> barcode lookup -> counts [-> NCCL all-reduce
-of the count vector when N > 1]) over the rank's reads, which are resident in HBM when the timed
-region starts.  Prints ONE JSON line (see the task contract): `value` is device-timed reads/s over
-all ranks, `e2e` the same metric through the file-level C-ABI call from host FASTQ text,
-`roofline` the dominant kernel against the measured HBM peak, `cpu_baseline` the compiled
-reference (kaori) on the host cores.
+  --config 1  countSingleBarcodes, 1,000 x 20-bp guides, 0 mismatches, forward strand, 1 M reads
+  --config 2  countSingleBarcodes, 77,441 x 20-bp guides, 1 mismatch, both strands, 200 M reads        (default; BASELINE configs[1])
+  --config 3  countDualBarcodes paired-end, 10,000 pairs of 20-bp guides, 1 mismatch per read, 100 M read pairs
+  --config 4  countComboBarcodes single-end, two 20-bp regions, 500 x 500 pools, 1 mismatch, 100 M reads
+  --config 5  countRandomBarcodes, 16-bp random barcodes, both strands, 500 M reads (about 12 M distinct barcodes)
+
+One step = one pass of the hot path (template scan -> barcode lookup -> counts [-> the exchange between the GPUs when
+N > 1]) over the rank's reads, which are resident in HBM when the timed region starts.  Prints ONE JSON line (see the task
+contract): `value` is device-timed units/s over all ranks, `e2e` the same metric through the file-level C-ABI call from
+host FASTQ text, `roofline` the pass's kernels against the measured HBM peak, `cpu_baseline` the compiled reference (kaori)
+on the host cores, run in forked children with its results checked equal to the GPU's.
 """
 import argparse
 import json
 import os
+import pickle
+import signal
 import subprocess
 import sys
 import threading
@@ -25,28 +31,23 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TEMPLATE = "CAGCTACGTACG" + "-" * 20 + "CCAGCTCGATCG"   # 12 + 20 + 12, flanks of R/countSingleBarcodes.R:63
-N_GUIDES = 77441
+FLANK_L, FLANK_R = "CAGCTACGTACG", "CCAGCTCGATCG"   # flanks of the reference's examples, R/countSingleBarcodes.R:63
 READ_LEN = 75
-MISMATCHES = 1
-STRAND = 2          # both
-USE_FIRST = True    # R default find.best = FALSE
+RECORD = 2 * READ_LEN + 7                            # bytes of one synthetic FASTQ record
 SEED = 42
-BYTES_PER_READ = 49  # 29 B packed read + 4 B outcome + 16 B table probe
-WORKLOAD = "countSingleBarcodes: 77,441 x 20-bp guides, 1 mismatch, both strands, 75-bp reads (BASELINE configs[1])"
 
 
-def make_library():
-    rng = np.random.default_rng(SEED)
+def distinct_sequences(seed, n, length):
+    rng = np.random.default_rng(seed)
     seen, out = set(), []
-    while len(out) < N_GUIDES:
-        codes = rng.integers(0, 4, size=(4096, 20))
+    while len(out) < n:
+        codes = rng.integers(0, 4, size=(4096, length))
         for row in codes:
             s = "".join("ACGT"[c] for c in row)
             if s not in seen:
                 seen.add(s)
                 out.append(s)
-                if len(out) == N_GUIDES:
+                if len(out) == n:
                     break
     return out
 
@@ -59,6 +60,303 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# =====================================================================================================================
+# workloads: everything a config needs -- synthetic inputs, the resident plan, the file-level call, the reference call
+# =====================================================================================================================
+class Workload:
+    number = 0
+    name = ""
+    unit = "reads/s"
+    what = "reads"
+    bytes_per_unit = 0
+    bytes_note = ""
+    default_units = 0          # units resident per GPU (the config's stated size)
+    e2e_units = 4_000_000
+    cpu_units = 1_000_000
+    side_figures = False
+
+    # --- inputs ---
+    def specs(self):
+        raise NotImplementedError
+
+    def texts(self, first, n, pinned=False, device=None):
+        return [s.fastq_pinned(first, n, device=device) if pinned else s.fastq(first, n) for s in self.specs()]
+
+    def resident(self, first, n, device):
+        return [s.on_device(first, n, device=device) for s in self.specs()]
+
+    @staticmethod
+    def same(a, b):
+        return len(a) == len(b) and all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
+
+
+class SingleWorkload(Workload):
+    def __init__(self, number):
+        self.number = number
+        self.template = FLANK_L + "-" * 20 + FLANK_R
+        if number == 1:
+            self.name = "countSingleBarcodes: 1,000 x 20-bp guides, 0 mismatches, forward strand, 75-bp reads (BASELINE configs[0])"
+            self.nguides, self.mm, self.strand = 1000, 0, 0
+            self.default_units, self.e2e_units, self.cpu_units = 1_000_000, 1_000_000, 1_000_000
+        else:
+            self.name = "countSingleBarcodes: 77,441 x 20-bp guides, 1 mismatch, both strands, 75-bp reads (BASELINE configs[1])"
+            self.nguides, self.mm, self.strand = 77441, 1, 2
+            self.default_units, self.e2e_units, self.cpu_units = 200_000_000, 8_000_000, 4_000_000
+            self.side_figures = True
+        self.use_first = True   # R default find.best = FALSE
+        self.bytes_per_unit = 49
+        self.bytes_note = "49 B/read = 29 B packed read + 4 B per-read outcome (written) + 16 B table probe (L2-resident)"
+        self.library = distinct_sequences(SEED, self.nguides, 20)
+
+    def specs(self):
+        from screencounter_b200.device import SynthSpec
+        return [SynthSpec(self.template, [self.library], seed=SEED, read_len=READ_LEN, strand=self.strand)]
+
+    def make_plan(self, device, units):
+        import torch
+        from screencounter_b200.device import SinglePlan
+        dev = torch.device("cuda", device)
+        self.plan = SinglePlan(self.template, self.strand, self.library, self.mm, self.use_first, device=device)
+        self.counts = torch.zeros(len(self.library), dtype=torch.int32, device=dev)
+        self.index = torch.empty(units, dtype=torch.int32, device=dev)   # per-read outcome: part of the 49 B/read figure
+
+    def reset(self, stream):
+        self.counts.zero_()
+
+    def run(self, reads, stream):
+        self.plan.run(reads[0], self.counts.data_ptr(), index_ptr=self.index.data_ptr(), stream=stream)
+
+    def dense_tensor(self):
+        return self.counts
+
+    def result(self):
+        return [self.counts.cpu().numpy()]
+
+    def matched(self):
+        return int(self.counts.sum().item())
+
+    def consistent(self):
+        return int((self.index >= 0).sum().item()) == self.matched()
+
+    def reference(self, engine, texts, threads):
+        counts, total = engine.count_single(texts[0], self.template, self.strand, self.library, self.mm, self.use_first, threads)
+        return [counts, np.array([total])]
+
+    def ours(self, texts, nthreads, device):
+        from screencounter_b200 import rcpp
+        counts, total = rcpp.count_single_barcodes(texts[0], self.template, self.strand, self.library, self.mm, self.use_first, nthreads, device=device)
+        return [counts, np.array([total])]
+
+    def d2h_bytes(self):
+        return 4 * len(self.library)
+
+    def config_extra(self):
+        return {"library": self.nguides, "mismatches": self.mm, "strand": ["original", "reverse", "both"][self.strand], "find_best": False}
+
+
+class DualWorkload(Workload):
+    number = 3
+    name = ("countDualBarcodes paired-end: 10,000 pairs drawn from 200 x 200 distinct 20-bp guides, templates 12+20+12, 1 mismatch per read, "
+            "75-bp reads (BASELINE configs[2])")
+    unit = "pairs/s"
+    what = "read pairs"
+    bytes_per_unit = 86
+    bytes_note = "86 B/pair = 2 x 29 B packed reads + 4 B per-pair outcome (written) + 24 B table probe of the 40-base key (L2-resident)"
+    default_units, e2e_units, cpu_units = 100_000_000, 4_000_000, 1_000_000
+
+    def __init__(self):
+        a, b = distinct_sequences(3, 200, 20), distinct_sequences(4, 200, 20)
+        rng = np.random.default_rng(5)
+        rows = set()
+        while len(rows) < 10000:
+            rows.add((int(rng.integers(0, 200)), int(rng.integers(0, 200))))
+        rows = sorted(rows)
+        self.pool1, self.pool2 = [a[i] for i, _ in rows], [b[j] for _, j in rows]
+        self.t1 = FLANK_L + "-" * 20 + FLANK_R
+        self.t2 = "GATTACAGGCTA" + "-" * 20 + "TTGACCGTAGCA"
+        self.use_first = True
+
+    def specs(self):
+        from screencounter_b200.device import SynthSpec
+        # the same seed picks the same library row, offset and noise pattern for both mates
+        return [SynthSpec(self.t1, [self.pool1], seed=7, read_len=READ_LEN, strand=0),
+                SynthSpec(self.t2, [self.pool2], seed=7, read_len=READ_LEN, strand=0)]
+
+    def make_plan(self, device, units):
+        import torch
+        from screencounter_b200.device import DualPlan
+        dev = torch.device("cuda", device)
+        self.plan = DualPlan(self.t1, False, 1, self.pool1, self.t2, False, 1, self.pool2, False, self.use_first, device=device)
+        self.counts = torch.zeros(len(self.pool1), dtype=torch.int32, device=dev)
+        self.index = torch.empty(units, dtype=torch.int32, device=dev)
+
+    def reset(self, stream):
+        self.counts.zero_()
+
+    def run(self, reads, stream):
+        self.plan.run(reads[0], reads[1], self.counts.data_ptr(), index_ptr=self.index.data_ptr(), stream=stream)
+
+    def dense_tensor(self):
+        return self.counts
+
+    def result(self):
+        return [self.counts.cpu().numpy()]
+
+    def matched(self):
+        return int(self.counts.sum().item())
+
+    def consistent(self):
+        return int((self.index >= 0).sum().item()) == self.matched()
+
+    def reference(self, engine, texts, threads):
+        out = engine.count_dual(texts[0], self.t1, False, 1, self.pool1, texts[1], self.t2, False, 1, self.pool2, False, self.use_first, False, threads)
+        return [out[0], np.array([int(out[1])])]
+
+    def ours(self, texts, nthreads, device):
+        from screencounter_b200 import rcpp
+        counts, total = rcpp.count_dual_barcodes(texts[0], self.t1, False, 1, self.pool1, texts[1], self.t2, False, 1, self.pool2, False,
+                                                 self.use_first, False, nthreads, device=device)
+        return [counts, np.array([int(total[0])])]
+
+    def d2h_bytes(self):
+        return 4 * len(self.pool1)
+
+    def config_extra(self):
+        return {"library_pairs": len(self.pool1), "mismatches": [1, 1], "strands": ["original", "original"], "find_best": False}
+
+
+class ComboWorkload(Workload):
+    number = 4
+    name = ("countComboBarcodes single-end: template 8+20+8+20+8, 500 x 500 pools of 20-bp barcodes, 1 mismatch, both strands, 75-bp reads "
+            "(BASELINE configs[3])")
+    bytes_per_unit = 69
+    bytes_note = "69 B/read = 29 B packed read + 8 B per-read pair (written) + 2 x 16 B table probes (L1/L2-resident)"
+    default_units, e2e_units, cpu_units = 100_000_000, 4_000_000, 1_000_000
+
+    def __init__(self):
+        self.p1, self.p2 = distinct_sequences(6, 500, 20), distinct_sequences(7, 500, 20)
+        self.template = "CAGCTACG" + "-" * 20 + "GGTACCTT" + "-" * 20 + "CGATCGAG"
+        self.mm, self.strand, self.use_first = 1, 2, True
+
+    def specs(self):
+        from screencounter_b200.device import SynthSpec
+        return [SynthSpec(self.template, [self.p1, self.p2], seed=11, read_len=READ_LEN, strand=self.strand)]
+
+    def make_plan(self, device, units):
+        import torch
+        from screencounter_b200.device import ComboPlan
+        dev = torch.device("cuda", device)
+        self.plan = ComboPlan(self.template, self.strand, self.p1, self.p2, self.mm, self.use_first, device=device)
+        self.pairs = torch.empty(2 * units, dtype=torch.int32, device=dev)
+
+    def reset(self, stream):
+        self.plan.reset(stream=stream)
+
+    def run(self, reads, stream):
+        self.plan.run(reads[0], pairs_ptr=self.pairs.data_ptr(), stream=stream)
+
+    def dense_tensor(self):
+        return None
+
+    def result(self):
+        keys, freq = self.plan.harvest()
+        return [keys, freq]
+
+    def matched(self):
+        return int(self.plan.harvest()[1].sum())
+
+    def consistent(self):
+        return int((self.pairs[0::2] >= 0).sum().item()) == self.matched()
+
+    def reference(self, engine, texts, threads):
+        keys, freq, total = engine.count_combo_single(texts[0], self.template, self.strand, self.p1, self.p2, self.mm, self.use_first, threads)
+        return [keys, freq, np.array([int(total)])]
+
+    def ours(self, texts, nthreads, device):
+        from screencounter_b200 import rcpp
+        keys, freq, total = rcpp.count_combo_barcodes_single(texts[0], self.template, self.strand, [self.p1, self.p2], self.mm, self.use_first,
+                                                             nthreads, device=device)
+        return [keys.T.copy(), freq, np.array([int(total[0])])]
+
+    def d2h_bytes(self):
+        return None
+
+    def config_extra(self):
+        sparse = os.environ.get("SCG_COMBO_FORCE_SPARSE", "0") not in ("", "0")
+        return {"pools": [500, 500], "mismatches": self.mm, "strand": "both", "find_best": False,
+                "tally": "device hash (SCG_COMBO_FORCE_SPARSE=1)" if sparse else "dense 500 x 500 matrix (SCG_COMBO_FORCE_SPARSE=1 selects the device hash)"}
+
+
+class RandomWorkload(Workload):
+    number = 5
+    name = ("countRandomBarcodes: template 12+16+12, both strands, 1 mismatch in the flanks, 75-bp reads, barcodes drawn from 4 M true 16-mers "
+            "with 0.1 % substitutions (about 12 M distinct per 500 M reads) (BASELINE configs[4])")
+    bytes_per_unit = 53
+    bytes_note = "53 B/read = 29 B packed read + 8 B barcode + 16 B count-table slot read-modify-write (the table, ~0.5 GB, lives in HBM)"
+    default_units, e2e_units, cpu_units = 500_000_000, 4_000_000, 1_000_000
+
+    def __init__(self):
+        self.template = FLANK_L + "-" * 16 + FLANK_R
+        self.mm, self.strand, self.use_first = 1, 2, True
+
+    def specs(self):
+        from screencounter_b200.device import SynthSpec
+        return [SynthSpec(self.template, [], seed=13, read_len=READ_LEN, strand=self.strand, random_space=4_000_000, sub_per_10k=10)]
+
+    def make_plan(self, device, units):
+        import torch
+        from screencounter_b200.device import RandomPlan
+        dev = torch.device("cuda", device)
+        # distinct barcodes: the 4 M true ones + the substituted copies (1.6 % of the constructs) + slack
+        expected = min(units, 4_000_000) + int(0.02 * units) + 1_000_000
+        self.plan = RandomPlan(self.template, self.strand, self.mm, self.use_first, expected_distinct=expected, device=device)
+        self.index = torch.empty(units, dtype=torch.int32, device=dev)
+
+    def reset(self, stream):
+        self.plan.reset(stream=stream)
+
+    def run(self, reads, stream):
+        self.plan.run(reads[0], index_ptr=self.index.data_ptr(), stream=stream)
+
+    def dense_tensor(self):
+        return None
+
+    def result(self):
+        seqs, freq = self.plan.harvest()
+        return [seqs, freq]
+
+    def matched(self):
+        return int(self.plan.harvest()[1].sum())
+
+    def consistent(self):
+        return int((self.index >= 0).sum().item()) == self.matched()
+
+    def reference(self, engine, texts, threads):
+        seqs, freq, total = engine.count_random(texts[0], self.template, self.strand, self.mm, self.use_first, threads)
+        order = np.argsort(np.array(seqs, dtype=object), kind="stable") if len(seqs) else np.zeros(0, dtype=np.int64)
+        return [np.array([seqs[i].encode() for i in order], dtype="S16"), np.asarray(freq)[order], np.array([int(total)])]
+
+    def ours(self, texts, nthreads, device):
+        from screencounter_b200 import rcpp
+        (seqs, freq), total = rcpp.count_random_barcodes(texts[0], self.template, self.strand, self.mm, self.use_first, nthreads, device=device)
+        return [seqs, freq, np.array([int(total)])]
+
+    def d2h_bytes(self):
+        return None   # the sorted table: counted from the result
+
+    def config_extra(self):
+        return {"barcode_bases": 16, "mismatches": self.mm, "strand": "both", "find_best": False, "true_barcodes": 4_000_000}
+
+
+def make_workload(number):
+    if number in (1, 2):
+        return SingleWorkload(number)
+    return {3: DualWorkload, 4: ComboWorkload, 5: RandomWorkload}[number]()
+
+
+# =====================================================================================================================
+# device clocks
+# =====================================================================================================================
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -136,23 +434,22 @@ def bind_near_gpu(local_rank):
         return None
 
 
+# =====================================================================================================================
+# the reference on the host cores, isolated
+# =====================================================================================================================
 def _kaori_engine():
     from oracle import kref, port
     return (kref, "reference") if kref.available() else (port, "port")
 
 
-def kaori_isolated(text, library, threads, mode="count", retries=3):
-    """One pass of the reference's CPU path in a FORKED CHILD, so that nothing it does can take this process down.
+def isolated(fn, retries=3):
+    """Runs fn() in a FORKED CHILD and returns (seconds inside fn, its result, crashes), so that nothing the reference does can
+    take this process down.
 
     kaori has a data race when num_threads > 1: reduce() merges a worker's search cache into the shared one
-    (inst/include/kaori/BarcodeSearch.hpp:192-195) while other workers read it (:65); with 1 mismatch the cache is hot
-    and an oversubscribed pool can crash (round 1: SIGSEGV on the driver's box).  A child that dies by a signal is run
-    again (up to `retries` times); the number of crashes is returned and reported.  The child only touches kaori and plain
-    host memory (never CUDA).  mode: "count" = process_single_end_data, "parse" = the FASTQ reader alone.
-    Returns (seconds inside the call, counts or None, total, crashes)."""
-    import pickle
-    import signal
-    engine, _ = _kaori_engine()
+    (inst/include/kaori/BarcodeSearch.hpp:192-195) while other workers read it (:65); with 1 mismatch the cache is hot and an
+    oversubscribed pool can crash (round 1: SIGSEGV on the driver's box).  A child that dies by a signal is run again (up to
+    `retries` times); the number of crashes is reported.  The child only touches kaori and plain host memory (never CUDA)."""
     crashes = 0
     for _attempt in range(retries + 1):
         rfd, wfd = os.pipe()
@@ -162,14 +459,10 @@ def kaori_isolated(text, library, threads, mode="count", retries=3):
             try:
                 os.close(rfd)
                 t0 = time.perf_counter()
-                if mode == "parse":
-                    total, _nbases = engine.count_reads(text)
-                    counts = None
-                else:
-                    counts, total = engine.count_single(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, threads)
+                result = fn()
                 dt = time.perf_counter() - t0
                 with os.fdopen(wfd, "wb") as f:
-                    pickle.dump((dt, None if counts is None else counts.tobytes(), int(total)), f)
+                    pickle.dump((dt, result), f, protocol=pickle.HIGHEST_PROTOCOL)
                 status = 0
             finally:
                 os._exit(status)
@@ -178,156 +471,152 @@ def kaori_isolated(text, library, threads, mode="count", retries=3):
             payload = f.read()
         _, st = os.waitpid(pid, 0)
         if os.WIFEXITED(st) and os.WEXITSTATUS(st) == 0 and payload:
-            dt, raw, total = pickle.loads(payload)
-            counts = None if raw is None else np.frombuffer(raw, dtype=np.int32).copy()
-            return dt, counts, total, crashes
+            dt, result = pickle.loads(payload)
+            return dt, result, crashes
         if os.WIFSIGNALED(st) and os.WTERMSIG(st) in (signal.SIGSEGV, signal.SIGABRT, signal.SIGBUS):
             crashes += 1
             continue
         raise RuntimeError("the reference child failed (wait status %d)" % st)
-    return None, None, 0, crashes
+    return None, None, crashes
 
 
-def kaori_multiprocess(text, library, procs, n_reads, record_bytes):
-    """The race-free way to use every core: `procs` single-threaded kaori processes, each on its own contiguous slice of
-    the reads (how the reference itself parallelises, one file per worker: R/countSingleBarcodes.R:113 bplapply).
-    Returns (wall seconds from the first fork to the last result, summed counts)."""
-    import pickle
+def multiprocess_figure(wl, texts, procs, n_units):
+    """The race-free way to use every core: `procs` single-threaded kaori processes, each on its own contiguous slice of the reads
+    (how the reference itself parallelises, one file per worker: R/countSingleBarcodes.R:113 bplapply).  Dense workloads only.
+    Returns (wall seconds from the first fork to the last result, summed result)."""
     engine, _ = _kaori_engine()
-    view = memoryview(text)
+    views = [memoryview(t) for t in texts]
     kids = []
     t0 = time.perf_counter()
     for k in range(procs):
-        b, e = (n_reads * k) // procs, (n_reads * (k + 1)) // procs
+        b, e = (n_units * k) // procs, (n_units * (k + 1)) // procs
         rfd, wfd = os.pipe()
         pid = os.fork()
         if pid == 0:
             status = 1
             try:
                 os.close(rfd)
-                counts, total = engine.count_single(bytes(view[b * record_bytes:e * record_bytes]), TEMPLATE, STRAND, library,
-                                                    MISMATCHES, USE_FIRST, 1)
+                out = wl.reference(engine, [bytes(v[b * RECORD:e * RECORD]) for v in views], 1)
                 with os.fdopen(wfd, "wb") as f:
-                    pickle.dump((counts.tobytes(), int(total)), f)
+                    pickle.dump(out, f, protocol=pickle.HIGHEST_PROTOCOL)
                 status = 0
             finally:
                 os._exit(status)
         os.close(wfd)
         kids.append((pid, rfd))
-    counts, total = None, 0
+    total = None
     for pid, rfd in kids:
         with os.fdopen(rfd, "rb") as f:
             payload = f.read()
         _, st = os.waitpid(pid, 0)
         if not (os.WIFEXITED(st) and os.WEXITSTATUS(st) == 0 and payload):
             raise RuntimeError("a single-threaded reference child failed (wait status %d)" % st)
-        raw, t = pickle.loads(payload)
-        c = np.frombuffer(raw, dtype=np.int32).astype(np.int64)
-        counts = c if counts is None else counts + c
-        total += t
-    return time.perf_counter() - t0, counts.astype(np.int32), total
+        out = pickle.loads(payload)
+        total = [np.asarray(x, dtype=np.int64) for x in out] if total is None else [a + np.asarray(x, dtype=np.int64) for a, x in zip(total, out)]
+    return time.perf_counter() - t0, total
 
 
-def cpu_side_figures(text, library, n_reads, threads, threaded_counts):
-    """The other CPU figures BASELINE.md section 3 asks for, each measured once on a bounded sample: every core used
-    race-free (one single-threaded process per core), one thread, and the FASTQ reader alone."""
-    record = 2 * READ_LEN + 7
+def cpu_side_figures(wl, texts, n_units, threads, threaded_result):
+    """The other CPU figures BASELINE.md section 3 asks for, each measured once on a bounded sample: every core used race-free
+    (one single-threaded process per core), one thread, and the FASTQ reader alone."""
+    engine, _ = _kaori_engine()
+    what = wl.what.replace(" ", "_")
     out = {}
     try:
-        wall, counts, total = kaori_multiprocess(text, library, threads, n_reads, record)
-        out["multiprocess"] = {"value": n_reads / wall, "unit": "reads/s", "processes": threads, "reads": n_reads,
+        wall, summed = multiprocess_figure(wl, texts, threads, n_units)
+        out["multiprocess"] = {"value": n_units / wall, "unit": wl.unit, "processes": threads, what: n_units,
                                "note": "race-free: one single-threaded kaori process per core, each on its own slice of the reads"}
-        if threaded_counts is not None:
-            out["multiprocess"]["counts_equal_threaded"] = bool(np.array_equal(counts, threaded_counts))
+        if threaded_result is not None:
+            out["multiprocess"]["counts_equal_threaded"] = bool(np.array_equal(summed[0], np.asarray(threaded_result[0], dtype=np.int64)))
     except Exception as exc:   # a baseline figure must never take the line down
         out["multiprocess"] = {"error": str(exc)[:200]}
-    one = max(1, min(n_reads, 500_000))
-    dt, _, _, crashes = kaori_isolated(text[: one * record], library, 1)
+    one = max(1, min(n_units, 500_000))
+    dt, _, _ = isolated(lambda: wl.reference(engine, [t[: one * RECORD] for t in texts], 1))
     if dt:
-        out["one_thread"] = {"value": one / dt, "unit": "reads/s", "reads": one}
-    dt, _, total, _ = kaori_isolated(text, library, 1, mode="parse")
+        out["one_thread"] = {"value": one / dt, "unit": wl.unit, what: one}
+    dt, res, _ = isolated(lambda: engine.count_reads(texts[0]))
     if dt:
-        out["parse_only"] = {"value": total / dt, "unit": "reads/s", "reads": total,
+        out["parse_only"] = {"value": res[0] / dt, "unit": "reads/s", "reads": res[0],
                              "note": "kaori::FastqReader over the sample, no handler (the serial part of the threaded run)"}
     return out
 
 
-def cpu_baseline_leg(args, library):
-    """`cpu_baseline` of our own line: the compiled reference on this box's host cores over the first reads of the
-    workload, in forked children.  Returns (dict, counts, sample) -- the counts are compared with the GPU's later."""
-    from screencounter_b200.device import SynthSpec
+def reference_threads():
+    # the cores this process may run on (the cgroup's share, not the machine's: os.cpu_count() oversubscribed kaori's pool on
+    # the round-1 box and it crashed)
     _, kind = _kaori_engine()
     cores = len(os.sched_getaffinity(0)) or 1
-    threads = cores if kind == "reference" else 1
-    sample = min(args.cpu_reads, args.e2e_reads)
-    spec = SynthSpec(TEMPLATE, [library], seed=SEED, read_len=READ_LEN, strand=STRAND)
-    text = spec.fastq(0, sample)
+    return (cores if kind == "reference" else 1), kind
+
+
+def cpu_baseline_leg(wl, args):
+    """`cpu_baseline` of our own line: the compiled reference on this box's host cores over the first units of the workload, in
+    forked children, BEFORE this process initialises CUDA.  Returns (dict, result, sample); the result is compared with the
+    GPU's later."""
+    engine, _ = _kaori_engine()
+    threads, kind = reference_threads()
+    sample = min(args.cpu_units or wl.cpu_units, args.e2e_units or wl.e2e_units)
+    texts = wl.texts(0, sample)
+    side, crashes = {}, 0
     try:
-        dt, counts, total, crashes = kaori_isolated(text, library, threads)
-        side = cpu_side_figures(text, library, sample, threads, counts)
+        dt, result, crashes = isolated(lambda: wl.reference(engine, texts, threads))
+        if wl.side_figures:
+            side = cpu_side_figures(wl, texts, sample, threads, result)
     except Exception as exc:
-        return {"value": None, "unit": "reads/s", "cores": threads, "kind": kind, "sample": "failed: %s" % str(exc)[:200]}, None, sample
+        return {"value": None, "unit": wl.unit, "cores": threads, "kind": kind, "sample": "failed: %s" % str(exc)[:200]}, None, sample
     if dt is None:
-        mp = side.get("multiprocess", {})
-        value = mp.get("value")
+        value = side.get("multiprocess", {}).get("value")
         note = "every threaded attempt crashed (kaori's cache race); value = the multi-process figure"
     else:
         value, note = sample / dt, "threaded, kaori num_threads = %d" % threads
-    out = {"value": value, "unit": "reads/s", "cores": threads, "kind": kind, "mode": note, "crashed_attempts_retried": crashes,
-           "sample": "first %d reads of the workload, FASTQ text in host memory" % sample}
+    out = {"value": value, "unit": wl.unit, "cores": threads, "kind": kind, "mode": note, "crashed_attempts_retried": crashes,
+           "sample": "first %d %s of the workload, FASTQ text in host memory" % (sample, wl.what)}
     out.update(side)
-    return out, counts, sample
+    return out, result, sample
 
 
-def reference_arm(args, library):
-    """The reference's own CPU implementation of the path (kaori compiled from /root/reference in
-    oracle/_ref, else the C restatement) on all host cores, on a bounded sample of the workload."""
-    from screencounter_b200.device import SynthSpec
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def reference_arm(wl, args):
+    """The reference's own CPU implementation of the path (kaori compiled from /root/reference in oracle/_ref, else the C
+    restatement) on all host cores, on a bounded sample of the workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    _, kind = _kaori_engine()
-    # the cores this process may run on (the cgroup's share, not the machine's: os.cpu_count() oversubscribed kaori's
-    # pool on the round-1 box and it crashed)
-    cores = len(os.sched_getaffinity(0)) or 1
-    threads = cores if kind == "reference" else 1
-    sample = args.cpu_reads
-    spec = SynthSpec(TEMPLATE, [library], seed=SEED, read_len=READ_LEN, strand=STRAND)
-    text = spec.fastq(0, sample)
-    crashes = 0
-    counts = None
+    engine, _ = _kaori_engine()
+    threads, kind = reference_threads()
+    sample = args.cpu_units or (4_000_000 if wl.number == 2 else wl.cpu_units)
+    texts = wl.texts(0, sample)
+    crashes, result = 0, None
     for _ in range(args.warmup):
-        _, counts, _, c = kaori_isolated(text, library, threads)
+        _, result, c = isolated(lambda: wl.reference(engine, texts, threads))
         crashes += c
     spent, steps_done = 0.0, 0
     for _ in range(args.steps):
-        dt, counts, total, c = kaori_isolated(text, library, threads)
+        dt, result, c = isolated(lambda: wl.reference(engine, texts, threads))
         crashes += c
         if dt is not None:
             spent += dt
             steps_done += 1
-    side = cpu_side_figures(text, library, sample, threads, counts)
+    side = cpu_side_figures(wl, texts, sample, threads, result) if wl.side_figures else {}
     mode = "threaded (kaori num_threads = %d)" % threads
     if steps_done == 0:
-        # every threaded attempt crashed: the race-free figure stands in
-        mp = side.get("multiprocess", {})
+        mp = side.get("multiprocess", {})   # every threaded attempt crashed: the race-free figure stands in
         if "value" not in mp:
             raise RuntimeError("the reference could not be run on this box")
         value, ms = mp["value"], 1000.0 * sample / mp["value"]
         mode = "multi-process (every threaded attempt crashed)"
     else:
         value, ms = sample * steps_done / spent, 1000.0 * spent / steps_done
+    what = wl.what.replace(" ", "_")
     line = {
-        "impl": "reference", "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "reads/sec", "value": value, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_step": sample, "mode": mode,
-                   "timing": "wall clock around kaori::process_single_end_data (tries built, parse + scan + lookup + reduce), FASTQ text in host "
-                             "memory, each step in a forked child; both tries are rebuilt every step, as every R call does"},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": kind,
-                         "sample": "%d reads of the same synthetic workload per step" % sample,
+        "config": {"workload": wl.name, "baseline_config": wl.number, "%s_per_step" % what: sample, "mode": mode,
+                   "timing": "wall clock around the kaori::process_*_end_data call (libraries built, parse + scan + lookup + reduce), FASTQ text "
+                             "in host memory, each step in a forked child; the libraries are rebuilt every step, as every R call does"},
+        "cpu_baseline": {"value": value, "unit": wl.unit, "cores": threads, "kind": kind,
+                         "sample": "%d %s of the same synthetic workload per step" % (sample, wl.what),
                          "crashed_attempts_retried": crashes, **side},
-        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
@@ -356,34 +645,39 @@ def _emit(line):
         os.write(_RESULT_FD, data)
 
 
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=200_000_000, help="reads resident per GPU (config 2: 200 M)")
-    ap.add_argument("--e2e-reads", type=int, default=8_000_000, help="reads per end-to-end step (host FASTQ text)")
-    ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-baseline sample")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config, 1-based (default 2 = the headline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's size per GPU; strong: the config's size in total, split over the GPUs")
+    ap.add_argument("--reads", type=int, default=0, help="units resident per GPU (weak) or in total (strong); default: the config's size")
+    ap.add_argument("--e2e-reads", dest="e2e_units", type=int, default=0, help="units per end-to-end step (host FASTQ text)")
+    ap.add_argument("--cpu-reads", dest="cpu_units", type=int, default=0, help="units in the bounded CPU-baseline sample")
     args = ap.parse_args()
     _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    library = make_library()
+    wl = make_workload(args.config)
     if args.impl == "reference":
-        reference_arm(args, library)
+        reference_arm(wl, args)
         return
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     # the CPU baseline runs in forked children BEFORE this process initialises CUDA (N = 1 only)
-    cpu_leg = cpu_baseline_leg(args, library) if world == 1 else None
+    cpu_leg = cpu_baseline_leg(wl, args) if world == 1 else None
 
     import torch
     import torch.distributed as dist
-    from screencounter_b200 import rcpp
-    from screencounter_b200.device import SynthSpec, SinglePlan
+    from screencounter_b200 import multi, rcpp
 
     binding = bind_near_gpu(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
@@ -391,21 +685,30 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    spec = SynthSpec(TEMPLATE, [library], seed=SEED, read_len=READ_LEN, strand=STRAND)
-    # contiguous read range per rank; weak scaling: `--reads` per GPU
-    first = rank * args.reads
-    reads = spec.on_device(first, args.reads, device=local_rank)
-    plan = SinglePlan(TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, device=local_rank)
-    counts = torch.zeros(len(library), dtype=torch.int32, device=dev)
-    # per-read outcome (pool index or -1): materialised every step, it is part of the 49 B/read figure
-    index = torch.empty(args.reads, dtype=torch.int32, device=dev)
+    total_units = args.reads or wl.default_units
+    if args.scaling == "strong":
+        first = (total_units * rank) // world
+        units = (total_units * (rank + 1)) // world - first
+    else:
+        units = total_units
+        first = rank * units   # contiguous range per rank
+    reads = wl.resident(first, units, local_rank)
+    wl.make_plan(local_rank, units)
     stream = torch.cuda.current_stream()
+    sid = stream.cuda_stream
+    resident_bytes = sum(r.device_bytes for r in reads)
+    # inputs smaller than the 126 MB L2 (config 1 at its stated size) would be re-read from L2: a buffer larger than L2 is
+    # written between the timed passes, outside the events
+    need_flush = resident_bytes < 512e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if need_flush else None
+
+    exchange = multi.Exchange(wl, world, dev) if world > 1 else None
 
     def step():
-        counts.zero_()
-        plan.run(reads, counts.data_ptr(), index_ptr=index.data_ptr(), stream=stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(counts)   # one NCCL all-reduce of the count vector over NVLink
+        wl.reset(sid)
+        wl.run(reads, sid)
+        if exchange is not None:
+            exchange.run()
 
     def barrier():
         if world > 1:
@@ -417,122 +720,167 @@ def main():
     barrier()
 
     # --- kernel-only timing for the roofline (events around the kernel launches alone) ---
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches_before = rcpp.kernel_launches(local_rank)
-    counts.zero_()
-    k0.record()
-    for _ in range(args.steps):
-        plan.run(reads, counts.data_ptr(), index_ptr=index.data_ptr(), stream=stream.cuda_stream)
-    k1.record()
+    wl.reset(sid)
+    kernel_ms = 0.0
+    if need_flush:
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            wl.run(reads, sid)
+            k1.record()
+            torch.cuda.synchronize()
+            kernel_ms += k0.elapsed_time(k1)
+    else:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            wl.run(reads, sid)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms = k0.elapsed_time(k1)
+    launches_per_pass = (rcpp.kernel_launches(local_rank) - launches_before) // args.steps
+    kernel_ms_per_pass = kernel_ms / args.steps
+    # one clean pass for the consistency checks (per-unit outcomes vs tallies)
+    wl.reset(sid)
+    wl.run(reads, sid)
     torch.cuda.synchronize()
-    launches_per_step = (rcpp.kernel_launches(local_rank) - launches_before) // args.steps
-    # the uniform-length kernel is followed by a (microseconds-long) kernel for its rare multi-window reads: the pair is
-    # one pass over the launch's reads
-    passes_per_step = launches_per_step // 2 if "filter+verify" in plan.kernel else launches_per_step
-    kernel_ms_per_step = k0.elapsed_time(k1) / args.steps
-    matched_per_step = int(counts.sum().item()) // args.steps
-    assert int((index >= 0).sum().item()) == matched_per_step, "per-read outcomes and counts disagree"
+    matched_per_pass = wl.matched()
+    assert wl.consistent(), "per-read outcomes and counts disagree"
+    kernel_name = wl.plan.kernel
 
     # --- the timed region: exactly K steps, barrier + synchronize on both sides, device clocks sampled ---
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches_before = rcpp.kernel_launches(local_rank)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
+    if need_flush:
+        elapsed = 0.0
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            elapsed += e0.elapsed_time(e1)
+        barrier()
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        elapsed = e0.elapsed_time(e1)
     gpu_launches = rcpp.kernel_launches(local_rank) - launches_before
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    elapsed_ms = torch.tensor([elapsed], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
-    total_reads = args.reads * world
-    value = total_reads * args.steps / (elapsed_ms / 1000.0)
-    final_counts = counts.cpu().numpy()
+    all_units = total_units if args.scaling == "strong" else units * world
+    value = all_units * args.steps / (elapsed_ms / 1000.0)
 
-    # --- end to end through the reference-facing call: host FASTQ text -> counts on the host ---
+    # --- N > 1: the sharded, exchanged result must be what ONE GPU computes over the union of the ranks' ranges ---
+    nccl_check = None
+    if world > 1:
+        nccl_check = multi.verify_sharded(wl, exchange, first, units, rank, world, local_rank, sid)
+
+    # --- end to end through the reference-facing call: host FASTQ text -> result on the host ---
     # The text sits in page-locked host memory (the contract's "inputs from pinned host memory"); every step copies it to
-    # the device (157 B/read over PCIe), splits and packs the records there, counts, and reads the count vector back.
-    e2e_reads = args.e2e_reads
-    text = spec.fastq_pinned(first, e2e_reads, device=local_rank)
+    # the device (157 B/read over PCIe), splits and packs the records there, counts, and reads the result back.
+    e2e_units = args.e2e_units or wl.e2e_units
+    texts = wl.texts(first, e2e_units, pinned=True, device=local_rank)
     nthreads = len(os.sched_getaffinity(0)) or 1
-    for _ in range(2):
-        rcpp.count_single_barcodes(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
+    # cold: the first call of this process on this design (library tables built and uploaded; kernels specialised -- from
+    # the on-disk cubin cache when an earlier process left them there, through NVRTC otherwise)
+    t0 = time.perf_counter()
+    e2e_result = wl.ours(texts, nthreads, local_rank)
+    torch.cuda.synchronize()
+    cold_s = time.perf_counter() - t0
+    cold_stage = rcpp.timing(local_rank)
+    wl.ours(texts, nthreads, local_rank)
     barrier()
     e2e_steps = max(3, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_counts, e2e_total = rcpp.count_single_barcodes(text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
+        e2e_result = wl.ours(texts, nthreads, local_rank)
     torch.cuda.synchronize()
     e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_dt = float(e2e_dt.item())
     stage = rcpp.timing(local_rank)
-    e2e_value = e2e_reads * world * e2e_steps / e2e_dt
-
-    # consistency: the end-to-end counts are the device-resident counts of the same read range
-    check_reads = min(e2e_reads, args.reads)
-    if check_reads == args.reads and world == 1:
-        assert np.array_equal(e2e_counts, final_counts), "end-to-end and resident counts differ"
+    e2e_value = e2e_units * world * e2e_steps / e2e_dt
+    d2h = wl.d2h_bytes()
+    if d2h is None:
+        d2h = int(sum(np.asarray(x).nbytes for x in e2e_result[:2]))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # --- CPU baseline (measured before CUDA was initialised, see cpu_baseline_leg): compare its counts with the GPU's ---
+    # --- CPU baseline (measured before CUDA was initialised, see cpu_baseline_leg): compare its result with the GPU's ---
     cpu_baseline = None
     if cpu_leg is not None:
-        cpu_baseline, ref_counts, sample = cpu_leg
-        if ref_counts is not None:
-            if sample == e2e_reads:
-                chk = e2e_counts
+        cpu_baseline, ref_result, sample = cpu_leg
+        if ref_result is not None:
+            if sample == e2e_units:
+                chk = e2e_result
             else:
-                sample_text = text.array[: sample * (2 * READ_LEN + 7)].tobytes()
-                chk, _ = rcpp.count_single_barcodes(sample_text, TEMPLATE, STRAND, library, MISMATCHES, USE_FIRST, nthreads, device=local_rank)
-            assert np.array_equal(ref_counts, chk), "GPU counts differ from the reference on the baseline sample"
-            cpu_baseline["sample"] += ", counts checked equal to the GPU's"
+                chk = wl.ours([t.array[: sample * RECORD].tobytes() for t in texts], nthreads, local_rank)
+            assert wl.same(ref_result, chk), "GPU result differs from the reference on the baseline sample"
+            cpu_baseline["sample"] += ", result checked equal to the GPU's"
 
     peak, peak_src = measured_peaks()
-    reads_per_launch = args.reads / max(passes_per_step, 1)
-    kernel_ms_per_launch = kernel_ms_per_step / max(passes_per_step, 1)
-    achieved = BYTES_PER_READ * reads_per_launch / (kernel_ms_per_launch / 1000.0) / 1e9
+    achieved = wl.bytes_per_unit * units / (kernel_ms_per_pass / 1000.0) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             t = json.load(f)
-        # dram bytes per read from the committed ncu --set full capture, scaled to this launch size
-        traffic = t.get("dram_bytes_per_read", 0) * reads_per_launch or None
+        per_unit = t.get("config%d" % wl.number, {}).get("dram_bytes_per_unit")
+        if per_unit is None and wl.number == 2:
+            per_unit = t.get("dram_bytes_per_read")
+        traffic = per_unit * units if per_unit else None
+    what = wl.what.replace(" ", "_")
     line = {
-        "metric": "reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "reads/sec", "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu": args.reads, "library": N_GUIDES, "read_len": READ_LEN,
-                   "mismatches": MISMATCHES, "strand": "both", "find_best": False, "seed": SEED,
-                   "parallelism": "reads sharded by contiguous range, %d rank(s); count vector combined with one NCCL all-reduce" % world,
-                   "l2": "inputs (%.1f GB packed reads per GPU) are larger than the 126 MB L2; no flush needed" % (reads.device_bytes / 1e9),
-                   "matched_fraction": matched_per_step / args.reads},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
-                "d2h_bytes_per_step": 4 * len(library), "reads_per_step": e2e_reads, "host_threads": nthreads,
-                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "total_s")},
-                "reader": stage.get("reader"), "cpu_binding": binding,
-                "note": "FASTQ text in page-locked host memory -> scg_count_single: text H2D in 32 MiB chunks, records split + packed "
-                        "by kernels (ingest.cu), scan/lookup/count kernel per chunk, counts D2H; wall clock around the calls"},
+        "config": {"workload": wl.name, "baseline_config": wl.number, "%s_per_gpu" % what: units, "read_len": READ_LEN, "seed": SEED,
+                   **wl.config_extra(),
+                   "parallelism": "%s sharded by contiguous range, %d rank(s); %s" % (
+                       wl.what, world, "no exchange (one GPU)" if world == 1 else exchange.describe()),
+                   "l2": ("inputs (%.1f MB packed) fit the 126 MB L2: a 256 MB buffer is written between the timed passes (outside the events)"
+                          % (resident_bytes / 1e6)) if need_flush else
+                         ("inputs (%.1f GB packed per GPU) are larger than the 126 MB L2; no flush needed" % (resident_bytes / 1e9)),
+                   "matched_fraction": matched_per_pass / units},
+        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
+                "d2h_bytes_per_step": int(d2h), "%s_per_step" % what: e2e_units, "host_threads": nthreads,
+                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "harvest_s", "total_s")},
+                "reader": stage.get("reader"), "kernel": stage.get("kernel"), "cpu_binding": binding,
+                "cold": {"value": e2e_units / cold_s, "unit": wl.unit, "seconds": cold_s, "setup_s": cold_stage.get("setup_s"),
+                         "note": "first call of this process on this design: library tables built + uploaded, kernels specialised (on-disk "
+                                 "cubin cache or NVRTC), buffers allocated; the CUDA context already existed.  The reference arm rebuilds its "
+                                 "libraries on every call; `value` above is our steady state (tables and kernels cached)"},
+                "note": "FASTQ text in page-locked host memory -> file-level C-ABI call: text H2D in 32 MiB chunks, records split + packed "
+                        "by kernels (ingest.cu), scan/lookup/count kernels per chunk, result D2H; wall clock around the calls"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "countSingleBarcodes scan+lookup+count, " + plan.kernel, "bytes_per_read": BYTES_PER_READ, "reads_per_launch": reads_per_launch,
-                     "kernel_ms_per_launch": kernel_ms_per_launch, "peak_source": peak_src,
-                     "note": "49 B/read = 29 B packed read + 4 B per-read outcome (written) + 16 B table probe (L2-resident); the kernel sits at about two thirds of the ALU pipe, the L1/TEX path and the L2 at once, well below HBM: see DESIGN.md"},
+                     "kernel": kernel_name, "bytes_per_unit": wl.bytes_per_unit, "units_per_pass": units,
+                     "kernel_ms_per_pass": kernel_ms_per_pass, "kernel_launches_per_pass": launches_per_pass, "peak_source": peak_src,
+                     "note": wl.bytes_note + "; all kernels of one pass over the resident %s (main kernel + its follow-ups), CUDA events" % wl.what},
         "cpu_baseline": cpu_baseline,
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
     }
+    if nccl_check is not None:
+        line["nccl_check"] = nccl_check
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -37,6 +37,7 @@ typedef struct scg_ctx scg_ctx;
 typedef struct scg_result scg_result;
 typedef struct scg_reads scg_reads;   /* packed reads resident in device memory */
 typedef struct scg_plan scg_plan;     /* a compiled handler: template + libraries on the device */
+typedef struct scg_table scg_table;   /* a sparse result as a sorted (key, count) table on the device */
 
 /* FASTQ input: path != NULL -> file (raw or .gz); else `data`/`size` hold FASTQ text. */
 typedef struct {
@@ -206,6 +207,28 @@ int scg_random_plan_create(scg_ctx* ctx, const char* constant, int strand, int m
 int scg_random_plan_run(scg_plan* plan, const scg_reads* reads, int32_t* d_index, void* cuda_stream);
 int scg_plan_reset(scg_plan* plan, void* cuda_stream);
 int scg_plan_harvest(scg_plan* plan, scg_result** table);
+
+/* Sparse results as sorted tables ON THE DEVICE: what GPUs exchange when the table of one file (or of several files) is
+ * merged across them -- the device-side counterpart of the reference's reduce() for random barcodes
+ * (inst/include/kaori/handlers/RandomBarcodeSingleEnd.hpp:197-207) and of the append + sort of combinations
+ * (handlers/CombinatorialBarcodesSingleEnd.hpp:268-305, R/combineComboCounts.R:31-57).  keys: unsigned 64-bit, ascending,
+ * unique -- combinations as first << 32 | second, random barcodes as three bits per base in text order (A < C < G < N < T),
+ * first base most significant; counts: unsigned 32-bit.  key_len > 0 marks random barcodes of that length.
+ *   scg_plan_sorted_table   the plan's tally, sorted (synchronises the device)
+ *   scg_plan_dense_tally    combinations tallied in a dense n1 x n2 matrix: its device address (else *d_matrix = NULL)
+ *   scg_table_from_device   a table from device arrays the caller owns (copied), e.g. rows received from another GPU
+ *   scg_table_merge         sorted union of two tables, counts of equal keys added
+ *   scg_table_render        the table as the file-level calls return it (rows stay on the device until copied) */
+int scg_plan_sorted_table(scg_plan* plan, scg_table** out);
+int scg_plan_dense_tally(scg_plan* plan, void** d_matrix, long long* cells);
+long long scg_table_rows(const scg_table* t);
+int scg_table_key_len(const scg_table* t);
+void* scg_table_keys(const scg_table* t);
+void* scg_table_counts(const scg_table* t);
+int scg_table_from_device(scg_ctx* ctx, const void* d_keys, const void* d_counts, long long rows, int key_len, scg_table** out);
+int scg_table_merge(scg_ctx* ctx, const scg_table* a, const scg_table* b, scg_table** out);
+int scg_table_render(scg_ctx* ctx, const scg_table* t, scg_result** out);
+void scg_table_free(scg_table* t);
 
 /* Host-only check of the FASTQ reader + packer (no device needed): parses `src`, packs every read into
  * the tile-planar 2-bit + N-mask layout and unpacks it again.  bases receives the concatenated

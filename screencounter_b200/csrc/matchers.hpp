@@ -319,3 +319,9 @@ struct scg_plan {
     scg::CountTable table;
     std::string kernel_note;
 };
+
+// A sorted (key, count) table resident on the device (include/scg.h scg_table_*).
+struct scg_table {
+    scg_ctx* owner = nullptr;
+    scg::SortedTable table;
+};

@@ -637,4 +637,97 @@ int scg_plan_harvest(scg_plan* plan, scg_result** table) {
     });
 }
 
+// ---- sorted tables resident on the device: what the GPUs exchange when a sparse result is merged across them ----
+
+int scg_plan_sorted_table(scg_plan* plan, scg_table** out) {
+    if (!plan || !out) return 1;
+    return guarded(plan->owner, [&] {
+        Context& c = plan->owner->impl;
+        SCG_CUDA_CHECK(cudaSetDevice(c.device));
+        SCG_CUDA_CHECK(cudaDeviceSynchronize());   // the runs may have been enqueued on the caller's stream
+        std::unique_ptr<scg_table> t(new scg_table);
+        t->owner = plan->owner;
+        if (plan->kind == scg_plan::COMBO) {
+            plan->tally.sorted(c, t->table);
+        } else if (plan->kind == scg_plan::RANDOM) {
+            if (plan->random->wide) throw Error("random barcodes longer than 21 bases have no sorted device table");
+            plan->table.sorted(c, plan->random->key_len, t->table);
+        } else {
+            throw Error("only combinatorial and random-barcode plans hold a table");
+        }
+        *out = t.release();
+    });
+}
+
+int scg_plan_dense_tally(scg_plan* plan, void** d_matrix, long long* cells) {
+    if (!plan || !d_matrix || !cells) return 1;
+    return guarded(plan->owner, [&] {
+        *d_matrix = nullptr;
+        *cells = 0;
+        if (plan->kind == scg_plan::COMBO && plan->tally.dense) {
+            *d_matrix = plan->tally.matrix.ptr;
+            *cells = (long long)plan->tally.n1 * plan->tally.n2;
+        }
+    });
+}
+
+long long scg_table_rows(const scg_table* t) { return t ? (long long)t->table.rows : 0; }
+int scg_table_key_len(const scg_table* t) { return t ? t->table.key_len : 0; }
+void* scg_table_keys(const scg_table* t) { return t ? t->table.keys.ptr : nullptr; }
+void* scg_table_counts(const scg_table* t) { return t ? t->table.counts.ptr : nullptr; }
+void scg_table_free(scg_table* t) { delete t; }
+
+int scg_table_from_device(scg_ctx* ctx, const void* d_keys, const void* d_counts, long long rows, int key_len, scg_table** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        c.ensure_ready();
+        if (rows < 0) throw Error("negative number of rows");
+        std::unique_ptr<scg_table> t(new scg_table);
+        t->owner = ctx;
+        t->table.rows = (size_t)rows;
+        t->table.key_len = key_len;
+        t->table.keys.alloc(std::max<size_t>((size_t)rows, 1) * 8, false);
+        t->table.counts.alloc(std::max<size_t>((size_t)rows, 1) * sizeof(uint32_t), false);
+        if (rows) {
+            SCG_CUDA_CHECK(cudaMemcpyAsync(t->table.keys.ptr, d_keys, (size_t)rows * 8, cudaMemcpyDeviceToDevice, c.stream));
+            SCG_CUDA_CHECK(cudaMemcpyAsync(t->table.counts.ptr, d_counts, (size_t)rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+            SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        }
+        *out = t.release();
+    });
+}
+
+int scg_table_merge(scg_ctx* ctx, const scg_table* a, const scg_table* b, scg_table** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        c.ensure_ready();
+        if (!a || !b) throw Error("null table");
+        std::unique_ptr<scg_table> t(new scg_table);
+        t->owner = ctx;
+        merge_sorted_tables(c, a->table, b->table, t->table);
+        *out = t.release();
+    });
+}
+
+int scg_table_render(scg_ctx* ctx, const scg_table* t, scg_result** out) {
+    return guarded(ctx, [&] {
+        Context& c = ctx->impl;
+        c.ensure_ready();
+        if (!t) throw Error("null table");
+        std::unique_ptr<scg_result> r(new scg_result);
+        if (t->table.key_len > 0) {
+            r->width = t->table.key_len;
+            render_barcodes(c, t->table, r->d_strings, r->d_freq);
+        } else {
+            r->width = 2;
+            render_combinations(c, t->table, r->d_keys, r->d_freq);
+        }
+        SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        r->on_device = true;
+        r->device = c.device;
+        r->d_rows = t->table.rows;
+        *out = r.release();
+    });
+}
+
 } // extern "C"

@@ -23,7 +23,9 @@ def gpu():
 def _uniform(rng, n, template, pools, strand, read_len, **kw):
     kw.setdefault("lower_rate", 0.0)
     kw.setdefault("short_frac", 0.0)
-    return adversarial_reads(rng, n, template, pools, strand=strand, read_len=read_len, **kw)
+    reads = adversarial_reads(rng, n, template, pools, strand=strand, read_len=read_len, **kw)
+    # junk reads come back at their own lengths: every read exactly read_len bases
+    return [(r + random_seq(rng, read_len))[:read_len] for r in reads]
 
 
 def _kernel():
