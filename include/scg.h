@@ -51,6 +51,12 @@ enum { SCG_STRAND_ORIGINAL = 0, SCG_STRAND_REVERSE = 1, SCG_STRAND_BOTH = 2 };
 
 /* ---- context ------------------------------------------------------------------------ */
 int scg_ctx_create(scg_ctx** out, int device);       /* device = CUDA ordinal; lazy init */
+/* One context over SEVERAL devices (the reference runs its threads inside one call, inst/include/kaori/process_data.hpp:131-177;
+ * this is the same for GPUs): scg_count_single cuts the text of a raw file (or of a memory buffer) at record boundaries into
+ * one part per device, and the scg_count_*_many calls deal their files to the devices.  Every other entry point runs on the
+ * first device.  Inputs that cannot be cut (gzip streams, small files) are read by the first device alone. */
+int scg_ctx_create_multi(scg_ctx** out, const int* devices, int n_devices);
+int scg_ctx_devices(const scg_ctx* ctx);
 void scg_ctx_destroy(scg_ctx* ctx);
 const char* scg_last_error(const scg_ctx* ctx);       /* ctx may be NULL for creation errors */
 const char* scg_version(void);
@@ -135,6 +141,27 @@ int scg_count_single_paired(scg_ctx* ctx, const scg_source* src1, const scg_sour
 int scg_match_barcodes(scg_ctx* ctx, const char* const* sequences, int nsequences,
                        const char* const* choices, int nchoices, int substitutions, int reverse,
                        int32_t* index, int32_t* mismatches);
+
+/* ---- many files, one call (the matrixOf* wrappers of the reference) ------------------------- */
+
+/* matrixOfSingleBarcodes (R/countSingleBarcodes.R:112-126): count_single_barcodes per file, columns bound.  matrix: npool x
+ * nfiles int32, column-major (column f = the counts of sources[f]); totals: nfiles.  The library is built and uploaded once per
+ * device; files are dealt to the context's devices (fewer files than devices: each file is cut over all of them). */
+int scg_count_single_many(scg_ctx* ctx, const scg_source* sources, int nfiles, const char* constant, int strand,
+                          const char* const* pool, int npool, int mismatches, int use_first, int nthreads,
+                          int32_t* matrix, int32_t* totals);
+/* countComboBarcodes per file + combineComboCounts (R/combineComboCounts.R:31-57): *table holds the sorted union of the files'
+ * combinations (scg_result_copy_table: keys, freq = row sums) and one column of counts per file (scg_result_copy_matrix).  The
+ * union is made on the device from the files' sorted tables. */
+int scg_count_combo_many(scg_ctx* ctx, const scg_source* sources, int nfiles, const char* constant, int strand,
+                         const char* const* pool1, int npool1, const char* const* pool2, int npool2,
+                         int mismatches, int use_first, int nthreads, scg_result** table, int32_t* totals);
+/* matrixOfRandomBarcodes (R/countRandomBarcodes.R:84-105): sort(union of the files' barcodes) and one column per file. */
+int scg_count_random_many(scg_ctx* ctx, const scg_source* sources, int nfiles, const char* constant, int strand,
+                          int mismatches, int use_first, int nthreads, scg_result** table, int32_t* totals);
+/* columns of a many-files result, and its matrix: rows x columns int32, column-major */
+int scg_result_columns(const scg_result* r);
+int scg_result_copy_matrix(const scg_result* r, int32_t* matrix);
 
 /* ---- resident objects (for callers that keep reads / libraries on the device) ---------- */
 

@@ -48,6 +48,10 @@ def lib():
         L.scg_kernel_launches.restype = C.c_longlong
         L.scg_kernel_launches.argtypes = [C.c_void_p]
         L.scg_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.scg_ctx_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+        L.scg_ctx_devices.argtypes = [C.c_void_p]
+        L.scg_result_columns.argtypes = [C.c_void_p]
+        L.scg_result_copy_matrix.argtypes = [C.c_void_p, C.c_void_p]
         L.scg_ctx_destroy.argtypes = [C.c_void_p]
         L.scg_ctx_destroy.restype = None
         L.scg_result_rows.restype = C.c_size_t
@@ -88,11 +92,12 @@ def lib():
 
 # every symbol include/scg.h declares (checked by tests/test_host.py::test_abi_exports_every_declared_symbol)
 EXPORTS = [
-    "scg_ctx_create", "scg_ctx_destroy", "scg_last_error", "scg_version", "scg_timing_json", "scg_kernel_launches",
+    "scg_ctx_create", "scg_ctx_create_multi", "scg_ctx_devices", "scg_ctx_destroy", "scg_last_error", "scg_version", "scg_timing_json", "scg_kernel_launches",
     "scg_result_rows", "scg_result_width", "scg_result_reads", "scg_result_copy_table", "scg_result_trace_width",
     "scg_result_copy_trace", "scg_result_free",
     "scg_count_single", "scg_count_random", "scg_count_combo_single", "scg_count_dual_single_end", "scg_count_dual",
     "scg_count_combo_paired", "scg_count_single_paired", "scg_match_barcodes",
+    "scg_count_single_many", "scg_count_combo_many", "scg_count_random_many", "scg_result_columns", "scg_result_copy_matrix",
     "scg_reads_from_source", "scg_reads_count", "scg_reads_device_bytes", "scg_reads_free",
     "scg_reads_synthesize", "scg_synth_fastq",
     "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",

@@ -213,6 +213,9 @@ void render_combinations(Context& ctx, const SortedTable& t, DeviceBuffer& keys,
 // c = sorted merge of a and b with the counts of equal keys added (a and b sorted ascending, keys unique within each)
 void merge_sorted_tables(Context& ctx, const SortedTable& a, const SortedTable& b, SortedTable& c);
 
+// column[i] = count of all_keys' row i in t (0 where t lacks the key): one column of a many-files count matrix
+void scatter_table_column(Context& ctx, const SortedTable& all_keys, const SortedTable& t, int32_t* column);
+
 // Tally of (i, j) combinations: dense matrix when small, count table otherwise.
 struct ComboTally {
     int n1 = 0, n2 = 0;

@@ -135,6 +135,9 @@ struct Context {
 // Opaque C-ABI types.
 struct scg_ctx {
     scg::Context impl;
+    // scg_ctx_create_multi: the contexts of the other devices.  `impl` is the first device's; file-level calls split a file
+    // (or deal the files of a many-files call) over impl and these, one host thread per device.
+    std::vector<std::unique_ptr<scg_ctx>> peers;
     explicit scg_ctx(int dev) : impl(dev) {}
 };
 
@@ -159,5 +162,9 @@ struct scg_result {
     int device = 0;
     size_t d_rows = 0;
     scg::DeviceBuffer d_keys, d_strings, d_freq;
+    // many-files calls: one column of counts per file over the rows of the table (column-major, like an R matrix)
+    int columns = 0;
+    std::vector<int32_t> matrix;
+    scg::DeviceBuffer d_matrix;
     size_t rows() const { return on_device ? d_rows : freq.size(); }
 };

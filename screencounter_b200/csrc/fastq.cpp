@@ -430,6 +430,8 @@ static size_t guess_record_start(const char* b, size_t n, size_t from) {
     return (size_t)-1;
 }
 
+size_t guess_fastq_record_start(const char* text, size_t size, size_t from) { return guess_record_start(text, size, from); }
+
 // Splits the next stretch of an in-memory input into chunks, parses them concurrently with the exact grammar and
 // keeps the longest prefix of chunks whose parses chain up (each ends exactly where the next one started).  Whatever
 // does not chain -- a wrong guess, a malformed record -- is left for the serial path, which then reproduces the

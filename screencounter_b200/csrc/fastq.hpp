@@ -78,6 +78,10 @@ private:
     uint32_t batch_min_len_ = 0xFFFFFFFFu, batch_max_len_ = 0;
 };
 
+// A likely record start at or after byte `from` of a FASTQ text, or (size_t)-1: a guess that the caller verifies by parsing
+// what precedes it (fastq.cpp).
+size_t guess_fastq_record_start(const char* text, size_t size, size_t from);
+
 // Packs records [first, first+count) into `out` (tile-planar, W words per plane, count padded
 // up to a multiple of 32 with empty reads).  lens receives the read lengths.  odd (nullable)
 // receives 1 for reads holding a character other than upper-case A, C, G, T, N.

@@ -22,4 +22,22 @@ void launch_combo(Context& ctx, const ReadsDev& reads, const ComboMatcher& m, co
 void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, CountTable& tab, const uint8_t* odd, OddOutcome* odd_out,
                    unsigned long long* odd_count, int32_t* out_index, cudaStream_t stream);
 
+// countSingleBarcodes over one input on one device (runners_single.cu); counts stay on the device
+long long count_single_core(Context& c, FastqReader* reader, const SingleMatcher& m, int nthreads, int32_t* d_counts, TraceSink& sink);
+
+// countComboBarcodes / countRandomBarcodes over one input on one device (runners_combo.cu, runners_random.cu).  With want_sorted
+// set, a result that can stay on the device as a sorted table is left there and *table stays null.
+void count_combo_core(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool1, int npool1,
+                      const char* const* pool2, int npool2, int mismatches, int use_first, int nthreads, int want_trace,
+                      SortedTable* want_sorted, scg_result** table, int32_t* total);
+void count_random_core(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, int mismatches, int use_first,
+                       int nthreads, SortedTable* want_sorted, scg_result** table, int32_t* total);
+
+// The same over SEVERAL devices (runners_multi.cu): the text is cut at record boundaries into one contiguous part per device,
+// every device counts its part on its own host thread, the count vectors are summed on the first device over peer memory.
+// false = the input cannot be split (a gzip stream, too small, no safe cut, or a part did not parse cleanly): the caller runs
+// the single-device path, which also produces the reference's error text where there is one.
+bool count_single_multi(scg_ctx* ctx, FastqReader& reader, const char* constant, int strand, const char* const* pool, int npool,
+                        int mismatches, bool use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace);
+
 } // namespace scg

@@ -21,10 +21,16 @@ using namespace scg;
 
 extern "C" {
 
-int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool1, int npool1,
-                           const char* const* pool2, int npool2, int mismatches, int use_first, int nthreads, int want_trace,
-                           scg_result** table, int32_t* total) {
-    return guarded(ctx, [&] {
+} // extern "C"
+
+namespace scg {
+
+// countComboBarcodes over one input on one device.  With want_sorted set the combinations stay on the device as a sorted
+// table (first << 32 | second) and *table stays null: what the many-files call unites on the device (runners_multi.cu).
+void count_combo_core(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool1, int npool1,
+                      const char* const* pool2, int npool2, int mismatches, int use_first, int nthreads, int want_trace,
+                      SortedTable* want_sorted, scg_result** table, int32_t* total) {
+    {
         Context& c = ctx->impl;
         const double t_start = now_s();
         c.timing = Timing();
@@ -63,17 +69,35 @@ int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* cons
             trace.collect(c, b.n, false);
             nreads += b.n;
         }
-        auto* r = new scg_result;
-        tally.harvest(c, *r);
-        if (trace.enabled) {
-            r->trace_width = 2;
-            r->trace_index.swap(trace.index);
+        if (want_sorted) {
+            tally.sorted(c, *want_sorted);
+            *table = nullptr;
+        } else {
+            auto* r = new scg_result;
+            tally.harvest(c, *r);
+            if (trace.enabled) {
+                r->trace_width = 2;
+                r->trace_index.swap(trace.index);
+            }
+            *table = r;
         }
-        *table = r;
         *total = (int32_t)nreads;
         c.timing.parse_s = source.reader->parse_seconds();
         c.timing.total_s = now_s() - t_start;
         c.finish_timing();
+    }
+}
+
+} // namespace scg
+
+extern "C" {
+
+int scg_count_combo_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool1, int npool1,
+                           const char* const* pool2, int npool2, int mismatches, int use_first, int nthreads, int want_trace,
+                           scg_result** table, int32_t* total) {
+    return guarded(ctx, [&] {
+        count_combo_core(ctx, src, constant, strand, pool1, npool1, pool2, npool2, mismatches, use_first, nthreads, want_trace, nullptr,
+                         table, total);
     });
 }
 

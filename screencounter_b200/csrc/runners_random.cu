@@ -396,6 +396,23 @@ void merge_sorted_tables(Context& ctx, const SortedTable& a, const SortedTable& 
     SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
 }
 
+// column[i] = count of all_keys[i] in table t, 0 where t does not hold the key (every key of t is in all_keys)
+__global__ void scatter_column_kernel(const unsigned long long* __restrict__ uk, size_t nu, const unsigned long long* __restrict__ tk,
+                                      const uint32_t* __restrict__ tc, size_t nt, int32_t* __restrict__ column) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < nt; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = lower_bound_dev(uk, nu, tk[j]);
+        if (p < nu && uk[p] == tk[j]) column[p] = (int32_t)tc[j];
+    }
+}
+
+void scatter_table_column(Context& ctx, const SortedTable& all_keys, const SortedTable& t, int32_t* column) {
+    if (t.rows == 0) return;
+    scatter_column_kernel<<<fill_grid(ctx, t.rows), 256, 0, ctx.stream>>>(all_keys.keys.as<unsigned long long>(), all_keys.rows,
+                                                                         t.keys.as<unsigned long long>(), t.counts.as<uint32_t>(), t.rows, column);
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ++ctx.launches;
+}
+
 // ---------------------------------------------------------------------------------------
 // ComboTally
 // ---------------------------------------------------------------------------------------
@@ -551,9 +568,16 @@ using namespace scg;
 
 extern "C" {
 
-int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, int mismatches, int use_first,
-                     int nthreads, scg_result** table, int32_t* total) {
-    return guarded(ctx, [&] {
+} // extern "C"
+
+namespace scg {
+
+// countRandomBarcodes over one input on one device.  With want_sorted set, a table that can stay on the device as sorted
+// 64-bit keys (barcodes of up to 21 bases, no key taken from raw read text) is handed over there and *table stays null:
+// what the many-files call unites on the device (runners_multi.cu).
+void count_random_core(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, int mismatches, int use_first,
+                       int nthreads, SortedTable* want_sorted, scg_result** table, int32_t* total) {
+    {
         Context& c = ctx->impl;
         const double t_start = now_s();
         c.timing = Timing();
@@ -636,7 +660,10 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
             // barcodes of up to 21 bases: sorted as text ON THE DEVICE (radix sort of rank-coded keys)
             SortedTable sorted;
             tab.sorted(c, key_len, sorted);
-            if (extra.empty()) {
+            if (extra.empty() && want_sorted) {
+                *want_sorted = std::move(sorted);
+                guard.reset();
+            } else if (extra.empty()) {
                 // ... rendered there too, and left there: scg_result_copy_table copies the finished table straight into the
                 // caller's arrays (one device-to-host copy, no host image in between)
                 render_barcodes(c, sorted, r->d_strings, r->d_freq);
@@ -702,7 +729,16 @@ int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, 
         c.timing.parse_s = source.reader->parse_seconds();
         c.timing.total_s = now_s() - t_start;
         c.finish_timing();
-    });
+    }
+}
+
+} // namespace scg
+
+extern "C" {
+
+int scg_count_random(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, int mismatches, int use_first,
+                     int nthreads, scg_result** table, int32_t* total) {
+    return guarded(ctx, [&] { count_random_core(ctx, src, constant, strand, mismatches, use_first, nthreads, nullptr, table, total); });
 }
 
 } // extern "C"

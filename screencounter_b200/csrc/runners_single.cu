@@ -10,6 +10,7 @@
 #include "hostpool.hpp"
 #include "handlers.cuh"
 #include "jit.hpp"
+#include "launchers.hpp"
 #include "matchers.hpp"
 
 namespace scg {
@@ -467,7 +468,12 @@ const char* scg_last_error(const scg_ctx* ctx) { return ctx ? ctx->impl.last_err
 
 const char* scg_timing_json(const scg_ctx* ctx) { return ctx ? ctx->impl.timing_json.c_str() : "{}"; }
 
-long long scg_kernel_launches(const scg_ctx* ctx) { return ctx ? ctx->impl.launches : 0; }
+long long scg_kernel_launches(const scg_ctx* ctx) {
+    if (!ctx) return 0;
+    long long n = ctx->impl.launches;
+    for (const auto& p : ctx->peers) n += p->impl.launches;
+    return n;
+}
 
 size_t scg_result_rows(const scg_result* r) { return r ? r->rows() : 0; }
 int scg_result_width(const scg_result* r) { return r ? r->width : 0; }
@@ -508,6 +514,31 @@ int scg_result_copy_trace(const scg_result* r, int32_t* index, uint32_t* info) {
 void scg_result_free(scg_result* r) { delete r; }
 
 // ---- countSingleBarcodes (reference src/count_single_barcodes.cpp:12-50) --------------------
+} // extern "C"
+
+namespace scg {
+
+// SingleBarcodeSingleEnd over one input on one device: every batch of the reader through the kernels, counts accumulated
+// in d_counts (left on the device).  Returns the number of reads.
+long long count_single_core(Context& c, FastqReader* reader, const SingleMatcher& m, int nthreads, int32_t* d_counts, TraceSink& sink) {
+    ReadPipeline pipe(c, reader, nullptr, nthreads, false);
+    ReadPipeline::Batch b;
+    long long nreads = 0;
+    while (pipe.next(b)) {
+        sink.prepare(b.n, true);
+        launch_single(c, b.reads1, m, d_counts, sink.enabled ? sink.d_index.as<int32_t>() : nullptr,
+                      sink.enabled ? sink.d_info.as<uint32_t>() : nullptr, c.stream);
+        pipe.submitted(b);
+        sink.collect(c, b.n, true);
+        nreads += b.n;
+    }
+    return nreads;
+}
+
+} // namespace scg
+
+extern "C" {
+
 int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
                      int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace) {
     return guarded(ctx, [&] {
@@ -522,22 +553,19 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         c.ensure_ready();
         c.timing.setup_s += now_s() - t_setup;
 
+        // several devices (scg_ctx_create_multi): the file's text is cut at record boundaries and every device counts its part
+        if (!ctx->peers.empty() &&
+            count_single_multi(ctx, *source.reader, constant, strand, pool, npool, mismatches, use_first != 0, nthreads, counts, total, trace)) {
+            c.timing.total_s = now_s() - t_start;
+            c.finish_timing();
+            return;
+        }
+
         DeviceBuffer d_counts;
         d_counts.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);
         TraceSink sink;
         sink.enabled = trace != nullptr;
-
-        ReadPipeline pipe(c, source.reader.get(), nullptr, nthreads, false);
-        ReadPipeline::Batch b;
-        long long nreads = 0;
-        while (pipe.next(b)) {
-            sink.prepare(b.n, true);
-            launch_single(c, b.reads1, m, d_counts.as<int32_t>(), sink.enabled ? sink.d_index.as<int32_t>() : nullptr,
-                          sink.enabled ? sink.d_info.as<uint32_t>() : nullptr, c.stream);
-            pipe.submitted(b);
-            sink.collect(c, b.n, true);
-            nreads += b.n;
-        }
+        const long long nreads = count_single_core(c, source.reader.get(), m, nthreads, d_counts.as<int32_t>(), sink);
         double t0 = now_s();
         SCG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts.ptr, (size_t)npool * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));

@@ -29,9 +29,17 @@ def context(device=None):
     cache = getattr(_local, "ctx", None)
     if cache is None:
         cache = _local.ctx = {}
+    if isinstance(device, (list, tuple)):
+        # one context over several devices (scg_ctx_create_multi): a file is cut over them, files of a many-files call are dealt to them
+        device = tuple(int(d) for d in device)
     if device not in cache:
         h = C.c_void_p()
-        if lib().scg_ctx_create(C.byref(h), int(device)) != 0:
+        if isinstance(device, tuple):
+            ids = (C.c_int * len(device))(*device)
+            status = lib().scg_ctx_create_multi(C.byref(h), ids, len(device))
+        else:
+            status = lib().scg_ctx_create(C.byref(h), int(device))
+        if status != 0:
             raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
         cache[device] = h
     return cache[device]
@@ -362,6 +370,67 @@ def count_combo_barcodes_paired(path1, constant1, reverse1, mismatches1, pool1, 
         out.append((index, info.astype(np.int32)))
     lib().scg_result_free(handle)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Many files, one call: what the matrixOf* wrappers of the reference assemble in R.
+def _sources(files):
+    keep = [_Src(f) for f in files]
+    arr = (ScgSource * max(len(keep), 1))(*[k.struct for k in keep])
+    return arr, keep
+
+
+def matrix_of_single_barcodes(files, constant, strand, pool, mismatches, use_first, nthreads, device=None):
+    """reference: R/countSingleBarcodes.R:112-126 -> (npool x nfiles count matrix, nreads per file)."""
+    ctx = context(device)
+    srcs, keep = _sources(files)
+    arr, keep2 = _strs(pool)
+    matrix = np.zeros((len(files), len(pool)), dtype=np.int32)   # row f here = column f of the R matrix
+    totals = np.zeros(max(len(files), 1), dtype=np.int32)
+    _check(ctx, lib().scg_count_single_many(ctx, srcs, len(files), constant.encode("latin-1"), int(strand), arr, len(pool),
+                                            int(mismatches), int(bool(use_first)), int(nthreads), _ip(matrix), _ip(totals)))
+    return matrix.T, totals[: len(files)]
+
+
+def _matrix(handle, nrows):
+    ncols = lib().scg_result_columns(handle)
+    m = np.zeros((ncols, nrows), dtype=np.int32)
+    if lib().scg_result_copy_matrix(handle, _ip(m)) != 0:
+        raise ScreenCounterError("could not read the count matrix back")
+    return m.T
+
+
+def matrix_of_combo_barcodes(files, constant, strand, pool, mismatches, use_first, nthreads, device=None):
+    """countComboBarcodes per file + combineComboCounts (reference R/combineComboCounts.R:31-57) ->
+    (2 x k matrix of the combinations seen in any file (0-based, sorted), k x nfiles counts, nreads per file)."""
+    if len(pool) != 2:
+        raise ScreenCounterError("currently expecting only 2 variable regions for single-end combinatorial barcodes")
+    ctx = context(device)
+    srcs, keep = _sources(files)
+    a1, k1 = _strs(pool[0])
+    a2, k2 = _strs(pool[1])
+    handle = C.c_void_p()
+    totals = np.zeros(max(len(files), 1), dtype=np.int32)
+    _check(ctx, lib().scg_count_combo_many(ctx, srcs, len(files), constant.encode("latin-1"), int(strand), a1, len(pool[0]), a2, len(pool[1]),
+                                           int(mismatches), int(bool(use_first)), int(nthreads), C.byref(handle), _ip(totals)))
+    keys, freq = _table(handle, "combo")
+    counts = _matrix(handle, len(freq))
+    lib().scg_result_free(handle)
+    return keys.T.copy(), counts, totals[: len(files)]
+
+
+def matrix_of_random_barcodes(files, constant, strand, mismatches, use_first, nthreads, device=None, as_array=True):
+    """reference: R/countRandomBarcodes.R:84-105 -> (sorted union of the files' barcodes, k x nfiles counts, nreads per file)."""
+    ctx = context(device)
+    srcs, keep = _sources(files)
+    handle = C.c_void_p()
+    totals = np.zeros(max(len(files), 1), dtype=np.int32)
+    _check(ctx, lib().scg_count_random_many(ctx, srcs, len(files), constant.encode("latin-1"), int(strand), int(mismatches),
+                                            int(bool(use_first)), int(nthreads), C.byref(handle), _ip(totals)))
+    seqs, freq = _table(handle, "random_array" if as_array else "random")
+    counts = _matrix(handle, len(freq))
+    lib().scg_result_free(handle)
+    return seqs, counts, totals[: len(files)]
 
 
 def host_pack_roundtrip(fastq, nthreads=1):
