@@ -163,6 +163,17 @@ int scg_count_random_many(scg_ctx* ctx, const scg_source* sources, int nfiles, c
 int scg_result_columns(const scg_result* r);
 int scg_result_copy_matrix(const scg_result* r, int32_t* matrix);
 
+/* ---- block gzip (BGZF: bgzip, bcl-convert) -------------------------------------------------- */
+/* A FASTQ source that is a block-gzip file -- or a block-gzip image in memory (scg_source.data) -- is read like raw text by
+ * the device-side reader: its members cross PCIe compressed and are inflated (and CRC-checked) on the device.  Plain gzip
+ * streams are inflated by zlib on the host like the reference does (inst/include/byteme/GzipFileReader.hpp:39-51).
+ *   scg_bgzf_compress   text -> block-gzip image on `nthreads` host threads (zlib `level`, members of `block_text` bytes of
+ *                       text, 0 = bgzip's 65280); call with out == NULL to get the capacity needed in *used.
+ *   scg_bgzf_inflate    the device inflater on its own: image (host) -> text (host); *device_ms = time of the kernels.
+ *                       Call with text == NULL to get the text's size. */
+int scg_bgzf_compress(const char* text, size_t size, int level, int block_text, int nthreads, void* out, size_t capacity, size_t* used);
+int scg_bgzf_inflate(scg_ctx* ctx, const void* image, size_t size, char* text, size_t capacity, size_t* text_size, double* device_ms);
+
 /* ---- resident objects (for callers that keep reads / libraries on the device) ---------- */
 
 /* Parse + pack a FASTQ into device memory (tile-planar 2-bit bases + N mask). */

@@ -52,6 +52,8 @@ def lib():
         L.scg_ctx_devices.argtypes = [C.c_void_p]
         L.scg_result_columns.argtypes = [C.c_void_p]
         L.scg_result_copy_matrix.argtypes = [C.c_void_p, C.c_void_p]
+        L.scg_bgzf_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.scg_bgzf_inflate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
         L.scg_ctx_destroy.argtypes = [C.c_void_p]
         L.scg_ctx_destroy.restype = None
         L.scg_result_rows.restype = C.c_size_t
@@ -98,6 +100,7 @@ EXPORTS = [
     "scg_count_single", "scg_count_random", "scg_count_combo_single", "scg_count_dual_single_end", "scg_count_dual",
     "scg_count_combo_paired", "scg_count_single_paired", "scg_match_barcodes",
     "scg_count_single_many", "scg_count_combo_many", "scg_count_random_many", "scg_result_columns", "scg_result_copy_matrix",
+    "scg_bgzf_compress", "scg_bgzf_inflate",
     "scg_reads_from_source", "scg_reads_count", "scg_reads_device_bytes", "scg_reads_free",
     "scg_reads_synthesize", "scg_synth_fastq",
     "scg_single_plan_create", "scg_single_plan_run", "scg_plan_free", "scg_plan_kernel",

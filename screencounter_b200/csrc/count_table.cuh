@@ -12,33 +12,43 @@ namespace scg {
 // factor of at most 1/2, where probe sequences are a handful of slots long)
 constexpr unsigned long long COUNT_MAX_PROBES = 1ull << 16;
 
+// Home of a key: an EVEN slot, so that the home and the slot after it share one aligned 32-byte sector -- a kernel that
+// requested that sector ahead of time has, for most keys, everything it needs (bucketised linear probing, buckets of two).
+__device__ __forceinline__ unsigned long long count_home(const CountTable64& t, unsigned long long key) {
+    return count_hash(key) & t.mask & ~1ull;
+}
+
 // Adds `add` to the count of `key`, inserting it when new, starting at slot `pos` whose key was already seen as `seen`
-// (callers that requested the slot earlier pass what they loaded; others pass the slot's current key).
-__device__ __forceinline__ void count_insert64_from(const CountTable64& t, unsigned long long key, uint32_t add, unsigned long long pos,
+// (callers that requested the slot earlier pass what they loaded; others pass the slot's current key).  Returns true
+// when the key was new; the caller accounts for it in t.live[0] (count_insert64 does, one atomic per key; kernels that
+// insert many keys add them up per warp first).
+__device__ __forceinline__ bool count_insert64_from(const CountTable64& t, unsigned long long key, uint32_t add, unsigned long long pos,
                                                     unsigned long long seen) {
+    bool fresh = false;
     for (unsigned long long probes = 0;; ++probes) {
         if (seen == key) break;
         if (seen == ~0ull) {
             const unsigned long long old = atomicCAS(&t.slots[pos].key, ~0ull, key);
             if (old == ~0ull) {
-                atomicAdd(t.live, 1ull);
+                fresh = true;
                 break;
             }
             if (old == key) break;
         }
         if (probes >= COUNT_MAX_PROBES || probes > t.mask) {
             atomicExch(t.live + 1, 1ull);
-            return;
+            return false;
         }
         pos = (pos + 1) & t.mask;
         seen = __ldcg(&t.slots[pos].key);
     }
     atomicAdd(&t.slots[pos].count, add);
+    return fresh;
 }
 
 __device__ __forceinline__ void count_insert64(const CountTable64& t, unsigned long long key, uint32_t add) {
-    const unsigned long long pos = count_hash(key) & t.mask;
-    count_insert64_from(t, key, add, pos, __ldcg(&t.slots[pos].key));
+    const unsigned long long pos = count_home(t, key);
+    if (count_insert64_from(t, key, add, pos, __ldcg(&t.slots[pos].key))) atomicAdd(t.live, 1ull);
 }
 
 // 128-bit compare-and-swap (atom.cas.b128, sm_90+).

@@ -199,6 +199,14 @@ void Context::ensure_ready() {
                     "; this library carries sm_100a code only");
     }
     sm_count = prop.multiProcessorCount;
+    // The tables of this engine are probed at random, 16 or 32 bytes at a time: let L2 fetch single 32-byte sectors from DRAM
+    // instead of pairs (the streams of packed reads arrive as whole lines by TMA either way).  SCG_L2_FETCH=64/128 restores more.
+    {
+        size_t granularity = 32;
+        if (const char* env = std::getenv("SCG_L2_FETCH")) granularity = (size_t)std::max(32, std::atoi(env));
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, granularity);
+        cudaGetLastError();
+    }
     SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     ready = true;
 }
@@ -239,6 +247,28 @@ void DeviceLibrary::upload(Context& ctx) {
     cand_rows.upload(host.cand_rows.data(), host.cand_rows.size() * sizeof(uint32_t), st);
     prefix_slots.upload(host.prefix_slots.data(), host.prefix_slots.size() * sizeof(uint32_t), st);
     trie.upload(host.trie.data(), host.trie.size() * sizeof(int32_t), st);
+    // seed buckets with their first candidate inline (libdev.hpp LibDev::ibuckets)
+    bool inline_buckets = host.KW == 1 && host.nseeds >= 1 && !host.cand_rows.empty() && host.nentries() < (1u << 24);
+    if (inline_buckets) {
+        for (const uint2& b : host.buckets) inline_buckets = inline_buckets && b.y < 255;
+    }
+    std::vector<uint32_t> inline_rows;
+    if (inline_buckets) {
+        inline_rows.assign(host.buckets.size() * 4, 0);
+        const size_t per_seed = host.nbuckets, E = host.nentries();
+        for (size_t b = 0; b < host.buckets.size(); ++b) {
+            const uint2 bk = host.buckets[b];
+            if (bk.y == 0) continue;
+            const uint32_t* first = &host.cand_rows[4 * ((b / per_seed) * E + bk.x)];
+            inline_rows[4 * b + 0] = first[0];
+            inline_rows[4 * b + 1] = first[1];
+            inline_rows[4 * b + 2] = first[2];
+            inline_rows[4 * b + 3] = bk.x | (bk.y << 24);
+        }
+        ibuckets.upload(inline_rows.data(), inline_rows.size() * sizeof(uint32_t), st);
+    } else {
+        ibuckets.release();
+    }
     SCG_CUDA_CHECK(cudaStreamSynchronize(st));
     std::memset(&dev, 0, sizeof dev);
     dev.L = host.L;
@@ -256,6 +286,7 @@ void DeviceLibrary::upload(Context& ctx) {
     dev.bucket_mask = host.nbuckets ? host.nbuckets - 1 : 0;
     dev.cands = cands.as<int32_t>();
     dev.cand_rows = host.cand_rows.empty() ? nullptr : cand_rows.as<uint4>();
+    dev.ibuckets = inline_buckets ? ibuckets.as<uint4>() : nullptr;
     dev.seg1 = host.opt.segmented ? host.opt.seg1 : 0;
     dev.prefix_slots = prefix_slots.as<uint32_t>();
     dev.prefix_mask = host.prefix_mask;
@@ -276,14 +307,26 @@ ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int n
     }
     // Text that is entirely in host memory (caller's buffer, mmap'd raw file) is read on the device (ingest.hpp); gzip
     // streams keep the host reader.  Paired input needs both files in memory.
+    // A block-gzip file (or image in memory) is read there too: its members cross PCIe compressed and are inflated on the device.
     if (device_ingest_enabled() && r1_) {
-        const char *t1 = nullptr, *t2 = nullptr;
-        size_t n1 = 0, n2 = 0;
-        const bool ok1 = r1_->memory_text(&t1, &n1) && n1 > 0;
-        const bool ok2 = r2_ ? (r2_->memory_text(&t2, &n2) && n2 > 0) : true;
-        if (ok1 && ok2) {
-            ingest_[0].reset(new DeviceIngest(ctx_, t1, n1, nthreads_, 0, want_odd_));
-            if (r2_) ingest_[1].reset(new DeviceIngest(ctx_, t2, n2, nthreads_, 1, false));
+        auto readable = [&](FastqReader* r) {
+            const char* t = nullptr;
+            size_t n = 0;
+            const BgzfIndex* image = nullptr;
+            if (r->memory_text(&t, &n)) return n > 0;
+            return device_inflate_enabled() && r->bgzf_image(&image) && image->text_size() > 0;
+        };
+        auto open = [&](FastqReader* r, int mate, bool odd) {
+            const char* t = nullptr;
+            size_t n = 0;
+            const BgzfIndex* image = nullptr;
+            if (r->memory_text(&t, &n)) return new DeviceIngest(ctx_, t, n, nthreads_, mate, odd);
+            r->bgzf_image(&image);
+            return new DeviceIngest(ctx_, image, nthreads_, mate, odd);
+        };
+        if (readable(r1_) && (!r2_ || readable(r2_))) {
+            ingest_[0].reset(open(r1_, 0, want_odd_));
+            if (r2_) ingest_[1].reset(open(r2_, 1, false));
         }
     }
 }
@@ -345,10 +388,7 @@ long long ReadPipeline::count_odd(const Batch& b) const {
 void ReadPipeline::raw_read(const Batch& b, long long index, std::string& seq) {
     seq.clear();
     if (!b.slot) {
-        const char* p = nullptr;
-        uint32_t len = 0;
-        ingest_[0]->raw_read(index, &p, &len);
-        seq.assign(p, len);
+        ingest_[0]->raw_read(index, seq);
         return;
     }
     const Record& r = b.recs1[index];

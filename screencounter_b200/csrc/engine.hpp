@@ -63,7 +63,7 @@ struct Timing {
 // A library resident on the device.
 struct DeviceLibrary {
     Library host;
-    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots, trie;
+    DeviceBuffer slots, ent_keys, ent_idx, seed_masks, buckets, cands, cand_rows, prefix_slots, trie, ibuckets;
     LibDev dev;
     void upload(struct Context& ctx);
 };

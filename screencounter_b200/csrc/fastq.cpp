@@ -1,5 +1,6 @@
 #include "fastq.hpp"
 
+#include "bgzf.hpp"
 #include "hostpool.hpp"
 
 #include <algorithm>
@@ -38,6 +39,13 @@ public:
     }
     // Host threads the input may use for its own work (block-gzip inflates its blocks in parallel).
     virtual void set_threads(int n) { (void)n; }
+    // Block-gzip inputs say where their members are (the device can inflate them)...
+    virtual const BgzfIndex* bgzf() const { return nullptr; }
+    // ... and can be positioned at a byte of their TEXT: the next window() starts there.  false = not supported.
+    virtual bool seek(size_t text_offset) {
+        (void)text_offset;
+        return false;
+    }
 };
 
 namespace {
@@ -123,10 +131,9 @@ private:
     bool eof_ = false;
 };
 
-// Block gzip (BGZF: what bgzip and Illumina's bcl-convert / bcl2fastq write): a chain of gzip members of at most 64 KiB,
-// each announcing its compressed size in a 'BC' extra field, so the members can be found without inflating and inflated
-// independently -- here on the host thread pool, where kaori (byteme::GzipFileReader over gzread, one thread) goes member
-// by member.  The text is the same; plain gzip streams keep GzInput.
+// Block gzip (bgzf.hpp): the member chain is indexed without inflating; the members are inflated in parallel on the host
+// thread pool here (kaori goes member by member on one thread), or on the device when the device-side reader takes the
+// input (ingest.cu + inflate.cu).  The text is the same; plain gzip streams keep GzInput.
 class BgzfInput : public FastqInput {
 public:
     // nullptr when the file is not a complete chain of BGZF members
@@ -135,11 +142,17 @@ public:
         void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (map == MAP_FAILED) return nullptr;
         std::unique_ptr<BgzfInput> in(new BgzfInput(fd, map, size));
-        if (!in->index()) {
+        if (!bgzf_index(static_cast<const unsigned char*>(map), size, in->index_)) {
             in->fd_ = -1;   // the caller keeps the descriptor
             return nullptr;
         }
         madvise(map, size, MADV_SEQUENTIAL);
+        return std::unique_ptr<FastqInput>(in.release());
+    }
+    // the same over an image in the caller's memory
+    static std::unique_ptr<FastqInput> open_memory(const char* data, size_t size) {
+        std::unique_ptr<BgzfInput> in(new BgzfInput(-1, nullptr, 0));
+        if (!bgzf_index(reinterpret_cast<const unsigned char*>(data), size, in->index_)) return nullptr;
         return std::unique_ptr<FastqInput>(in.release());
     }
     ~BgzfInput() override {
@@ -147,7 +160,16 @@ public:
         if (fd_ >= 0) close(fd_);
     }
     void set_threads(int n) override { threads_ = n < 1 ? 1 : n; }
+    const BgzfIndex* bgzf() const override { return &index_; }
+    bool seek(size_t text_offset) override {
+        const size_t b = std::min(index_.block_of(text_offset), index_.blocks.size());
+        next_ = b;
+        filled_ = 0;
+        skip_ = b < index_.blocks.size() ? text_offset - index_.text_off[b] : 0;
+        return true;
+    }
     void window(size_t keep_from, const char** base, size_t* avail, bool* final) override {
+        const std::vector<BgzfBlock>& blocks_ = index_.blocks;
         const size_t tail = filled_ - keep_from;
         if (keep_from > 0 && tail > 0) std::memmove(buf_.data(), buf_.data() + keep_from, tail);
         filled_ = tail;
@@ -162,38 +184,28 @@ public:
             const int pieces = std::max(1, std::min(nblocks, threads_ * 4));
             std::vector<int> failed((size_t)pieces, 0);
             char* out = buf_.data();
-            const unsigned char* file = static_cast<const unsigned char*>(map_);
             const size_t first = next_;
             HostPool::instance().parallel_for(pieces, std::min(pieces, threads_), [&](int p) {
                 const int b = (int)((long long)nblocks * p / pieces), e = (int)((long long)nblocks * (p + 1) / pieces);
-                z_stream z;
-                std::memset(&z, 0, sizeof z);
-                if (inflateInit2(&z, -15) != Z_OK) {
-                    failed[(size_t)p] = 1;
-                    return;
-                }
                 for (int k = b; k < e; ++k) {
-                    const Block& blk = blocks_[first + (size_t)k];
-                    inflateReset(&z);
-                    z.next_in = const_cast<unsigned char*>(file + blk.data);
-                    z.avail_in = blk.csize;
-                    z.next_out = reinterpret_cast<unsigned char*>(out + at[(size_t)k]);
-                    z.avail_out = blk.isize;
-                    const int rc = blk.isize == 0 && blk.csize == 2 ? Z_STREAM_END : inflate(&z, Z_FINISH);
-                    const bool empty = blk.isize == 0;
-                    if (!empty && (rc != Z_STREAM_END || z.avail_out != 0 ||
-                                   crc32(0L, reinterpret_cast<const unsigned char*>(out + at[(size_t)k]), blk.isize) != blk.crc)) {
+                    if (!bgzf_inflate_block(index_, first + (size_t)k, out + at[(size_t)k])) {
                         failed[(size_t)p] = 1;
                         break;
                     }
                 }
-                inflateEnd(&z);
             });
             for (int f : failed) {
                 if (f) throw Error("failed to inflate the block-gzip file (corrupt member)");
             }
             filled_ = at.back();
             next_ = last;
+            if (skip_) {
+                // a reader resumed inside a member: drop the text in front of that byte
+                const size_t drop = std::min(skip_, filled_);
+                std::memmove(buf_.data(), buf_.data() + drop, filled_ - drop);
+                filled_ -= drop;
+                skip_ = 0;
+            }
         }
         *base = buf_.data();
         *avail = filled_;
@@ -201,57 +213,30 @@ public:
     }
 
 private:
-    struct Block {
-        size_t data;       // offset of the raw deflate stream
-        uint32_t csize;    // its length
-        uint32_t isize;    // text bytes
-        uint32_t crc;
-    };
     static constexpr size_t kBatch = 64u << 20;
 
     BgzfInput(int fd, void* map, size_t size) : fd_(fd), map_(map), size_(size) {}
-
-    // walks the member chain; false unless every byte of the file belongs to a well-formed BGZF member
-    bool index() {
-        const unsigned char* f = static_cast<const unsigned char*>(map_);
-        size_t p = 0;
-        while (p < size_) {
-            if (size_ - p < 18) return false;
-            if (f[p] != 0x1f || f[p + 1] != 0x8b || f[p + 2] != 8 || f[p + 3] != 4) return false;   // FLG = FEXTRA only
-            const size_t xlen = f[p + 10] | ((size_t)f[p + 11] << 8);
-            if (size_ - p < 12 + xlen + 8) return false;
-            size_t bsize = 0;
-            for (size_t q = p + 12; q + 4 <= p + 12 + xlen;) {
-                const size_t slen = f[q + 2] | ((size_t)f[q + 3] << 8);
-                if (f[q] == 'B' && f[q + 1] == 'C' && slen == 2 && q + 6 <= p + 12 + xlen) bsize = (f[q + 4] | ((size_t)f[q + 5] << 8)) + 1;
-                q += 4 + slen;
-            }
-            if (bsize < 12 + xlen + 8 || bsize > size_ - p) return false;
-            Block b;
-            b.data = p + 12 + xlen;
-            b.csize = (uint32_t)(bsize - 12 - xlen - 8);
-            const unsigned char* t = f + p + bsize - 8;
-            b.crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-            b.isize = t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
-            if (b.isize > (1u << 16)) return false;   // BGZF members hold at most 64 KiB of text
-            blocks_.push_back(b);
-            p += bsize;
-        }
-        return !blocks_.empty();
-    }
 
     int fd_;
     void* map_;
     size_t size_;
     int threads_ = 1;
-    std::vector<Block> blocks_;
+    BgzfIndex index_;
     size_t next_ = 0;
+    size_t skip_ = 0;
     std::vector<char> buf_;
     size_t filled_ = 0;
 };
 
 std::unique_ptr<FastqInput> open_input(const char* path, const char* data, size_t size) {
-    if (!path) return std::unique_ptr<FastqInput>(new MemoryInput(data, size));
+    if (!path) {
+        // a block-gzip image in the caller's memory is read like the file it would be on disk; anything else is FASTQ text
+        if (size >= 28 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b && !std::getenv("SCG_NO_BGZF")) {
+            std::unique_ptr<FastqInput> bgzf = BgzfInput::open_memory(data, size);
+            if (bgzf) return bgzf;
+        }
+        return std::unique_ptr<FastqInput>(new MemoryInput(data, size));
+    }
     // byteme::SomeFileReader (inst/include/byteme/SomeFileReader.hpp:31-44): sniff the gzip magic.
     int fd = open(path, O_RDONLY);
     if (fd < 0) throw Error(std::string("failed to open file at '") + path + "'");
@@ -307,9 +292,22 @@ bool FastqReader::memory_text(const char** data, size_t* size) const {
     return !started_ && in_->memory(data, size);
 }
 
+bool FastqReader::bgzf_image(const BgzfIndex** index) const {
+    if (started_ || !in_->bgzf()) return false;
+    *index = in_->bgzf();
+    return true;
+}
+
 void FastqReader::resume_at(size_t offset, long long nrecords) {
-    if (!started_) refill();
-    pos_ = offset;
+    if (in_->seek(offset)) {
+        // (block gzip: the input inflates from the member that holds the byte)
+        in_->window(0, &base_, &avail_, &final_);
+        started_ = true;
+        pos_ = 0;
+    } else {
+        if (!started_) refill();
+        pos_ = offset;
+    }
     nrecords_ = nrecords;
     okay_ = pos_ < avail_;
 }

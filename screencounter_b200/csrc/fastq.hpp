@@ -51,6 +51,8 @@ public:
     // The whole input as one span of host memory, for inputs that are (caller's buffer, mmap'd raw file) and have not
     // been read from yet: the device-side reader (ingest.hpp) takes the text from there.
     bool memory_text(const char** data, size_t* size) const;
+    // A block-gzip input that has not been read from yet: its member index (the device-side reader inflates the members itself).
+    bool bgzf_image(const struct BgzfIndex** index) const;
     // Continues the host parse at byte `offset` of such an input -- the start of record number `nrecords` (0-based),
     // everything before it having been consumed elsewhere as four-line records.
     void resume_at(size_t offset, long long nrecords);

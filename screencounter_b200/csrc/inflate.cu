@@ -1,0 +1,514 @@
+// DEFLATE on the device, one warp per gzip member (inflate.cuh).
+//
+// A BGZF member holds at most 64 KiB of text and is a DEFLATE stream of its own (no preset dictionary), so members inflate
+// independently: one WARP takes one member.  Huffman decoding is sequential by nature; the warp runs it UNIFORMLY (every lane
+// holds the same bit buffer and decodes the same symbol, table lookups are shared-memory broadcasts) and uses its width where
+// the format allows it:
+//   * the compressed bytes arrive as coalesced 128-byte lines, one 32-bit word per lane, two lines ahead of the bit buffer;
+//     a refill takes its word from the owning lane with a shuffle -- no global-memory latency on the decoding chain;
+//   * code tables are built by all lanes (counting by shared atomics, canonical codes by __match_any ranks, table fill
+//     per symbol);
+//   * symbols are decoded in batches of 32, symbol k parked in lane k; the batch's output offsets are one warp scan; literals
+//     are stored by their lanes, matches whose source lies wholly before the batch are copied without any ordering between
+//     them (their loads overlap), and only matches that read bytes of their own batch take the ordered path.
+// Tables: 10-bit literal/length and 8-bit distance lookup (4-byte entries: value, extra bits, code length), longer codes go
+// through the canonical count/symbol arrays bit by bit (rare by construction: a code longer than 10 bits has probability
+// < 2^-10).  Text is written to global memory (the FASTQ reader's ring), source bytes of a match are read back from there.
+// A second kernel checks the members' CRC-32 (gzip trailer), one warp per member, 2 KiB per lane, slice-by-4 tables in shared
+// memory, the lanes' partial CRCs combined with the "2 KiB of zeros" operator.
+#include "inflate.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace scg {
+
+namespace {
+
+constexpr int LIT_BITS = 10, DIST_BITS = 8;
+constexpr int INFL_WARPS = 4;   // warps per block
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// table entry: value << 16 | kind << 8 | extra bits << 4 | code length.  0 = no such code.
+constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_END = 2, K_LONG = 3;
+
+struct WarpTables {
+    uint32_t lit[1 << LIT_BITS];
+    uint32_t dist[1 << DIST_BITS];
+    uint32_t lit_count[16], dist_count[16];   // codes per length (kept for the bit-by-bit path)
+    uint32_t next[16], offs[16];              // scratch of the table build
+    uint16_t lit_sorted[288 + 32];            // symbols in canonical order (per length, ascending)
+    uint16_t dist_sorted[32 + 32];
+    uint8_t lens[288 + 32 + 32];              // code lengths of the block being set up
+};
+
+__constant__ uint16_t c_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
+__constant__ uint8_t c_len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
+__constant__ uint16_t c_dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
+                                          4097, 6145, 8193, 12289, 16385, 24577 };
+__constant__ uint8_t c_dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+__constant__ uint8_t c_clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+
+// what a code of `len` bits for `sym` stands for, as a table entry (0 = a symbol the format does not define)
+__device__ __forceinline__ uint32_t lit_entry(int sym, int len) {
+    if (sym < 256) return ((uint32_t)sym << 16) | (K_LITERAL << 8) | (uint32_t)len;
+    if (sym == 256) return (K_END << 8) | (uint32_t)len;
+    if (sym > 285) return 0u;
+    return ((uint32_t)c_len_base[sym - 257] << 16) | (K_MATCH << 8) | ((uint32_t)c_len_extra[sym - 257] << 4) | (uint32_t)len;
+}
+__device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
+    if (sym > 29) return 0u;
+    return ((uint32_t)c_dist_base[sym] << 16) | (K_MATCH << 8) | ((uint32_t)c_dist_extra[sym] << 4) | (uint32_t)len;
+}
+// code-length alphabet: the symbol itself is the value
+__device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 16) | (uint32_t)len; }
+
+// Builds the lookup table of a canonical Huffman code from the code lengths lens[0 .. n).  KIND 0 literal/length, 1 distance,
+// 2 code lengths.  All lanes take part.  false = over-subscribed set of lengths.
+template <int KIND, int TBITS>
+__device__ bool build_table(const uint8_t* lens, int n, uint32_t* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
+                            int lane) {
+    for (int i = lane; i < (1 << TBITS); i += 32) table[i] = 0;
+    if (lane < 16) count[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < n; s += 32) {
+        const int l = lens[s];
+        if (l) atomicAdd(&count[l], 1u);
+    }
+    __syncwarp();
+    bool ok = true;
+    if (lane == 0) {
+        uint32_t code = 0, off = 0;
+        int left = 1;
+        for (int l = 1; l <= 15; ++l) {
+            next[l] = code;
+            offs[l] = off;
+            left = (left << 1) - (int)count[l];
+            if (left < 0) ok = false;
+            code = (code + count[l]) << 1;
+            off += count[l];
+        }
+    }
+    ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+    if (!ok) return false;
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+        const int s = base + lane;
+        const int l = s < n ? lens[s] : 0;
+        const uint32_t peers = __match_any_sync(FULL, l);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (l) {
+            const uint32_t code = next[l] + (uint32_t)rank;
+            sorted[offs[l] + (uint32_t)rank] = (uint16_t)s;
+            const uint32_t r = __brev(code) >> (32 - l);   // the code as it appears in the bit stream (first bit = bit 0)
+            if (l <= TBITS) {
+                const uint32_t e = KIND == 0 ? lit_entry(s, l) : (KIND == 1 ? dist_entry(s, l) : clen_entry(s, l));
+                for (uint32_t k = r; k < (1u << TBITS); k += (1u << l)) table[k] = e;
+            } else {
+                table[r & ((1u << TBITS) - 1u)] = K_LONG << 8;
+            }
+        }
+        __syncwarp();
+        if (l && rank == 0) {
+            next[l] += (uint32_t)__popc(peers);
+            offs[l] += (uint32_t)__popc(peers);
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// a code longer than the lookup table: bit by bit over the canonical counts (the first TBITS bits cannot end a code either,
+// so the walk starts from the top)
+__device__ __forceinline__ bool slow_symbol(unsigned long long bits, const uint32_t* count, const uint16_t* sorted, int& sym, int& len) {
+    uint32_t code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; ++l) {
+        code |= (uint32_t)(bits & 1ull);
+        bits >>= 1;
+        const uint32_t c = count[l];
+        if (code < first + c) {
+            sym = sorted[index + (code - first)];
+            len = l;
+            return true;
+        }
+        index += c;
+        first = (first + c) << 1;
+        code <<= 1;
+    }
+    return false;
+}
+
+// The compressed stream as seen by the warp: 64 bits of look-ahead, refilled from two register-resident 128-byte lines.
+struct BitReader {
+    const uint32_t* words;      // 4-byte aligned base of the stream
+    uint32_t line_cur, line_next;
+    uint32_t widx;              // words consumed so far (warp-uniform)
+    unsigned long long bits;
+    int cnt;
+    int lane;
+
+    __device__ __forceinline__ void open(const uint8_t* comp, size_t byte_off, int lane_) {
+        lane = lane_;
+        words = reinterpret_cast<const uint32_t*>(comp + (byte_off & ~(size_t)3));
+        line_cur = words[lane];
+        line_next = words[32 + lane];
+        widx = 0;
+        bits = 0;
+        cnt = 0;
+        refill();
+        const int skip = (int)(byte_off & 3) * 8;
+        bits >>= skip;
+        cnt -= skip;
+        refill();
+    }
+    __device__ __forceinline__ uint32_t next_word() {
+        const uint32_t w = __shfl_sync(FULL, line_cur, (int)(widx & 31u));
+        ++widx;
+        if ((widx & 31u) == 0) {
+            line_cur = line_next;
+            line_next = words[widx + 32 + lane];
+        }
+        return w;
+    }
+    // at least 33 bits afterwards
+    __device__ __forceinline__ void refill() {
+        if (cnt <= 32) {
+            bits |= (unsigned long long)next_word() << cnt;
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bits & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) {
+        bits >>= n;
+        cnt -= n;
+    }
+    __device__ __forceinline__ uint32_t take(int n) {
+        const uint32_t v = peek(n);
+        drop(n);
+        return v;
+    }
+    // bytes of the stream consumed, counted from the aligned base (after drop-to-byte)
+    __device__ __forceinline__ size_t byte_pos() const { return (size_t)widx * 4 - (size_t)(cnt >> 3); }
+};
+
+// copies a match: out[dst + j] = out[dst - dist + j] for j in [0, len), sources read as they were BEFORE the match when
+// dist >= len, the repeating pattern of the last `dist` bytes otherwise -- all of them already written
+__device__ __forceinline__ void copy_match(uint8_t* out, uint32_t dst, uint32_t len, uint32_t dist, int lane) {
+    if (dist >= len) {
+        for (uint32_t j = lane; j < len; j += 32) out[dst + j] = out[dst - dist + j];
+    } else {
+        for (uint32_t j = lane; j < len; j += 32) out[dst + j] = out[dst - dist + (j % dist)];
+    }
+}
+
+__global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, const InflateMember* __restrict__ members, int n,
+                                                                  uint8_t* out_base, uint32_t* __restrict__ errors) {
+    __shared__ WarpTables tables[INFL_WARPS];
+    const int lane = threadIdx.x & 31;
+    WarpTables& T = tables[threadIdx.x >> 5];
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+
+    for (int mi = warp; mi < n; mi += nwarps) {
+        const InflateMember M = members[mi];
+        uint8_t* out = out_base + M.out_off;
+        uint32_t pos = 0;
+        bool bad = false;
+        if (M.out_len == 0 && M.in_len <= 2) continue;   // the empty member that closes a BGZF file
+        BitReader br;
+        br.open(comp, M.in_off, lane);
+        bool last = false;
+        while (!last && !bad) {
+            br.refill();
+            last = br.take(1) != 0;
+            const uint32_t type = br.take(2);
+            if (type == 0) {
+                // ---- stored block: to the byte boundary, LEN, NLEN, LEN raw bytes ----
+                br.drop(br.cnt & 7);
+                br.refill();
+                const uint32_t len = br.take(16);
+                br.refill();
+                const uint32_t nlen = br.take(16);
+                if ((len ^ nlen) != 0xFFFFu || pos + len > M.out_len) {
+                    bad = true;
+                    break;
+                }
+                const size_t from = (size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) + br.byte_pos();
+                for (uint32_t j = lane; j < len; j += 32) out[pos + j] = comp[from + j];
+                pos += len;
+                __syncwarp();
+                br.open(comp, from + len, lane);
+                continue;
+            }
+            if (type == 3) {
+                bad = true;
+                break;
+            }
+            int nlit = 288, ndist = 30;
+            if (type == 1) {
+                // ---- fixed codes (RFC 1951 3.2.6) ----
+                for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+                if (lane < 30) T.lens[288 + lane] = 5;
+            } else {
+                // ---- dynamic codes: the code-length code first, then the two alphabets' lengths through it ----
+                br.refill();
+                nlit = (int)br.take(5) + 257;
+                ndist = (int)br.take(5) + 1;
+                const int nclen = (int)br.take(4) + 4;
+                if (nlit > 286 || ndist > 30) {
+                    bad = true;
+                    break;
+                }
+                if (lane < 19) T.lens[320 + lane] = 0;
+                __syncwarp();
+                for (int k = 0; k < nclen; ++k) {
+                    br.refill();
+                    const uint32_t v = br.take(3);
+                    if (lane == 0) T.lens[320 + c_clen_order[k]] = (uint8_t)v;
+                }
+                __syncwarp();
+                if (!build_table<2, 7>(T.lens + 320, 19, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, lane)) {
+                    bad = true;
+                    break;
+                }
+                __syncwarp();
+                int i = 0;
+                uint32_t prev = 0;
+                while (i < nlit + ndist) {
+                    br.refill();
+                    const uint32_t e = T.dist[br.peek(7)];
+                    if ((e & 0xFu) == 0) {
+                        bad = true;
+                        break;
+                    }
+                    br.drop((int)(e & 0xFu));
+                    const uint32_t sym = e >> 16;
+                    uint32_t rep = 1, val = sym;
+                    if (sym == 16) {
+                        if (i == 0) {
+                            bad = true;
+                            break;
+                        }
+                        val = prev;
+                        rep = 3 + br.take(2);
+                    } else if (sym == 17) {
+                        val = 0;
+                        rep = 3 + br.take(3);
+                    } else if (sym == 18) {
+                        val = 0;
+                        rep = 11 + br.take(7);
+                    }
+                    if (i + (int)rep > nlit + ndist) {
+                        bad = true;
+                        break;
+                    }
+                    // lengths of the distance alphabet are kept from offset 288 on
+                    for (uint32_t k = lane; k < rep; k += 32) {
+                        const int at = i + (int)k;
+                        T.lens[at < nlit ? at : 288 + (at - nlit)] = (uint8_t)val;
+                    }
+                    i += (int)rep;
+                    prev = val;
+                }
+                if (bad) break;
+                __syncwarp();
+                if (T.lens[256] == 0) {   // no end-of-block code
+                    bad = true;
+                    break;
+                }
+            }
+            __syncwarp();
+            if (!build_table<0, LIT_BITS>(T.lens, nlit, T.lit, T.lit_sorted, T.lit_count, T.next, T.offs, lane) ||
+                !build_table<1, DIST_BITS>(T.lens + 288, ndist, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, lane)) {
+                bad = true;
+                break;
+            }
+            __syncwarp();
+
+            // ---- the block's symbols, 32 at a time ----
+            bool end_of_block = false;
+            while (!end_of_block && !bad) {
+                uint32_t my = 0;   // symbol parked in this lane: literal = 1 << 31 | 1 << 16 | byte; match = len << 16 | dist
+                int nsym = 0;
+#pragma unroll 1
+                for (; nsym < 32; ++nsym) {
+                    br.refill();
+                    uint32_t e = T.lit[br.peek(LIT_BITS)];
+                    if (((e >> 8) & 3u) == K_LONG) {
+                        int sym = 0, len = 0;
+                        e = slow_symbol(br.bits, T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : 0u;
+                    }
+                    if ((e & 0xFu) == 0) {
+                        bad = true;
+                        break;
+                    }
+                    br.drop((int)(e & 0xFu));
+                    const uint32_t kind = (e >> 8) & 3u;
+                    uint32_t sym;
+                    if (kind == K_LITERAL) {
+                        sym = 0x80010000u | (e >> 16);
+                    } else if (kind == K_END) {
+                        end_of_block = true;
+                        break;
+                    } else {
+                        const uint32_t len = (e >> 16) + br.take((int)((e >> 4) & 0xFu));
+                        br.refill();
+                        uint32_t d = T.dist[br.peek(DIST_BITS)];
+                        if (((d >> 8) & 3u) == K_LONG) {
+                            int dsym = 0, dlen = 0;
+                            d = slow_symbol(br.bits, T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : 0u;
+                        }
+                        if ((d & 0xFu) == 0) {
+                            bad = true;
+                            break;
+                        }
+                        br.drop((int)(d & 0xFu));
+                        const uint32_t dist = (d >> 16) + br.take((int)((d >> 4) & 0xFu));
+                        sym = (len << 16) | dist;
+                    }
+                    if (lane == nsym) my = sym;
+                }
+                if (bad) break;
+                // ---- where the batch's symbols go ----
+                const uint32_t mylen = lane < nsym ? ((my >> 16) & 0x1FFu) : 0u;
+                uint32_t incl = mylen;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                const uint32_t off = incl - mylen;   // relative to the batch's first byte
+                const bool is_match = lane < nsym && !(my >> 31);
+                const uint32_t mydist = my & 0xFFFFu;
+                if (pos + total > M.out_len || __any_sync(FULL, is_match && mydist > pos + off)) {
+                    bad = true;
+                    break;
+                }
+                if (lane < nsym && (my >> 31)) out[pos + off] = (uint8_t)my;
+                // matches whose source ends before the batch begins: no ordering among them
+                const bool indep = is_match && off + mylen <= mydist;
+                uint32_t todo = __ballot_sync(FULL, indep);
+                while (todo) {
+                    const int k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t s = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
+                    copy_match(out, pos + o, (s >> 16) & 0x1FFu, s & 0xFFFFu, lane);
+                }
+                // the others read bytes of this batch: in order, each after what precedes it has landed
+                todo = __ballot_sync(FULL, is_match && !indep);
+                while (todo) {
+                    __syncwarp();
+                    const int k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t s = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
+                    copy_match(out, pos + o, (s >> 16) & 0x1FFu, s & 0xFFFFu, lane);
+                }
+                __syncwarp();
+                pos += total;
+            }
+        }
+        // the stream must end inside the member and produce exactly its text
+        if (!bad) {
+            const size_t end_bit = (size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt;
+            bad = pos != M.out_len || end_bit > ((size_t)M.in_off + M.in_len) * 8;
+        }
+        if (bad && lane == 0) atomicOr(errors, 1u);
+        __syncwarp();
+    }
+}
+
+// ---- CRC-32 of the inflated members -------------------------------------------------------------------------------------------
+struct CrcOperator {
+    uint32_t zeros2k[32];   // register after 2 KiB of zero bytes, per start bit
+};
+
+__global__ void __launch_bounds__(INFL_WARPS * 32) crc_kernel(const InflateMember* __restrict__ members, int n, const uint8_t* __restrict__ out_base,
+                                                              CrcOperator op, uint32_t* __restrict__ errors) {
+    __shared__ uint32_t tab[4][256];
+    {
+        // slice-by-4 tables of the reflected polynomial 0xEDB88320
+        const int t = threadIdx.x;
+        for (int v = t; v < 256; v += blockDim.x) {
+            uint32_t c = (uint32_t)v;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+            tab[0][v] = c;
+        }
+        __syncthreads();
+        for (int s = 1; s < 4; ++s) {
+            for (int v = t; v < 256; v += blockDim.x) tab[s][v] = (tab[s - 1][v] >> 8) ^ tab[0][tab[s - 1][v] & 0xFFu];
+            __syncthreads();
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int mi = warp; mi < n; mi += nwarps) {
+        const InflateMember M = members[mi];
+        if (M.out_len == 0) continue;
+        // segment 0 = the first (len - 2048 * nfull) bytes, 1 .. 2048 of them; segments 1 .. nfull are 2 KiB each
+        const uint32_t nfull = (M.out_len - 1) / 2048;
+        const uint32_t head = M.out_len - 2048 * nfull;
+        uint32_t crc = 0;
+        if ((uint32_t)lane <= nfull) {
+            const uint32_t begin = lane == 0 ? 0u : head + 2048u * (uint32_t)(lane - 1);
+            const uint32_t len = lane == 0 ? head : 2048u;
+            const uint8_t* p = out_base + M.out_off + begin;
+            crc = lane == 0 ? 0xFFFFFFFFu : 0u;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<size_t>(p) & ~(size_t)3);
+            const uint32_t sh = (uint32_t)(reinterpret_cast<size_t>(p) & 3) * 8;
+            uint32_t lo = *w;
+            const uint32_t nwords = len / 4;
+            for (uint32_t k = 0; k < nwords; ++k) {
+                const uint32_t hi = sh ? w[k + 1] : 0u;
+                const uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : w[k];
+                lo = hi;
+                crc ^= v;
+                crc = tab[3][crc & 0xFFu] ^ tab[2][(crc >> 8) & 0xFFu] ^ tab[1][(crc >> 16) & 0xFFu] ^ tab[0][crc >> 24];
+            }
+            for (uint32_t k = nwords * 4; k < len; ++k) crc = tab[0][(crc ^ p[k]) & 0xFFu] ^ (crc >> 8);
+        }
+        // state after segment k = zeros2k(state after segment k - 1) ^ raw CRC of segment k
+        uint32_t acc = __shfl_sync(FULL, crc, 0);
+        for (uint32_t k = 1; k <= nfull; ++k) {
+            const uint32_t part = __shfl_sync(FULL, crc, (int)k);
+            uint32_t moved = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) moved ^= ((acc >> b) & 1u) ? op.zeros2k[b] : 0u;
+            acc = moved ^ part;
+        }
+        if (lane == 0 && ~acc != M.crc) atomicOr(errors, 2u);
+    }
+}
+
+// host: the "2 KiB of zero bytes" operator of CRC-32
+CrcOperator make_crc_operator() {
+    uint32_t table[256];
+    for (uint32_t v = 0; v < 256; ++v) {
+        uint32_t c = v;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+        table[v] = c;
+    }
+    CrcOperator op;
+    for (int b = 0; b < 32; ++b) {
+        uint32_t c = 1u << b;
+        for (int k = 0; k < 2048; ++k) c = table[c & 0xFFu] ^ (c >> 8);
+        op.zeros2k[b] = c;
+    }
+    return op;
+}
+
+} // namespace
+
+int launch_inflate(const uint8_t* comp, const InflateMember* members, int n, uint8_t* out, uint32_t* errors, int sm_count, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    static const CrcOperator op = make_crc_operator();
+    static const bool check_crc = !std::getenv("SCG_BGZF_NO_CRC");
+    const int blocks = std::max(1, std::min((n + INFL_WARPS - 1) / INFL_WARPS, sm_count * 8));
+    inflate_kernel<<<blocks, INFL_WARPS * 32, 0, stream>>>(comp, members, n, out, errors);
+    if (!check_crc) return 1;
+    crc_kernel<<<blocks, INFL_WARPS * 32, 0, stream>>>(members, n, out, op, errors);
+    return 2;
+}
+
+} // namespace scg

@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "hostpool.hpp"
+#include "inflate.cuh"
 #include "layout.hpp"
 
 namespace scg {
@@ -330,7 +331,21 @@ IngestBuffers::~IngestBuffers() {
     if (copy_stream) cudaStreamDestroy(copy_stream);
 }
 
-void IngestBuffers::ensure(size_t chunk, size_t carry, bool need_bounce) {
+bool device_inflate_enabled() {
+    const char* v = std::getenv("SCG_BGZF_HOST");
+    return !(v && *v && *v != '0');
+}
+
+void IngestBuffers::ensure_bgzf(size_t comp_bytes, size_t nmembers) {
+    for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+        comp[k].reserve(comp_bytes + 1024);   // the inflate kernel's readers fetch whole lines ahead
+        members[k].reserve(std::max<size_t>(nmembers, 1) * sizeof(InflateMember));
+        members_host[k].reserve(std::max<size_t>(nmembers, 1) * sizeof(InflateMember));
+    }
+    inflate_errors.reserve(16);
+}
+
+void IngestBuffers::ensure(size_t chunk, size_t carry, size_t bounce_bytes) {
     const size_t stride = carry + chunk + 256, line_cap = (carry + chunk) / 4;
     if (!copy_stream) {
         SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -346,47 +361,119 @@ void IngestBuffers::ensure(size_t chunk, size_t carry, bool need_bounce) {
     block_counts.reserve((stride / kBlockBytes + 2) * sizeof(uint32_t));
     seq_off.reserve((line_cap / 4 + 1) * sizeof(uint32_t));
     state.reserve(sizeof(IngestState));
-    meta.reserve(sizeof(IngestState));
+    meta.reserve(sizeof(IngestState) + 16);
     for (int k = 0; k < 2; ++k) {
         lens[k].reserve((line_cap / 4 + TILE) * sizeof(uint16_t));
         odd[k].reserve(line_cap / 4 + TILE);
     }
-    if (need_bounce) {
-        for (int k = 0; k < DeviceIngest::kSlots; ++k) bounce[k].reserve(chunk);
+    if (bounce_bytes) {
+        for (int k = 0; k < DeviceIngest::kSlots; ++k) bounce[k].reserve(bounce_bytes);
     }
     for (int k = 0; k < DeviceIngest::kSlots; ++k) released_valid[k] = bounced_valid[k] = false;
 }
 
 IngestBuffers& DeviceIngest::buffers() const { return *ctx_.ingest[mate_]; }
 
+namespace {
+
+bool page_locked(const void* first, const void* last) {
+    // a page-locked source (scg_host_alloc, cudaHostRegister) feeds the copy engine directly
+    cudaPointerAttributes a0, a1;
+    const bool ok0 = cudaPointerGetAttributes(&a0, first) == cudaSuccess && a0.type == cudaMemoryTypeHost;
+    const bool ok1 = ok0 && cudaPointerGetAttributes(&a1, last) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // an unregistered pointer may leave a sticky-free error behind on old drivers
+    return ok0 && ok1;
+}
+
+size_t env_size(const char* name, size_t fallback, size_t lo, size_t hi) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return fallback;
+    const long long x = std::atoll(v);
+    return (size_t)std::min<long long>((long long)hi, std::max<long long>((long long)lo, x));
+}
+
+} // namespace
+
 DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads, int mate, bool want_odd)
     : ctx_(ctx), text_(text), size_(size), nthreads_(std::max(1, nthreads)), mate_(mate ? 1 : 0), want_odd_(want_odd) {
     ctx_.ensure_ready();
-    // a page-locked source (scg_host_alloc, cudaHostRegister) feeds the copy engine directly
-    cudaPointerAttributes a0, a1;
-    const bool ok0 = cudaPointerGetAttributes(&a0, text_) == cudaSuccess && a0.type == cudaMemoryTypeHost;
-    const bool ok1 = ok0 && cudaPointerGetAttributes(&a1, text_ + size_ - 1) == cudaSuccess && a1.type == cudaMemoryTypeHost;
-    cudaGetLastError();   // an unregistered pointer may leave a sticky-free error behind on old drivers
-    pinned_source_ = ok0 && ok1;
     virtual_newline_ = text_[size_ - 1] != '\n';
-    auto env_size = [](const char* name, size_t fallback, size_t lo, size_t hi) {
-        const char* v = std::getenv(name);
-        if (!v || !*v) return fallback;
-        const long long x = std::atoll(v);
-        return (size_t)std::min<long long>((long long)hi, std::max<long long>((long long)lo, x));
-    };
     // multiples of 16 keep the slots' data areas aligned for the 16-byte loads of the line kernels
     chunk_ = env_size("SCG_INGEST_CHUNK", kChunk, 64, 1u << 30) / 16 * 16;
+    for (size_t at = 0; at < size_; at += chunk_) chunk_begin_.push_back(at);
+    chunk_begin_.push_back(size_);
+    setup(page_locked(text_, text_ + size_ - 1));
+}
+
+DeviceIngest::DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd)
+    : bgzf_(image), ctx_(ctx), text_(nullptr), size_(image->text_size()), nthreads_(std::max(1, nthreads)), mate_(mate ? 1 : 0),
+      want_odd_(want_odd) {
+    ctx_.ensure_ready();
+    // the text's last byte decides whether a newline has to be appended: the last member that holds text, inflated here
+    {
+        size_t b = bgzf_->blocks.size();
+        while (b > 0 && bgzf_->blocks[b - 1].isize == 0) --b;
+        std::string last;
+        if (b > 0) fetch_text(bgzf_->text_off[b] - 1, 1, last);
+        virtual_newline_ = last.empty() || last[0] != '\n';
+    }
+    // a chunk = a run of whole members holding at most chunk_ bytes of text (never less than one member can hold)
+    chunk_ = std::max<size_t>(env_size("SCG_INGEST_CHUNK", kBgzfChunk, 64, 1u << 30), 1u << 16) / 16 * 16;
+    const size_t nb = bgzf_->blocks.size();
+    size_t b = 0;
+    while (b < nb) {
+        const size_t first = b;
+        size_t bytes = 0;
+        while (b < nb && bytes + bgzf_->blocks[b].isize <= chunk_) bytes += bgzf_->blocks[b++].isize;
+        chunk_begin_.push_back(bgzf_->text_off[first]);
+        chunk_block_.push_back(first);
+        const BgzfBlock& lastb = bgzf_->blocks[b - 1];
+        max_comp_ = std::max(max_comp_, lastb.data + lastb.csize - bgzf_->blocks[first].data);
+        max_members_ = std::max(max_members_, b - first);
+    }
+    chunk_begin_.push_back(size_);
+    chunk_block_.push_back(nb);
+    setup(page_locked(bgzf_->image, bgzf_->image + bgzf_->image_size - 1));
+}
+
+void DeviceIngest::setup(bool source_pinned) {
+    pinned_source_ = source_pinned;
     carry_ = env_size("SCG_INGEST_CARRY", kCarry, 16, 64u << 20) / 16 * 16;
     stride_ = carry_ + chunk_ + 256;
     line_cap_ = (carry_ + chunk_) / 4;
     if (!ctx_.ingest[mate_]) ctx_.ingest[mate_].reset(new IngestBuffers);
     IngestBuffers& B = buffers();
-    B.ensure(chunk_, carry_, !pinned_source_);
+    B.ensure(chunk_, carry_, pinned_source_ ? 0 : (bgzf_ ? max_comp_ : chunk_));
+    if (bgzf_) {
+        B.ensure_bgzf(max_comp_, max_members_);
+        SCG_CUDA_CHECK(cudaMemsetAsync(B.inflate_errors.ptr, 0, 16, B.copy_stream));
+    }
     ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_));
     SCG_CUDA_CHECK(cudaGetLastError());
     ++ctx_.launches;
-    ctx_.timing.reader = pinned_source_ ? "device (text copied from page-locked memory)" : "device (text staged through pinned bounce buffers)";
+    ctx_.timing.reader = bgzf_ ? (pinned_source_ ? "device (block-gzip members copied from page-locked memory, inflated on the device)"
+                                                 : "device (block-gzip members staged through pinned bounce buffers, inflated on the device)")
+                               : (pinned_source_ ? "device (text copied from page-locked memory)" : "device (text staged through pinned bounce buffers)");
+}
+
+// text [offset, offset + len) of a block-gzip input, inflated on the host member by member (raw_read and the constructor)
+void DeviceIngest::fetch_text(size_t offset, size_t len, std::string& out) {
+    out.clear();
+    while (len > 0) {
+        const size_t b = bgzf_->block_of(offset);
+        if (b >= bgzf_->blocks.size()) throw Error("raw_read: offset beyond the text");
+        if (block_cached_ != b) {
+            block_cache_.resize(std::max<size_t>(bgzf_->blocks[b].isize, 1));
+            if (!bgzf_inflate_block(*bgzf_, b, block_cache_.data())) throw Error("failed to inflate the block-gzip file (corrupt member)");
+            block_cached_ = b;
+        }
+        const size_t in_block = offset - bgzf_->text_off[b];
+        const size_t take = std::min(len, (size_t)bgzf_->blocks[b].isize - in_block);
+        if (take == 0) throw Error("raw_read: empty member");
+        out.append(block_cache_.data() + in_block, take);
+        offset += take;
+        len -= take;
+    }
 }
 
 DeviceIngest::~DeviceIngest() {
@@ -394,11 +481,58 @@ DeviceIngest::~DeviceIngest() {
     if (ctx_.ingest[mate_] && ctx_.ingest[mate_]->copy_stream) cudaStreamSynchronize(ctx_.ingest[mate_]->copy_stream);
 }
 
-void DeviceIngest::issue_copy(size_t chunk) {
+// block-gzip input: the chunk's members cross PCIe compressed and are inflated into the slot's data area
+void DeviceIngest::issue_inflate(size_t chunk) {
     IngestBuffers& B = buffers();
     const int s = (int)(chunk % kSlots);
-    const size_t off = chunk * chunk_;
-    const size_t bytes = std::min(chunk_, size_ - off);
+    const size_t fb = chunk_block_[chunk], lb = chunk_block_[chunk + 1];
+    const size_t from = bgzf_->blocks[fb].data, bytes = bgzf_->blocks[lb - 1].data + bgzf_->blocks[lb - 1].csize - from;
+    uint8_t* dst = B.text.as<uint8_t>() + slot_base(chunk) + carry_;
+    if (B.released_valid[s]) SCG_CUDA_CHECK(cudaStreamWaitEvent(B.copy_stream, B.released[s], 0));
+    // the slot's host staging (member table, bounce buffer) is free once the copies of its previous chunk are done
+    if (B.bounced_valid[s]) SCG_CUDA_CHECK(cudaEventSynchronize(B.bounced[s]));
+    InflateMember* table = B.members_host[s].as<InflateMember>();
+    for (size_t b = fb; b < lb; ++b) {
+        const BgzfBlock& blk = bgzf_->blocks[b];
+        table[b - fb] = InflateMember{ (uint32_t)(blk.data - from), blk.csize, (uint32_t)(bgzf_->text_off[b] - bgzf_->text_off[fb]), blk.isize, blk.crc };
+    }
+    const void* src = bgzf_->image + from;
+    if (!pinned_source_) {
+        const double t0 = now_s();
+        char* bb = B.bounce[s].as<char>();
+        const int pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads_, bytes >> 20));
+        const size_t per = (bytes + pieces - 1) / pieces;
+        const unsigned char* image = bgzf_->image;
+        HostPool::instance().parallel_for(pieces, pieces, [&](int k) {
+            const size_t b = (size_t)k * per, e = std::min(bytes, b + per);
+            if (b < e) std::memcpy(bb + b, image + from + b, e - b);
+        });
+        ctx_.timing.pack_s += now_s() - t0;
+        src = bb;
+    }
+    SCG_CUDA_CHECK(cudaMemcpyAsync(B.comp[s].ptr, src, bytes, cudaMemcpyHostToDevice, B.copy_stream));
+    SCG_CUDA_CHECK(cudaMemcpyAsync(B.members[s].ptr, table, (lb - fb) * sizeof(InflateMember), cudaMemcpyHostToDevice, B.copy_stream));
+    SCG_CUDA_CHECK(cudaEventRecord(B.bounced[s], B.copy_stream));
+    B.bounced_valid[s] = true;
+    const int launched = launch_inflate(B.comp[s].as<uint8_t>(), B.members[s].as<InflateMember>(), (int)(lb - fb), dst,
+                                        B.inflate_errors.as<uint32_t>(), ctx_.sm_count, B.copy_stream);
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ctx_.launches += launched;
+    ctx_.timing.launches += launched;
+    if (chunk + 1 == nchunks() && virtual_newline_) SCG_CUDA_CHECK(cudaMemsetAsync(dst + chunk_bytes(chunk), '\n', 1, B.copy_stream));
+    SCG_CUDA_CHECK(cudaEventRecord(B.copied[s], B.copy_stream));
+    ctx_.timing.bytes_h2d += (long long)(bytes + (lb - fb) * sizeof(InflateMember));
+}
+
+void DeviceIngest::issue_copy(size_t chunk) {
+    if (bgzf_) {
+        issue_inflate(chunk);
+        return;
+    }
+    IngestBuffers& B = buffers();
+    const int s = (int)(chunk % kSlots);
+    const size_t off = chunk_begin_[chunk];
+    const size_t bytes = chunk_bytes(chunk);
     uint8_t* dst = B.text.as<uint8_t>() + slot_base(chunk) + carry_;
     // the slot's previous text must have been parsed and packed
     if (B.released_valid[s]) SCG_CUDA_CHECK(cudaStreamWaitEvent(B.copy_stream, B.released[s], 0));
@@ -444,7 +578,7 @@ bool DeviceIngest::stage() {
     }
     const int s = (int)(k % kSlots);
     const bool final_chunk = k + 1 == nchunks();
-    const size_t bytes = std::min(chunk_, size_ - k * chunk_) + ((final_chunk && virtual_newline_) ? 1 : 0);
+    const size_t bytes = chunk_bytes(k) + ((final_chunk && virtual_newline_) ? 1 : 0);
     const uint32_t slot0 = (uint32_t)slot_base(k);
     const uint32_t end = slot0 + (uint32_t)carry_ + (uint32_t)bytes;
     cudaStream_t st = ctx_.stream;
@@ -484,7 +618,7 @@ bool DeviceIngest::complete(Result& out) {
     const size_t k = parsed_;
     const int s = (int)(k % kSlots);
     const bool final_chunk = k + 1 == nchunks();
-    const size_t bytes = std::min(chunk_, size_ - k * chunk_) + ((final_chunk && virtual_newline_) ? 1 : 0);
+    const size_t bytes = chunk_bytes(k) + ((final_chunk && virtual_newline_) ? 1 : 0);
     const uint32_t slot0 = (uint32_t)slot_base(k);
     const uint32_t data0 = slot0 + (uint32_t)carry_;
     const uint32_t end = data0 + (uint32_t)bytes;
@@ -500,16 +634,29 @@ bool DeviceIngest::complete(Result& out) {
     SCG_CUDA_CHECK(cudaGetLastError());
     ++ctx_.launches;
     SCG_CUDA_CHECK(cudaMemcpyAsync(B.meta.ptr, state, sizeof(IngestState), cudaMemcpyDeviceToHost, st));
+    uint32_t* inflate_flag = reinterpret_cast<uint32_t*>(B.meta.as<char>() + sizeof(IngestState));
+    if (bgzf_) SCG_CUDA_CHECK(cudaMemcpyAsync(inflate_flag, B.inflate_errors.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SCG_CUDA_CHECK(cudaEventRecord(B.meta_ready, st));
     {
         const double t0 = now_s();
         SCG_CUDA_CHECK(cudaEventSynchronize(B.meta_ready));
         ctx_.timing.device_s += now_s() - t0;
     }
+    if (bgzf_ && *inflate_flag != 0) {
+        // a member of this chunk (or of one inflated ahead of it) did not inflate or failed its CRC: nothing of the chunk is
+        // used; the host reader resumes where the previous chunk ended, inflates with zlib and raises the error
+        SCG_CUDA_CHECK(cudaEventRecord(B.released[s], st));
+        B.released_valid[s] = true;
+        stopped_ = true;
+        out.handover = true;
+        out.resume_offset = consumed_;
+        last_n_ = 0;
+        return true;
+    }
     const IngestState m = *B.meta.as<IngestState>();
     ++parsed_;
 
-    const long long tail_off = (long long)(k * chunk_) + ((long long)m.tail - (long long)data0);
+    const long long tail_off = (long long)chunk_begin_[k] + ((long long)m.tail - (long long)data0);
     consumed_ = (size_t)std::min<long long>(std::max<long long>(tail_off, 0), (long long)size_);
     last_n_ = 0;
     if (m.nrec > 0) {
@@ -531,7 +678,7 @@ bool DeviceIngest::complete(Result& out) {
         out.odd = odd;
         records_ += m.nrec;
         last_n_ = m.nrec;
-        last_text_base_ = (long long)(k * chunk_) - (long long)data0;
+        last_text_base_ = (long long)chunk_begin_[k] - (long long)data0;
         last_out_slot_ = out_slot;
         last_off_.clear();
     }
@@ -547,7 +694,7 @@ bool DeviceIngest::complete(Result& out) {
     return parsed_ < nchunks() || out.n > 0;
 }
 
-void DeviceIngest::raw_read(long long index, const char** seq, uint32_t* len) {
+void DeviceIngest::raw_read(long long index, std::string& seq) {
     if (index < 0 || index >= last_n_) throw Error("raw_read: no such read in the current batch");
     if (last_off_.empty()) {
         // sequence offsets (ring positions) and lengths of the batch: still in place until the next chunk is staged
@@ -559,8 +706,13 @@ void DeviceIngest::raw_read(long long index, const char** seq, uint32_t* len) {
                                        ctx_.stream));
         SCG_CUDA_CHECK(cudaStreamSynchronize(ctx_.stream));
     }
-    *seq = text_ + (last_text_base_ + (long long)last_off_[(size_t)index]);
-    *len = last_len_[(size_t)index];
+    const size_t at = (size_t)(last_text_base_ + (long long)last_off_[(size_t)index]);
+    const size_t len = last_len_[(size_t)index];
+    if (bgzf_) {
+        fetch_text(at, len, seq);
+    } else {
+        seq.assign(text_ + at, len);
+    }
 }
 
 } // namespace scg

@@ -13,8 +13,10 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <string>
 #include <vector>
 
+#include "bgzf.hpp"
 #include "engine.hpp"
 
 namespace scg {
@@ -26,6 +28,7 @@ struct IngestBuffers;
 class DeviceIngest {
 public:
     static constexpr size_t kChunk = 32u << 20;     // text bytes per H2D copy (SCG_INGEST_CHUNK overrides, for tests)
+    static constexpr size_t kBgzfChunk = 64u << 20; // text bytes per chunk of a block-gzip input (1024 members of 64 KiB: one warp each)
     static constexpr size_t kCarry = 1u << 20;      // room in front of every chunk for the unfinished tail of the previous one (SCG_INGEST_CARRY)
     static constexpr int kSlots = 3;                // chunks in flight (copying, being parsed, being consumed)
 
@@ -40,6 +43,11 @@ public:
     // `mate` selects the context's buffer set (0, or 1 for the second file of paired input); `want_odd` makes the pack
     // kernel flag reads that hold anything but upper-case A, C, G, T, N.
     DeviceIngest(Context& ctx, const char* text, size_t size, int nthreads, int mate, bool want_odd);
+    // The same over a block-gzip image (bgzf.hpp): the COMPRESSED members cross PCIe, chunk by chunk (a chunk = a run of whole
+    // members), and are inflated on the device (inflate.cuh) straight into the text ring; everything after that is the same.
+    // A member the device cannot inflate (or whose CRC does not match) stops the device reader before that chunk and the
+    // host reader, which raises the error, takes over.
+    DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd);
     ~DeviceIngest();
 
     // Parses the next chunk.  false = the text is exhausted (and `out.n` is 0).  Same as stage() + complete().
@@ -54,18 +62,32 @@ public:
     size_t consumed() const { return consumed_; }
     bool exhausted() const { return stopped_ || parsed_ >= nchunks(); }
 
-    // Raw text of read `index` of the batch handed out last (single-line records): pointer into the caller's text.
-    void raw_read(long long index, const char** seq, uint32_t* len);
+    // Raw text of read `index` of the batch handed out last (single-line records).
+    void raw_read(long long index, std::string& seq);
 
 private:
+    void setup(bool source_pinned);
     void issue_copy(size_t chunk);
-    size_t nchunks() const { return (size_ + chunk_ - 1) / chunk_; }
+    void issue_inflate(size_t chunk);
+    void fetch_text(size_t offset, size_t len, std::string& out);
+    size_t nchunks() const { return chunk_begin_.size() - 1; }
+    size_t chunk_bytes(size_t k) const { return chunk_begin_[k + 1] - chunk_begin_[k]; }
     size_t slot_base(size_t chunk) const { return (chunk % kSlots) * stride_; }
     IngestBuffers& buffers() const;
 
     size_t chunk_ = kChunk, carry_ = kCarry;
     size_t stride_ = 0;      // carry + chunk + 256 (room for an appended newline; keeps slot bases 16-byte aligned)
     size_t line_cap_ = 0;    // newline positions kept per chunk
+
+    std::vector<size_t> chunk_begin_;   // text offset where each chunk starts, and the text's size at the end
+
+    // block-gzip input
+    const BgzfIndex* bgzf_ = nullptr;
+    std::vector<size_t> chunk_block_;   // first member of each chunk, and the number of members at the end
+    size_t max_comp_ = 0;               // most compressed bytes any chunk holds
+    size_t max_members_ = 0;
+    std::vector<char> block_cache_;     // host-inflated member for raw_read()
+    size_t block_cached_ = (size_t)-1;
 
     Context& ctx_;
     const char* text_;
@@ -100,6 +122,9 @@ struct IngestBuffers {
     DeviceBuffer packed[2], lens[2], odd[2];
     PinnedBuffer bounce[DeviceIngest::kSlots];
     PinnedBuffer meta;
+    // block-gzip input: the compressed members of the chunk in each slot, their table, the inflate kernels' error word
+    DeviceBuffer comp[DeviceIngest::kSlots], members[DeviceIngest::kSlots], inflate_errors;
+    PinnedBuffer members_host[DeviceIngest::kSlots];
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copied[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };     // chunk text is in HBM
     cudaEvent_t bounced[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };    // bounce buffer may be refilled
@@ -108,10 +133,13 @@ struct IngestBuffers {
     bool released_valid[DeviceIngest::kSlots] = { false, false, false };
     bool bounced_valid[DeviceIngest::kSlots] = { false, false, false };
     ~IngestBuffers();
-    void ensure(size_t chunk, size_t carry, bool need_bounce);
+    void ensure(size_t chunk, size_t carry, size_t bounce_bytes);
+    void ensure_bgzf(size_t comp_bytes, size_t nmembers);
 };
 
 // false when the device reader is switched off (environment SCG_HOST_PARSE=1): every input then takes the host parser.
 bool device_ingest_enabled();
+// false when block-gzip members are to be inflated by host threads (environment SCG_BGZF_HOST=1) and parsed there.
+bool device_inflate_enabled();
 
 } // namespace scg

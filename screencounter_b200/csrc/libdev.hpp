@@ -28,6 +28,9 @@ struct LibDev {
     const int32_t* cands;     // nseeds * nentries entry ids, grouped by bucket
     // KW == 1 only: the same candidates as rows (h, l, pool index, 0), so that a candidate costs one 16-byte load
     const uint4* cand_rows;
+    // KW == 1 only (nullptr when not built): the seed buckets with their first candidate inline -- (H word, L word, pool index,
+    // start | count << 24) per bucket, indexed like `buckets` -- so that a seed costs ONE 16-byte load in nine cases out of ten
+    const uint4* ibuckets;
     // segmented search (dual paired-end): first segment = bases [0, seg1), second = [seg1, L)
     int seg1;
     // table of library rows with their last base dropped (SURVEY 8.1 T8 root rule)

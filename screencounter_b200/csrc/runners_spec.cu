@@ -49,6 +49,136 @@ __global__ void __launch_bounds__(128) dual_deferred_kernel(DeferredList def, co
     }
 }
 
+// Best-unique bookkeeping of the mismatch-tolerant search over candidate rows (h, l, pool index, -): the rules of
+// MismatchTrie.hpp:266-343 as lookup_seeded_body applies them.
+struct BestRow {
+    int dist, index;
+    bool ambiguous;
+    __device__ __forceinline__ void consider(const uint4 row, uint32_t kh, uint32_t kl, uint32_t kn, int cap, bool valid, bool dup_first) {
+        if (!valid) return;
+        const int d = __popc((row.x ^ kh) | (row.y ^ kl) | kn);
+        if (d > cap || d > dist) return;
+        const int idx = (int)row.z;
+        if (d < dist) {
+            dist = d;
+            index = idx;
+            ambiguous = false;
+        } else if (idx != index) {
+            if (dup_first) {
+                index = min(index, idx);
+            } else {
+                ambiguous = true;
+            }
+        }
+    }
+};
+
+// countComboBarcodes with libraries of one word per plane, two seeds and inline buckets (a budget of one mismatch -- the
+// usual design): the same search as combo_deferred_kernel with the dependent chains flattened.  The exact probes of BOTH
+// regions go out together (four loads), then the seed buckets of every region that missed (up to four loads, each carrying
+// its first candidate); only a bucket with more than one candidate costs further loads.  Two round trips to the tables
+// where the generic search walks bucket -> candidate list -> entry keys -> entry index per seed and per region.
+__global__ void __launch_bounds__(128) combo_deferred_flat_kernel(DeferredList def, ComboParams P, ComboSink sink, int32_t* __restrict__ out_pairs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < def.regions; r += nwarps) {
+        const uint32_t cnt = def.warp_counts[r];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= cnt) continue;
+            const unsigned long long at = (unsigned long long)r * def.per_warp + e;
+            const uint32_t i = def.words[at], m = def.words[def.stride + at];
+            const bool rev = (m & 0x100u) != 0;
+            const int obs0 = (int)(m & 0xFFu);
+            uint32_t kh[2], kl[2], kn[2];
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                kh[reg] = def.words[(2 + 3 * reg) * def.stride + at];
+                kl[reg] = def.words[(3 + 3 * reg) * def.stride + at];
+                kn[reg] = def.words[(4 + 3 * reg) * def.stride + at];
+            }
+            const LibDev* __restrict__ libs = P.libs + (rev ? 2 : 0);
+            // ---- round 1: exact probes of both regions ----
+            uint4 ea[2], eb[2];
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                ea[reg] = eb[reg] = make_uint4(0, 0, 0xFFFFFFFFu, 0);
+                if (kn[reg] == 0) {
+                    const uint4* __restrict__ slots = reinterpret_cast<const uint4*>(libs[reg].slots);
+                    const uint32_t mask = libs[reg].slot_mask;
+                    const uint32_t acc = hash_key(&kh[reg], &kl[reg], 1, 0);
+                    ea[reg] = __ldg(slots + (acc & mask));
+                    eb[reg] = __ldg(slots + (size_t)(mask + 1) + (hash_second(acc) & mask));
+                }
+            }
+            int exact[2];
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                const int ra = (kn[reg] == 0 && ea[reg].x == kh[reg] && ea[reg].y == kl[reg]) ? (int)ea[reg].z : -1;
+                const int rb = (kn[reg] == 0 && eb[reg].x == kh[reg] && eb[reg].y == kl[reg]) ? (int)eb[reg].z : -1;
+                exact[reg] = max(ra, rb);
+            }
+            // ---- round 2: the seed buckets (first candidate inline) of the regions that missed ----
+            const int cap0 = P.max_mm - obs0;
+            uint4 first[2][2];
+            uint2 bk[2][2];
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                const bool search = exact[reg] < 0 && cap0 >= 1 && __popc(kn[reg]) <= cap0;
+                const uint32_t bmask = libs[reg].bucket_mask;
+#pragma unroll
+                for (int sd = 0; sd < 2; ++sd) {
+                    first[reg][sd] = make_uint4(0, 0, 0, 0);
+                    const uint32_t sm = __ldg(libs[reg].seed_masks + sd);
+                    const uint32_t mh = kh[reg] & sm, ml = kl[reg] & sm;
+                    if (search && !(kn[reg] & sm)) {
+                        const uint32_t b = hash_key(&mh, &ml, 1, 0x5EED0000u + sd) & bmask;
+                        first[reg][sd] = __ldg(libs[reg].ibuckets + (size_t)sd * (bmask + 1) + b);
+                    }
+                    bk[reg][sd] = make_uint2(first[reg][sd].w & 0xFFFFFFu, first[reg][sd].w >> 24);
+                }
+            }
+            // ---- the regions in read order with the shared budget (find_match, :149-186) ----
+            int obs = obs0;
+            int ids[2] = { -1, -1 };
+            bool ok = true;
+#pragma unroll
+            for (int reg = 0; reg < 2; ++reg) {
+                if (!ok) continue;
+                int found = exact[reg], dist = 0;
+                if (found < 0) {
+                    const int cap = min(P.max_mm - obs, libs[reg].L);
+                    if (cap >= 1 && __popc(kn[reg]) <= cap) {
+                        const bool dup_first = libs[reg].dup_first != 0;
+                        BestRow best{ cap + 1, -1, false };
+#pragma unroll
+                        for (int sd = 0; sd < 2; ++sd) {
+                            best.consider(first[reg][sd], kh[reg], kl[reg], kn[reg], cap, bk[reg][sd].y > 0, dup_first);
+                            for (uint32_t c = 1; c < bk[reg][sd].y; ++c) {
+                                best.consider(__ldg(libs[reg].cand_rows + (size_t)sd * libs[reg].nentries + bk[reg][sd].x + c), kh[reg], kl[reg],
+                                              kn[reg], cap, true, dup_first);
+                            }
+                        }
+                        if (best.index >= 0 && !best.ambiguous) {
+                            found = best.index;
+                            dist = best.dist;
+                        }
+                    }
+                }
+                if (found < 0) {
+                    ok = false;
+                } else {
+                    obs += dist;
+                    ids[rev ? 1 - reg : reg] = found;
+                }
+            }
+            if (ok) combo_count(sink, ids[0], ids[1]);
+            if (out_pairs) __stcs(reinterpret_cast<int2*>(out_pairs) + i, ok ? make_int2(ids[0], ids[1]) : make_int2(-1, -1));
+        }
+    }
+}
+
 // countComboBarcodes: both regions of the read's one verified window through the mismatch-tolerant lookups, in read
 // order with the shared budget (find_match, handlers/CombinatorialBarcodesSingleEnd.hpp:149-186).
 __global__ void __launch_bounds__(128) combo_deferred_kernel(DeferredList def, ComboParams P, ComboSink sink, int32_t* __restrict__ out_pairs) {
@@ -88,6 +218,64 @@ __global__ void __launch_bounds__(128) combo_deferred_kernel(DeferredList def, C
             }
         }
     }
+}
+
+// countRandomBarcodes: the barcodes the main kernel did not find in their home sector -- new ones, and ones a collision
+// pushed further along -- inserted (or found) with the full probing loop.  Every entry is independent of every other, so the
+// compare-and-swap round trips of thousands of lanes overlap; new keys are added up per warp before they reach the
+// table's counter of distinct keys.
+__global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, CountTable64 table) {
+    constexpr int U = 4;   // entries per lane in flight: their slot loads, then their compare-and-swaps, overlap
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long fresh = 0;
+    for (uint32_t r = warp; r < def.regions; r += nwarps) {
+        const uint32_t cnt = def.warp_counts[r];
+        const unsigned long long base = (unsigned long long)r * def.per_warp;
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32 * U) {
+            unsigned long long key[U], pos[U], seen[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t e = e0 + 32 * u + lane;
+                valid[u] = e < cnt;
+                key[u] = valid[u] ? ((unsigned long long)def.words[base + e] | ((unsigned long long)def.words[def.stride + base + e] << 32)) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pos[u] = count_home(table, key[u]);
+                seen[u] = valid[u] ? __ldcg(&table.slots[pos[u]].key) : 0ull;
+            }
+            // an empty home: claim it (the answers of the U claims arrive together)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (valid[u] && seen[u] == ~0ull) {
+                    const unsigned long long old = atomicCAS(&table.slots[pos[u]].key, ~0ull, key[u]);
+                    if (old == ~0ull) {
+                        ++fresh;
+                        seen[u] = key[u];
+                    } else {
+                        seen[u] = old;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!valid[u]) continue;
+                if (seen[u] == key[u]) {
+                    atomicAdd(&table.slots[pos[u]].count, 1u);
+                } else {
+                    // someone else's key sits there: along the probe sequence
+                    const unsigned long long next = (pos[u] + 1) & table.mask;
+                    if (count_insert64_from(table, key[u], 1u, next, __ldcg(&table.slots[next].key))) ++fresh;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, d);
+    if (lane == 0 && fresh) atomicAdd(table.live, fresh);
 }
 
 namespace {
@@ -351,7 +539,17 @@ void launch_combo(Context& ctx, const ReadsDev& reads, const ComboMatcher& m, co
     ++ctx.launches;
     ++ctx.timing.launches;
     if (P.max_mm > 0) {
-        combo_deferred_kernel<<<followup_grid(ctx, reads.n), 128, 0, stream>>>(sc.def, P, sink, out_pairs);
+        // libraries of one word per plane with two seeds and inline buckets (a budget of one mismatch): the flattened search
+        bool flat = P.max_mm == 1 && !std::getenv("SCG_COMBO_NO_FLAT");
+        for (int k = 0; k < 4 && flat; ++k) {
+            const bool used = k < 2 ? m.tmpl.fwd : m.tmpl.rev;
+            if (used) flat = m.lib[k].dev.KW == 1 && m.lib[k].dev.nseeds == 2 && m.lib[k].dev.ibuckets != nullptr && m.lib[k].dev.slot_words == 4;
+        }
+        if (flat) {
+            combo_deferred_flat_kernel<<<followup_grid(ctx, reads.n), 128, 0, stream>>>(sc.def, P, sink, out_pairs);
+        } else {
+            combo_deferred_kernel<<<followup_grid(ctx, reads.n), 128, 0, stream>>>(sc.def, P, sink, out_pairs);
+        }
         SCG_CUDA_CHECK(cudaGetLastError());
         ++ctx.launches;
         ++ctx.timing.launches;
@@ -407,23 +605,25 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     }
     cudaKernel_t k = mod->kernels[0];
     const int grid = spec_grid(ctx, k, reads.n, group);
-    ctx.slow_list.reserve((size_t)(ntiles * TILE) * sizeof(uint32_t));
-    ctx.slow_count.reserve(sizeof(uint32_t));
-    SlowList slow{ ctx.slow_list.as<uint32_t>(), ctx.slow_count.as<uint32_t>() };
-    SCG_CUDA_CHECK(cudaMemsetAsync(slow.count, 0, sizeof(uint32_t), stream));
+    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, 2, stream);
+    SlowList slow = sc.slow;
     ReadsDev a = reads;
     CountTable64 t64 = tab.view64();
     long long read_offset = 0;
-    void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &slow };
+    void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &sc.def, &slow };
     SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
-    ++ctx.launches;
-    ++ctx.timing.launches;
+    // barcodes that were not in their home sector yet: inserted (or found further along) by the follow-up kernel
+    random_insert_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(sc.def, t64);
+    SCG_CUDA_CHECK(cudaGetLastError());
+    ctx.launches += 2;
+    ctx.timing.launches += 2;
     if (!m.params.use_first) {
         // best mode: reads with several verified windows take the full scan (the minimum must be attained once)
         launch_random_generic(ctx, reads, m, tab, odd, odd_out, odd_count, out_index, ReadList{ slow.list, slow.count }, ctx.sm_count * 2, stream);
     }
-    ctx.kernel_note = "specialised (NVRTC) spec_random_kernel, filter+verify + 16-byte-slot count table, " +
-                      std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM" + (m.params.use_first ? "" : " + random_kernel on the multi-window reads");
+    ctx.kernel_note = "specialised (NVRTC) spec_random_kernel, filter+verify + 16-byte-slot count table (home sector requested a tile ahead), " +
+                      std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM; + random_insert_kernel (new and displaced barcodes)" +
+                      (m.params.use_first ? "" : " + random_kernel on the multi-window reads");
 }
 
 } // namespace scg
@@ -574,8 +774,9 @@ int scg_random_plan_create(scg_ctx* ctx, const char* constant, int strand, int m
         plan->random = std::make_shared<RandomMatcher>();
         plan->random->prepare(constant, strand, mismatches, use_first != 0);
         c.ensure_ready();
-        // sized once for the distinct barcodes the caller expects (load factor <= 1/2); 0 = grow as the reference's map does
-        plan->table.init(c, plan->random->wide, expected_distinct > 0 ? (size_t)(2 * expected_distinct) : (size_t)1 << 20);
+        // sized once for the distinct barcodes the caller expects: a load factor of at most 1/4 keeps 19 barcodes in 20 inside
+        // their home sector (the main kernel counts those on the spot); 0 = grow as the reference's map does
+        plan->table.init(c, plan->random->wide, expected_distinct > 0 ? (size_t)((plan->random->wide ? 2 : 4) * expected_distinct) : (size_t)1 << 20);
         plan->table.fixed = expected_distinct > 0;
         SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         *out = plan.release();

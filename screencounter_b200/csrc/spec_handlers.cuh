@@ -329,18 +329,27 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     const uint32_t region_base = (uint32_t)warp * def.per_warp;
     uint32_t cursor = 0;
 
+    // carried from one tile to the next: the four slots requested for the two regions, the regions, the flags
+    constexpr uint32_t PM_PROBED1 = 1u << 29;   // region 1's slots were requested (PM_PROBED: region 0's)
+    uint4 pa0 = make_uint4(0, 0, 0, 0), pb0 = pa0, pa1 = pa0, pb1 = pa0;
+    uint32_t pmeta = 0, pi = 0, pk0h = 0, pk0l = 0, pk0n = 0, pk1h = 0, pk1l = 0, pk1n = 0;
+
     uint32_t stage = 0, parity = 0;
-    for (int group = warp; group < ngroups; group += nwarps) {
-        mbar_wait(bar_base + 8u * stage, parity);
-        const int tiles_here = min(GROUP, ntiles - GROUP * group);
-        for (int t = 0; t < tiles_here; ++t) {
-            const uint32_t i = (uint32_t)(group * GROUP + t) * TILE + lane;
+    int group = warp, tile_in_group = 0, tiles_here = 0;
+    bool have = group < ngroups;
+    if (have) {
+        mbar_wait(bar_base, 0);
+        tiles_here = min(GROUP, ntiles - GROUP * group);
+    }
+    for (;;) {
+        uint32_t meta = 0, i = 0, k0h = 0, k0l = 0, k0n = 0, k1h = 0, k1l = 0, k1n = 0;   // regions in READ order
+        if (have) {
+            i = (uint32_t)(group * GROUP + tile_in_group) * TILE + lane;
             const bool inrange = i < n;
-            uint32_t meta = 0, k0h = 0, k0l = 0, k0n = 0, k1h = 0, k1l = 0, k1n = 0;   // regions in READ order
             int ncand = 0;
             {
                 Words<TrA::W> R;
-                load_words<TrA::W>(stage_a[wib][stage] + t * DA::TILE_WORDS + lane, R);
+                load_words<TrA::W>(stage_a[wib][stage] + tile_in_group * DA::TILE_WORDS + lane, R);
                 Planes<TrA::W> P;
                 make_planes<TrA::W>(R, P);
                 scan_blocks<TrA, 0>(R, P, inrange, ncand, meta, [&](const uint32_t(&wh)[DA::TW + 1], const uint32_t(&wl)[DA::TW + 1],
@@ -363,58 +372,88 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
                     }
                 });
             }
-            const bool cand = (meta & SM_CAND) != 0, many = ncand > 1;
-            const bool rev = (meta & SM_REV) != 0;
-            const int c = (int)((meta >> 16) & 0xFFu);
-            // ---- one verified window: each region against its pool's exact table (find_match, :149-186) ----
+            // the buffers go back to the TMA once every lane has consumed the group's last tile
+            if (++tile_in_group == tiles_here) {
+                __syncwarp();
+                const int ahead = group + STAGES * nwarps;
+                if (ahead < ngroups) fetch(ahead, stage);
+            }
+            meta = (meta & (SM_CAND | SM_REV | 0x00FF0000u)) + (inrange ? PM_INRANGE : 0u) + (((meta & SM_CAND) && ncand > 1) ? PM_SLOW : 0u);
+        }
+
+        // ---- settle the PREVIOUS tile: its slots were requested one scan ago (find_match, :149-186) ----
+        {
+            const uint32_t m = pmeta;
+            const bool cand = (m & SM_CAND) != 0, many = (m & PM_SLOW) != 0, rev = (m & SM_REV) != 0;
+            const int c = (int)((m >> 16) & 0xFFu);
             int id_a = -1, id_b = -1;   // pool indices found for region 0 / region 1 (read order)
-            if (cand && !many) {
-                const int l0 = rev ? 2 : 0;
-                const uint4* __restrict__ s0 = tb.slots[l0];
-                const uint4* __restrict__ s1 = tb.slots[l0 + 1];
-                const uint32_t m0 = tb.mask[l0], m1 = tb.mask[l0 + 1];
-                const uint32_t acc0 = hash_key(&k0h, &k0l, 1, 0), acc1 = hash_key(&k1h, &k1l, 1, 0);
-                uint4 a0 = make_uint4(0, 0, 0xFFFFFFFFu, 0), b0 = a0, a1 = a0, b1 = a0;
-                if (k0n == 0) {
-                    a0 = __ldg(s0 + (acc0 & m0));
-                    b0 = __ldg(s0 + (size_t)(m0 + 1) + (hash_second(acc0) & m0));
-                }
-                if (k1n == 0) {
-                    a1 = __ldg(s1 + (acc1 & m1));
-                    b1 = __ldg(s1 + (size_t)(m1 + 1) + (hash_second(acc1) & m1));
-                }
-                if (k0n == 0) {
-                    const int ra = (a0.x == k0h && a0.y == k0l) ? (int)a0.z : -1;
-                    const int rb = (b0.x == k0h && b0.y == k0l) ? (int)b0.z : -1;
-                    id_a = max(ra, rb);
-                }
-                if (k1n == 0) {
-                    const int ra = (a1.x == k1h && a1.y == k1l) ? (int)a1.z : -1;
-                    const int rb = (b1.x == k1h && b1.y == k1l) ? (int)b1.z : -1;
-                    id_b = max(ra, rb);
-                }
+            if (m & PM_PROBED) {
+                const int ra = (pa0.x == pk0h && pa0.y == pk0l) ? (int)pa0.z : -1;
+                const int rb = (pb0.x == pk0h && pb0.y == pk0l) ? (int)pb0.z : -1;
+                id_a = max(ra, rb);
+            }
+            if (m & PM_PROBED1) {
+                const int ra = (pa1.x == pk1h && pa1.y == pk1l) ? (int)pa1.z : -1;
+                const int rb = (pb1.x == pk1h && pb1.y == pk1l) ? (int)pb1.z : -1;
+                id_b = max(ra, rb);
             }
             const bool found = id_a >= 0 && id_b >= 0;
             const bool defer = cand && !many && !found && (SPH_A_MAXMM - c >= 1);
             const bool slowp = cand && many;
             // reverse strand: region r of the read is pool 1 - r (:111-116)
             const int id0 = rev ? id_b : id_a, id1 = rev ? id_a : id_b;
-            if (inrange && !defer && !slowp) {
+            if ((m & PM_INRANGE) && !defer && !slowp) {
                 if (found) combo_count(sink, id0, id1);
                 if (SPH_HAS_INDEX) {
-                    __stcs(reinterpret_cast<int2*>(out_pairs) + i, found ? make_int2(id0, id1) : make_int2(-1, -1));
+                    __stcs(reinterpret_cast<int2*>(out_pairs) + pi, found ? make_int2(id0, id1) : make_int2(-1, -1));
                 }
             }
-            const uint32_t entry[COMBO_DEFER_WORDS] = { i, (rev ? 0x100u : 0u) | (uint32_t)c, k0h, k0l, k0n, k1h, k1l, k1n };
+            const uint32_t entry[COMBO_DEFER_WORDS] = { pi, (rev ? 0x100u : 0u) | (uint32_t)c, pk0h, pk0l, pk0n, pk1h, pk1l, pk1n };
             defer_append<COMBO_DEFER_WORDS>(def, region_base, cursor, defer, lane, entry);
-            slow_append(slow, slowp, lane, i);
+            slow_append(slow, slowp, lane, pi);
         }
-        __syncwarp();
-        const int ahead = group + STAGES * nwarps;
-        if (ahead < ngroups) fetch(ahead, stage);
-        if (++stage == STAGES) {
-            stage = 0;
-            parity ^= 1u;
+
+        // ---- this tile: request the two slots of each region in its pool's exact table ----
+        pmeta = meta;
+        pi = i;
+        pk0h = k0h;
+        pk0l = k0l;
+        pk0n = k0n;
+        pk1h = k1h;
+        pk1l = k1l;
+        pk1n = k1n;
+        if ((meta & SM_CAND) && !(meta & PM_SLOW)) {
+            const int l0 = (meta & SM_REV) ? 2 : 0;
+            const uint4* __restrict__ s0 = tb.slots[l0];
+            const uint4* __restrict__ s1 = tb.slots[l0 + 1];
+            const uint32_t m0 = tb.mask[l0], m1 = tb.mask[l0 + 1];
+            if (k0n == 0) {
+                const uint32_t acc0 = hash_key(&k0h, &k0l, 1, 0);
+                pa0 = __ldg(s0 + (acc0 & m0));
+                pb0 = __ldg(s0 + (size_t)(m0 + 1) + (hash_second(acc0) & m0));
+                pmeta += PM_PROBED;
+            }
+            if (k1n == 0) {
+                const uint32_t acc1 = hash_key(&k1h, &k1l, 1, 0);
+                pa1 = __ldg(s1 + (acc1 & m1));
+                pb1 = __ldg(s1 + (size_t)(m1 + 1) + (hash_second(acc1) & m1));
+                pmeta += PM_PROBED1;
+            }
+        }
+
+        if (!have) break;
+        if (tile_in_group == tiles_here) {
+            group += nwarps;
+            tile_in_group = 0;
+            if (++stage == STAGES) {
+                stage = 0;
+                parity ^= 1u;
+            }
+            have = group < ngroups;
+            if (have) {
+                mbar_wait(bar_base + 8u * stage, parity);
+                tiles_here = min(GROUP, ntiles - GROUP * group);
+            }
         }
     }
     if (lane == 0) def.warp_counts[warp] = cursor;
@@ -428,7 +467,7 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
 extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     spec_random_kernel(const scg::ReadsDev reads, const scg::CountTable64 table, const uint8_t* __restrict__ odd, long long read_offset,
                        scg::OddOutcome* __restrict__ odd_out, unsigned long long* __restrict__ odd_count, int32_t* __restrict__ out_index,
-                       const scg::SlowList slow) {
+                       const scg::DeferredList def, const scg::SlowList slow) {
     using namespace scg;
     using namespace scg::sph;
     using DA = Dims<TrA>;
@@ -465,9 +504,13 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
         if (warp + s * nwarps < ngroups) fetch(warp + s * nwarps, (uint32_t)s);
     }
 
-    // carried from one tile to the next: the barcode, its slot in the count table and what the slot held when requested
-    unsigned long long pkey = 0, ppos = 0, pseen = 0;
+    // carried from one tile to the next: the barcode, its home in the count table and what the home's two slots (one
+    // 32-byte sector) held when requested
+    unsigned long long pkey = 0, ppos = 0;
+    uint4 pa = make_uint4(0, 0, 0, 0), pb = make_uint4(0, 0, 0, 0);
     bool pinsert = false;
+    const uint32_t region_base = (uint32_t)warp * def.per_warp;
+    uint32_t cursor = 0;   // warp-uniform: entries in this warp's region of the deferred list
 
     uint32_t stage = 0, parity = 0;
     int group = warp, tile_in_group = 0, tiles_here = 0;
@@ -529,15 +572,27 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             key = random_key64(kh, kl, kn);
         }
 
-        // ---- count the PREVIOUS tile's barcodes: their slots were requested one scan ago ----
-        if (pinsert) count_insert64_from(table, pkey, 1u, ppos, pseen);
+        // ---- count the PREVIOUS tile's barcodes: their homes were requested one scan ago.  A barcode found in its home
+        // sector is counted with one fire-and-forget atomic; one that is not there yet (new, or pushed further along by a
+        // collision) goes to the deferred list and the follow-up kernel inserts it -- no compare-and-swap round trip, no
+        // probing loop, nothing this warp has to wait for ----
+        {
+            const unsigned long long ka = (unsigned long long)pa.x | ((unsigned long long)pa.y << 32);
+            const unsigned long long kb = (unsigned long long)pb.x | ((unsigned long long)pb.y << 32);
+            const bool hit_a = pinsert && ka == pkey, hit_b = pinsert && kb == pkey;
+            if (hit_a || hit_b) atomicAdd(&table.slots[ppos + (hit_a ? 0u : 1u)].count, 1u);
+            const uint32_t entry[2] = { (uint32_t)pkey, (uint32_t)(pkey >> 32) };
+            defer_append<2>(def, region_base, cursor, pinsert && !hit_a && !hit_b, lane, entry);
+        }
 
-        // ---- this tile's barcodes: request their slots ----
+        // ---- this tile's barcodes: request their home sectors ----
         pinsert = insert;
         pkey = key;
         if (insert) {
-            ppos = count_hash(key) & table.mask;
-            pseen = __ldcg(&table.slots[ppos].key);
+            ppos = count_home(table, key);
+            const uint4* __restrict__ home = reinterpret_cast<const uint4*>(table.slots + ppos);
+            pa = __ldcg(home);
+            pb = __ldcg(home + 1);
         }
 
         if (!have) break;
@@ -555,5 +610,6 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             }
         }
     }
+    if (lane == 0) def.warp_counts[warp] = cursor;
 }
 #endif  // SPH_KIND == 3

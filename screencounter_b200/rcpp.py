@@ -433,6 +433,31 @@ def matrix_of_random_barcodes(files, constant, strand, mismatches, use_first, nt
     return seqs, counts, totals[: len(files)]
 
 
+def bgzf_compress(text, level=6, block_text=0, nthreads=None):
+    """FASTQ text (bytes / uint8 array) -> block-gzip image (numpy uint8), what bgzip writes; host threads + zlib."""
+    arr = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+    nthreads = nthreads or len(os.sched_getaffinity(0)) or 1
+    used = C.c_size_t()
+    if lib().scg_bgzf_compress(_ip(arr), arr.size, int(level), int(block_text), int(nthreads), None, 0, C.byref(used)) != 0:
+        raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+    out = np.empty(used.value, dtype=np.uint8)
+    if lib().scg_bgzf_compress(_ip(arr), arr.size, int(level), int(block_text), int(nthreads), _ip(out), out.size, C.byref(used)) != 0:
+        raise ScreenCounterError(lib().scg_last_error(None).decode("latin-1"))
+    return out[: used.value]
+
+
+def bgzf_inflate(image, device=None):
+    """The device inflater on its own: block-gzip image -> (text as numpy uint8, milliseconds of the kernels)."""
+    ctx = context(device)
+    arr = np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray, memoryview)) else np.ascontiguousarray(image, dtype=np.uint8)
+    size = C.c_size_t()
+    ms = C.c_double()
+    _check(ctx, lib().scg_bgzf_inflate(ctx, _ip(arr), arr.size, None, 0, C.byref(size), None))
+    out = np.empty(max(size.value, 1), dtype=np.uint8)
+    _check(ctx, lib().scg_bgzf_inflate(ctx, _ip(arr), arr.size, _ip(out), out.size, C.byref(size), C.byref(ms)))
+    return out[: size.value], ms.value
+
+
 def host_pack_roundtrip(fastq, nthreads=1):
     """Host-only: parse + pack + unpack a FASTQ; returns the reads as the packed layout sees them
     (upper-case ACGT, N for anything else).  Needs no device."""

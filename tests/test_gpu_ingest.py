@@ -215,7 +215,8 @@ def test_files_take_the_device_reader(gpu, kref, monkeypatch, tmp_path):
 
 
 def test_block_gzip_file(gpu, kref, monkeypatch, tmp_path):
-    """A BGZF file is inflated member-parallel on the host and parsed there; a plain gzip file goes member by member."""
+    """A BGZF file crosses PCIe compressed and is inflated on the device (tests/test_gpu_bgzf.py has the details); a plain gzip
+    file is inflated by zlib on the host, member by member, and parsed there."""
     import gzip
     from util import bgzf
     pool, reads = _case(16, n=30000)
@@ -226,7 +227,8 @@ def test_block_gzip_file(gpu, kref, monkeypatch, tmp_path):
         path = tmp_path / name
         path.write_bytes(blob)
         got = gpu.count_single(str(path), TEMPLATE, 2, pool, 1, True, nthreads=6)
-        assert rcpp.timing()["reader"] == "host"
+        reader = rcpp.timing()["reader"]
+        assert reader == "host" if name.startswith("p.") else ("block-gzip" in reader and "then host" not in reader), reader
         assert got[1] == want[1] and np.array_equal(got[0], want[0])
 
 

@@ -37,7 +37,7 @@ def _device_sets():
 
 
 def _files(rng, template, pools, sizes, **kw):
-    return [fastq(adversarial_reads(rng, n, template, pools, strand="both", **kw)).encode() if n else b"" for n in sizes]
+    return [fastq(adversarial_reads(rng, n, template, pools, strand="both", **kw)) if n else b"" for n in sizes]
 
 
 @pytest.mark.parametrize("devices", _device_sets(), ids=str)
@@ -63,7 +63,7 @@ def test_one_file_cut_over_the_devices(devices, monkeypatch):
     rng = np.random.default_rng(6)
     pool = distinct_pool(rng, 200, 20)
     reads = adversarial_reads(rng, 20000, TEMPLATE, [pool], strand="both")
-    text = fastq(reads).encode()
+    text = fastq(reads)
     counts, total, (index, info) = rcpp.count_single_barcodes(text, TEMPLATE, 2, pool, 1, False, 2, trace=True, device=devices)
     want_index, want_info = _oracle().trace_single(text, TEMPLATE, 2, pool, 1, False)
     assert total == len(reads)
@@ -72,15 +72,16 @@ def test_one_file_cut_over_the_devices(devices, monkeypatch):
     assert "devices" in rcpp.timing(devices)["kernel"]
     # a text that cannot be cut cleanly (a wrapped record in the middle) is read by one device, with the same answer
     half = len(reads) // 2
-    odd = fastq(reads[:half]) + "@wrapped\n" + reads[half][:10] + "\n" + reads[half][10:] + "\n+\n" + "I" * len(reads[half]) + "\n" + fastq(reads[half + 1:])
-    c2, t2 = rcpp.count_single_barcodes(odd.encode(), TEMPLATE, 2, pool, 1, False, 2, device=devices)
+    wrapped = ("@wrapped\n" + reads[half][:10] + "\n" + reads[half][10:] + "\n+\n" + "I" * len(reads[half]) + "\n").encode()
+    odd = fastq(reads[:half]) + wrapped + fastq(reads[half + 1:])
+    c2, t2 = rcpp.count_single_barcodes(odd, TEMPLATE, 2, pool, 1, False, 2, device=devices)
     assert t2 == len(reads) and np.array_equal(c2, counts)
     # a malformed record raises the reference's error, line number included, whichever part it sits in
-    bad = fastq(reads[:half]) + "@broken\nACGT\n+\nII\n" + fastq(reads[half:])
+    bad = fastq(reads[:half]) + b"@broken\nACGT\n+\nII\n" + fastq(reads[half:])
     with pytest.raises(rcpp.ScreenCounterError) as e:
-        rcpp.count_single_barcodes(bad.encode(), TEMPLATE, 2, pool, 1, False, 2, device=devices)
+        rcpp.count_single_barcodes(bad, TEMPLATE, 2, pool, 1, False, 2, device=devices)
     try:
-        _oracle().count_single(bad.encode(), TEMPLATE, 2, pool, 1, False)
+        _oracle().count_single(bad, TEMPLATE, 2, pool, 1, False)
         raise AssertionError("the reference accepted the malformed file")
     except Exception as ref_error:
         assert str(ref_error) in str(e.value) or str(e.value) in str(ref_error)
