@@ -118,8 +118,10 @@ size_t bgzf_compress(const char* text, size_t size, int level, size_t block_text
         if (at != k * per_block) std::memmove(out + at, out + k * per_block, sizes[k]);
         at += sizes[k];
     }
-    at += member(nblocks, text, 0, out + at);   // the empty member that marks the end of a BGZF file
-    return at;
+    // the empty member that marks the end of a BGZF file: bgzip's fixed 28 bytes, whatever the level
+    static const unsigned char eof_marker[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    std::memcpy(out + at, eof_marker, sizeof eof_marker);
+    return at + sizeof eof_marker;
 }
 
 } // namespace scg

@@ -8,9 +8,11 @@
 //     a refill takes its word from the owning lane with a shuffle -- no global-memory latency on the decoding chain;
 //   * code tables are built by all lanes (counting by shared atomics, canonical codes by __match_any ranks, table fill
 //     per symbol);
-//   * symbols are decoded in batches of 32, symbol k parked in lane k; the batch's output offsets are one warp scan; literals
-//     are stored by their lanes, matches whose source lies wholly before the batch are copied without any ordering between
-//     them (their loads overlap), and only matches that read bytes of their own batch take the ordered path.
+//   * symbols are decoded in batches of up to 32 (about 2 KiB of text at most), symbol k parked in lane k; the batch's output
+//     offsets are one warp scan; the batch's text is ASSEMBLED IN SHARED MEMORY: literals are stored by their lanes, matches
+//     whose source lies wholly before the batch are fetched from global memory without any ordering between them (their loads
+//     overlap), matches that read bytes of their own batch -- the rule in FASTQ, where a record repeats most of the one before
+//     it -- are copied in order at shared-memory latency; the finished batch goes out to global memory as aligned words.
 // Tables: 10-bit literal/length and 8-bit distance lookup (4-byte entries: value, extra bits, code length), longer codes go
 // through the canonical count/symbol arrays bit by bit (rare by construction: a code longer than 10 bits has probability
 // < 2^-10).  Text is written to global memory (the FASTQ reader's ring), source bytes of a match are read back from there.
@@ -28,18 +30,23 @@ namespace {
 constexpr int LIT_BITS = 10, DIST_BITS = 8;
 constexpr int INFL_WARPS = 4;   // warps per block
 constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr uint32_t STAGE_BYTES = 2048;   // text assembled per batch at most; a batch closes once it could not take another 258-byte match
 
-// table entry: value << 16 | kind << 8 | extra bits << 4 | code length.  0 = no such code.
+// table entry (16 bits, so that a warp's tables stay under 3 KiB and 32 warps fit an SM): value << 6 | kind << 4 | code length,
+// value = the literal byte, or the index of the length / distance symbol (base and extra bits come from the constant arrays).
+// 0 = no such code.
 constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_END = 2, K_LONG = 3;
+using Entry = uint16_t;
 
 struct WarpTables {
-    uint32_t lit[1 << LIT_BITS];
-    uint32_t dist[1 << DIST_BITS];
+    Entry lit[1 << LIT_BITS];
+    Entry dist[1 << DIST_BITS];
     uint32_t lit_count[16], dist_count[16];   // codes per length (kept for the bit-by-bit path)
     uint32_t next[16], offs[16];              // scratch of the table build
     uint16_t lit_sorted[288 + 32];            // symbols in canonical order (per length, ascending)
     uint16_t dist_sorted[32 + 32];
     uint8_t lens[288 + 32 + 32];              // code lengths of the block being set up
+    uint32_t stage[STAGE_BYTES / 4 + 2];      // the text of the batch being assembled (+ alignment slack)
 };
 
 __constant__ uint16_t c_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
@@ -51,22 +58,22 @@ __constant__ uint8_t c_clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 
 
 // what a code of `len` bits for `sym` stands for, as a table entry (0 = a symbol the format does not define)
 __device__ __forceinline__ uint32_t lit_entry(int sym, int len) {
-    if (sym < 256) return ((uint32_t)sym << 16) | (K_LITERAL << 8) | (uint32_t)len;
-    if (sym == 256) return (K_END << 8) | (uint32_t)len;
+    if (sym < 256) return ((uint32_t)sym << 6) | (K_LITERAL << 4) | (uint32_t)len;
+    if (sym == 256) return (K_END << 4) | (uint32_t)len;
     if (sym > 285) return 0u;
-    return ((uint32_t)c_len_base[sym - 257] << 16) | (K_MATCH << 8) | ((uint32_t)c_len_extra[sym - 257] << 4) | (uint32_t)len;
+    return ((uint32_t)(sym - 257) << 6) | (K_MATCH << 4) | (uint32_t)len;
 }
 __device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
     if (sym > 29) return 0u;
-    return ((uint32_t)c_dist_base[sym] << 16) | (K_MATCH << 8) | ((uint32_t)c_dist_extra[sym] << 4) | (uint32_t)len;
+    return ((uint32_t)sym << 6) | (K_MATCH << 4) | (uint32_t)len;
 }
 // code-length alphabet: the symbol itself is the value
-__device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 16) | (uint32_t)len; }
+__device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 6) | (uint32_t)len; }
 
 // Builds the lookup table of a canonical Huffman code from the code lengths lens[0 .. n).  KIND 0 literal/length, 1 distance,
 // 2 code lengths.  All lanes take part.  false = over-subscribed set of lengths.
 template <int KIND, int TBITS>
-__device__ bool build_table(const uint8_t* lens, int n, uint32_t* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
+__device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
                             int lane) {
     for (int i = lane; i < (1 << TBITS); i += 32) table[i] = 0;
     if (lane < 16) count[lane] = 0;
@@ -103,9 +110,9 @@ __device__ bool build_table(const uint8_t* lens, int n, uint32_t* table, uint16_
             const uint32_t r = __brev(code) >> (32 - l);   // the code as it appears in the bit stream (first bit = bit 0)
             if (l <= TBITS) {
                 const uint32_t e = KIND == 0 ? lit_entry(s, l) : (KIND == 1 ? dist_entry(s, l) : clen_entry(s, l));
-                for (uint32_t k = r; k < (1u << TBITS); k += (1u << l)) table[k] = e;
+                for (uint32_t k = r; k < (1u << TBITS); k += (1u << l)) table[k] = (Entry)e;
             } else {
-                table[r & ((1u << TBITS) - 1u)] = K_LONG << 8;
+                table[r & ((1u << TBITS) - 1u)] = (Entry)(K_LONG << 4);
             }
         }
         __syncwarp();
@@ -191,13 +198,13 @@ struct BitReader {
     __device__ __forceinline__ size_t byte_pos() const { return (size_t)widx * 4 - (size_t)(cnt >> 3); }
 };
 
-// copies a match: out[dst + j] = out[dst - dist + j] for j in [0, len), sources read as they were BEFORE the match when
-// dist >= len, the repeating pattern of the last `dist` bytes otherwise -- all of them already written
-__device__ __forceinline__ void copy_match(uint8_t* out, uint32_t dst, uint32_t len, uint32_t dist, int lane) {
-    if (dist >= len) {
-        for (uint32_t j = lane; j < len; j += 32) out[dst + j] = out[dst - dist + j];
-    } else {
-        for (uint32_t j = lane; j < len; j += 32) out[dst + j] = out[dst - dist + (j % dist)];
+// A match of the batch, copied into the stage: byte j comes from batch-relative position off - dist + j (the repeating
+// pattern of the last `dist` bytes when the match overlaps itself); positions before the batch are text already in global
+// memory (`done` = the batch's first byte there), the others are bytes of the stage written by earlier symbols.
+__device__ __forceinline__ void copy_match(uint8_t* stage, const uint8_t* done, uint32_t off, uint32_t len, uint32_t dist, int lane) {
+    for (uint32_t j = lane; j < len; j += 32) {
+        const int src = (int)off - (int)dist + (int)(dist >= len ? j : j % dist);
+        stage[off + j] = src < 0 ? done[src] : stage[src];
     }
 }
 
@@ -219,6 +226,12 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
         br.open(comp, M.in_off, lane);
         bool last = false;
         while (!last && !bad) {
+            // a block header beyond the member's bytes: a damaged stream running away (it must not leave the image)
+            if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt >
+                ((size_t)M.in_off + M.in_len) * 8) {
+                bad = true;
+                break;
+            }
             br.refill();
             last = br.take(1) != 0;
             const uint32_t type = br.take(2);
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                         break;
                     }
                     br.drop((int)(e & 0xFu));
-                    const uint32_t sym = e >> 16;
+                    const uint32_t sym = e >> 6;
                     uint32_t rep = 1, val = sym;
                     if (sym == 16) {
                         if (i == 0) {
@@ -325,16 +338,17 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
             }
             __syncwarp();
 
-            // ---- the block's symbols, 32 at a time ----
+            // ---- the block's symbols, a batch at a time ----
             bool end_of_block = false;
             while (!end_of_block && !bad) {
                 uint32_t my = 0;   // symbol parked in this lane: literal = 1 << 31 | 1 << 16 | byte; match = len << 16 | dist
                 int nsym = 0;
+                uint32_t staged = 0;   // bytes the batch produces so far (warp-uniform)
 #pragma unroll 1
-                for (; nsym < 32; ++nsym) {
+                for (; nsym < 32 && staged <= STAGE_BYTES - 258; ++nsym) {
                     br.refill();
                     uint32_t e = T.lit[br.peek(LIT_BITS)];
-                    if (((e >> 8) & 3u) == K_LONG) {
+                    if (((e >> 4) & 3u) == K_LONG) {
                         int sym = 0, len = 0;
                         e = slow_symbol(br.bits, T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : 0u;
                     }
@@ -343,18 +357,20 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                         break;
                     }
                     br.drop((int)(e & 0xFu));
-                    const uint32_t kind = (e >> 8) & 3u;
+                    const uint32_t kind = (e >> 4) & 3u;
                     uint32_t sym;
                     if (kind == K_LITERAL) {
-                        sym = 0x80010000u | (e >> 16);
+                        sym = 0x80010000u | (e >> 6);
+                        staged += 1;
                     } else if (kind == K_END) {
                         end_of_block = true;
                         break;
                     } else {
-                        const uint32_t len = (e >> 16) + br.take((int)((e >> 4) & 0xFu));
+                        const uint32_t li = e >> 6;
+                        const uint32_t len = (uint32_t)c_len_base[li] + br.take((int)c_len_extra[li]);
                         br.refill();
                         uint32_t d = T.dist[br.peek(DIST_BITS)];
-                        if (((d >> 8) & 3u) == K_LONG) {
+                        if (((d >> 4) & 3u) == K_LONG) {
                             int dsym = 0, dlen = 0;
                             d = slow_symbol(br.bits, T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : 0u;
                         }
@@ -363,8 +379,10 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                             break;
                         }
                         br.drop((int)(d & 0xFu));
-                        const uint32_t dist = (d >> 16) + br.take((int)((d >> 4) & 0xFu));
+                        const uint32_t di = d >> 6;
+                        const uint32_t dist = (uint32_t)c_dist_base[di] + br.take((int)c_dist_extra[di]);
                         sym = (len << 16) | dist;
+                        staged += len;
                     }
                     if (lane == nsym) my = sym;
                 }
@@ -377,7 +395,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                     const uint32_t v = __shfl_up_sync(FULL, incl, d);
                     if (lane >= d) incl += v;
                 }
-                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                const uint32_t total = staged;
                 const uint32_t off = incl - mylen;   // relative to the batch's first byte
                 const bool is_match = lane < nsym && !(my >> 31);
                 const uint32_t mydist = my & 0xFFFFu;
@@ -385,24 +403,66 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                     bad = true;
                     break;
                 }
-                if (lane < nsym && (my >> 31)) out[pos + off] = (uint8_t)my;
-                // matches whose source ends before the batch begins: no ordering among them
+                // the stage mirrors the alignment of the text in global memory, so that it can be flushed as aligned words
+                uint8_t* const done = out + pos;
+                const uint32_t skew = (uint32_t)(reinterpret_cast<size_t>(done) & 3);
+                uint8_t* const stage = reinterpret_cast<uint8_t*>(T.stage) + skew;
+                if (lane < nsym && (my >> 31)) stage[off] = (uint8_t)my;
+                // matches whose source ends before the batch begins: no ordering among them, their loads overlap
                 const bool indep = is_match && off + mylen <= mydist;
+                // (four at a time: a warp issues in order, so the loads of four matches go out before the first store waits)
                 uint32_t todo = __ballot_sync(FULL, indep);
                 while (todo) {
-                    const int k = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const uint32_t s = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
-                    copy_match(out, pos + o, (s >> 16) & 0x1FFu, s & 0xFFFFu, lane);
+                    uint32_t sy[4], o[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        sy[u] = 0;
+                        o[u] = 0;
+                        if (todo) {
+                            const int k = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            sy[u] = __shfl_sync(FULL, my, k);
+                            o[u] = __shfl_sync(FULL, off, k);
+                        }
+                    }
+                    uint8_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[u] = 0;
+                        if ((uint32_t)lane < ((sy[u] >> 16) & 0x1FFu)) v[u] = done[(int)o[u] - (int)(sy[u] & 0xFFFFu) + lane];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if ((uint32_t)lane < ((sy[u] >> 16) & 0x1FFu)) stage[o[u] + lane] = v[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t len = (sy[u] >> 16) & 0x1FFu;
+                        for (uint32_t j = lane + 32; j < len; j += 32) stage[o[u] + j] = done[(int)o[u] - (int)(sy[u] & 0xFFFFu) + (int)j];
+                    }
                 }
-                // the others read bytes of this batch: in order, each after what precedes it has landed
+                // the others read bytes of this batch: in order, each after what precedes it has landed in the stage
                 todo = __ballot_sync(FULL, is_match && !indep);
                 while (todo) {
                     __syncwarp();
                     const int k = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const uint32_t s = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
-                    copy_match(out, pos + o, (s >> 16) & 0x1FFu, s & 0xFFFFu, lane);
+                    const uint32_t sy = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
+                    copy_match(stage, done, o, (sy >> 16) & 0x1FFu, sy & 0xFFFFu, lane);
+                }
+                __syncwarp();
+                // ---- the finished batch goes out: whole aligned words, the ragged ends byte by byte ----
+                {
+                    const uint32_t span = skew + total;                 // bytes of the stage in use, from its aligned base
+                    const uint32_t first_word = skew ? 1u : 0u;         // word 0 is partial when the text does not start aligned
+                    const uint32_t full_words = span / 4;               // words [first_word, full_words) are complete
+                    uint32_t* gw = reinterpret_cast<uint32_t*>(done - skew);
+                    for (uint32_t w = first_word + lane; w < full_words; w += 32) gw[w] = T.stage[w];
+                    const uint8_t* sb = reinterpret_cast<const uint8_t*>(T.stage);
+                    uint8_t* gb = done - skew;
+                    if (skew && (uint32_t)lane >= skew && (uint32_t)lane < min(4u, span)) gb[lane] = sb[lane];
+                    const uint32_t tail = full_words * 4;               // bytes [tail, span) of a last partial word
+                    if (full_words >= first_word && tail + lane < span && tail + lane >= skew) gb[tail + lane] = sb[tail + lane];
                 }
                 __syncwarp();
                 pos += total;

@@ -322,13 +322,15 @@ bool device_ingest_enabled() {
 }
 
 IngestBuffers::~IngestBuffers() {
-    for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+    for (int k = 0; k < DeviceIngest::kMaxSlots; ++k) {
         if (copied[k]) cudaEventDestroy(copied[k]);
         if (bounced[k]) cudaEventDestroy(bounced[k]);
         if (released[k]) cudaEventDestroy(released[k]);
     }
     if (meta_ready) cudaEventDestroy(meta_ready);
-    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (cudaStream_t st : copy_streams) {
+        if (st) cudaStreamDestroy(st);
+    }
 }
 
 bool device_inflate_enabled() {
@@ -336,8 +338,8 @@ bool device_inflate_enabled() {
     return !(v && *v && *v != '0');
 }
 
-void IngestBuffers::ensure_bgzf(size_t comp_bytes, size_t nmembers) {
-    for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+void IngestBuffers::ensure_bgzf(size_t comp_bytes, size_t nmembers, int slots) {
+    for (int k = 0; k < slots; ++k) {
         comp[k].reserve(comp_bytes + 1024);   // the inflate kernel's readers fetch whole lines ahead
         members[k].reserve(std::max<size_t>(nmembers, 1) * sizeof(InflateMember));
         members_host[k].reserve(std::max<size_t>(nmembers, 1) * sizeof(InflateMember));
@@ -345,18 +347,19 @@ void IngestBuffers::ensure_bgzf(size_t comp_bytes, size_t nmembers) {
     inflate_errors.reserve(16);
 }
 
-void IngestBuffers::ensure(size_t chunk, size_t carry, size_t bounce_bytes) {
+void IngestBuffers::ensure(size_t chunk, size_t carry, size_t bounce_bytes, int slots) {
     const size_t stride = carry + chunk + 256, line_cap = (carry + chunk) / 4;
     if (!copy_stream) {
-        SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < DeviceIngest::kSlots; ++k) {
+        for (cudaStream_t& st : copy_streams) SCG_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        copy_stream = copy_streams[0];
+        for (int k = 0; k < DeviceIngest::kMaxSlots; ++k) {
             SCG_CUDA_CHECK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
             SCG_CUDA_CHECK(cudaEventCreateWithFlags(&bounced[k], cudaEventDisableTiming));
             SCG_CUDA_CHECK(cudaEventCreateWithFlags(&released[k], cudaEventDisableTiming));
         }
         SCG_CUDA_CHECK(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming));
     }
-    text.reserve(DeviceIngest::kSlots * stride + 2 * kBlockBytes);
+    text.reserve((size_t)slots * stride + 2 * kBlockBytes);
     lines.reserve((line_cap + 4) * sizeof(uint32_t));
     block_counts.reserve((stride / kBlockBytes + 2) * sizeof(uint32_t));
     seq_off.reserve((line_cap / 4 + 1) * sizeof(uint32_t));
@@ -367,9 +370,9 @@ void IngestBuffers::ensure(size_t chunk, size_t carry, size_t bounce_bytes) {
         odd[k].reserve(line_cap / 4 + TILE);
     }
     if (bounce_bytes) {
-        for (int k = 0; k < DeviceIngest::kSlots; ++k) bounce[k].reserve(bounce_bytes);
+        for (int k = 0; k < slots; ++k) bounce[k].reserve(bounce_bytes);
     }
-    for (int k = 0; k < DeviceIngest::kSlots; ++k) released_valid[k] = bounced_valid[k] = false;
+    for (int k = 0; k < DeviceIngest::kMaxSlots; ++k) released_valid[k] = bounced_valid[k] = false;
 }
 
 IngestBuffers& DeviceIngest::buffers() const { return *ctx_.ingest[mate_]; }
@@ -443,10 +446,12 @@ void DeviceIngest::setup(bool source_pinned) {
     line_cap_ = (carry_ + chunk_) / 4;
     if (!ctx_.ingest[mate_]) ctx_.ingest[mate_].reset(new IngestBuffers);
     IngestBuffers& B = buffers();
-    B.ensure(chunk_, carry_, pinned_source_ ? 0 : (bgzf_ ? max_comp_ : chunk_));
+    slots_ = bgzf_ ? (int)env_size("SCG_BGZF_SLOTS", kBgzfSlots, 2, kMaxSlots) : kSlots;
+    B.ensure(chunk_, carry_, pinned_source_ ? 0 : (bgzf_ ? max_comp_ : chunk_), slots_);
     if (bgzf_) {
-        B.ensure_bgzf(max_comp_, max_members_);
+        B.ensure_bgzf(max_comp_, max_members_, slots_);
         SCG_CUDA_CHECK(cudaMemsetAsync(B.inflate_errors.ptr, 0, 16, B.copy_stream));
+        SCG_CUDA_CHECK(cudaStreamSynchronize(B.copy_stream));   // (the chunks' kernels run on several streams)
     }
     ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_));
     SCG_CUDA_CHECK(cudaGetLastError());
@@ -478,17 +483,22 @@ void DeviceIngest::fetch_text(size_t offset, size_t len, std::string& out) {
 
 DeviceIngest::~DeviceIngest() {
     // copies still in flight read the caller's text (or the bounce buffers): let them finish
-    if (ctx_.ingest[mate_] && ctx_.ingest[mate_]->copy_stream) cudaStreamSynchronize(ctx_.ingest[mate_]->copy_stream);
+    if (ctx_.ingest[mate_]) {
+        for (cudaStream_t st : ctx_.ingest[mate_]->copy_streams) {
+            if (st) cudaStreamSynchronize(st);
+        }
+    }
 }
 
 // block-gzip input: the chunk's members cross PCIe compressed and are inflated into the slot's data area
 void DeviceIngest::issue_inflate(size_t chunk) {
     IngestBuffers& B = buffers();
-    const int s = (int)(chunk % kSlots);
+    const int s = (int)(chunk % (size_t)slots_);
+    cudaStream_t cs = B.copy_streams[chunk % kCopyStreams];
     const size_t fb = chunk_block_[chunk], lb = chunk_block_[chunk + 1];
     const size_t from = bgzf_->blocks[fb].data, bytes = bgzf_->blocks[lb - 1].data + bgzf_->blocks[lb - 1].csize - from;
     uint8_t* dst = B.text.as<uint8_t>() + slot_base(chunk) + carry_;
-    if (B.released_valid[s]) SCG_CUDA_CHECK(cudaStreamWaitEvent(B.copy_stream, B.released[s], 0));
+    if (B.released_valid[s]) SCG_CUDA_CHECK(cudaStreamWaitEvent(cs, B.released[s], 0));
     // the slot's host staging (member table, bounce buffer) is free once the copies of its previous chunk are done
     if (B.bounced_valid[s]) SCG_CUDA_CHECK(cudaEventSynchronize(B.bounced[s]));
     InflateMember* table = B.members_host[s].as<InflateMember>();
@@ -510,17 +520,17 @@ void DeviceIngest::issue_inflate(size_t chunk) {
         ctx_.timing.pack_s += now_s() - t0;
         src = bb;
     }
-    SCG_CUDA_CHECK(cudaMemcpyAsync(B.comp[s].ptr, src, bytes, cudaMemcpyHostToDevice, B.copy_stream));
-    SCG_CUDA_CHECK(cudaMemcpyAsync(B.members[s].ptr, table, (lb - fb) * sizeof(InflateMember), cudaMemcpyHostToDevice, B.copy_stream));
-    SCG_CUDA_CHECK(cudaEventRecord(B.bounced[s], B.copy_stream));
+    SCG_CUDA_CHECK(cudaMemcpyAsync(B.comp[s].ptr, src, bytes, cudaMemcpyHostToDevice, cs));
+    SCG_CUDA_CHECK(cudaMemcpyAsync(B.members[s].ptr, table, (lb - fb) * sizeof(InflateMember), cudaMemcpyHostToDevice, cs));
+    SCG_CUDA_CHECK(cudaEventRecord(B.bounced[s], cs));
     B.bounced_valid[s] = true;
     const int launched = launch_inflate(B.comp[s].as<uint8_t>(), B.members[s].as<InflateMember>(), (int)(lb - fb), dst,
-                                        B.inflate_errors.as<uint32_t>(), ctx_.sm_count, B.copy_stream);
+                                        B.inflate_errors.as<uint32_t>(), ctx_.sm_count, cs);
     SCG_CUDA_CHECK(cudaGetLastError());
     ctx_.launches += launched;
     ctx_.timing.launches += launched;
-    if (chunk + 1 == nchunks() && virtual_newline_) SCG_CUDA_CHECK(cudaMemsetAsync(dst + chunk_bytes(chunk), '\n', 1, B.copy_stream));
-    SCG_CUDA_CHECK(cudaEventRecord(B.copied[s], B.copy_stream));
+    if (chunk + 1 == nchunks() && virtual_newline_) SCG_CUDA_CHECK(cudaMemsetAsync(dst + chunk_bytes(chunk), '\n', 1, cs));
+    SCG_CUDA_CHECK(cudaEventRecord(B.copied[s], cs));
     ctx_.timing.bytes_h2d += (long long)(bytes + (lb - fb) * sizeof(InflateMember));
 }
 
@@ -530,7 +540,7 @@ void DeviceIngest::issue_copy(size_t chunk) {
         return;
     }
     IngestBuffers& B = buffers();
-    const int s = (int)(chunk % kSlots);
+    const int s = (int)(chunk % (size_t)slots_);
     const size_t off = chunk_begin_[chunk];
     const size_t bytes = chunk_bytes(chunk);
     uint8_t* dst = B.text.as<uint8_t>() + slot_base(chunk) + carry_;
@@ -570,13 +580,13 @@ bool DeviceIngest::stage() {
     if (exhausted()) return false;
     IngestBuffers& B = buffers();
     const size_t k = parsed_;
-    // chunk k + kSlots - 1 reuses the slot of chunk k - 1, whose kernels (and `released` event) are already enqueued;
+    // chunk k + slots - 1 reuses the slot of chunk k - 1, whose kernels (and `released` event) are already enqueued;
     // one further would need the slot this call is about to parse
-    while (issued_ < nchunks() && issued_ <= k + kSlots - 1) {
+    while (issued_ < nchunks() && issued_ <= k + (size_t)slots_ - 1) {
         issue_copy(issued_);
         ++issued_;
     }
-    const int s = (int)(k % kSlots);
+    const int s = (int)(k % (size_t)slots_);
     const bool final_chunk = k + 1 == nchunks();
     const size_t bytes = chunk_bytes(k) + ((final_chunk && virtual_newline_) ? 1 : 0);
     const uint32_t slot0 = (uint32_t)slot_base(k);
@@ -616,7 +626,7 @@ bool DeviceIngest::complete(Result& out) {
     staged_ = false;
     IngestBuffers& B = buffers();
     const size_t k = parsed_;
-    const int s = (int)(k % kSlots);
+    const int s = (int)(k % (size_t)slots_);
     const bool final_chunk = k + 1 == nchunks();
     const size_t bytes = chunk_bytes(k) + ((final_chunk && virtual_newline_) ? 1 : 0);
     const uint32_t slot0 = (uint32_t)slot_base(k);

@@ -28,9 +28,15 @@ struct IngestBuffers;
 class DeviceIngest {
 public:
     static constexpr size_t kChunk = 32u << 20;     // text bytes per H2D copy (SCG_INGEST_CHUNK overrides, for tests)
-    static constexpr size_t kBgzfChunk = 64u << 20; // text bytes per chunk of a block-gzip input (1024 members of 64 KiB: one warp each)
+    static constexpr size_t kBgzfChunk = 128u << 20; // text bytes per chunk of a block-gzip input (2056 members of 64 KiB: one warp each)
     static constexpr size_t kCarry = 1u << 20;      // room in front of every chunk for the unfinished tail of the previous one (SCG_INGEST_CARRY)
     static constexpr int kSlots = 3;                // chunks in flight (copying, being parsed, being consumed)
+    // Block-gzip input: a chunk's members are inflated by one warp each and a warp is slow (Huffman decoding is serial), so the
+    // inflater needs thousands of members in flight: chunks are issued further ahead (SCG_BGZF_SLOTS) and their kernels run
+    // side by side on several streams.
+    static constexpr int kBgzfSlots = 6;
+    static constexpr int kMaxSlots = 12;
+    static constexpr int kCopyStreams = 4;
 
     struct Result {
         bool handover = false;      // the device reader stops here: resume the host reader at `resume_offset`
@@ -72,9 +78,10 @@ private:
     void fetch_text(size_t offset, size_t len, std::string& out);
     size_t nchunks() const { return chunk_begin_.size() - 1; }
     size_t chunk_bytes(size_t k) const { return chunk_begin_[k + 1] - chunk_begin_[k]; }
-    size_t slot_base(size_t chunk) const { return (chunk % kSlots) * stride_; }
+    size_t slot_base(size_t chunk) const { return (chunk % (size_t)slots_) * stride_; }
     IngestBuffers& buffers() const;
 
+    int slots_ = kSlots;
     size_t chunk_ = kChunk, carry_ = kCarry;
     size_t stride_ = 0;      // carry + chunk + 256 (room for an appended newline; keeps slot bases 16-byte aligned)
     size_t line_cap_ = 0;    // newline positions kept per chunk
@@ -120,21 +127,22 @@ struct IngestBuffers {
     DeviceBuffer seq_off, seq_len;
     DeviceBuffer state;        // IngestState
     DeviceBuffer packed[2], lens[2], odd[2];
-    PinnedBuffer bounce[DeviceIngest::kSlots];
+    PinnedBuffer bounce[DeviceIngest::kMaxSlots];
     PinnedBuffer meta;
     // block-gzip input: the compressed members of the chunk in each slot, their table, the inflate kernels' error word
-    DeviceBuffer comp[DeviceIngest::kSlots], members[DeviceIngest::kSlots], inflate_errors;
-    PinnedBuffer members_host[DeviceIngest::kSlots];
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t copied[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };     // chunk text is in HBM
-    cudaEvent_t bounced[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };    // bounce buffer may be refilled
-    cudaEvent_t released[DeviceIngest::kSlots] = { nullptr, nullptr, nullptr };   // the parse no longer needs the slot's text
+    DeviceBuffer comp[DeviceIngest::kMaxSlots], members[DeviceIngest::kMaxSlots], inflate_errors;
+    PinnedBuffer members_host[DeviceIngest::kMaxSlots];
+    cudaStream_t copy_stream = nullptr;                                  // = copy_streams[0]
+    cudaStream_t copy_streams[DeviceIngest::kCopyStreams] = {};          // block-gzip chunks take them in turn
+    cudaEvent_t copied[DeviceIngest::kMaxSlots] = {};     // chunk text is in HBM
+    cudaEvent_t bounced[DeviceIngest::kMaxSlots] = {};    // bounce buffer may be refilled
+    cudaEvent_t released[DeviceIngest::kMaxSlots] = {};   // the parse no longer needs the slot's text
     cudaEvent_t meta_ready = nullptr;
-    bool released_valid[DeviceIngest::kSlots] = { false, false, false };
-    bool bounced_valid[DeviceIngest::kSlots] = { false, false, false };
+    bool released_valid[DeviceIngest::kMaxSlots] = {};
+    bool bounced_valid[DeviceIngest::kMaxSlots] = {};
     ~IngestBuffers();
-    void ensure(size_t chunk, size_t carry, size_t bounce_bytes);
-    void ensure_bgzf(size_t comp_bytes, size_t nmembers);
+    void ensure(size_t chunk, size_t carry, size_t bounce_bytes, int slots);
+    void ensure_bgzf(size_t comp_bytes, size_t nmembers, int slots);
 };
 
 // false when the device reader is switched off (environment SCG_HOST_PARSE=1): every input then takes the host parser.

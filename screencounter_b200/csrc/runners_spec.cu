@@ -774,9 +774,10 @@ int scg_random_plan_create(scg_ctx* ctx, const char* constant, int strand, int m
         plan->random = std::make_shared<RandomMatcher>();
         plan->random->prepare(constant, strand, mismatches, use_first != 0);
         c.ensure_ready();
-        // sized once for the distinct barcodes the caller expects: a load factor of at most 1/4 keeps 19 barcodes in 20 inside
-        // their home sector (the main kernel counts those on the spot); 0 = grow as the reference's map does
-        plan->table.init(c, plan->random->wide, expected_distinct > 0 ? (size_t)((plan->random->wide ? 2 : 4) * expected_distinct) : (size_t)1 << 20);
+        // sized once for the distinct barcodes the caller expects (load factor <= 1/2; a table twice the size keeps more barcodes
+        // inside their home sector but measured slower: its footprint costs more than the displaced keys do); 0 = grow as the
+        // reference's map does
+        plan->table.init(c, plan->random->wide, expected_distinct > 0 ? (size_t)(2 * expected_distinct) : (size_t)1 << 20);
         plan->table.fixed = expected_distinct > 0;
         SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         *out = plan.release();

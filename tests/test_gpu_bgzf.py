@@ -207,8 +207,11 @@ def test_paired_and_random_designs_read_block_gzip(gpu, kref, monkeypatch):
     r2 = adversarial_reads(rng, 3000, t2, [p2], strand="original", short_frac=0.0)
     f1, f2 = fastq(r1), fastq(r2)
     want = kref.count_combo_paired(f1, t1, False, 1, p1, f2, t2, False, 1, p2, False, True)
-    got = gpu.count_combo_paired(bgzf(f1, 7000), t1, False, 1, p1, f2, t2, False, 1, p2, False, True)
-    assert "inflated on the device" in rcpp.timing()["reader"]
-    assert len(got) == len(want)
-    for a, b in zip(want, got):
-        assert np.array_equal(np.asarray(a), np.asarray(b))
+    for chunk in (65536, None):
+        for g1, g2 in ((bgzf(f1, 7000), f2), (f1, bgzf(f2, 65280)), (bgzf(f1, 3000), bgzf(f2, 11000))):
+            _set(monkeypatch, chunk, 4096)
+            got = gpu.count_combo_paired(g1, t1, False, 1, p1, g2, t2, False, 1, p2, False, True)
+            assert rcpp.timing()["reader"].startswith("device"), rcpp.timing()   # (the line names the mate set up last)
+            assert len(got) == len(want)
+            for a, b in zip(want, got):
+                assert np.array_equal(np.asarray(a), np.asarray(b))

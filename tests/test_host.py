@@ -310,3 +310,36 @@ def test_block_gzip_edge_cases(tmp_path, monkeypatch):
     mixed = tmp_path / "mixed.fastq.gz"
     mixed.write_bytes(bgzf(good)[:-28] + gzip.compress(good))
     assert len(rcpp.host_pack_roundtrip(str(mixed), 4)) == 4
+
+
+def test_block_gzip_on_the_host(tmp_path):
+    """Host side of block gzip (csrc/bgzf.cpp): the library's compressor writes what gzip and the BGZF readers accept (members of at
+    most 64 KiB with their 'BC' size field, closed by the empty member), and the host reader takes such an image from a file or
+    from memory, inflating member-parallel, with the text's records."""
+    import gzip
+    import struct
+    from screencounter_b200 import rcpp
+    from util import bgzf
+    rng = np.random.default_rng(4)
+    reads = [mutate(rng, random_seq(rng, int(rng.integers(0, 200))), 0, 0.02, 0.05) for _ in range(20000)]
+    text = fastq(reads)
+    want = [_norm(s) for s in reads]
+    for level, block in ((6, 0), (1, 5000), (0, 65280)):
+        image = rcpp.bgzf_compress(text, level=level, block_text=block, nthreads=3).tobytes()
+        assert gzip.decompress(image) == text
+        at, members = 0, 0
+        while at < len(image):
+            assert image[at:at + 4] == b"\x1f\x8b\x08\x04" and image[at + 12:at + 16] == b"BC\x02\x00"
+            at += struct.unpack("<H", image[at + 16:at + 18])[0] + 1
+            members += 1
+        assert at == len(image) and members == -(-len(text) // (block or 65280)) + 1
+        assert image[-28:] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")   # bgzip's end-of-file marker
+        assert rcpp.host_pack_roundtrip(image, 3) == want               # an image in memory
+    path = tmp_path / "reads.fastq.gz"
+    path.write_bytes(bgzf(text, 30000))
+    assert rcpp.host_pack_roundtrip(str(path), 4) == want               # a file
+    assert gzip.decompress(rcpp.bgzf_compress(b"").tobytes()) == b""
+    damaged = bytearray(bgzf(text, 30000))
+    damaged[5000] ^= 0xFF
+    with pytest.raises(Exception, match="corrupt member"):
+        rcpp.host_pack_roundtrip(bytes(damaged), 2)

@@ -26,4 +26,4 @@ for fn, h in hist.items():
     if want not in fn:
         continue
     print("%s: %d instructions" % (fn, sum(h.values())))
-    print("   " + ", ".join("%s %d" % kv for kv in h.most_common(24)))
+    print("   " + ", ".join("%s %d" % kv for kv in h.most_common(48)))
