@@ -126,6 +126,18 @@ struct SlowList {
     uint32_t* list;
     uint32_t* count;
 };
+// Random barcodes of one launch sorted by the PART of the count table they live in (part = the top bits of the home slot): the
+// main kernel appends every barcode to the list of (part, warp) -- no atomics, one cursor per part in shared memory -- and a
+// second kernel counts the lists part by part, so that the slice of the table it works on (a few megabytes) stays in L2 and
+// HBM sees the table once per launch, sequentially, instead of one random 32-byte read-modify-write per read.
+struct PartitionedKeys {
+    unsigned long long* keys;   // region r = part * nwarps + warp holds keys[r * cap .. r * cap + counts[r])
+    uint32_t* counts;           // [nparts * nwarps]
+    uint32_t cap;               // keys per region (a region that runs over sends its keys straight to the table)
+    uint32_t nwarps;
+    uint32_t shift;             // part of a key = home slot >> shift
+    uint32_t nparts;            // <= 32
+};
 // Exact table of the dual paired-end design for keys of up to 48 bases (both variable regions concatenated): a two-table
 // cuckoo hash of 16-byte slots (H bits 0..31, L bits 0..31, H bits 32..47 | L bits 32..47 << 16, pool row; empty = row -1).
 // Table 1 holds 1 << (32 - shift) slots, table 2 the next as many.

@@ -278,6 +278,62 @@ __global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, Co
     if (lane == 0 && fresh) atomicAdd(table.live, fresh);
 }
 
+// countRandomBarcodes, partitioned (libdev.hpp PartitionedKeys): the lists of table part 0 are counted first, then part 1's, ...
+// -- regions are numbered part-major and the warps take them in that order, so at any moment the kernel works on one or two
+// parts of the table, which stay in L2: the random traffic of the inserts never reaches HBM.  Four keys per lane in flight.
+__global__ void __launch_bounds__(256) random_count_parts_kernel(PartitionedKeys parts, CountTable64 table) {
+    constexpr int U = 4;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t regions = parts.nparts * parts.nwarps;
+    unsigned long long fresh = 0;
+    for (uint32_t r = warp; r < regions; r += nwarps) {
+        const uint32_t cnt = parts.counts[r];
+        const unsigned long long* __restrict__ list = parts.keys + (size_t)r * parts.cap;
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32 * U) {
+            unsigned long long key[U], pos[U], seen[U];
+            bool valid[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t e = e0 + 32 * u + lane;
+                valid[u] = e < cnt;
+                key[u] = valid[u] ? __ldcs(list + e) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pos[u] = count_home(table, key[u]);
+                seen[u] = valid[u] ? __ldcg(&table.slots[pos[u]].key) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (valid[u] && seen[u] == ~0ull) {
+                    const unsigned long long old = atomicCAS(&table.slots[pos[u]].key, ~0ull, key[u]);
+                    if (old == ~0ull) {
+                        ++fresh;
+                        seen[u] = key[u];
+                    } else {
+                        seen[u] = old;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!valid[u]) continue;
+                if (seen[u] == key[u]) {
+                    atomicAdd(&table.slots[pos[u]].count, 1u);
+                } else {
+                    const unsigned long long next = (pos[u] + 1) & table.mask;
+                    if (count_insert64_from(table, key[u], 1u, next, __ldcg(&table.slots[next].key))) ++fresh;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) fresh += __shfl_xor_sync(0xFFFFFFFFu, fresh, d);
+    if (lane == 0 && fresh) atomicAdd(table.live, fresh);
+}
+
 namespace {
 
 // ---- program text of a specialised handler kernel ----
@@ -355,9 +411,10 @@ JitProgram combo_program(const TemplateSpec& t, const ScanSpec& s, int mm, const
     return prog;
 }
 
-JitProgram random_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index) {
+JitProgram random_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index, int partitioned) {
     std::ostringstream src;
     common_macros(src, 3, 8, 2, use_first, has_index);
+    src << "#define SPH_PARTITIONED " << partitioned << "\n";
     template_macros(src, "A", t, s, mm, r);
     src << "#include \"spec_handlers.cuh\"\n";
     JitProgram prog;
@@ -587,6 +644,7 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     std::string why;
     const JitModule* mod = nullptr;
     int group = 2;
+    int nparts = 0;
     bool ok = !spec_disabled();
     if (!ok) why = "disabled by SCG_NO_SPEC_HANDLERS";
     if (ok && m.wide) {
@@ -596,7 +654,22 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     if (ok) ok = template_fits(m.tmpl, m.params.spec, reads, &why);
     if (ok) {
         group = jit_env_int("SCG_SPH_GROUP", 2, 1, 8);
-        mod = jit_module(random_program(m.tmpl, m.params.spec, m.params.max_mm, reads, m.params.use_first, out_index ? 1 : 0), ctx.device, &why);
+        // a table too large to live in L2 is filled part by part (libdev.hpp PartitionedKeys); SCG_RANDOM_PARTS = 0 / 2..32 overrides
+        const size_t table_bytes = tab.capacity * sizeof(CountSlot);
+        nparts = 0;
+        if (table_bytes > ((size_t)48 << 20)) {
+            nparts = 2;
+            while (nparts < 32 && table_bytes / (size_t)nparts > ((size_t)12 << 20)) nparts *= 2;
+        }
+        if (const char* env = std::getenv("SCG_RANDOM_PARTS")) {
+            const int want = std::atoi(env);
+            nparts = want <= 1 ? 0 : 2;
+            while (nparts && nparts < std::min(want, 32)) nparts *= 2;
+        }
+        while (nparts > 0 && (size_t)nparts * 2 > tab.capacity) nparts /= 2;
+        if (nparts < 2) nparts = 0;
+        mod = jit_module(random_program(m.tmpl, m.params.spec, m.params.max_mm, reads, m.params.use_first, out_index ? 1 : 0, nparts ? 1 : 0),
+                         ctx.device, &why);
     }
     if (!mod) {
         launch_random_generic(ctx, reads, m, tab, odd, odd_out, odd_count, out_index, ReadList{ nullptr, nullptr }, ctx.grid_for(ntiles), stream);
@@ -605,15 +678,38 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     }
     cudaKernel_t k = mod->kernels[0];
     const int grid = spec_grid(ctx, k, reads.n, group);
-    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, 2, stream);
+    // (the partitioned route keeps its key lists where the other route keeps its deferred entries: two words per read at most)
+    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, nparts ? 3 : 2, stream);
     SlowList slow = sc.slow;
     ReadsDev a = reads;
     CountTable64 t64 = tab.view64();
     long long read_offset = 0;
-    void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &sc.def, &slow };
+    PartitionedKeys parts{ nullptr, nullptr, 0, 0, 0, 0 };
+    if (nparts) {
+        // a warp's reads spread evenly over the parts (the part is a hash of the barcode): half as much again, and a margin
+        const unsigned long long per_warp = sc.def.per_warp;
+        parts.nwarps = sc.def.regions;
+        parts.nparts = (uint32_t)nparts;
+        parts.cap = (uint32_t)(per_warp / (unsigned)nparts + per_warp / (2u * (unsigned)nparts) + 64);
+        while ((unsigned long long)parts.cap * parts.nparts * parts.nwarps * 2 > 3ull * sc.def.stride && parts.cap > 64) parts.cap -= 1 + parts.cap / 64;
+        int log2cap = 0;
+        while (((size_t)1 << log2cap) < tab.capacity) ++log2cap;
+        int log2parts = 0;
+        while ((1 << log2parts) < nparts) ++log2parts;
+        parts.shift = (uint32_t)(log2cap - log2parts);
+        parts.keys = reinterpret_cast<unsigned long long*>(sc.def.words);
+        ctx.part_counts.reserve((size_t)parts.nparts * parts.nwarps * sizeof(uint32_t));
+        parts.counts = ctx.part_counts.as<uint32_t>();
+        SCG_CUDA_CHECK(cudaMemsetAsync(parts.counts, 0, (size_t)parts.nparts * parts.nwarps * sizeof(uint32_t), stream));
+    }
+    void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &sc.def, &slow, &parts };
     SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
-    // barcodes that were not in their home sector yet: inserted (or found further along) by the follow-up kernel
-    random_insert_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(sc.def, t64);
+    if (nparts) {
+        random_count_parts_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(parts, t64);
+    } else {
+        // barcodes that were not in their home sector yet: inserted (or found further along) by the follow-up kernel
+        random_insert_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(sc.def, t64);
+    }
     SCG_CUDA_CHECK(cudaGetLastError());
     ctx.launches += 2;
     ctx.timing.launches += 2;
@@ -621,9 +717,11 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
         // best mode: reads with several verified windows take the full scan (the minimum must be attained once)
         launch_random_generic(ctx, reads, m, tab, odd, odd_out, odd_count, out_index, ReadList{ slow.list, slow.count }, ctx.sm_count * 2, stream);
     }
-    ctx.kernel_note = "specialised (NVRTC) spec_random_kernel, filter+verify + 16-byte-slot count table (home sector requested a tile ahead), " +
-                      std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM; + random_insert_kernel (new and displaced barcodes)" +
-                      (m.params.use_first ? "" : " + random_kernel on the multi-window reads");
+    ctx.kernel_note = nparts ? "specialised (NVRTC) spec_random_kernel, filter+verify, barcodes listed by table part (" + std::to_string(nparts) + " parts), " +
+                                   std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM; + random_count_parts_kernel (16-byte-slot count table filled part by part in L2)"
+                             : "specialised (NVRTC) spec_random_kernel, filter+verify + 16-byte-slot count table (home sector requested a tile ahead), " +
+                                   std::to_string(specialised_blocks_per_sm(k)) + " blocks/SM; + random_insert_kernel (new and displaced barcodes)";
+    if (!m.params.use_first) ctx.kernel_note += " + random_kernel on the multi-window reads";
 }
 
 } // namespace scg
@@ -667,9 +765,9 @@ int scg_jit_selftest_handler(int kind, const char* constant_a, int strand_a, int
         } else if (kind == 2) {
             if (ta.fwd_regions.size() != 2) throw Error("expected 2 variable regions in the constant template");
             prog = combo_program(ta, sa, mismatches_a, fake, use_first, 1);
-        } else if (kind == 3) {
+        } else if (kind == 3 || kind == 4) {   // 4 = the variant that lists the barcodes by table part
             if (ta.fwd_regions.empty()) throw Error("expected at least one variable region in the constant template");
-            prog = random_program(ta, sa, mismatches_a, fake, use_first, 1);
+            prog = random_program(ta, sa, mismatches_a, fake, use_first, 1, kind == 4 ? 1 : 0);
         } else {
             throw Error("unknown handler kind");
         }

@@ -29,6 +29,9 @@
 #include "count_table.cuh"
 #include "spec_scan.cuh"
 
+#ifndef SPH_PARTITIONED
+#define SPH_PARTITIONED 0
+#endif
 #ifndef SPH_A_FSTART1
 #define SPH_A_FSTART1 0
 #define SPH_A_FLEN1 1
@@ -467,7 +470,7 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
 extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     spec_random_kernel(const scg::ReadsDev reads, const scg::CountTable64 table, const uint8_t* __restrict__ odd, long long read_offset,
                        scg::OddOutcome* __restrict__ odd_out, unsigned long long* __restrict__ odd_count, int32_t* __restrict__ out_index,
-                       const scg::DeferredList def, const scg::SlowList slow) {
+                       const scg::DeferredList def, const scg::SlowList slow, const scg::PartitionedKeys parts) {
     using namespace scg;
     using namespace scg::sph;
     using DA = Dims<TrA>;
@@ -477,6 +480,9 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     constexpr uint32_t BYTES_A = GROUP * DA::TILE_BYTES;
     __shared__ __align__(128) uint32_t stage_a[WARPS][STAGES][GROUP * DA::TILE_WORDS];
     __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
+#if SPH_PARTITIONED
+    __shared__ uint32_t part_cursor[WARPS][32];   // keys this warp has appended to each part's list
+#endif
 
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -492,6 +498,9 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
         for (int s = 0; s < STAGES; ++s) mbar_init(bar_base + 8u * s, 1);
         fence_barrier_init();
     }
+#if SPH_PARTITIONED
+    part_cursor[wib][lane] = 0;
+#endif
     __syncwarp();
     const uint64_t policy = evict_first_policy();
     auto fetch = [&](int g, uint32_t stage) {
@@ -572,6 +581,28 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             key = random_key64(kh, kl, kn);
         }
 
+#if SPH_PARTITIONED
+        // ---- this tile's barcodes go to the lists of the table parts they live in (libdev.hpp PartitionedKeys): lanes with
+        // the same part line up behind that part's cursor; nothing here touches the table ----
+        {
+            const uint32_t part = insert ? (uint32_t)(count_home(table, key) >> parts.shift) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, part);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            const uint32_t base = insert ? part_cursor[wib][part] : 0u;
+            __syncwarp();
+            if (insert) {
+                if (rank == 0) part_cursor[wib][part] = base + __popc(peers);
+                const uint32_t at = base + rank;
+                if (at < parts.cap) {
+                    __stcs(parts.keys + ((size_t)part * parts.nwarps + warp) * parts.cap + at, key);
+                } else {
+                    count_insert64(table, key, 1u);   // the list is full (a very uneven batch): straight to the table
+                }
+            }
+            __syncwarp();
+        }
+        if (!have) break;
+#else
         // ---- count the PREVIOUS tile's barcodes: their homes were requested one scan ago.  A barcode found in its home
         // sector is counted with one fire-and-forget atomic; one that is not there yet (new, or pushed further along by a
         // collision) goes to the deferred list and the follow-up kernel inserts it -- no compare-and-swap round trip, no
@@ -596,6 +627,7 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
         }
 
         if (!have) break;
+#endif
         if (tile_in_group == tiles_here) {
             group += nwarps;
             tile_in_group = 0;
@@ -610,6 +642,11 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             }
         }
     }
+#if SPH_PARTITIONED
+    if ((uint32_t)lane < parts.nparts) parts.counts[(size_t)lane * parts.nwarps + warp] = min(part_cursor[wib][lane], parts.cap);
+    (void)pa; (void)pb; (void)ppos; (void)pkey; (void)pinsert; (void)region_base; (void)cursor;
+#else
     if (lane == 0) def.warp_counts[warp] = cursor;
+#endif
 }
 #endif  // SPH_KIND == 3

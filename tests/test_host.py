@@ -209,6 +209,8 @@ F12, R12 = "CAGCTACGTACG", "CCAGCTCGATCG"
     (3, F12 + "-" * 16 + R12, 2, 1, "", 0, 0, 75, 1),                                           # BASELINE configs[4]
     (3, F12 + "-" * 16 + "CCAGCTCG", 2, 1, "", 0, 0, 75, 0),                                    # asymmetric flanks (Quirk B), best mode
     (3, F12 + "-" * 21 + R12, 0, 0, "", 0, 0, 101, 1),
+    (4, F12 + "-" * 16 + R12, 2, 1, "", 0, 0, 75, 1),                                           # the same, barcodes listed by table part
+    (4, F12 + "-" * 9 + R12, 1, 0, "", 0, 0, 150, 0),
 ])
 def test_handler_kernels_compile(kind, a, strand_a, mm_a, b, strand_b, mm_b, read_len, use_first):
     """The specialised dual / combinatorial / random-barcode kernels (spec_handlers.cuh) through NVRTC, without a device."""
