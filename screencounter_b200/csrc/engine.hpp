@@ -113,6 +113,7 @@ struct Context {
     DeviceBuffer slow_list, slow_count;      // reads a specialised kernel hands to its full-search follow-up (spec_single.cuh, spec_handlers.cuh)
     DeviceBuffer defer_words, defer_counts;  // per-warp regions of deferred lookups (libdev.hpp DeferredList)
     DeviceBuffer part_counts;                // keys per (table part, warp) of a partitioned random-barcode launch (libdev.hpp PartitionedKeys)
+    DeviceBuffer part_keys;                  // ... and the lists themselves
     std::shared_ptr<IngestBuffers> ingest[2];   // text ring, line tables and streams of the device-side FASTQ reader, per mate
     int device = 0;
     bool ready = false;

@@ -590,7 +590,7 @@ void count_random_core(scg_ctx* ctx, const scg_source* src, const char* constant
 
         c.ensure_ready();
         CountTable tab;
-        tab.init(c, wide, 1u << 20);
+        tab.init(c, wide, wide ? (1u << 20) : (1u << 23));   // 8 M slots (128 MB) to start with: a few million distinct barcodes need no rehash
         DeviceBuffer d_odd_out, d_odd_count;
         d_odd_count.alloc(sizeof(unsigned long long), true);
         std::map<std::string, int> extra;   // keys of reads that need their raw text

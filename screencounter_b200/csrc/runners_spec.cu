@@ -224,6 +224,59 @@ __global__ void __launch_bounds__(128) combo_deferred_kernel(DeferredList def, C
 // pushed further along -- inserted (or found) with the full probing loop.  Every entry is independent of every other, so the
 // compare-and-swap round trips of thousands of lanes overlap; new keys are added up per warp before they reach the
 // table's counter of distinct keys.
+// U barcodes per lane through the count table at once: the two slots of every barcode's home sector are requested together
+// (bucketised linear probing, count_table.cuh), then the sector's slots are visited in probing order -- a match is counted, an
+// empty slot claimed by compare-and-swap (the claims of the U barcodes overlap) -- and only a barcode whose home sector is taken
+// by two others walks on, slot by slot.  Returns the number of new keys this lane inserted.
+template <int U>
+__device__ __forceinline__ unsigned int count_batch(const CountTable64& table, const unsigned long long (&key)[U], const bool (&valid)[U]) {
+    unsigned long long pos[U], ka[U], kb[U];
+    int at[U];   // -1: not settled yet, 0 / 1: the barcode's slot is home + 0 / 1
+    unsigned int fresh = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        pos[u] = count_home(table, key[u]);
+        ka[u] = valid[u] ? __ldcg(&table.slots[pos[u]].key) : 0ull;
+        kb[u] = valid[u] ? __ldcg(&table.slots[pos[u] + 1].key) : 0ull;
+        at[u] = -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        if (ka[u] == ~0ull) {
+            ka[u] = atomicCAS(&table.slots[pos[u]].key, ~0ull, key[u]);
+            if (ka[u] == ~0ull) {
+                ++fresh;
+                ka[u] = key[u];
+            }
+        }
+        if (ka[u] == key[u]) at[u] = 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u] || at[u] >= 0) continue;
+        if (kb[u] == ~0ull) {
+            kb[u] = atomicCAS(&table.slots[pos[u] + 1].key, ~0ull, key[u]);
+            if (kb[u] == ~0ull) {
+                ++fresh;
+                kb[u] = key[u];
+            }
+        }
+        if (kb[u] == key[u]) at[u] = 1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        if (at[u] >= 0) {
+            atomicAdd(&table.slots[pos[u] + (unsigned)at[u]].count, 1u);
+        } else {
+            const unsigned long long next = (pos[u] + 2) & table.mask;
+            if (count_insert64_from(table, key[u], 1u, next, __ldcg(&table.slots[next].key))) ++fresh;
+        }
+    }
+    return fresh;
+}
+
 __global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, CountTable64 table) {
     constexpr int U = 4;   // entries per lane in flight: their slot loads, then their compare-and-swaps, overlap
     const int lane = threadIdx.x & 31;
@@ -234,7 +287,7 @@ __global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, Co
         const uint32_t cnt = def.warp_counts[r];
         const unsigned long long base = (unsigned long long)r * def.per_warp;
         for (uint32_t e0 = 0; e0 < cnt; e0 += 32 * U) {
-            unsigned long long key[U], pos[U], seen[U];
+            unsigned long long key[U];
             bool valid[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -242,35 +295,8 @@ __global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, Co
                 valid[u] = e < cnt;
                 key[u] = valid[u] ? ((unsigned long long)def.words[base + e] | ((unsigned long long)def.words[def.stride + base + e] << 32)) : 0ull;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                pos[u] = count_home(table, key[u]);
-                seen[u] = valid[u] ? __ldcg(&table.slots[pos[u]].key) : 0ull;
-            }
-            // an empty home: claim it (the answers of the U claims arrive together)
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (valid[u] && seen[u] == ~0ull) {
-                    const unsigned long long old = atomicCAS(&table.slots[pos[u]].key, ~0ull, key[u]);
-                    if (old == ~0ull) {
-                        ++fresh;
-                        seen[u] = key[u];
-                    } else {
-                        seen[u] = old;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!valid[u]) continue;
-                if (seen[u] == key[u]) {
-                    atomicAdd(&table.slots[pos[u]].count, 1u);
-                } else {
-                    // someone else's key sits there: along the probe sequence
-                    const unsigned long long next = (pos[u] + 1) & table.mask;
-                    if (count_insert64_from(table, key[u], 1u, next, __ldcg(&table.slots[next].key))) ++fresh;
-                }
-            }
+            fresh += count_batch<U>(table, key, valid);
+            __syncwarp();
         }
     }
 #pragma unroll
@@ -292,7 +318,7 @@ __global__ void __launch_bounds__(256) random_count_parts_kernel(PartitionedKeys
         const uint32_t cnt = parts.counts[r];
         const unsigned long long* __restrict__ list = parts.keys + (size_t)r * parts.cap;
         for (uint32_t e0 = 0; e0 < cnt; e0 += 32 * U) {
-            unsigned long long key[U], pos[U], seen[U];
+            unsigned long long key[U];
             bool valid[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -300,33 +326,8 @@ __global__ void __launch_bounds__(256) random_count_parts_kernel(PartitionedKeys
                 valid[u] = e < cnt;
                 key[u] = valid[u] ? __ldcs(list + e) : 0ull;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                pos[u] = count_home(table, key[u]);
-                seen[u] = valid[u] ? __ldcg(&table.slots[pos[u]].key) : 0ull;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (valid[u] && seen[u] == ~0ull) {
-                    const unsigned long long old = atomicCAS(&table.slots[pos[u]].key, ~0ull, key[u]);
-                    if (old == ~0ull) {
-                        ++fresh;
-                        seen[u] = key[u];
-                    } else {
-                        seen[u] = old;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!valid[u]) continue;
-                if (seen[u] == key[u]) {
-                    atomicAdd(&table.slots[pos[u]].count, 1u);
-                } else {
-                    const unsigned long long next = (pos[u] + 1) & table.mask;
-                    if (count_insert64_from(table, key[u], 1u, next, __ldcg(&table.slots[next].key))) ++fresh;
-                }
-            }
+            fresh += count_batch<U>(table, key, valid);
+            __syncwarp();   // lanes that walked a probe sequence rejoin here: the warp stays on one part of the table
         }
     }
 #pragma unroll
@@ -679,7 +680,7 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     cudaKernel_t k = mod->kernels[0];
     const int grid = spec_grid(ctx, k, reads.n, group);
     // (the partitioned route keeps its key lists where the other route keeps its deferred entries: two words per read at most)
-    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, nparts ? 3 : 2, stream);
+    Scratch sc = prepare_scratch(ctx, reads.n, grid, group, nparts ? 0 : 2, stream);
     SlowList slow = sc.slow;
     ReadsDev a = reads;
     CountTable64 t64 = tab.view64();
@@ -691,13 +692,13 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
         parts.nwarps = sc.def.regions;
         parts.nparts = (uint32_t)nparts;
         parts.cap = (uint32_t)(per_warp / (unsigned)nparts + per_warp / (2u * (unsigned)nparts) + 64);
-        while ((unsigned long long)parts.cap * parts.nparts * parts.nwarps * 2 > 3ull * sc.def.stride && parts.cap > 64) parts.cap -= 1 + parts.cap / 64;
+        ctx.part_keys.reserve((size_t)parts.cap * parts.nparts * parts.nwarps * sizeof(unsigned long long));
         int log2cap = 0;
         while (((size_t)1 << log2cap) < tab.capacity) ++log2cap;
         int log2parts = 0;
         while ((1 << log2parts) < nparts) ++log2parts;
         parts.shift = (uint32_t)(log2cap - log2parts);
-        parts.keys = reinterpret_cast<unsigned long long*>(sc.def.words);
+        parts.keys = ctx.part_keys.as<unsigned long long>();
         ctx.part_counts.reserve((size_t)parts.nparts * parts.nwarps * sizeof(uint32_t));
         parts.counts = ctx.part_counts.as<uint32_t>();
         SCG_CUDA_CHECK(cudaMemsetAsync(parts.counts, 0, (size_t)parts.nparts * parts.nwarps * sizeof(uint32_t), stream));
@@ -705,7 +706,14 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     void* args[] = { &a, &t64, &odd, &read_offset, &odd_out, &odd_count, &out_index, &sc.def, &slow, &parts };
     SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
     if (nparts) {
-        random_count_parts_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(parts, t64);
+        // exactly the blocks that are resident together: every warp then walks the parts in the same order at the same pace, and
+        // the slices of the table pass through L2 one after the other
+        static int blocks_per_sm = 0;
+        if (blocks_per_sm == 0) {
+            SCG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, random_count_parts_kernel, 256, 0));
+            blocks_per_sm = std::max(1, blocks_per_sm);
+        }
+        random_count_parts_kernel<<<ctx.sm_count * blocks_per_sm, 256, 0, stream>>>(parts, t64);
     } else {
         // barcodes that were not in their home sector yet: inserted (or found further along) by the follow-up kernel
         random_insert_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(sc.def, t64);
