@@ -838,13 +838,26 @@ def main():
         bgzf_line = {"value": e2e_units * world * e2e_steps / float(gz_dt.item()), "unit": wl.unit,
                      "h2d_bytes_per_step": int(gz_stage.get("bytes_h2d", 0)),
                      "text_bytes_per_step": int(sum(t.size for t in texts)), "image_bytes": int(sum(i.size for i in images)),
-                     "reader": gz_stage.get("reader"), "stages_s": {k: gz_stage.get(k) for k in ("device_s", "setup_s", "harvest_s", "total_s")},
+                     "reader": gz_stage.get("reader"),
+                     "stages_s": {k: gz_stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "harvest_s", "total_s")},
                      "note": "same reads, same call; input = bgzip-style image (zlib level 6, 65280-byte members, compressed here on %d host "
                              "threads in %.1f s, outside the timed region) in page-locked memory; result asserted equal to the text's" % (nthreads, compress_s)}
         del images
     d2h = wl.d2h_bytes()
     if d2h is None:
         d2h = int(sum(np.asarray(x).nbytes for x in e2e_result[:2]))
+    # The headline end-to-end figure is the block-gzip one: .fastq.gz is what FASTQ is on disk, and the compressed image is what
+    # has to cross PCIe (a sixth of the text here).  The raw-text figure stays beside it.
+    raw_line = {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)), "reader": stage.get("reader"),
+                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "harvest_s", "total_s")},
+                "note": "same reads, same call; input = the FASTQ text itself in page-locked memory"}
+    if bgzf_line is not None:
+        e2e_head = {"value": bgzf_line["value"], "unit": wl.unit, "h2d_bytes_per_step": bgzf_line["h2d_bytes_per_step"],
+                    "input": "block-gzip image of the FASTQ text (bgzip layout, zlib level 6) in page-locked host memory",
+                    "reader": bgzf_line["reader"], "stages_s": bgzf_line["stages_s"]}
+    else:
+        e2e_head = {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
+                    "input": "FASTQ text in page-locked host memory", "reader": stage.get("reader"), "stages_s": raw_line["stages_s"]}
 
     if rank != 0:
         if world > 1:
@@ -887,16 +900,15 @@ def main():
                           % (resident_bytes / 1e6)) if need_flush else
                          ("inputs (%.1f GB packed per GPU) are larger than the 126 MB L2; no flush needed" % (resident_bytes / 1e9)),
                    "matched_fraction": matched_per_pass / units},
-        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": int(stage.get("bytes_h2d", 0)),
-                "d2h_bytes_per_step": int(d2h), "%s_per_step" % what: e2e_units, "host_threads": nthreads,
-                "stages_s": {k: stage.get(k) for k in ("parse_s", "pack_s", "device_s", "setup_s", "harvest_s", "total_s")},
-                "reader": stage.get("reader"), "kernel": stage.get("kernel"), "cpu_binding": binding, "block_gzip": bgzf_line,
+        "e2e": {**e2e_head, "d2h_bytes_per_step": int(d2h), "%s_per_step" % what: e2e_units, "host_threads": nthreads,
+                "kernel": stage.get("kernel"), "cpu_binding": binding, "raw_text": raw_line, "block_gzip": bgzf_line,
                 "cold": {"value": e2e_units / cold_s, "unit": wl.unit, "seconds": cold_s, "setup_s": cold_stage.get("setup_s"),
                          "note": "first call of this process on this design: library tables built + uploaded, kernels specialised (on-disk "
                                  "cubin cache or NVRTC), buffers allocated; the CUDA context already existed.  The reference arm rebuilds its "
                                  "libraries on every call; `value` above is our steady state (tables and kernels cached)"},
-                "note": "FASTQ text in page-locked host memory -> file-level C-ABI call: text H2D in 32 MiB chunks, records split + packed "
-                        "by kernels (ingest.cu), scan/lookup/count kernels per chunk, result D2H; wall clock around the calls"},
+                "note": "input in page-locked host memory -> file-level C-ABI call: compressed members (or text) H2D chunk by chunk, members "
+                        "inflated + CRC-checked by kernels (inflate.cu), records split + packed by kernels (ingest.cu), scan/lookup/count kernels "
+                        "per chunk, result D2H; wall clock around the calls"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": kernel_name, "bytes_per_unit": wl.bytes_per_unit, "units_per_pass": units,
                      "kernel_ms_per_pass": kernel_ms_per_pass, "kernel_launches_per_pass": launches_per_pass, "peak_source": peak_src,

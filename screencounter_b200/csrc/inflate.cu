@@ -34,8 +34,10 @@ constexpr uint32_t STAGE_BYTES = 2048;   // text assembled per batch at most; a 
 
 // table entry (16 bits, so that a warp's tables stay under 3 KiB and 32 warps fit an SM): value << 6 | kind << 4 | code length,
 // value = the literal byte, or the index of the length / distance symbol (base and extra bits come from the constant arrays).
-// 0 = no such code.
-constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_END = 2, K_LONG = 3;
+// Everything that is not a plain literal or match is K_SPECIAL, told apart off the hot path: code length 0 with value 1 = a code
+// longer than the table (bit-by-bit walk), code length 0 with value 0 = no such code, otherwise the end-of-block code.
+constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_SPECIAL = 2;
+constexpr uint32_t E_INVALID = K_SPECIAL << 4, E_LONG = (1u << 6) | (K_SPECIAL << 4);
 using Entry = uint16_t;
 
 struct WarpTables {
@@ -59,12 +61,12 @@ __constant__ uint8_t c_clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 
 // what a code of `len` bits for `sym` stands for, as a table entry (0 = a symbol the format does not define)
 __device__ __forceinline__ uint32_t lit_entry(int sym, int len) {
     if (sym < 256) return ((uint32_t)sym << 6) | (K_LITERAL << 4) | (uint32_t)len;
-    if (sym == 256) return (K_END << 4) | (uint32_t)len;
-    if (sym > 285) return 0u;
+    if (sym == 256) return (K_SPECIAL << 4) | (uint32_t)len;
+    if (sym > 285) return E_INVALID;
     return ((uint32_t)(sym - 257) << 6) | (K_MATCH << 4) | (uint32_t)len;
 }
 __device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
-    if (sym > 29) return 0u;
+    if (sym > 29) return E_INVALID;
     return ((uint32_t)sym << 6) | (K_MATCH << 4) | (uint32_t)len;
 }
 // code-length alphabet: the symbol itself is the value
@@ -75,7 +77,7 @@ __device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint
 template <int KIND, int TBITS>
 __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
                             int lane) {
-    for (int i = lane; i < (1 << TBITS); i += 32) table[i] = 0;
+    for (int i = lane; i < (1 << TBITS); i += 32) table[i] = (Entry)(KIND == 2 ? 0u : E_INVALID);
     if (lane < 16) count[lane] = 0;
     __syncwarp();
     for (int s = lane; s < n; s += 32) {
@@ -112,7 +114,7 @@ __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* 
                 const uint32_t e = KIND == 0 ? lit_entry(s, l) : (KIND == 1 ? dist_entry(s, l) : clen_entry(s, l));
                 for (uint32_t k = r; k < (1u << TBITS); k += (1u << l)) table[k] = (Entry)e;
             } else {
-                table[r & ((1u << TBITS) - 1u)] = (Entry)(K_LONG << 4);
+                table[r & ((1u << TBITS) - 1u)] = (Entry)E_LONG;
             }
         }
         __syncwarp();
@@ -348,35 +350,41 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                 for (; nsym < 32 && staged <= STAGE_BYTES - 258; ++nsym) {
                     br.refill();
                     uint32_t e = T.lit[br.peek(LIT_BITS)];
-                    if (((e >> 4) & 3u) == K_LONG) {
-                        int sym = 0, len = 0;
-                        e = slow_symbol(br.bits, T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : 0u;
-                    }
-                    if ((e & 0xFu) == 0) {
-                        bad = true;
-                        break;
+                    if (((e >> 4) & 3u) == K_SPECIAL) {
+                        // off the hot path: a code longer than the table, the end of the block, or no code at all
+                        if (e == E_LONG) {
+                            int sym = 0, len = 0;
+                            e = slow_symbol(br.bits, T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : E_INVALID;
+                        }
+                        if (((e >> 4) & 3u) == K_SPECIAL) {
+                            if ((e & 0xFu) == 0) {
+                                bad = true;
+                            } else {
+                                br.drop((int)(e & 0xFu));
+                                end_of_block = true;
+                            }
+                            break;
+                        }
                     }
                     br.drop((int)(e & 0xFu));
-                    const uint32_t kind = (e >> 4) & 3u;
                     uint32_t sym;
-                    if (kind == K_LITERAL) {
+                    if (((e >> 4) & 3u) == K_LITERAL) {
                         sym = 0x80010000u | (e >> 6);
                         staged += 1;
-                    } else if (kind == K_END) {
-                        end_of_block = true;
-                        break;
                     } else {
                         const uint32_t li = e >> 6;
                         const uint32_t len = (uint32_t)c_len_base[li] + br.take((int)c_len_extra[li]);
                         br.refill();
                         uint32_t d = T.dist[br.peek(DIST_BITS)];
-                        if (((d >> 4) & 3u) == K_LONG) {
-                            int dsym = 0, dlen = 0;
-                            d = slow_symbol(br.bits, T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : 0u;
-                        }
-                        if ((d & 0xFu) == 0) {
-                            bad = true;
-                            break;
+                        if (((d >> 4) & 3u) == K_SPECIAL) {
+                            if (d == E_LONG) {
+                                int dsym = 0, dlen = 0;
+                                d = slow_symbol(br.bits, T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : E_INVALID;
+                            }
+                            if (((d >> 4) & 3u) == K_SPECIAL) {
+                                bad = true;
+                                break;
+                            }
                         }
                         br.drop((int)(d & 0xFu));
                         const uint32_t di = d >> 6;

@@ -189,36 +189,43 @@ __global__ void __launch_bounds__(kBlockThreads) scatter_newlines(const uint8_t*
     }
 }
 
-// pass 4: conditions (a)-(d) for every group of four lines; sequence offsets and lengths
+// pass 4: conditions (a)-(d) for every group of four lines; sequence offsets and lengths; shortest and longest sequence among
+// the groups that are records (a superset of the records finish_chunk accepts when one of them fails: the batch is then
+// treated as ragged at worst, never wrongly as uniform)
 __global__ void __launch_bounds__(256) validate_records(const uint8_t* __restrict__ ring, const uint32_t* __restrict__ lines, IngestState* st,
                                                         uint32_t* __restrict__ seq_off, uint16_t* __restrict__ seq_len) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= st->nrec) return;
-    const uint32_t e0 = lines[4 * r], e1 = lines[4 * r + 1], e2 = lines[4 * r + 2], e3 = lines[4 * r + 3];
-    const uint32_t start = r ? lines[4 * r - 1] + 1 : st->begin;
-    const uint32_t s = e0 + 1, len = e1 - s, qlen = e3 - (e2 + 1);
-    bool ok = ring[start] == '@' && ring[e1 + 1] == '+' && qlen == len && len <= (uint32_t)MAX_READ_LEN;
-    if (ok) {
-        for (uint32_t k = 0; k < len; ++k) {
-            if (ring[s + k] == '+') {
-                ok = false;
-                break;
+    const bool active = r < st->nrec;
+    bool ok = false;
+    uint32_t len = 0;
+    if (active) {
+        const uint32_t e0 = lines[4 * r], e1 = lines[4 * r + 1], e2 = lines[4 * r + 2], e3 = lines[4 * r + 3];
+        const uint32_t start = r ? lines[4 * r - 1] + 1 : st->begin;
+        const uint32_t s = e0 + 1, qlen = e3 - (e2 + 1);
+        len = e1 - s;
+        ok = ring[start] == '@' && ring[e1 + 1] == '+' && qlen == len && len <= (uint32_t)MAX_READ_LEN;
+        if (ok && len) {
+            // a '+' anywhere in the sequence line: four bytes at a time over the aligned words that hold it, the bytes in front of
+            // and behind the line made harmless first (the zero-byte test is exact for "does any byte match")
+            const uint32_t lead = s & 3u, nwords = (lead + len + 3u) / 4u;
+            const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(ring + (s - lead));
+            uint32_t found = 0;
+            for (uint32_t k = 0; k < nwords; ++k) {
+                uint32_t v = w[k];
+                if (k == 0 && lead) v |= (1u << (8u * lead)) - 1u;
+                const uint32_t upto = lead + len - 4u * k;   // bytes of this word that belong to the line (>= 1)
+                if (upto < 4u) v |= 0xFFFFFFFFu << (8u * upto);
+                const uint32_t t = v ^ 0x2B2B2B2Bu;
+                found |= (t - 0x01010101u) & ~t & 0x80808080u;
             }
+            ok = found == 0;
         }
+        seq_off[r] = s;
+        seq_len[r] = (uint16_t)(ok ? len : 0u);
+        if (!ok) atomicMin(&st->bad_rec, r);
     }
-    seq_off[r] = s;
-    seq_len[r] = (uint16_t)(ok ? len : 0u);
-    if (!ok) atomicMin(&st->bad_rec, r);
-}
-
-// pass 5: shortest and longest sequence among the accepted records
-__global__ void __launch_bounds__(256) record_extent(const uint16_t* __restrict__ seq_len, IngestState* st) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = min(st->nrec, st->bad_rec);
-    uint32_t lo = 0xFFFFFFFFu, hi = 0;
-    if (r < n) lo = hi = seq_len[r];
-    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, ok ? len : 0xFFFFFFFFu);
+    const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, ok ? len : 0u);
     if ((threadIdx.x & 31) == 0 && lo != 0xFFFFFFFFu) {
         atomicMin(&st->min_len, lo);
         atomicMax(&st->max_len, hi);
@@ -289,26 +296,45 @@ __global__ void __launch_bounds__(128) pack_records_dev(const uint8_t* __restric
         seq_len[r] = 0;   // the length array is padded to whole tiles like the host packer's
     }
     uint32_t* base = out + (size_t)warp * 3 * W * TILE + lane;
-    bool plain = true;   // only upper-case A, C, G, T, N (what the random-barcode handler can take from the packed form)
+    // Four bases per step: the sequence is read as the aligned 32-bit words that hold it (funnel-shifted into place), the
+    // per-byte tests run on all four bytes of a word at once, and a multiply gathers one bit per byte into four adjacent bits.
+    const uint32_t lead = (uint32_t)(reinterpret_cast<size_t>(s) & 3u);
+    const uint32_t* __restrict__ aligned = reinterpret_cast<const uint32_t*>(s - lead);
+    const uint32_t shift = 8u * lead;
+    uint32_t not_plain = 0;   // bytes that are not upper-case A, C, G, T or N (what the random-barcode handler cannot render)
+    uint32_t lo = aligned[0];
     for (int w = 0; w < W; ++w) {
         uint32_t hh = 0, ll = 0, nn = 0;
         const int first = 32 * w;
         const int cnt = (int)len > first ? min(32, (int)len - first) : 0;
-        for (int j = 0; j < cnt; ++j) {
-            const uint32_t c = s[first + j];
-            const uint32_t u = c & 0xDFu;   // fold case: only X and x map to X
-            const bool valid = u == 'A' || u == 'C' || u == 'G' || u == 'T';
-            plain = plain && ((valid && c == u) || c == 'N');
+        for (int j = 0; j < cnt; j += 4) {
+            const uint32_t hi = aligned[(first + j) / 4 + 1];
+            const uint32_t v = shift ? __funnelshift_r(lo, hi, shift) : lo;   // bases first + j .. first + j + 3
+            lo = hi;
+            const uint32_t keep = cnt - j >= 4 ? 0xFFFFFFFFu : ((1u << (8u * (uint32_t)(cnt - j))) - 1u);
+            const uint32_t u = v & 0xDFDFDFDFu;   // fold case
+            // byte == K, exactly, for all four bytes: high bit of (((t & 0x7f..) + 0x7f..) | t) is set iff the byte of t is non-zero
+            auto equals = [](uint32_t x, uint32_t k) {
+                const uint32_t t = x ^ (k * 0x01010101u);
+                return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+            };
+            const uint32_t acgt = equals(u, 'A') | equals(u, 'C') | equals(u, 'G') | equals(u, 'T');   // 0x80 per valid byte
+            const uint32_t valid = (acgt >> 7) & keep;                                                 // 0x01 per valid byte
+            if (odd) {
+                const uint32_t upper = equals(v, 'A') | equals(v, 'C') | equals(v, 'G') | equals(v, 'T') | equals(v, 'N');
+                not_plain |= ~(upper >> 7) & 0x01010101u & keep;
+            }
             // ASCII: bit 2 of A/C/G/T (either case) is 0/0/1/1 = plane H, bit 1 is 0/1/1/0, so L = bit 1 ^ bit 2
-            const uint32_t hb = (c >> 2) & 1u, lb = ((c >> 1) ^ (c >> 2)) & 1u;
-            hh |= (valid ? hb : 0u) << j;
-            ll |= (valid ? lb : 0u) << j;
-            nn |= (valid ? 0u : 1u) << j;
+            const uint32_t hb = (v >> 2) & valid, lb = ((v >> 1) ^ (v >> 2)) & valid, nb = ~valid & 0x01010101u & keep;
+            hh |= ((hb * 0x01020408u) >> 24) << j;
+            ll |= ((lb * 0x01020408u) >> 24) << j;
+            nn |= ((nb * 0x01020408u) >> 24) << j;
         }
         base[(size_t)(PLANE_H * W + w) * TILE] = hh;
         base[(size_t)(PLANE_L * W + w) * TILE] = ll;
         base[(size_t)(PLANE_N * W + w) * TILE] = nn;
     }
+    const bool plain = not_plain == 0;
     if (odd) odd[r] = plain ? 0 : 1;
 }
 
@@ -607,9 +633,8 @@ bool DeviceIngest::stage() {
     const uint32_t max_rec = (uint32_t)std::min<size_t>(line_cap_ / 4, (end - slot0) / 4 + 1);
     const int rec_blocks = (int)((max_rec + 255) / 256);
     validate_records<<<rec_blocks, 256, 0, st>>>(ring, lines, state, B.seq_off.as<uint32_t>(), lens);
-    record_extent<<<rec_blocks, 256, 0, st>>>(lens, state);
     SCG_CUDA_CHECK(cudaGetLastError());
-    ctx_.launches += 5;
+    ctx_.launches += 4;
     staged_ = true;
     return true;
 }
