@@ -21,6 +21,7 @@
 #include "inflate.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace scg {
@@ -73,20 +74,22 @@ __device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
 __device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 6) | (uint32_t)len; }
 
 // Builds the lookup table of a canonical Huffman code from the code lengths lens[0 .. n).  KIND 0 literal/length, 1 distance,
-// 2 code lengths.  All lanes take part.  false = over-subscribed set of lengths.
-template <int KIND, int TBITS>
+// 2 code lengths.  All GL lanes of the group take part (gm = their mask, gl = this lane's place among them).  false =
+// over-subscribed set of lengths.
+template <int KIND, int TBITS, int GL>
 __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
-                            int lane) {
-    for (int i = lane; i < (1 << TBITS); i += 32) table[i] = (Entry)(KIND == 2 ? 0u : E_INVALID);
-    if (lane < 16) count[lane] = 0;
-    __syncwarp();
-    for (int s = lane; s < n; s += 32) {
+                            uint32_t gm, int gl) {
+    const uint32_t below = (1u << (threadIdx.x & 31)) - 1u;   // the lanes in front of this one
+    for (int i = gl; i < (1 << TBITS); i += GL) table[i] = (Entry)(KIND == 2 ? 0u : E_INVALID);
+    for (int i = gl; i < 16; i += GL) count[i] = 0;
+    __syncwarp(gm);
+    for (int s = gl; s < n; s += GL) {
         const int l = lens[s];
         if (l) atomicAdd(&count[l], 1u);
     }
-    __syncwarp();
+    __syncwarp(gm);
     bool ok = true;
-    if (lane == 0) {
+    if (gl == 0) {
         uint32_t code = 0, off = 0;
         int left = 1;
         for (int l = 1; l <= 15; ++l) {
@@ -98,14 +101,14 @@ __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* 
             off += count[l];
         }
     }
-    ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+    ok = __shfl_sync(gm, ok ? 1 : 0, 0, GL) != 0;
     if (!ok) return false;
-    __syncwarp();
-    for (int base = 0; base < n; base += 32) {
-        const int s = base + lane;
+    __syncwarp(gm);
+    for (int base = 0; base < n; base += GL) {
+        const int s = base + gl;
         const int l = s < n ? lens[s] : 0;
-        const uint32_t peers = __match_any_sync(FULL, l);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t peers = __match_any_sync(gm, l);
+        const int rank = __popc(peers & below);
         if (l) {
             const uint32_t code = next[l] + (uint32_t)rank;
             sorted[offs[l] + (uint32_t)rank] = (uint16_t)s;
@@ -117,12 +120,12 @@ __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* 
                 table[r & ((1u << TBITS) - 1u)] = (Entry)E_LONG;
             }
         }
-        __syncwarp();
+        __syncwarp(gm);
         if (l && rank == 0) {
             next[l] += (uint32_t)__popc(peers);
             offs[l] += (uint32_t)__popc(peers);
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
     return true;
 }
@@ -147,20 +150,23 @@ __device__ __forceinline__ bool slow_symbol(unsigned long long bits, const uint3
     return false;
 }
 
-// The compressed stream as seen by the warp: 64 bits of look-ahead, refilled from two register-resident 128-byte lines.
+// The compressed stream as seen by the group: 64 bits of look-ahead, refilled from two register-resident lines of GL words.
+template <int GL>
 struct BitReader {
     const uint32_t* words;      // 4-byte aligned base of the stream
     uint32_t line_cur, line_next;
-    uint32_t widx;              // words consumed so far (warp-uniform)
+    uint32_t widx;              // words consumed so far (uniform in the group)
     unsigned long long bits;
     int cnt;
-    int lane;
+    uint32_t gm;
+    int gl;
 
-    __device__ __forceinline__ void open(const uint8_t* comp, size_t byte_off, int lane_) {
-        lane = lane_;
+    __device__ __forceinline__ void open(const uint8_t* comp, size_t byte_off, uint32_t gm_, int gl_) {
+        gm = gm_;
+        gl = gl_;
         words = reinterpret_cast<const uint32_t*>(comp + (byte_off & ~(size_t)3));
-        line_cur = words[lane];
-        line_next = words[32 + lane];
+        line_cur = words[gl];
+        line_next = words[GL + gl];
         widx = 0;
         bits = 0;
         cnt = 0;
@@ -171,11 +177,11 @@ struct BitReader {
         refill();
     }
     __device__ __forceinline__ uint32_t next_word() {
-        const uint32_t w = __shfl_sync(FULL, line_cur, (int)(widx & 31u));
+        const uint32_t w = __shfl_sync(gm, line_cur, (int)(widx & (uint32_t)(GL - 1)), GL);
         ++widx;
-        if ((widx & 31u) == 0) {
+        if ((widx & (uint32_t)(GL - 1)) == 0) {
             line_cur = line_next;
-            line_next = words[widx + 32 + lane];
+            line_next = words[widx + GL + gl];
         }
         return w;
     }
@@ -203,29 +209,37 @@ struct BitReader {
 // A match of the batch, copied into the stage: byte j comes from batch-relative position off - dist + j (the repeating
 // pattern of the last `dist` bytes when the match overlaps itself); positions before the batch are text already in global
 // memory (`done` = the batch's first byte there), the others are bytes of the stage written by earlier symbols.
-__device__ __forceinline__ void copy_match(uint8_t* stage, const uint8_t* done, uint32_t off, uint32_t len, uint32_t dist, int lane) {
-    for (uint32_t j = lane; j < len; j += 32) {
+template <int GL>
+__device__ __forceinline__ void copy_match(uint8_t* stage, const uint8_t* done, uint32_t off, uint32_t len, uint32_t dist, int gl) {
+    for (uint32_t j = gl; j < len; j += GL) {
         const int src = (int)off - (int)dist + (int)(dist >= len ? j : j % dist);
         stage[off + j] = src < 0 ? done[src] : stage[src];
     }
 }
 
-__global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, const InflateMember* __restrict__ members, int n,
-                                                                  uint8_t* out_base, uint32_t* __restrict__ errors) {
-    __shared__ WarpTables tables[INFL_WARPS];
-    const int lane = threadIdx.x & 31;
-    WarpTables& T = tables[threadIdx.x >> 5];
-    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+// GL lanes per member: 32 = one warp per member (what runs); 8 = four members per warp (an experiment, see launch_inflate).
+// WARPS warps per block.
+template <int GL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, const InflateMember* __restrict__ members, int n,
+                                                             uint8_t* out_base, uint32_t* __restrict__ errors) {
+    constexpr int GROUPS = 32 / GL;   // members per warp
+    __shared__ WarpTables tables[WARPS * GROUPS];
+    const int lane32 = threadIdx.x & 31;
+    const int lane = lane32 % GL;                  // this lane's place in its group
+    const int group = lane32 / GL;
+    const uint32_t gm = GL == 32 ? 0xFFFFFFFFu : (((1u << (GL & 31)) - 1u) << (group * GL));
+    WarpTables& T = tables[(threadIdx.x >> 5) * GROUPS + group];
+    const int first_member = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GROUPS + group;
+    const int member_stride = (int)((gridDim.x * blockDim.x) >> 5) * GROUPS;
 
-    for (int mi = warp; mi < n; mi += nwarps) {
+    for (int mi = first_member; mi < n; mi += member_stride) {
         const InflateMember M = members[mi];
         uint8_t* out = out_base + M.out_off;
         uint32_t pos = 0;
         bool bad = false;
         if (M.out_len == 0 && M.in_len <= 2) continue;   // the empty member that closes a BGZF file
-        BitReader br;
-        br.open(comp, M.in_off, lane);
+        BitReader<GL> br;
+        br.open(comp, M.in_off, gm, lane);
         bool last = false;
         while (!last && !bad) {
             // a block header beyond the member's bytes: a damaged stream running away (it must not leave the image)
@@ -249,10 +263,10 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                     break;
                 }
                 const size_t from = (size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) + br.byte_pos();
-                for (uint32_t j = lane; j < len; j += 32) out[pos + j] = comp[from + j];
+                for (uint32_t j = lane; j < len; j += GL) out[pos + j] = comp[from + j];
                 pos += len;
-                __syncwarp();
-                br.open(comp, from + len, lane);
+                __syncwarp(gm);
+                br.open(comp, from + len, gm, lane);
                 continue;
             }
             if (type == 3) {
@@ -262,8 +276,8 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
             int nlit = 288, ndist = 30;
             if (type == 1) {
                 // ---- fixed codes (RFC 1951 3.2.6) ----
-                for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
-                if (lane < 30) T.lens[288 + lane] = 5;
+                for (int s = lane; s < 288; s += GL) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+                for (int s = lane; s < 30; s += GL) T.lens[288 + s] = 5;
             } else {
                 // ---- dynamic codes: the code-length code first, then the two alphabets' lengths through it ----
                 br.refill();
@@ -274,19 +288,19 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                     bad = true;
                     break;
                 }
-                if (lane < 19) T.lens[320 + lane] = 0;
-                __syncwarp();
+                for (int s = lane; s < 19; s += GL) T.lens[320 + s] = 0;
+                __syncwarp(gm);
                 for (int k = 0; k < nclen; ++k) {
                     br.refill();
                     const uint32_t v = br.take(3);
                     if (lane == 0) T.lens[320 + c_clen_order[k]] = (uint8_t)v;
                 }
-                __syncwarp();
-                if (!build_table<2, 7>(T.lens + 320, 19, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, lane)) {
+                __syncwarp(gm);
+                if (!build_table<2, 7, GL>(T.lens + 320, 19, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, gm, lane)) {
                     bad = true;
                     break;
                 }
-                __syncwarp();
+                __syncwarp(gm);
                 int i = 0;
                 uint32_t prev = 0;
                 while (i < nlit + ndist) {
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                         break;
                     }
                     // lengths of the distance alphabet are kept from offset 288 on
-                    for (uint32_t k = lane; k < rep; k += 32) {
+                    for (uint32_t k = lane; k < rep; k += GL) {
                         const int at = i + (int)k;
                         T.lens[at < nlit ? at : 288 + (at - nlit)] = (uint8_t)val;
                     }
@@ -326,19 +340,19 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                     prev = val;
                 }
                 if (bad) break;
-                __syncwarp();
+                __syncwarp(gm);
                 if (T.lens[256] == 0) {   // no end-of-block code
                     bad = true;
                     break;
                 }
             }
-            __syncwarp();
-            if (!build_table<0, LIT_BITS>(T.lens, nlit, T.lit, T.lit_sorted, T.lit_count, T.next, T.offs, lane) ||
-                !build_table<1, DIST_BITS>(T.lens + 288, ndist, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, lane)) {
+            __syncwarp(gm);
+            if (!build_table<0, LIT_BITS, GL>(T.lens, nlit, T.lit, T.lit_sorted, T.lit_count, T.next, T.offs, gm, lane) ||
+                !build_table<1, DIST_BITS, GL>(T.lens + 288, ndist, T.dist, T.dist_sorted, T.dist_count, T.next, T.offs, gm, lane)) {
                 bad = true;
                 break;
             }
-            __syncwarp();
+            __syncwarp(gm);
 
             // ---- the block's symbols, a batch at a time ----
             bool end_of_block = false;
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                 int nsym = 0;
                 uint32_t staged = 0;   // bytes the batch produces so far (warp-uniform)
 #pragma unroll 1
-                for (; nsym < 32 && staged <= STAGE_BYTES - 258; ++nsym) {
+                for (; nsym < GL && staged <= STAGE_BYTES - 258; ++nsym) {
                     br.refill();
                     uint32_t e = T.lit[br.peek(LIT_BITS)];
                     if (((e >> 4) & 3u) == K_SPECIAL) {
@@ -399,15 +413,15 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                 const uint32_t mylen = lane < nsym ? ((my >> 16) & 0x1FFu) : 0u;
                 uint32_t incl = mylen;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(FULL, incl, d);
+                for (int d = 1; d < GL; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(gm, incl, d, GL);
                     if (lane >= d) incl += v;
                 }
                 const uint32_t total = staged;
                 const uint32_t off = incl - mylen;   // relative to the batch's first byte
                 const bool is_match = lane < nsym && !(my >> 31);
                 const uint32_t mydist = my & 0xFFFFu;
-                if (pos + total > M.out_len || __any_sync(FULL, is_match && mydist > pos + off)) {
+                if (pos + total > M.out_len || __any_sync(gm, is_match && mydist > pos + off)) {
                     bad = true;
                     break;
                 }
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                 // matches whose source ends before the batch begins: no ordering among them, their loads overlap
                 const bool indep = is_match && off + mylen <= mydist;
                 // (four at a time: a warp issues in order, so the loads of four matches go out before the first store waits)
-                uint32_t todo = __ballot_sync(FULL, indep);
+                uint32_t todo = __ballot_sync(gm, indep);
                 while (todo) {
                     uint32_t sy[4], o[4];
 #pragma unroll
@@ -429,8 +443,8 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
                         if (todo) {
                             const int k = __ffs(todo) - 1;
                             todo &= todo - 1;
-                            sy[u] = __shfl_sync(FULL, my, k);
-                            o[u] = __shfl_sync(FULL, off, k);
+                            sy[u] = __shfl_sync(gm, my, k);
+                            o[u] = __shfl_sync(gm, off, k);
                         }
                     }
                     uint8_t v[4];
@@ -446,33 +460,33 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const uint32_t len = (sy[u] >> 16) & 0x1FFu;
-                        for (uint32_t j = lane + 32; j < len; j += 32) stage[o[u] + j] = done[(int)o[u] - (int)(sy[u] & 0xFFFFu) + (int)j];
+                        for (uint32_t j = lane + GL; j < len; j += GL) stage[o[u] + j] = done[(int)o[u] - (int)(sy[u] & 0xFFFFu) + (int)j];
                     }
                 }
                 // the others read bytes of this batch: in order, each after what precedes it has landed in the stage
-                todo = __ballot_sync(FULL, is_match && !indep);
+                todo = __ballot_sync(gm, is_match && !indep);
                 while (todo) {
-                    __syncwarp();
+                    __syncwarp(gm);
                     const int k = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const uint32_t sy = __shfl_sync(FULL, my, k), o = __shfl_sync(FULL, off, k);
-                    copy_match(stage, done, o, (sy >> 16) & 0x1FFu, sy & 0xFFFFu, lane);
+                    const uint32_t sy = __shfl_sync(gm, my, k), o = __shfl_sync(gm, off, k);
+                    copy_match<GL>(stage, done, o, (sy >> 16) & 0x1FFu, sy & 0xFFFFu, lane);
                 }
-                __syncwarp();
+                __syncwarp(gm);
                 // ---- the finished batch goes out: whole aligned words, the ragged ends byte by byte ----
                 {
                     const uint32_t span = skew + total;                 // bytes of the stage in use, from its aligned base
                     const uint32_t first_word = skew ? 1u : 0u;         // word 0 is partial when the text does not start aligned
                     const uint32_t full_words = span / 4;               // words [first_word, full_words) are complete
                     uint32_t* gw = reinterpret_cast<uint32_t*>(done - skew);
-                    for (uint32_t w = first_word + lane; w < full_words; w += 32) gw[w] = T.stage[w];
+                    for (uint32_t w = first_word + lane; w < full_words; w += GL) gw[w] = T.stage[w];
                     const uint8_t* sb = reinterpret_cast<const uint8_t*>(T.stage);
                     uint8_t* gb = done - skew;
                     if (skew && (uint32_t)lane >= skew && (uint32_t)lane < min(4u, span)) gb[lane] = sb[lane];
                     const uint32_t tail = full_words * 4;               // bytes [tail, span) of a last partial word
                     if (full_words >= first_word && tail + lane < span && tail + lane >= skew) gb[tail + lane] = sb[tail + lane];
                 }
-                __syncwarp();
+                __syncwarp(gm);
                 pos += total;
             }
         }
@@ -482,7 +496,7 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) inflate_kernel(const uint8_t*
             bad = pos != M.out_len || end_bit > ((size_t)M.in_off + M.in_len) * 8;
         }
         if (bad && lane == 0) atomicOr(errors, 1u);
-        __syncwarp();
+        __syncwarp(gm);
     }
 }
 
@@ -573,7 +587,22 @@ int launch_inflate(const uint8_t* comp, const InflateMember* members, int n, uin
     static const CrcOperator op = make_crc_operator();
     static const bool check_crc = !std::getenv("SCG_BGZF_NO_CRC");
     const int blocks = std::max(1, std::min((n + INFL_WARPS - 1) / INFL_WARPS, sm_count * 8));
-    inflate_kernel<<<blocks, INFL_WARPS * 32, 0, stream>>>(comp, members, n, out, errors);
+    // One warp per member.  SCG_INFLATE_LANES=8 gives every member eight lanes instead, so that four members share a warp's
+    // (per-lane identical) decoding instructions: measured on the B200, that makes a member 2.5 times slower (the four streams
+    // diverge at every literal / match / refill decision and the warp runs the paths one after the other; copies and table
+    // builds have a quarter of the lanes) and the kernel tops out at 49 GB/s of text instead of 83 -- not adopted.
+    static const int lanes = [] {
+        const char* env = std::getenv("SCG_INFLATE_LANES");
+        return env && std::atoi(env) == 8 ? 8 : 32;
+    }();
+    if (lanes == 32) {
+        inflate_kernel<32, INFL_WARPS><<<blocks, INFL_WARPS * 32, 0, stream>>>(comp, members, n, out, errors);
+    } else {
+        constexpr int W8 = 2;   // warps per block: 8 members' tables fit the 48 KB of static shared memory
+        const int per_block = W8 * 4;
+        const int blocks8 = std::max(1, std::min((n + per_block - 1) / per_block, sm_count * 4));
+        inflate_kernel<8, W8><<<blocks8, W8 * 32, 0, stream>>>(comp, members, n, out, errors);
+    }
     if (!check_crc) return 1;
     crc_kernel<<<blocks, INFL_WARPS * 32, 0, stream>>>(members, n, out, op, errors);
     return 2;
