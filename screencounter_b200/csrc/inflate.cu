@@ -52,11 +52,17 @@ struct WarpTables {
     uint32_t stage[STAGE_BYTES / 4 + 2];      // the text of the batch being assembled (+ alignment slack)
 };
 
-__constant__ uint16_t c_len_base[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
-__constant__ uint8_t c_len_extra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
-__constant__ uint16_t c_dist_base[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
-                                          4097, 6145, 8193, 12289, 16385, 24577 };
-__constant__ uint8_t c_dist_extra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+// base value | extra bits << 16 of the length symbols 257 .. 285 and of the distance symbols 0 .. 29 (RFC 1951 3.2.5)
+#define SCG_BE(base, extra) ((uint32_t)(base) | ((uint32_t)(extra) << 16))
+__constant__ uint32_t c_len_sym[29] = { SCG_BE(3, 0),  SCG_BE(4, 0),  SCG_BE(5, 0),  SCG_BE(6, 0),   SCG_BE(7, 0),   SCG_BE(8, 0),   SCG_BE(9, 0),   SCG_BE(10, 0),
+                                        SCG_BE(11, 1), SCG_BE(13, 1), SCG_BE(15, 1), SCG_BE(17, 1),  SCG_BE(19, 2),  SCG_BE(23, 2),  SCG_BE(27, 2),  SCG_BE(31, 2),
+                                        SCG_BE(35, 3), SCG_BE(43, 3), SCG_BE(51, 3), SCG_BE(59, 3),  SCG_BE(67, 4),  SCG_BE(83, 4),  SCG_BE(99, 4),  SCG_BE(115, 4),
+                                        SCG_BE(131, 5), SCG_BE(163, 5), SCG_BE(195, 5), SCG_BE(227, 5), SCG_BE(258, 0) };
+__constant__ uint32_t c_dist_sym[30] = { SCG_BE(1, 0),     SCG_BE(2, 0),     SCG_BE(3, 0),     SCG_BE(4, 0),      SCG_BE(5, 1),      SCG_BE(7, 1),
+                                         SCG_BE(9, 2),     SCG_BE(13, 2),    SCG_BE(17, 3),    SCG_BE(25, 3),     SCG_BE(33, 4),     SCG_BE(49, 4),
+                                         SCG_BE(65, 5),    SCG_BE(97, 5),    SCG_BE(129, 6),   SCG_BE(193, 6),    SCG_BE(257, 7),    SCG_BE(385, 7),
+                                         SCG_BE(513, 8),   SCG_BE(769, 8),   SCG_BE(1025, 9),  SCG_BE(1537, 9),   SCG_BE(2049, 10),  SCG_BE(3073, 10),
+                                         SCG_BE(4097, 11), SCG_BE(6145, 11), SCG_BE(8193, 12), SCG_BE(12289, 12), SCG_BE(16385, 13), SCG_BE(24577, 13) };
 __constant__ uint8_t c_clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
 
 // what a code of `len` bits for `sym` stands for, as a table entry (0 = a symbol the format does not define)
@@ -386,8 +392,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                         sym = 0x80010000u | (e >> 6);
                         staged += 1;
                     } else {
-                        const uint32_t li = e >> 6;
-                        const uint32_t len = (uint32_t)c_len_base[li] + br.take((int)c_len_extra[li]);
+                        const uint32_t ls = c_len_sym[e >> 6];
+                        const uint32_t len = (ls & 0xFFFFu) + br.take((int)(ls >> 16));
                         br.refill();
                         uint32_t d = T.dist[br.peek(DIST_BITS)];
                         if (((d >> 4) & 3u) == K_SPECIAL) {
@@ -401,8 +407,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                             }
                         }
                         br.drop((int)(d & 0xFu));
-                        const uint32_t di = d >> 6;
-                        const uint32_t dist = (uint32_t)c_dist_base[di] + br.take((int)c_dist_extra[di]);
+                        const uint32_t ds = c_dist_sym[d >> 6];
+                        const uint32_t dist = (ds & 0xFFFFu) + br.take((int)(ds >> 16));
                         sym = (len << 16) | dist;
                         staged += len;
                     }
@@ -432,8 +438,16 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                 if (lane < nsym && (my >> 31)) stage[off] = (uint8_t)my;
                 // matches whose source ends before the batch begins: no ordering among them, their loads overlap
                 const bool indep = is_match && off + mylen <= mydist;
-                // (four at a time: a warp issues in order, so the loads of four matches go out before the first store waits)
-                uint32_t todo = __ballot_sync(gm, indep);
+                // Short ones (the rule for the bases of a FASTQ record) are copied by the lanes that hold them, all at once: the
+                // warp runs as many byte steps as the longest of them has bytes, instead of a round of shuffles per match.
+                constexpr uint32_t SHORT_MATCH = 12;
+                if (indep && mylen <= SHORT_MATCH) {
+                    const uint8_t* src = done + ((int)off - (int)mydist);
+                    for (uint32_t j = 0; j < mylen; ++j) stage[off + j] = src[j];
+                }
+                // the longer ones by all lanes together, four matches at a time: a warp issues in order, so the loads of four
+                // matches go out before the first store waits
+                uint32_t todo = __ballot_sync(gm, indep && mylen > SHORT_MATCH);
                 while (todo) {
                     uint32_t sy[4], o[4];
 #pragma unroll

@@ -447,6 +447,8 @@ DeviceIngest::DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, i
         virtual_newline_ = last.empty() || last[0] != '\n';
     }
     // a chunk = a run of whole members holding at most chunk_ bytes of text (never less than one member can hold)
+    // (cutting a small file into several chunks so that its parse starts while members still inflate was measured: slower, 6.4
+    // against 4.5 ms for 157 MB of text -- a member takes 1.7 ms however few there are, and every chunk costs a host round trip)
     chunk_ = std::max<size_t>(env_size("SCG_INGEST_CHUNK", kBgzfChunk, 64, 1u << 30), 1u << 16) / 16 * 16;
     const size_t nb = bgzf_->blocks.size();
     size_t b = 0;
