@@ -148,6 +148,24 @@ struct DualTables {
 SCG_HD uint32_t dual_hash(uint32_t x, uint32_t y, uint32_t z) { return x * 0x9E3779B1u + y * 0x85EBCA6Bu + z * 0xC2B2AE35u; }
 SCG_HD uint32_t dual_hash2(uint32_t h) { return h * 0x27D4EB2Fu + 0x165667B1u; }
 constexpr int DUAL_MAX_KEYLEN = 48;
+// The mismatch-tolerant side of the dual paired-end library for keys of up to 48 bases and budgets of at most one mismatch per
+// read (four seeds at most), flattened for the follow-up kernel: candidates as 16-byte rows in the layout of DualTables (H lo, L lo,
+// H hi | L hi << 16, pool row), and seed buckets of 32 bytes that carry their first candidate -- (row)(start, count, -, -) -- so
+// that a seed costs one aligned 32-byte fetch where the generic search walks bucket -> candidate list -> entry keys -> entry index.
+struct DualFlat {
+    const uint4* ibuckets;      // nseeds * (bucket_mask + 1) * 2
+    const uint4* rows;          // nseeds * nentries
+    uint32_t bucket_mask;
+    int nentries;
+    int nseeds;                 // 1 .. 4
+    uint32_t seed_lo[4], seed_hi[4];   // base positions of each seed, words 0 and 1 of the key
+    uint32_t seg1_lo, seg1_hi;         // base positions of the first segment
+    int kw, seg1, L;
+    int dup_first;
+    const uint32_t* prefix_slots;      // rows with their last base dropped (root rule), the library's own table
+    uint32_t prefix_mask;
+    int slot_words;
+};
 // Exact tables of the four libraries of the single-end combinatorial design, [2 * reverse + region in read order]: the
 // libraries' own cuckoo tables (library.cpp CuckooTable, keys of one word per plane, 16-byte slots).
 struct ComboTables {

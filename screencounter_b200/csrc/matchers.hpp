@@ -105,6 +105,68 @@ struct DualPEMatcher {
         params.lib = upload_lib_array(ctx, std::vector<LibDev>{ lib.dev }, lib_dev);
         params.kw = lib.dev.KW;
         build_exact16(ctx);
+        build_flat(ctx);
+    }
+
+    // The flattened mismatch-tolerant tables of the follow-up kernel (libdev.hpp DualFlat); flat.nseeds == 0 when the library does
+    // not qualify (keys over 48 bases, two or more mismatches on a read, a seed without positions).
+    DeviceBuffer flat_ibuckets, flat_rows;
+    DualFlat flat;
+    void build_flat(Context& ctx) {
+        std::memset(&flat, 0, sizeof flat);
+        flat_ibuckets.release();
+        flat_rows.release();
+        const Library& host = lib.host;
+        if (host.L > DUAL_MAX_KEYLEN || host.L < 1 || host.KW > 2 || host.nseeds < 1 || host.nseeds > 4 || host.opt.max_mismatches1 > 1 ||
+            host.opt.max_mismatches2 > 1 || host.nentries() >= (1u << 24) || host.nbuckets == 0) {
+            return;
+        }
+        const int kw = host.KW;
+        for (int sd = 0; sd < host.nseeds; ++sd) {
+            uint32_t any = 0;
+            for (int w = 0; w < kw; ++w) any |= host.seed_masks[(size_t)sd * kw + w];
+            if (!any) return;
+        }
+        const size_t E = host.nentries(), B = host.nbuckets;
+        std::vector<uint32_t> rows((size_t)host.nseeds * E * 4, 0), ib((size_t)host.nseeds * B * 8, 0);
+        for (size_t k = 0; k < (size_t)host.nseeds * E; ++k) {
+            const size_t e = (size_t)host.cands[k];
+            const uint32_t* ek = &host.ent_keys[e * 2 * kw];
+            rows[4 * k + 0] = ek[0];
+            rows[4 * k + 1] = ek[kw];
+            rows[4 * k + 2] = kw > 1 ? (ek[1] | (ek[kw + 1] << 16)) : 0u;
+            rows[4 * k + 3] = (uint32_t)host.ent_idx[e];
+        }
+        for (size_t b = 0; b < (size_t)host.nseeds * B; ++b) {
+            const uint2 bk = host.buckets[b];
+            if (bk.y == 0) continue;
+            const size_t sd = b / B;
+            std::memcpy(&ib[8 * b], &rows[4 * (sd * E + bk.x)], 16);
+            ib[8 * b + 4] = bk.x;
+            ib[8 * b + 5] = bk.y;
+        }
+        flat_rows.upload(rows.data(), rows.size() * sizeof(uint32_t), ctx.stream);
+        flat_ibuckets.upload(ib.data(), ib.size() * sizeof(uint32_t), ctx.stream);
+        SCG_CUDA_CHECK(cudaStreamSynchronize(ctx.stream));
+        flat.ibuckets = flat_ibuckets.as<uint4>();
+        flat.rows = flat_rows.as<uint4>();
+        flat.bucket_mask = (uint32_t)B - 1;
+        flat.nentries = (int)E;
+        flat.nseeds = host.nseeds;
+        for (int sd = 0; sd < host.nseeds; ++sd) {
+            flat.seed_lo[sd] = host.seed_masks[(size_t)sd * kw];
+            flat.seed_hi[sd] = kw > 1 ? host.seed_masks[(size_t)sd * kw + 1] : 0u;
+        }
+        const int s1 = host.opt.seg1;
+        flat.seg1_lo = s1 >= 32 ? 0xFFFFFFFFu : ((1u << s1) - 1u);
+        flat.seg1_hi = s1 > 32 ? ((1u << (s1 - 32)) - 1u) : 0u;
+        flat.kw = kw;
+        flat.seg1 = s1;
+        flat.L = host.L;
+        flat.dup_first = host.opt.duplicates == Duplicates::FIRST;
+        flat.prefix_slots = lib.dev.prefix_slots;
+        flat.prefix_mask = lib.dev.prefix_mask;
+        flat.slot_words = lib.dev.slot_words;
     }
 
     // The 16-byte-slot exact table of the specialised kernel (libdev.hpp DualTables), filled from the library's own cuckoo

@@ -49,6 +49,112 @@ __global__ void __launch_bounds__(128) dual_deferred_kernel(DeferredList def, co
     }
 }
 
+// The same search with its dependent chains flattened (libdev.hpp DualFlat; budgets of at most one mismatch per read): the
+// root-rule probe and the seed buckets of ALL seeds are requested together, each bucket arriving with its first candidate; only
+// a bucket with several candidates costs further loads.  Outcomes equal lookup_segmented_inexact's.
+template <int KW>
+__global__ void __launch_bounds__(128) dual_deferred_flat_kernel(DeferredList def, DualFlat F, int32_t* __restrict__ counts,
+                                                                 int32_t* __restrict__ out_index) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < def.regions; r += nwarps) {
+        const uint32_t cnt = def.warp_counts[r];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e >= cnt) continue;
+            const unsigned long long at = (unsigned long long)r * def.per_warp + e;
+            const uint32_t i = def.words[at], x = def.words[def.stride + at], y = def.words[2 * def.stride + at],
+                           z = def.words[3 * def.stride + at], n_lo = def.words[4 * def.stride + at], w = def.words[5 * def.stride + at];
+            const uint32_t zh = KW > 1 ? (z & 0xFFFFu) : 0u, zl = KW > 1 ? (z >> 16) : 0u, n_hi = KW > 1 ? (w & 0xFFFFu) : 0u;
+            const int c1 = min((int)((w >> 16) & 0xFFu), F.seg1), c2 = min((int)(w >> 24), F.L - F.seg1);
+            int index = -1;
+            if (c1 > 0 || c2 > 0) {
+                // root rule: second cap 0, first cap 1 -- the exact chain down to the last base makes the search miss
+                bool phantom = false;
+                if (c2 == 0 && c1 >= 1) {
+                    uint32_t ph[KW], pl[KW], pn = 0;
+                    const int lw = (F.L - 1) >> 5;
+                    const uint32_t lastbit = 1u << ((F.L - 1) & 31);
+                    ph[0] = x;
+                    pl[0] = y;
+                    uint32_t nn0 = n_lo, nn1 = n_hi;
+                    if (KW > 1) {
+                        ph[KW - 1] = zh;
+                        pl[KW - 1] = zl;
+                    }
+                    if (lw == 0) {
+                        ph[0] &= ~lastbit;
+                        pl[0] &= ~lastbit;
+                        nn0 &= ~lastbit;
+                    } else if (KW > 1) {
+                        ph[KW - 1] &= ~lastbit;
+                        pl[KW - 1] &= ~lastbit;
+                        nn1 &= ~lastbit;
+                    }
+                    pn = nn0 | nn1;
+                    phantom = !pn && probe_table<KW>(F.prefix_slots, F.prefix_mask, F.slot_words, F.kw, ph, pl) >= 0;
+                }
+                if (!phantom) {
+                    uint4 first[4], meta[4];
+#pragma unroll
+                    for (int sd = 0; sd < 4; ++sd) {
+                        first[sd] = meta[sd] = make_uint4(0, 0, 0, 0);
+                        if (sd < F.nseeds) {
+                            const uint32_t mlo = F.seed_lo[sd], mhi = F.seed_hi[sd];
+                            if (!((n_lo & mlo) | (n_hi & mhi))) {   // an N inside the seed: no row agrees with the key there
+                                uint32_t mh[KW], ml[KW];
+                                mh[0] = x & mlo;
+                                ml[0] = y & mlo;
+                                if (KW > 1) {
+                                    mh[KW - 1] = zh & mhi;
+                                    ml[KW - 1] = zl & mhi;
+                                }
+                                const uint32_t b = hash_key(mh, ml, F.kw, 0x5EED0000u + sd) & F.bucket_mask;
+                                const uint4* __restrict__ bucket = F.ibuckets + 2 * ((size_t)sd * (F.bucket_mask + 1) + b);
+                                first[sd] = __ldg(bucket);
+                                meta[sd] = __ldg(bucket + 1);
+                            }
+                        }
+                    }
+                    int best = c1 + c2 + 1, bidx = -1;
+                    bool ambiguous = false;
+                    auto consider = [&](const uint4 row) {
+                        const uint32_t dlo = (row.x ^ x) | (row.y ^ y) | n_lo;
+                        const uint32_t dhi = KW > 1 ? (((row.z & 0xFFFFu) ^ zh) | ((row.z >> 16) ^ zl) | n_hi) : 0u;
+                        const int d1 = __popc(dlo & F.seg1_lo) + __popc(dhi & F.seg1_hi);
+                        const int d2 = __popc(dlo & ~F.seg1_lo) + __popc(dhi & ~F.seg1_hi);
+                        if (d1 > c1 || d2 > c2) return;
+                        const int d = d1 + d2;
+                        if (d > best) return;
+                        const int idx = (int)row.w;
+                        if (d < best) {
+                            best = d;
+                            bidx = idx;
+                            ambiguous = false;
+                        } else if (idx != bidx) {
+                            if (F.dup_first) {
+                                bidx = min(bidx, idx);
+                            } else {
+                                ambiguous = true;
+                            }
+                        }
+                    };
+#pragma unroll
+                    for (int sd = 0; sd < 4; ++sd) {
+                        if (meta[sd].y == 0) continue;
+                        consider(first[sd]);
+                        for (uint32_t c = 1; c < meta[sd].y; ++c) consider(__ldg(F.rows + (size_t)sd * F.nentries + meta[sd].x + c));
+                    }
+                    if (bidx >= 0 && !ambiguous) index = bidx;
+                }
+            }
+            if (index >= 0) atomicAdd(counts + index, 1);
+            if (out_index) out_index[i] = index;
+        }
+    }
+}
+
 // Best-unique bookkeeping of the mismatch-tolerant search over candidate rows (h, l, pool index, -): the rules of
 // MismatchTrie.hpp:266-343 as lookup_seeded_body applies them.
 struct BestRow {
@@ -530,10 +636,19 @@ void launch_dual_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const 
     void* args[] = { &a1, &a2, &tb, &d_counts, &d_index, &sc.def, &sc.slow };
     SCG_CUDA_CHECK(cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(128), args, 0, stream));
     const int fgrid = followup_grid(ctx, r1.n);
+    const bool flat = m.flat.nseeds > 0 && !std::getenv("SCG_DUAL_NO_FLAT");
     if (m.params.kw <= 1) {
-        dual_deferred_kernel<1><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+        if (flat) {
+            dual_deferred_flat_kernel<1><<<fgrid, 128, 0, stream>>>(sc.def, m.flat, d_counts, d_index);
+        } else {
+            dual_deferred_kernel<1><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+        }
     } else {
-        dual_deferred_kernel<2><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+        if (flat) {
+            dual_deferred_flat_kernel<2><<<fgrid, 128, 0, stream>>>(sc.def, m.flat, d_counts, d_index);
+        } else {
+            dual_deferred_kernel<2><<<fgrid, 128, 0, stream>>>(sc.def, m.params.lib, d_counts, d_index);
+        }
     }
     SCG_CUDA_CHECK(cudaGetLastError());
     ctx.launches += 2;
@@ -541,7 +656,7 @@ void launch_dual_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const 
     // pairs with several verified windows: the full per-pair search of the generic kernel on exactly those
     launch_dual_pe_generic(ctx, r1, r2, m, d_counts, d_index, ReadList{ sc.slow.list, sc.slow.count }, ctx.sm_count * 2, stream);
     ctx.kernel_note = "specialised (NVRTC) spec_dual_pe_kernel, filter+verify on both mates, " + std::to_string(specialised_blocks_per_sm(k)) +
-                      " blocks/SM; + dual_deferred_kernel (mismatch lookups) + dual_pe_kernel on the multi-window pairs";
+                      " blocks/SM; + " + (flat ? "dual_deferred_flat_kernel" : "dual_deferred_kernel") + " (mismatch lookups) + dual_pe_kernel on the multi-window pairs";
 }
 
 // ---------------------------------------------------------------------------------------
