@@ -33,6 +33,11 @@ void count_combo_core(scg_ctx* ctx, const scg_source* src, const char* constant,
 void count_random_core(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, int mismatches, int use_first,
                        int nthreads, SortedTable* want_sorted, scg_result** table, int32_t* total);
 
+// countSingleBarcodes for one input (runners_single.cu): on the context's first device, or cut over all its devices
+void count_single_file(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
+                       int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace,
+                       bool split_over_devices);
+
 // The same over SEVERAL devices (runners_multi.cu): the text is cut at record boundaries into one contiguous part per device,
 // every device counts its part on its own host thread, the count vectors are summed on the first device over peer memory.
 // false = the input cannot be split (a gzip stream, too small, no safe cut, or a part did not parse cleanly): the caller runs

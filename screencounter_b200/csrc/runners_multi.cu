@@ -367,16 +367,10 @@ int scg_count_single_many(scg_ctx* ctx, const scg_source* sources, int nfiles, c
             }
             return;
         }
+        // one file per device at a time, each on that device alone (its tables are cached in that device's context)
         deal_files(ctx, nfiles, [&](scg_ctx* dc, int f) {
-            // (a peer context has no peers of its own: this is the one-device path, tables cached in that device's context)
-            struct Solo {
-                scg_ctx* c;
-                std::vector<std::unique_ptr<scg_ctx>> held;
-                explicit Solo(scg_ctx* c_) : c(c_) { held.swap(c->peers); }
-                ~Solo() { held.swap(c->peers); }
-            } solo(dc);
-            status_or_throw(dc, scg_count_single(dc, &sources[f], constant, strand, pool, npool, mismatches, use_first, nthreads,
-                                                 matrix + (size_t)f * npool, &totals[f], nullptr));
+            count_single_file(dc, &sources[f], constant, strand, pool, npool, mismatches, use_first, nthreads, matrix + (size_t)f * npool,
+                              &totals[f], nullptr, false);
         });
         if (all.size() > 1) combine_timing(ctx->impl, all, now_s() - t_start);
     });

@@ -540,9 +540,16 @@ long long count_single_core(Context& c, FastqReader* reader, const SingleMatcher
 
 extern "C" {
 
-int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
-                     int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace) {
-    return guarded(ctx, [&] {
+} // extern "C"
+
+namespace scg {
+
+// countSingleBarcodes on the context's first device, or -- split_over_devices, a context of several devices and an input that
+// can be cut -- on all of them (runners_multi.cu).  Throws; the C entry points wrap it.
+void count_single_file(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
+                       int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace,
+                       bool split_over_devices) {
+    {
         Context& c = ctx->impl;
         const double t_start = now_s();
         c.timing = Timing();
@@ -555,7 +562,7 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         c.timing.setup_s += now_s() - t_setup;
 
         // several devices (scg_ctx_create_multi): the file's text is cut at record boundaries and every device counts its part
-        if (!ctx->peers.empty() &&
+        if (split_over_devices && !ctx->peers.empty() &&
             count_single_multi(ctx, *source.reader, constant, strand, pool, npool, mismatches, use_first != 0, nthreads, counts, total, trace)) {
             c.timing.total_s = now_s() - t_start;
             c.finish_timing();
@@ -582,6 +589,17 @@ int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, 
         c.timing.parse_s = source.reader->parse_seconds();
         c.timing.total_s = now_s() - t_start;
         c.finish_timing();
+    }
+}
+
+} // namespace scg
+
+extern "C" {
+
+int scg_count_single(scg_ctx* ctx, const scg_source* src, const char* constant, int strand, const char* const* pool, int npool,
+                     int mismatches, int use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace) {
+    return guarded(ctx, [&] {
+        count_single_file(ctx, src, constant, strand, pool, npool, mismatches, use_first, nthreads, counts, total, trace, true);
     });
 }
 
