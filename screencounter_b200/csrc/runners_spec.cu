@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(256) random_insert_kernel(DeferredList def, Co
 // countRandomBarcodes, partitioned (libdev.hpp PartitionedKeys): the lists of table part 0 are counted first, then part 1's, ...
 // -- regions are numbered part-major and the warps take them in that order, so at any moment the kernel works on one or two
 // parts of the table, which stay in L2: the random traffic of the inserts never reaches HBM.  Four keys per lane in flight.
+template <int U>
 __global__ void __launch_bounds__(256) random_count_parts_kernel(PartitionedKeys parts, CountTable64 table) {
-    constexpr int U = 4;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -831,12 +831,20 @@ void launch_random(Context& ctx, const ReadsDev& reads, const RandomMatcher& m, 
     if (nparts) {
         // exactly the blocks that are resident together: every warp then walks the parts in the same order at the same pace, and
         // the slices of the table pass through L2 one after the other
-        static int blocks_per_sm = 0;
-        if (blocks_per_sm == 0) {
-            SCG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, random_count_parts_kernel, 256, 0));
-            blocks_per_sm = std::max(1, blocks_per_sm);
+        // (keys per lane in flight: SCG_RANDOM_UNROLL = 2 / 4 / 8, measured in DESIGN.md 5.2)
+        static const int unroll = jit_env_int("SCG_RANDOM_UNROLL", 4, 2, 8);
+        auto launch = [&](auto kernel) {
+            int blocks_per_sm = 0;
+            SCG_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, 256, 0));
+            kernel<<<ctx.sm_count * std::max(1, blocks_per_sm), 256, 0, stream>>>(parts, t64);
+        };
+        if (unroll <= 2) {
+            launch(random_count_parts_kernel<2>);
+        } else if (unroll >= 8) {
+            launch(random_count_parts_kernel<8>);
+        } else {
+            launch(random_count_parts_kernel<4>);
         }
-        random_count_parts_kernel<<<ctx.sm_count * blocks_per_sm, 256, 0, stream>>>(parts, t64);
     } else {
         // barcodes that were not in their home sector yet: inserted (or found further along) by the follow-up kernel
         random_insert_kernel<<<ctx.sm_count * 8, 256, 0, stream>>>(sc.def, t64);

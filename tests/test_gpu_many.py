@@ -124,3 +124,25 @@ def test_matrix_of_random_barcodes(devices, lower_rate):
     rows = sorted(want)
     assert list(seqs) == rows
     assert np.array_equal(counts, np.array([want[r] for r in rows], dtype=np.int32).reshape(len(rows), len(files)))
+
+
+def test_files_of_every_format_in_one_call(tmp_path):
+    """A list that mixes a raw file, a block-gzip file, a plain gzip file, text in memory and a block-gzip image in memory:
+    every column equals the reference's counts of that input's text (the reference sniffs gzip like we do,
+    inst/include/byteme/SomeFileReader.hpp:25-66)."""
+    import gzip
+    from screencounter_b200 import rcpp
+    from util import bgzf
+    rng = np.random.default_rng(12)
+    pool = distinct_pool(rng, 120, 20)
+    texts = _files(rng, TEMPLATE, [pool], [4000, 3000, 2000, 1500, 2500])
+    raw, blk, gz = tmp_path / "a.fastq", tmp_path / "b.fastq.gz", tmp_path / "c.fastq.gz"
+    raw.write_bytes(texts[0])
+    blk.write_bytes(bgzf(texts[1], 9000))
+    gz.write_bytes(gzip.compress(texts[2], 3))
+    inputs = [str(raw), str(blk), str(gz), texts[3], bgzf(texts[4], 30000)]
+    for devices in _device_sets():
+        matrix, totals = rcpp.matrix_of_single_barcodes(inputs, TEMPLATE, 2, pool, 1, False, 3, device=devices)
+        for f, text in enumerate(texts):
+            counts, total = _oracle().count_single(text, TEMPLATE, 2, pool, 1, False)
+            assert total == totals[f] and np.array_equal(matrix[:, f], counts), (devices, f)
