@@ -39,7 +39,14 @@ constexpr uint32_t STAGE_BYTES = 2048;   // text assembled per batch at most; a 
 // longer than the table (bit-by-bit walk), code length 0 with value 0 = no such code, otherwise the end-of-block code.
 constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_SPECIAL = 2;
 constexpr uint32_t E_INVALID = K_SPECIAL << 4, E_LONG = (1u << 6) | (K_SPECIAL << 4);
+#ifndef INFL_WIDE
+#define INFL_WIDE 0   // 1: 32-bit entries that carry a match symbol's base value and extra bits themselves (measured, not adopted)
+#endif
+#if INFL_WIDE
+using Entry = uint32_t;
+#else
 using Entry = uint16_t;
+#endif
 
 struct WarpTables {
     Entry lit[1 << LIT_BITS];
@@ -70,11 +77,19 @@ __device__ __forceinline__ uint32_t lit_entry(int sym, int len) {
     if (sym < 256) return ((uint32_t)sym << 6) | (K_LITERAL << 4) | (uint32_t)len;
     if (sym == 256) return (K_SPECIAL << 4) | (uint32_t)len;
     if (sym > 285) return E_INVALID;
+#if INFL_WIDE
+    return ((c_len_sym[sym - 257] & 0xFFFFu) << 10) | ((c_len_sym[sym - 257] >> 16) << 6) | (K_MATCH << 4) | (uint32_t)len;
+#else
     return ((uint32_t)(sym - 257) << 6) | (K_MATCH << 4) | (uint32_t)len;
+#endif
 }
 __device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
     if (sym > 29) return E_INVALID;
+#if INFL_WIDE
+    return ((c_dist_sym[sym] & 0xFFFFu) << 10) | ((c_dist_sym[sym] >> 16) << 6) | (K_MATCH << 4) | (uint32_t)len;
+#else
     return ((uint32_t)sym << 6) | (K_MATCH << 4) | (uint32_t)len;
+#endif
 }
 // code-length alphabet: the symbol itself is the value
 __device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 6) | (uint32_t)len; }
@@ -392,8 +407,12 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                         sym = 0x80010000u | (e >> 6);
                         staged += 1;
                     } else {
+#if INFL_WIDE
+                        const uint32_t len = (e >> 10) + br.take((int)((e >> 6) & 0xFu));
+#else
                         const uint32_t ls = c_len_sym[e >> 6];
                         const uint32_t len = (ls & 0xFFFFu) + br.take((int)(ls >> 16));
+#endif
                         br.refill();
                         uint32_t d = T.dist[br.peek(DIST_BITS)];
                         if (((d >> 4) & 3u) == K_SPECIAL) {
@@ -407,8 +426,12 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                             }
                         }
                         br.drop((int)(d & 0xFu));
+#if INFL_WIDE
+                        const uint32_t dist = (d >> 10) + br.take((int)((d >> 6) & 0xFu));
+#else
                         const uint32_t ds = c_dist_sym[d >> 6];
                         const uint32_t dist = (ds & 0xFFFFu) + br.take((int)(ds >> 16));
+#endif
                         sym = (len << 16) | dist;
                         staged += len;
                     }
@@ -612,7 +635,7 @@ int launch_inflate(const uint8_t* comp, const InflateMember* members, int n, uin
     if (lanes == 32) {
         inflate_kernel<32, INFL_WARPS><<<blocks, INFL_WARPS * 32, 0, stream>>>(comp, members, n, out, errors);
     } else {
-        constexpr int W8 = 2;   // warps per block: 8 members' tables fit the 48 KB of static shared memory
+        constexpr int W8 = INFL_WIDE ? 1 : 2;   // warps per block: the members' tables must fit the 48 KB of static shared memory
         const int per_block = W8 * 4;
         const int blocks8 = std::max(1, std::min((n + per_block - 1) / per_block, sm_count * 4));
         inflate_kernel<8, W8><<<blocks8, W8 * 32, 0, stream>>>(comp, members, n, out, errors);
