@@ -314,15 +314,17 @@ ReadPipeline::ReadPipeline(Context& ctx, FastqReader* r1, FastqReader* r2, int n
             size_t n = 0;
             const BgzfIndex* image = nullptr;
             if (r->memory_text(&t, &n)) return n > 0;
-            return device_inflate_enabled() && r->bgzf_image(&image) && image->text_size() > 0;
+            size_t begin = 0, end = 0;
+            return device_inflate_enabled() && r->bgzf_image(&image, &begin, &end) && end > begin;
         };
         auto open = [&](FastqReader* r, int mate, bool odd) {
             const char* t = nullptr;
             size_t n = 0;
             const BgzfIndex* image = nullptr;
             if (r->memory_text(&t, &n)) return new DeviceIngest(ctx_, t, n, nthreads_, mate, odd);
-            r->bgzf_image(&image);
-            return new DeviceIngest(ctx_, image, nthreads_, mate, odd);
+            size_t begin = 0, end = 0;
+            r->bgzf_image(&image, &begin, &end);
+            return new DeviceIngest(ctx_, image, nthreads_, mate, odd, begin, end);
         };
         if (readable(r1_) && (!r2_ || readable(r2_))) {
             ingest_[0].reset(open(r1_, 0, want_odd_));

@@ -46,6 +46,15 @@ public:
         (void)text_offset;
         return false;
     }
+    // ... and can be told to end at a byte of their text (a part of a file that several devices share)
+    virtual void set_text_range(size_t begin, size_t end) {
+        (void)begin;
+        (void)end;
+    }
+    virtual void text_range(size_t* begin, size_t* end) const {
+        *begin = 0;
+        *end = 0;
+    }
 };
 
 namespace {
@@ -168,15 +177,27 @@ public:
         skip_ = b < index_.blocks.size() ? text_offset - index_.text_off[b] : 0;
         return true;
     }
+    void set_text_range(size_t begin, size_t end) override {
+        begin_ = std::min(begin, index_.text_size());
+        limit_ = std::min(std::max(end, begin_), index_.text_size());
+        seek(begin_);
+    }
+    void text_range(size_t* begin, size_t* end) const override {
+        *begin = begin_;
+        *end = limit_ == (size_t)-1 ? index_.text_size() : limit_;
+    }
     void window(size_t keep_from, const char** base, size_t* avail, bool* final) override {
         const std::vector<BgzfBlock>& blocks_ = index_.blocks;
         const size_t tail = filled_ - keep_from;
         if (keep_from > 0 && tail > 0) std::memmove(buf_.data(), buf_.data() + keep_from, tail);
         filled_ = tail;
-        if (next_ < blocks_.size()) {
-            // the next batch of members: about kBatch bytes of text
+        const size_t limit = limit_ == (size_t)-1 ? index_.text_size() : limit_;
+        if (next_ < blocks_.size() && index_.text_off[next_] < limit) {
+            // the next batch of members: about kBatch bytes of text (never beyond the member that holds the end of the range)
             size_t last = next_, bytes = 0;
-            while (last < blocks_.size() && (bytes == 0 || bytes + blocks_[last].isize <= kBatch)) bytes += blocks_[last++].isize;
+            while (last < blocks_.size() && index_.text_off[last] < limit && (bytes == 0 || bytes + blocks_[last].isize <= kBatch)) {
+                bytes += blocks_[last++].isize;
+            }
             if (buf_.size() < filled_ + bytes) buf_.resize(filled_ + bytes);
             std::vector<size_t> at(last - next_ + 1, filled_);
             for (size_t k = next_; k < last; ++k) at[k - next_ + 1] = at[k - next_] + blocks_[k].isize;
@@ -199,6 +220,8 @@ public:
             }
             filled_ = at.back();
             next_ = last;
+            // text beyond the end of the range is not this reader's
+            if (index_.text_off[last] > limit) filled_ -= std::min(filled_, index_.text_off[last] - limit);
             if (skip_) {
                 // a reader resumed inside a member: drop the text in front of that byte
                 const size_t drop = std::min(skip_, filled_);
@@ -209,13 +232,15 @@ public:
         }
         *base = buf_.data();
         *avail = filled_;
-        *final = next_ >= blocks_.size();
+        *final = next_ >= blocks_.size() || index_.text_off[next_] >= limit;
     }
 
 private:
     static constexpr size_t kBatch = 64u << 20;
 
     BgzfInput(int fd, void* map, size_t size) : fd_(fd), map_(map), size_(size) {}
+
+    size_t begin_ = 0, limit_ = (size_t)-1;   // the part of the text this reader delivers
 
     int fd_;
     void* map_;
@@ -292,11 +317,17 @@ bool FastqReader::memory_text(const char** data, size_t* size) const {
     return !started_ && in_->memory(data, size);
 }
 
-bool FastqReader::bgzf_image(const BgzfIndex** index) const {
+bool FastqReader::bgzf_image(const BgzfIndex** index, size_t* text_begin, size_t* text_end) const {
     if (started_ || !in_->bgzf()) return false;
     *index = in_->bgzf();
+    size_t b = 0, e = 0;
+    in_->text_range(&b, &e);
+    if (text_begin) *text_begin = b;
+    if (text_end) *text_end = e;
     return true;
 }
+
+void FastqReader::set_text_range(size_t begin, size_t end) { in_->set_text_range(begin, end); }
 
 void FastqReader::resume_at(size_t offset, long long nrecords) {
     if (in_->seek(offset)) {

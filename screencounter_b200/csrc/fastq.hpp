@@ -52,7 +52,10 @@ public:
     // been read from yet: the device-side reader (ingest.hpp) takes the text from there.
     bool memory_text(const char** data, size_t* size) const;
     // A block-gzip input that has not been read from yet: its member index (the device-side reader inflates the members itself).
-    bool bgzf_image(const struct BgzfIndex** index) const;
+    // [*text_begin, *text_end): the part of the text this reader delivers (the whole of it unless set_text_range() narrowed it).
+    bool bgzf_image(const struct BgzfIndex** index, size_t* text_begin = nullptr, size_t* text_end = nullptr) const;
+    // Block-gzip inputs only, before the first read: deliver the bytes [begin, end) of the text, both record boundaries.
+    void set_text_range(size_t begin, size_t end);
     // Continues the host parse at byte `offset` of such an input -- the start of record number `nrecords` (0-based),
     // everything before it having been consumed elsewhere as four-line records.
     void resume_at(size_t offset, long long nrecords);

@@ -434,24 +434,27 @@ DeviceIngest::DeviceIngest(Context& ctx, const char* text, size_t size, int nthr
     setup(page_locked(text_, text_ + size_ - 1));
 }
 
-DeviceIngest::DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd)
-    : bgzf_(image), ctx_(ctx), text_(nullptr), size_(image->text_size()), nthreads_(std::max(1, nthreads)), mate_(mate ? 1 : 0),
-      want_odd_(want_odd) {
+DeviceIngest::DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd, size_t text_begin, size_t text_end)
+    : bgzf_(image), ctx_(ctx), text_(nullptr), size_(std::min(text_end, image->text_size())), nthreads_(std::max(1, nthreads)),
+      mate_(mate ? 1 : 0), want_odd_(want_odd) {
     ctx_.ensure_ready();
-    // the text's last byte decides whether a newline has to be appended: the last member that holds text, inflated here
+    text_begin = std::min(text_begin, size_);
+    if (text_begin >= size_) throw Error("empty part of a block-gzip text");
+    consumed_ = text_begin;
+    // the part's last byte decides whether a newline has to be appended: the member that holds it, inflated here
     {
-        size_t b = bgzf_->blocks.size();
-        while (b > 0 && bgzf_->blocks[b - 1].isize == 0) --b;
         std::string last;
-        if (b > 0) fetch_text(bgzf_->text_off[b] - 1, 1, last);
+        fetch_text(size_ - 1, 1, last);
         virtual_newline_ = last.empty() || last[0] != '\n';
     }
     // a chunk = a run of whole members holding at most chunk_ bytes of text (never less than one member can hold)
     // (cutting a small file into several chunks so that its parse starts while members still inflate was measured: slower, 6.4
     // against 4.5 ms for 157 MB of text -- a member takes 1.7 ms however few there are, and every chunk costs a host round trip)
     chunk_ = std::max<size_t>(env_size("SCG_INGEST_CHUNK", kBgzfChunk, 64, 1u << 30), 1u << 16) / 16 * 16;
-    const size_t nb = bgzf_->blocks.size();
-    size_t b = 0;
+    // the members that hold the part: from the one with its first byte to the one with its last
+    size_t b = bgzf_->block_of(text_begin);
+    const size_t nb = bgzf_->block_of(size_ - 1) + 1;
+    skip_front_ = text_begin - bgzf_->text_off[b];
     while (b < nb) {
         const size_t first = b;
         size_t bytes = 0;
@@ -481,7 +484,7 @@ void DeviceIngest::setup(bool source_pinned) {
         SCG_CUDA_CHECK(cudaMemsetAsync(B.inflate_errors.ptr, 0, 16, B.copy_stream));
         SCG_CUDA_CHECK(cudaStreamSynchronize(B.copy_stream));   // (the chunks' kernels run on several streams)
     }
-    ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_));
+    ingest_init<<<1, 1, 0, ctx_.stream>>>(B.state.as<IngestState>(), (uint32_t)(slot_base(0) + carry_ + skip_front_));
     SCG_CUDA_CHECK(cudaGetLastError());
     ++ctx_.launches;
     ctx_.timing.reader = bgzf_ ? (pinned_source_ ? "device (block-gzip members copied from page-locked memory, inflated on the device)"

@@ -53,7 +53,10 @@ public:
     // members), and are inflated on the device (inflate.cuh) straight into the text ring; everything after that is the same.
     // A member the device cannot inflate (or whose CRC does not match) stops the device reader before that chunk and the
     // host reader, which raises the error, takes over.
-    DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd);
+    // [text_begin, text_end): the part of the text to read (both ends record boundaries; (size_t)-1 = up to the end of the text) --
+    // one device's share of a file that several devices read.
+    DeviceIngest(Context& ctx, const BgzfIndex* image, int nthreads, int mate, bool want_odd, size_t text_begin = 0,
+                 size_t text_end = (size_t)-1);
     ~DeviceIngest();
 
     // Parses the next chunk.  false = the text is exhausted (and `out.n` is 0).  Same as stage() + complete().
@@ -91,6 +94,7 @@ private:
     // block-gzip input
     const BgzfIndex* bgzf_ = nullptr;
     std::vector<size_t> chunk_block_;   // first member of each chunk, and the number of members at the end
+    size_t skip_front_ = 0;             // text bytes of the first member that precede the part being read
     size_t max_comp_ = 0;               // most compressed bytes any chunk holds
     size_t max_members_ = 0;
     std::vector<char> block_cache_;     // host-inflated member for raw_read()

@@ -18,6 +18,8 @@
 #include <thread>
 
 #include "api_common.hpp"
+#include "bgzf.hpp"
+#include "ingest.hpp"
 #include "launchers.hpp"
 #include "matchers.hpp"
 
@@ -72,13 +74,33 @@ bool count_single_multi(scg_ctx* ctx, FastqReader& reader, const char* constant,
                         int mismatches, bool use_first, int nthreads, int32_t* counts, int32_t* total, scg_result** trace) {
     const char* text = nullptr;
     size_t size = 0;
-    if (!reader.memory_text(&text, &size)) return false;   // a gzip stream: one device reads it
+    const BgzfIndex* image = nullptr;
+    const bool raw = reader.memory_text(&text, &size);
+    if (!raw) {
+        // a block-gzip file is cut the same way, in the coordinates of its TEXT: a part begins inside some member, at a record
+        // start guessed on that member's (and the next one's) text, inflated here on the host; a plain gzip stream cannot be cut
+        size_t b = 0;
+        if (!device_inflate_enabled() || !reader.bgzf_image(&image, &b, &size) || b != 0) return false;
+    }
     const std::vector<scg_ctx*> all = device_contexts(ctx);
     const int ndev = (int)all.size();
     if (size < split_threshold() * (size_t)ndev) return false;
     std::vector<size_t> cuts{ 0 };
+    std::vector<char> around;
     for (int k = 1; k < ndev; ++k) {
-        const size_t g = guess_fastq_record_start(text, size, size / ndev * k);
+        const size_t target = size / ndev * k;
+        size_t g = (size_t)-1;
+        if (raw) {
+            g = guess_fastq_record_start(text, size, target);
+        } else {
+            const size_t blk = image->block_of(target);
+            if (blk >= image->blocks.size()) return false;
+            const size_t n0 = image->blocks[blk].isize, n1 = blk + 1 < image->blocks.size() ? image->blocks[blk + 1].isize : 0;
+            around.resize(n0 + n1 + 1);
+            if (!bgzf_inflate_block(*image, blk, around.data()) || (n1 && !bgzf_inflate_block(*image, blk + 1, around.data() + n0))) return false;
+            const size_t local = guess_fastq_record_start(around.data(), n0 + n1, target - image->text_off[blk]);
+            if (local != (size_t)-1) g = image->text_off[blk] + local;
+        }
         if (g == (size_t)-1 || g <= cuts.back() || g >= size) return false;
         cuts.push_back(g);
     }
@@ -107,7 +129,8 @@ bool count_single_multi(scg_ctx* ctx, FastqReader& reader, const char* constant,
             // end proves that the next cut is one too (the parser never looks behind a record's start), so by induction the
             // parts are exactly the records of the whole file.  Anything else throws here and the caller starts over on one
             // device, which also raises the reference's error with the right line number.
-            FastqReader sub(nullptr, text + cuts[d], cuts[d + 1] - cuts[d]);
+            FastqReader sub(nullptr, raw ? text + cuts[d] : reinterpret_cast<const char*>(image->image), raw ? cuts[d + 1] - cuts[d] : image->image_size);
+            if (!raw) sub.set_text_range(cuts[d], cuts[d + 1]);
             part.reads = count_single_core(c, &sub, *m, nthreads, part.d_counts.as<int32_t>(), part.sink);
             SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
             c.timing.parse_s = sub.parse_seconds();

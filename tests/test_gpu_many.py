@@ -146,3 +146,34 @@ def test_files_of_every_format_in_one_call(tmp_path):
         for f, text in enumerate(texts):
             counts, total = _oracle().count_single(text, TEMPLATE, 2, pool, 1, False)
             assert total == totals[f] and np.array_equal(matrix[:, f], counts), (devices, f)
+
+
+@pytest.mark.parametrize("devices", _device_sets()[1:], ids=str)
+@pytest.mark.parametrize("block", [1500, 65280])
+def test_one_block_gzip_file_cut_over_the_devices(devices, block, monkeypatch, tmp_path):
+    """The same for a block-gzip input: the cuts are made in the coordinates of the TEXT (a part begins inside some member, at a
+    record start found on that member's text), every device inflates and reads the members that hold its part."""
+    from screencounter_b200 import rcpp
+    from util import bgzf
+    monkeypatch.setenv("SCG_MULTI_MIN_BYTES", "1000")
+    rng = np.random.default_rng(14)
+    pool = distinct_pool(rng, 200, 20)
+    reads = adversarial_reads(rng, 15000, TEMPLATE, [pool], strand="both")
+    text = fastq(reads)
+    want_index, want_info = _oracle().trace_single(text, TEMPLATE, 2, pool, 1, False)
+    image = bgzf(text, block)
+    path = tmp_path / "reads.fastq.gz"
+    path.write_bytes(image)
+    for src in (image, str(path)):
+        counts, total, (index, info) = rcpp.count_single_barcodes(src, TEMPLATE, 2, pool, 1, False, 2, trace=True, device=devices)
+        t = rcpp.timing(devices)
+        assert "devices" in t["kernel"] and "inflated on the device" in t["reader"], t
+        assert total == len(reads)
+        assert np.array_equal(index, want_index) and np.array_equal(info, want_info)
+        assert np.array_equal(counts, np.bincount(want_index[want_index >= 0], minlength=len(pool)))
+    # a wrapped record in the middle: some part does not parse cleanly, one device reads the whole file, same answer
+    half = len(reads) // 2
+    wrapped = ("@wrapped\n" + reads[half][:10] + "\n" + reads[half][10:] + "\n+\n" + "I" * len(reads[half]) + "\n").encode()
+    odd = fastq(reads[:half]) + wrapped + fastq(reads[half + 1:])
+    c2, t2 = rcpp.count_single_barcodes(bgzf(odd, block), TEMPLATE, 2, pool, 1, False, 2, device=devices)
+    assert t2 == len(reads) and np.array_equal(c2, np.bincount(want_index[want_index >= 0], minlength=len(pool)))
