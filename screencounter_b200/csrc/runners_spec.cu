@@ -500,10 +500,17 @@ void common_macros(std::ostringstream& o, int kind, int min_blocks, int group, i
       << "#define SPH_HAS_INDEX " << has_index << "\n";
 }
 
+// counters of at most this many cells are privatised per block in shared memory (4 bytes a cell: 4 KB keep 8 blocks per SM resident)
+int hist_cells(long long cells) {
+    const long long most = jit_env_int("SCG_SPEC_HIST_MAX", 1024, 0, 8192);
+    return cells > 0 && cells <= most ? (int)((cells + 31) / 32 * 32) : 0;
+}
+
 JitProgram dual_program(const TemplateSpec& t1, const ScanSpec& s1, int mm1, const ReadsDev& r1, const TemplateSpec& t2, const ScanSpec& s2,
-                        int mm2, const ReadsDev& r2, int use_first, int has_index) {
+                        int mm2, const ReadsDev& r2, int use_first, int has_index, int hist) {
     std::ostringstream src;
     common_macros(src, 1, 8, 1, use_first, has_index);
+    src << "#define SPH_HIST " << hist << "\n";
     template_macros(src, "A", t1, s1, mm1, r1);
     template_macros(src, "B", t2, s2, mm2, r2);
     src << "#include \"spec_handlers.cuh\"\n";
@@ -514,9 +521,10 @@ JitProgram dual_program(const TemplateSpec& t1, const ScanSpec& s1, int mm1, con
     return prog;
 }
 
-JitProgram combo_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index) {
+JitProgram combo_program(const TemplateSpec& t, const ScanSpec& s, int mm, const ReadsDev& r, int use_first, int has_index, int hist) {
     std::ostringstream src;
     common_macros(src, 2, 8, 2, use_first, has_index);
+    src << "#define SPH_HIST " << hist << "\n";
     template_macros(src, "A", t, s, mm, r);
     src << "#include \"spec_handlers.cuh\"\n";
     JitProgram prog;
@@ -620,7 +628,7 @@ void launch_dual_pe(Context& ctx, const ReadsDev& r1, const ReadsDev& r2, const 
     } else if (template_fits(m.t1, m.params.spec1, r1, &why) && template_fits(m.t2, m.params.spec2, r2, &why)) {
         group = jit_env_int("SCG_SPH_GROUP", 1, 1, 8);
         mod = jit_module(dual_program(m.t1, m.params.spec1, m.params.mm1, r1, m.t2, m.params.spec2, m.params.mm2, r2, m.params.use_first,
-                                      d_index ? 1 : 0),
+                                      d_index ? 1 : 0, hist_cells((long long)m.lib.host.nchoices)),
                          ctx.device, &why);
     }
     if (!mod) {
@@ -695,7 +703,9 @@ void launch_combo(Context& ctx, const ReadsDev& reads, const ComboMatcher& m, co
     if (ok) ok = template_fits(m.tmpl, P.spec, reads, &why);
     if (ok) {
         group = jit_env_int("SCG_SPH_GROUP", 2, 1, 8);
-        mod = jit_module(combo_program(m.tmpl, P.spec, P.max_mm, reads, P.use_first, out_pairs ? 1 : 0), ctx.device, &why);
+        mod = jit_module(combo_program(m.tmpl, P.spec, P.max_mm, reads, P.use_first, out_pairs ? 1 : 0,
+                                       sink.dense ? hist_cells((long long)P.n1 * P.n2) : 0),
+                         ctx.device, &why);
     }
     if (!mod) {
         launch_combo_generic(ctx, reads, P, sink, skip_if_found, out_pairs, ReadList{ nullptr, nullptr }, ctx.grid_for(ntiles), stream);
@@ -900,10 +910,10 @@ int scg_jit_selftest_handler(int kind, const char* constant_a, int strand_a, int
             TemplateSpec tb(constant_b, strand_b);
             const ScanSpec sb = tb.scan_spec(mismatches_b);
             if (!template_fits(tb, sb, fake, &why)) throw Error(why);
-            prog = dual_program(ta, sa, mismatches_a, fake, tb, sb, mismatches_b, fake, use_first, 1);
+            prog = dual_program(ta, sa, mismatches_a, fake, tb, sb, mismatches_b, fake, use_first, 1, read_len % 2 ? 64 : 0);
         } else if (kind == 2) {
             if (ta.fwd_regions.size() != 2) throw Error("expected 2 variable regions in the constant template");
-            prog = combo_program(ta, sa, mismatches_a, fake, use_first, 1);
+            prog = combo_program(ta, sa, mismatches_a, fake, use_first, 1, read_len % 2 ? 64 : 0);
         } else if (kind == 3 || kind == 4) {   // 4 = the variant that lists the barcodes by table part
             if (ta.fwd_regions.empty()) throw Error("expected at least one variable region in the constant template");
             prog = random_program(ta, sa, mismatches_a, fake, use_first, 1, kind == 4 ? 1 : 0);

@@ -32,6 +32,9 @@
 #ifndef SPH_PARTITIONED
 #define SPH_PARTITIONED 0
 #endif
+#ifndef SPH_HIST
+#define SPH_HIST 0   // > 0: the design's counters (pool rows / cells of the dense combination matrix) privatised per block in shared memory
+#endif
 #ifndef SPH_A_FSTART1
 #define SPH_A_FSTART1 0
 #define SPH_A_FLEN1 1
@@ -127,6 +130,11 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     __shared__ __align__(128) uint32_t stage_a[WARPS][STAGES][GROUP * DA::TILE_WORDS];
     __shared__ __align__(128) uint32_t stage_b[WARPS][STAGES][GROUP * DB::TILE_WORDS];
     __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
+#if SPH_HIST
+    __shared__ int32_t hist[SPH_HIST];
+    for (int k = threadIdx.x; k < SPH_HIST; k += BLOCK) hist[k] = 0;
+    __syncthreads();
+#endif
 
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -246,7 +254,11 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             const bool slowp = (m & PM_SLOW) != 0;
             const bool defer = (m & PM_MISS_DEFERS) && index < 0;
             if ((m & PM_INRANGE) && !defer && !slowp) {
+#if SPH_HIST
+                if (index >= 0) atomicAdd(&hist[index], 1);
+#else
                 if (index >= 0) atomicAdd(counts + index, 1);
+#endif
                 if (SPH_HAS_INDEX) __stcs(out_index + pi, index);
             }
             const uint32_t entry[DUAL_DEFER_WORDS] = { pi, px, py, pz, pn_lo, pn_hi_caps };
@@ -286,6 +298,14 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
         }
     }
     if (lane == 0) def.warp_counts[warp] = cursor;
+#if SPH_HIST
+    // flush the block's private counters: one global atomic per row that was hit
+    __syncthreads();
+    for (int k = threadIdx.x; k < SPH_HIST; k += BLOCK) {
+        const int32_t v = hist[k];
+        if (v) atomicAdd(counts + k, v);
+    }
+#endif
 }
 #endif  // SPH_KIND == 1
 
@@ -303,6 +323,11 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
     constexpr uint32_t BYTES_A = GROUP * DA::TILE_BYTES;
     __shared__ __align__(128) uint32_t stage_a[WARPS][STAGES][GROUP * DA::TILE_WORDS];
     __shared__ __align__(8) unsigned long long bar_all[WARPS][STAGES];
+#if SPH_HIST
+    __shared__ int32_t hist[SPH_HIST];   // the dense n1 x n2 matrix of a small design
+    for (int k = threadIdx.x; k < SPH_HIST; k += BLOCK) hist[k] = 0;
+    __syncthreads();
+#endif
 
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -406,7 +431,11 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
             // reverse strand: region r of the read is pool 1 - r (:111-116)
             const int id0 = rev ? id_b : id_a, id1 = rev ? id_a : id_b;
             if ((m & PM_INRANGE) && !defer && !slowp) {
+#if SPH_HIST
+                if (found) atomicAdd(&hist[id0 * sink.n2 + id1], 1);
+#else
                 if (found) combo_count(sink, id0, id1);
+#endif
                 if (SPH_HAS_INDEX) {
                     __stcs(reinterpret_cast<int2*>(out_pairs) + pi, found ? make_int2(id0, id1) : make_int2(-1, -1));
                 }
@@ -460,6 +489,13 @@ extern "C" __global__ void __launch_bounds__(128, SPH_MIN_BLOCKS)
         }
     }
     if (lane == 0) def.warp_counts[warp] = cursor;
+#if SPH_HIST
+    __syncthreads();
+    for (int k = threadIdx.x; k < SPH_HIST; k += BLOCK) {
+        const int32_t v = hist[k];
+        if (v) atomicAdd(sink.dense + k, v);
+    }
+#endif
 }
 #endif  // SPH_KIND == 2
 
