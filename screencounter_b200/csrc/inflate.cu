@@ -378,6 +378,12 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
             // ---- the block's symbols, a batch at a time ----
             bool end_of_block = false;
             while (!end_of_block && !bad) {
+                // a damaged stream must not read its way out of the image: no batch starts beyond the member's own bytes
+                if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt >
+                    ((size_t)M.in_off + M.in_len) * 8) {
+                    bad = true;
+                    break;
+                }
                 uint32_t my = 0;   // symbol parked in this lane: literal = 1 << 31 | 1 << 16 | byte; match = len << 16 | dist
                 int nsym = 0;
                 uint32_t staged = 0;   // bytes the batch produces so far (warp-uniform)

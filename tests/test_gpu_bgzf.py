@@ -83,7 +83,7 @@ def test_library_compressor_round_trip():
     assert gzip.decompress(rcpp.bgzf_compress(b"").tobytes()) == b""
 
 
-@pytest.mark.parametrize("damage", ["payload", "crc", "isize_short", "isize_long"])
+@pytest.mark.parametrize("damage", ["payload", "payload_of_the_last_member", "crc", "isize_short", "isize_long"])
 def test_corrupt_members_are_refused(gpu, kref, damage, tmp_path, monkeypatch):
     """A member whose stream is damaged, whose CRC does not match or whose declared size is wrong is an error, on the device
     inflater alone and through the counting call (where the host reader takes over at that chunk and raises it)."""
@@ -98,6 +98,17 @@ def test_corrupt_members_are_refused(gpu, kref, damage, tmp_path, monkeypatch):
     if damage == "payload":
         for k in range(40, 60):
             image[second + 18 + k] ^= 0x5A
+    elif damage == "payload_of_the_last_member":
+        # the last member that holds text, its whole stream turned into noise: the inflater must neither run out of the image
+        # nor take long to notice
+        at, members = 0, []
+        while at < len(image):
+            members.append(at)
+            at += struct.unpack("<H", image[at + 16:at + 18])[0] + 1
+        last = members[-2]
+        size = struct.unpack("<H", image[last + 16:last + 18])[0] + 1
+        noise = np.random.default_rng(1).integers(0, 256, size - 26, dtype=np.uint8).tobytes()
+        image[last + 18:last + size - 8] = noise
     elif damage == "crc":
         image[second + second_len - 8] ^= 1
     else:
