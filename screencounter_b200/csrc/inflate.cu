@@ -33,20 +33,15 @@ constexpr int INFL_WARPS = 4;   // warps per block
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr uint32_t STAGE_BYTES = 2048;   // text assembled per batch at most; a batch closes once it could not take another 258-byte match
 
-// table entry (16 bits, so that a warp's tables stay under 3 KiB and 32 warps fit an SM): value << 6 | kind << 4 | code length,
-// value = the literal byte, or the index of the length / distance symbol (base and extra bits come from the constant arrays).
-// Everything that is not a plain literal or match is K_SPECIAL, told apart off the hot path: code length 0 with value 1 = a code
-// longer than the table (bit-by-bit walk), code length 0 with value 0 = no such code, otherwise the end-of-block code.
-constexpr uint32_t K_LITERAL = 0, K_MATCH = 1, K_SPECIAL = 2;
-constexpr uint32_t E_INVALID = K_SPECIAL << 4, E_LONG = (1u << 6) | (K_SPECIAL << 4);
-#ifndef INFL_WIDE
-#define INFL_WIDE 0   // 1: 32-bit entries that carry a match symbol's base value and extra bits themselves (measured, not adopted)
-#endif
-#if INFL_WIDE
-using Entry = uint32_t;
-#else
+// table entry (16 bits, so that a warp's tables stay under 3 KiB and 32 warps fit an SM); bits 0-3 = code length, 0 for
+// everything off the hot path (E_INVALID no such code, E_LONG a code longer than the table: bit-by-bit walk, E_EOB end of block).
+//   literal/length table: literal  = byte << 8 | code length
+//                         length   = (base - 3) << 8 | extra bits << 5 | 1 << 4 | code length      (RFC 1951 3.2.5: base 3 .. 258)
+//   distance table:       distance = m << 8 | extra bits << 4 | code length, base = (m << extra bits) + 1  (m = 0 .. 3)
+// so a match costs no further table: the symbol's base and its number of extra bits travel in the entry.
+constexpr uint32_t E_INVALID = 0, E_LONG = 1u << 8, E_EOB = 2u << 8;
+constexpr uint32_t E_MATCH = 1u << 4;
 using Entry = uint16_t;
-#endif
 
 struct WarpTables {
     Entry lit[1 << LIT_BITS];
@@ -56,40 +51,32 @@ struct WarpTables {
     uint16_t lit_sorted[288 + 32];            // symbols in canonical order (per length, ascending)
     uint16_t dist_sorted[32 + 32];
     uint8_t lens[288 + 32 + 32];              // code lengths of the block being set up
+    uint32_t syms[32], sym_off[32];           // the batch: its symbols (see the kernel) and where their text starts in the batch
     uint32_t stage[STAGE_BYTES / 4 + 2];      // the text of the batch being assembled (+ alignment slack)
 };
 
-// base value | extra bits << 16 of the length symbols 257 .. 285 and of the distance symbols 0 .. 29 (RFC 1951 3.2.5)
+// base value | extra bits << 16 of the length symbols 257 .. 285 (RFC 1951 3.2.5); only the table build reads it
 #define SCG_BE(base, extra) ((uint32_t)(base) | ((uint32_t)(extra) << 16))
 __constant__ uint32_t c_len_sym[29] = { SCG_BE(3, 0),  SCG_BE(4, 0),  SCG_BE(5, 0),  SCG_BE(6, 0),   SCG_BE(7, 0),   SCG_BE(8, 0),   SCG_BE(9, 0),   SCG_BE(10, 0),
                                         SCG_BE(11, 1), SCG_BE(13, 1), SCG_BE(15, 1), SCG_BE(17, 1),  SCG_BE(19, 2),  SCG_BE(23, 2),  SCG_BE(27, 2),  SCG_BE(31, 2),
                                         SCG_BE(35, 3), SCG_BE(43, 3), SCG_BE(51, 3), SCG_BE(59, 3),  SCG_BE(67, 4),  SCG_BE(83, 4),  SCG_BE(99, 4),  SCG_BE(115, 4),
                                         SCG_BE(131, 5), SCG_BE(163, 5), SCG_BE(195, 5), SCG_BE(227, 5), SCG_BE(258, 0) };
-__constant__ uint32_t c_dist_sym[30] = { SCG_BE(1, 0),     SCG_BE(2, 0),     SCG_BE(3, 0),     SCG_BE(4, 0),      SCG_BE(5, 1),      SCG_BE(7, 1),
-                                         SCG_BE(9, 2),     SCG_BE(13, 2),    SCG_BE(17, 3),    SCG_BE(25, 3),     SCG_BE(33, 4),     SCG_BE(49, 4),
-                                         SCG_BE(65, 5),    SCG_BE(97, 5),    SCG_BE(129, 6),   SCG_BE(193, 6),    SCG_BE(257, 7),    SCG_BE(385, 7),
-                                         SCG_BE(513, 8),   SCG_BE(769, 8),   SCG_BE(1025, 9),  SCG_BE(1537, 9),   SCG_BE(2049, 10),  SCG_BE(3073, 10),
-                                         SCG_BE(4097, 11), SCG_BE(6145, 11), SCG_BE(8193, 12), SCG_BE(12289, 12), SCG_BE(16385, 13), SCG_BE(24577, 13) };
 __constant__ uint8_t c_clen_order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
 
-// what a code of `len` bits for `sym` stands for, as a table entry (0 = a symbol the format does not define)
+// what a code of `len` bits for `sym` stands for, as a table entry (E_INVALID = a symbol the format does not define)
 __device__ __forceinline__ uint32_t lit_entry(int sym, int len) {
-    if (sym < 256) return ((uint32_t)sym << 6) | (K_LITERAL << 4) | (uint32_t)len;
-    if (sym == 256) return (K_SPECIAL << 4) | (uint32_t)len;
+    if (sym < 256) return ((uint32_t)sym << 8) | (uint32_t)len;
+    if (sym == 256) return E_EOB;   // its code length is looked up where the block ends
     if (sym > 285) return E_INVALID;
-#if INFL_WIDE
-    return ((c_len_sym[sym - 257] & 0xFFFFu) << 10) | ((c_len_sym[sym - 257] >> 16) << 6) | (K_MATCH << 4) | (uint32_t)len;
-#else
-    return ((uint32_t)(sym - 257) << 6) | (K_MATCH << 4) | (uint32_t)len;
-#endif
+    const uint32_t be = c_len_sym[sym - 257];
+    return (((be & 0xFFFFu) - 3u) << 8) | ((be >> 16) << 5) | E_MATCH | (uint32_t)len;
 }
+// distance symbol s >= 2 has s / 2 - 1 extra bits and base ((2 | s & 1) << extra bits) + 1; symbols 0 and 1 are distances 1 and 2
 __device__ __forceinline__ uint32_t dist_entry(int sym, int len) {
     if (sym > 29) return E_INVALID;
-#if INFL_WIDE
-    return ((c_dist_sym[sym] & 0xFFFFu) << 10) | ((c_dist_sym[sym] >> 16) << 6) | (K_MATCH << 4) | (uint32_t)len;
-#else
-    return ((uint32_t)sym << 6) | (K_MATCH << 4) | (uint32_t)len;
-#endif
+    const uint32_t extra = sym < 2 ? 0u : (uint32_t)(sym / 2 - 1);
+    const uint32_t m = sym < 2 ? (uint32_t)sym : (2u | ((uint32_t)sym & 1u));
+    return (m << 8) | (extra << 4) | (uint32_t)len;
 }
 // code-length alphabet: the symbol itself is the value
 __device__ __forceinline__ uint32_t clen_entry(int sym, int len) { return ((uint32_t)sym << 6) | (uint32_t)len; }
@@ -101,7 +88,7 @@ template <int KIND, int TBITS, int GL>
 __device__ bool build_table(const uint8_t* lens, int n, Entry* table, uint16_t* sorted, uint32_t* count, uint32_t* next, uint32_t* offs,
                             uint32_t gm, int gl) {
     const uint32_t below = (1u << (threadIdx.x & 31)) - 1u;   // the lanes in front of this one
-    for (int i = gl; i < (1 << TBITS); i += GL) table[i] = (Entry)(KIND == 2 ? 0u : E_INVALID);
+    for (int i = gl; i < (1 << TBITS); i += GL) table[i] = (Entry)E_INVALID;
     for (int i = gl; i < 16; i += GL) count[i] = 0;
     __syncwarp(gm);
     for (int s = gl; s < n; s += GL) {
@@ -171,14 +158,16 @@ __device__ __forceinline__ bool slow_symbol(unsigned long long bits, const uint3
     return false;
 }
 
-// The compressed stream as seen by the group: 64 bits of look-ahead, refilled from two register-resident lines of GL words.
+// The compressed stream as seen by the group: a window of 64 bits of the stream that stays put between refills, and the
+// number of its bits already consumed -- taking bits moves the position (one add), looking at bits is one 64-bit shift.  The
+// window is refilled, 32 bits at a time, from two register-resident lines of GL words.
 template <int GL>
 struct BitReader {
     const uint32_t* words;      // 4-byte aligned base of the stream
     uint32_t line_cur, line_next;
-    uint32_t widx;              // words consumed so far (uniform in the group)
-    unsigned long long bits;
-    int cnt;
+    uint32_t widx;              // words taken into the window so far (uniform in the group)
+    unsigned long long bits;    // stream bits [32 * (widx - 2), 32 * widx)
+    int bp;                     // bits of the window consumed
     uint32_t gm;
     int gl;
 
@@ -189,13 +178,9 @@ struct BitReader {
         line_cur = words[gl];
         line_next = words[GL + gl];
         widx = 0;
-        bits = 0;
-        cnt = 0;
-        refill();
-        const int skip = (int)(byte_off & 3) * 8;
-        bits >>= skip;
-        cnt -= skip;
-        refill();
+        const uint32_t lo = next_word();
+        bits = (unsigned long long)lo | ((unsigned long long)next_word() << 32);
+        bp = (int)(byte_off & 3) * 8;
     }
     __device__ __forceinline__ uint32_t next_word() {
         const uint32_t w = __shfl_sync(gm, line_cur, (int)(widx & (uint32_t)(GL - 1)), GL);
@@ -206,25 +191,27 @@ struct BitReader {
         }
         return w;
     }
-    // at least 33 bits afterwards
+    // at least 33 unconsumed bits afterwards
     __device__ __forceinline__ void refill() {
-        if (cnt <= 32) {
-            bits |= (unsigned long long)next_word() << cnt;
-            cnt += 32;
+        if (bp >= 32) {
+            bits = (bits >> 32) | ((unsigned long long)next_word() << 32);
+            bp -= 32;
         }
     }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bits & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(int n) {
-        bits >>= n;
-        cnt -= n;
-    }
+    // the next 32 bits of the stream (all of them valid right after a refill; 64 - bp of them in general)
+    __device__ __forceinline__ uint32_t window() const { return (uint32_t)(bits >> bp); }
+    __device__ __forceinline__ unsigned long long window64() const { return bits >> bp; }
+    __device__ __forceinline__ uint32_t peek(int n) const { return window() & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { bp += n; }
     __device__ __forceinline__ uint32_t take(int n) {
         const uint32_t v = peek(n);
         drop(n);
         return v;
     }
-    // bytes of the stream consumed, counted from the aligned base (after drop-to-byte)
-    __device__ __forceinline__ size_t byte_pos() const { return (size_t)widx * 4 - (size_t)(cnt >> 3); }
+    __device__ __forceinline__ void to_byte_boundary() { bp = (bp + 7) & ~7; }
+    // bits / bytes of the stream consumed, counted from the aligned base
+    __device__ __forceinline__ size_t bit_pos() const { return (size_t)widx * 32 - 64 + (size_t)bp; }
+    __device__ __forceinline__ size_t byte_pos() const { return (size_t)widx * 4 - 8 + (size_t)(bp >> 3); }
 };
 
 // A match of the batch, copied into the stage: byte j comes from batch-relative position off - dist + j (the repeating
@@ -244,6 +231,8 @@ template <int GL, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __restrict__ comp, const InflateMember* __restrict__ members, int n,
                                                              uint8_t* out_base, uint32_t* __restrict__ errors) {
     constexpr int GROUPS = 32 / GL;   // members per warp
+    constexpr int SPL = 32 / GL;      // symbols of a batch per lane
+    constexpr uint32_t SHORT_MATCH = 12;
     __shared__ WarpTables tables[WARPS * GROUPS];
     const int lane32 = threadIdx.x & 31;
     const int lane = lane32 % GL;                  // this lane's place in its group
@@ -264,7 +253,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
         bool last = false;
         while (!last && !bad) {
             // a block header beyond the member's bytes: a damaged stream running away (it must not leave the image)
-            if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt >
+            if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + br.bit_pos() >
                 ((size_t)M.in_off + M.in_len) * 8) {
                 bad = true;
                 break;
@@ -274,7 +263,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
             const uint32_t type = br.take(2);
             if (type == 0) {
                 // ---- stored block: to the byte boundary, LEN, NLEN, LEN raw bytes ----
-                br.drop(br.cnt & 7);
+                br.to_byte_boundary();
                 br.refill();
                 const uint32_t len = br.take(16);
                 br.refill();
@@ -379,84 +368,99 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
             bool end_of_block = false;
             while (!end_of_block && !bad) {
                 // a damaged stream must not read its way out of the image: no batch starts beyond the member's own bytes
-                if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt >
+                if ((size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + br.bit_pos() >
                     ((size_t)M.in_off + M.in_len) * 8) {
                     bad = true;
                     break;
                 }
-                uint32_t my = 0;   // symbol parked in this lane: literal = 1 << 31 | 1 << 16 | byte; match = len << 16 | dist
+                // symbols are parked in shared memory: literal = 1 << 31 | 1 << 16 | byte; match = len << 16 | dist
                 int nsym = 0;
-                uint32_t staged = 0;   // bytes the batch produces so far (warp-uniform)
+                uint32_t staged = 0;   // bytes the batch produces so far (uniform in the group)
 #pragma unroll 1
-                for (; nsym < GL && staged <= STAGE_BYTES - 258; ++nsym) {
+                for (; nsym < 32 && staged <= STAGE_BYTES - 258; ++nsym) {
                     br.refill();
-                    uint32_t e = T.lit[br.peek(LIT_BITS)];
-                    if (((e >> 4) & 3u) == K_SPECIAL) {
+                    const uint32_t w = br.window();   // 32 valid bits: the code (15 at most) and a length's extra bits (5)
+                    uint32_t e = T.lit[w & ((1u << LIT_BITS) - 1u)];
+                    if ((e & 0xFu) == 0) {
                         // off the hot path: a code longer than the table, the end of the block, or no code at all
-                        if (e == E_LONG) {
-                            int sym = 0, len = 0;
-                            e = slow_symbol(br.bits, T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : E_INVALID;
-                        }
-                        if (((e >> 4) & 3u) == K_SPECIAL) {
-                            if ((e & 0xFu) == 0) {
-                                bad = true;
-                            } else {
-                                br.drop((int)(e & 0xFu));
+                        int sym = 256, len = T.lens[256];
+                        if (e == E_LONG) e = slow_symbol(br.window64(), T.lit_count, T.lit_sorted, sym, len) ? lit_entry(sym, len) : E_INVALID;
+                        if ((e & 0xFu) == 0) {
+                            if (e == E_EOB) {
+                                br.drop(len);
                                 end_of_block = true;
+                            } else {
+                                bad = true;
                             }
                             break;
                         }
                     }
-                    br.drop((int)(e & 0xFu));
+                    const uint32_t elen = e & 0xFu;
                     uint32_t sym;
-                    if (((e >> 4) & 3u) == K_LITERAL) {
-                        sym = 0x80010000u | (e >> 6);
+                    if (!(e & E_MATCH)) {
+                        br.drop((int)elen);
+                        sym = 0x80010000u | (e >> 8);
                         staged += 1;
                     } else {
-#if INFL_WIDE
-                        const uint32_t len = (e >> 10) + br.take((int)((e >> 6) & 0xFu));
-#else
-                        const uint32_t ls = c_len_sym[e >> 6];
-                        const uint32_t len = (ls & 0xFFFFu) + br.take((int)(ls >> 16));
-#endif
+                        const uint32_t xl = (e >> 5) & 7u;
+                        const uint32_t len = (e >> 8) + 3u + ((w >> elen) & ((1u << xl) - 1u));
+                        br.drop((int)(elen + xl));
                         br.refill();
-                        uint32_t d = T.dist[br.peek(DIST_BITS)];
-                        if (((d >> 4) & 3u) == K_SPECIAL) {
-                            if (d == E_LONG) {
-                                int dsym = 0, dlen = 0;
-                                d = slow_symbol(br.bits, T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : E_INVALID;
-                            }
-                            if (((d >> 4) & 3u) == K_SPECIAL) {
+                        const uint32_t w2 = br.window();   // the distance code (15 bits at most) and its extra bits (13)
+                        uint32_t d = T.dist[w2 & ((1u << DIST_BITS) - 1u)];
+                        if ((d & 0xFu) == 0) {
+                            int dsym = 0, dlen = 0;
+                            if (d == E_LONG) d = slow_symbol(br.window64(), T.dist_count, T.dist_sorted, dsym, dlen) ? dist_entry(dsym, dlen) : E_INVALID;
+                            if ((d & 0xFu) == 0) {
                                 bad = true;
                                 break;
                             }
                         }
-                        br.drop((int)(d & 0xFu));
-#if INFL_WIDE
-                        const uint32_t dist = (d >> 10) + br.take((int)((d >> 6) & 0xFu));
-#else
-                        const uint32_t ds = c_dist_sym[d >> 6];
-                        const uint32_t dist = (ds & 0xFFFFu) + br.take((int)(ds >> 16));
-#endif
+                        const uint32_t dl = d & 0xFu, xd = (d >> 4) & 0xFu;
+                        const uint32_t dist = ((d >> 8) << xd) + 1u + ((w2 >> dl) & ((1u << xd) - 1u));
+                        br.drop((int)(dl + xd));
                         sym = (len << 16) | dist;
                         staged += len;
                     }
-                    if (lane == nsym) my = sym;
+                    T.syms[nsym] = sym;   // every lane of the group stores the same word
                 }
                 if (bad) break;
-                // ---- where the batch's symbols go ----
-                const uint32_t mylen = lane < nsym ? ((my >> 16) & 0x1FFu) : 0u;
-                uint32_t incl = mylen;
+                __syncwarp(gm);
+                // ---- where the batch's symbols go: lane l looks after symbols [l * SPL, (l + 1) * SPL) ----
+                uint32_t my[SPL], mylen[SPL], off[SPL];
+                uint32_t mine = 0;
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    const int k = lane * SPL + j;
+                    my[j] = k < nsym ? T.syms[k] : 0u;
+                    mylen[j] = (my[j] >> 16) & 0x1FFu;
+                    off[j] = mine;
+                    mine += mylen[j];
+                }
+                uint32_t incl = mine;
 #pragma unroll
                 for (int d = 1; d < GL; d <<= 1) {
                     const uint32_t v = __shfl_up_sync(gm, incl, d, GL);
                     if (lane >= d) incl += v;
                 }
                 const uint32_t total = staged;
-                const uint32_t off = incl - mylen;   // relative to the batch's first byte
-                const bool is_match = lane < nsym && !(my >> 31);
-                const uint32_t mydist = my & 0xFFFFu;
-                if (pos + total > M.out_len || __any_sync(gm, is_match && mydist > pos + off)) {
+                bool too_far = false;
+                uint32_t long_bits = 0, dep_bits = 0;   // this lane's symbols among the batch's 32, by what copies them
+                bool indep_short[SPL];
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    off[j] += incl - mine;   // relative to the batch's first byte
+                    T.sym_off[lane * SPL + j] = off[j];
+                    const bool is_match = mylen[j] != 0 && !(my[j] >> 31);
+                    const uint32_t dist = my[j] & 0xFFFFu;
+                    too_far |= is_match && dist > pos + off[j];
+                    // matches whose source ends before the batch begins: no ordering among them, their loads overlap
+                    const bool indep = is_match && off[j] + mylen[j] <= dist;
+                    indep_short[j] = indep && mylen[j] <= SHORT_MATCH;
+                    if (indep && mylen[j] > SHORT_MATCH) long_bits |= 1u << (lane * SPL + j);
+                    if (is_match && !indep) dep_bits |= 1u << (lane * SPL + j);
+                }
+                if (pos + total > M.out_len || __any_sync(gm, too_far)) {
                     bad = true;
                     break;
                 }
@@ -464,19 +468,23 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                 uint8_t* const done = out + pos;
                 const uint32_t skew = (uint32_t)(reinterpret_cast<size_t>(done) & 3);
                 uint8_t* const stage = reinterpret_cast<uint8_t*>(T.stage) + skew;
-                if (lane < nsym && (my >> 31)) stage[off] = (uint8_t)my;
-                // matches whose source ends before the batch begins: no ordering among them, their loads overlap
-                const bool indep = is_match && off + mylen <= mydist;
-                // Short ones (the rule for the bases of a FASTQ record) are copied by the lanes that hold them, all at once: the
-                // warp runs as many byte steps as the longest of them has bytes, instead of a round of shuffles per match.
-                constexpr uint32_t SHORT_MATCH = 12;
-                if (indep && mylen <= SHORT_MATCH) {
-                    const uint8_t* src = done + ((int)off - (int)mydist);
-                    for (uint32_t j = 0; j < mylen; ++j) stage[off + j] = src[j];
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    if (my[j] >> 31) stage[off[j]] = (uint8_t)my[j];
                 }
-                // the longer ones by all lanes together, four matches at a time: a warp issues in order, so the loads of four
-                // matches go out before the first store waits
-                uint32_t todo = __ballot_sync(gm, indep && mylen > SHORT_MATCH);
+                // Short independent matches (the rule for the bases of a FASTQ record) are copied by the lanes that hold them, all
+                // at once: the warp runs as many byte steps as the longest of them has bytes, instead of a round per match.
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) {
+                    if (indep_short[j]) {
+                        const uint8_t* src = done + ((int)off[j] - (int)(my[j] & 0xFFFFu));
+                        for (uint32_t i = 0; i < mylen[j]; ++i) stage[off[j] + i] = src[i];
+                    }
+                }
+                __syncwarp(gm);   // T.sym_off is read below
+                // the longer ones by all lanes of the group together, four matches at a time: a warp issues in order, so the
+                // loads of four matches go out before the first store waits
+                uint32_t todo = __reduce_or_sync(gm, long_bits);
                 while (todo) {
                     uint32_t sy[4], o[4];
 #pragma unroll
@@ -486,8 +494,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                         if (todo) {
                             const int k = __ffs(todo) - 1;
                             todo &= todo - 1;
-                            sy[u] = __shfl_sync(gm, my, k);
-                            o[u] = __shfl_sync(gm, off, k);
+                            sy[u] = T.syms[k];
+                            o[u] = T.sym_off[k];
                         }
                     }
                     uint8_t v[4];
@@ -507,12 +515,12 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
                     }
                 }
                 // the others read bytes of this batch: in order, each after what precedes it has landed in the stage
-                todo = __ballot_sync(gm, is_match && !indep);
+                todo = __reduce_or_sync(gm, dep_bits);
                 while (todo) {
                     __syncwarp(gm);
                     const int k = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const uint32_t sy = __shfl_sync(gm, my, k), o = __shfl_sync(gm, off, k);
+                    const uint32_t sy = T.syms[k], o = T.sym_off[k];
                     copy_match<GL>(stage, done, o, (sy >> 16) & 0x1FFu, sy & 0xFFFFu, lane);
                 }
                 __syncwarp(gm);
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(const uint8_t* __re
         }
         // the stream must end inside the member and produce exactly its text
         if (!bad) {
-            const size_t end_bit = (size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + (size_t)br.widx * 32 - (size_t)br.cnt;
+            const size_t end_bit = (size_t)(reinterpret_cast<const uint8_t*>(br.words) - comp) * 8 + br.bit_pos();
             bad = pos != M.out_len || end_bit > ((size_t)M.in_off + M.in_len) * 8;
         }
         if (bad && lane == 0) atomicOr(errors, 1u);
@@ -630,21 +638,22 @@ int launch_inflate(const uint8_t* comp, const InflateMember* members, int n, uin
     static const CrcOperator op = make_crc_operator();
     static const bool check_crc = !std::getenv("SCG_BGZF_NO_CRC");
     const int blocks = std::max(1, std::min((n + INFL_WARPS - 1) / INFL_WARPS, sm_count * 8));
-    // One warp per member.  SCG_INFLATE_LANES=8 gives every member eight lanes instead, so that four members share a warp's
-    // (per-lane identical) decoding instructions: measured on the B200, that makes a member 2.5 times slower (the four streams
-    // diverge at every literal / match / refill decision and the warp runs the paths one after the other; copies and table
-    // builds have a quarter of the lanes) and the kernel tops out at 49 GB/s of text instead of 83 -- not adopted.
+    // SCG_INFLATE_LANES = lanes per member: 32 = one warp per member; 16 / 8 = two / four members per warp, which then share
+    // the (per-lane identical) decoding instructions as long as their streams take the same turns, each member's batch of 32
+    // symbols spread over fewer lanes.  Blocks are sized so that the members' tables fit the 48 KB of static shared memory.
     static const int lanes = [] {
         const char* env = std::getenv("SCG_INFLATE_LANES");
-        return env && std::atoi(env) == 8 ? 8 : 32;
+        const int v = env ? std::atoi(env) : 0;
+        return v == 8 || v == 16 ? v : 32;
     }();
     if (lanes == 32) {
         inflate_kernel<32, INFL_WARPS><<<blocks, INFL_WARPS * 32, 0, stream>>>(comp, members, n, out, errors);
+    } else if (lanes == 16) {
+        constexpr int W = 2, per_block = W * 2;
+        inflate_kernel<16, W><<<std::max(1, std::min((n + per_block - 1) / per_block, sm_count * 9)), W * 32, 0, stream>>>(comp, members, n, out, errors);
     } else {
-        constexpr int W8 = INFL_WIDE ? 1 : 2;   // warps per block: the members' tables must fit the 48 KB of static shared memory
-        const int per_block = W8 * 4;
-        const int blocks8 = std::max(1, std::min((n + per_block - 1) / per_block, sm_count * 4));
-        inflate_kernel<8, W8><<<blocks8, W8 * 32, 0, stream>>>(comp, members, n, out, errors);
+        constexpr int W = 1, per_block = W * 4;
+        inflate_kernel<8, W><<<std::max(1, std::min((n + per_block - 1) / per_block, sm_count * 9)), W * 32, 0, stream>>>(comp, members, n, out, errors);
     }
     if (!check_crc) return 1;
     crc_kernel<<<blocks, INFL_WARPS * 32, 0, stream>>>(members, n, out, op, errors);

@@ -345,3 +345,30 @@ def test_block_gzip_on_the_host(tmp_path):
     damaged[5000] ^= 0xFF
     with pytest.raises(Exception, match="corrupt member"):
         rcpp.host_pack_roundtrip(bytes(damaged), 2)
+
+
+def test_block_gzip_index_of_a_large_image_is_walked_in_pieces(monkeypatch):
+    """bgzf_index (csrc/bgzf.cpp) walks an image of more than 8 MiB in pieces on the host pool, each piece starting where three
+    well-formed members follow each other, and accepts the pieces only if their chains link up; the records are those of the
+    text either way, and an image whose chain is broken in the middle is still refused."""
+    from screencounter_b200 import rcpp
+    rng = np.random.default_rng(21)
+    reads = [random_seq(rng, 100) for _ in range(2000)]
+    text = fastq(reads) * 60                                               # 120 000 records, 25 MB of text
+    want = rcpp.host_pack_roundtrip(text, 4)
+    assert len(want) == 120000
+    for level, block in ((0, 65280), (1, 9000)):                           # stored members (image = 25 MB) and small deflated ones
+        image = rcpp.bgzf_compress(text, level=level, block_text=block, nthreads=4).tobytes()
+        if level == 0:
+            assert len(image) > (16 << 20)                                 # at least four pieces
+        assert rcpp.host_pack_roundtrip(image, 4) == want
+        if level == 0:
+            # the magic of a member in the middle is damaged: no chain from the start reaches the end
+            at, k = 0, 0
+            while k < 200:
+                at += int.from_bytes(image[at + 16:at + 18], "little") + 1
+                k += 1
+            damaged = bytearray(image)
+            damaged[at + 1] ^= 0x40
+            with pytest.raises(Exception):
+                rcpp.host_pack_roundtrip(bytes(damaged), 4)
