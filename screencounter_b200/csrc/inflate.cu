@@ -8,12 +8,12 @@
 //     a refill takes its word from the owning lane with a shuffle -- no global-memory latency on the decoding chain;
 //   * code tables are built by all lanes (counting by shared atomics, canonical codes by __match_any ranks, table fill
 //     per symbol);
-//   * symbols are decoded in batches of up to 32 (about 2 KiB of text at most), symbol k parked in lane k; the batch's output
+//   * symbols are decoded in batches of up to 32 (about 2 KiB of text at most), parked in shared memory; the batch's output
 //     offsets are one warp scan; the batch's text is ASSEMBLED IN SHARED MEMORY: literals are stored by their lanes, matches
 //     whose source lies wholly before the batch are fetched from global memory without any ordering between them (their loads
 //     overlap), matches that read bytes of their own batch -- the rule in FASTQ, where a record repeats most of the one before
 //     it -- are copied in order at shared-memory latency; the finished batch goes out to global memory as aligned words.
-// Tables: 10-bit literal/length and 8-bit distance lookup (4-byte entries: value, extra bits, code length), longer codes go
+// Tables: 10-bit literal/length and 8-bit distance lookup (2-byte entries: value or base, extra bits, code length), longer codes go
 // through the canonical count/symbol arrays bit by bit (rare by construction: a code longer than 10 bits has probability
 // < 2^-10).  Text is written to global memory (the FASTQ reader's ring), source bytes of a match are read back from there.
 // A second kernel checks the members' CRC-32 (gzip trailer), one warp per member, 2 KiB per lane, slice-by-4 tables in shared

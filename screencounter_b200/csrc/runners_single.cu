@@ -560,8 +560,6 @@ void count_single_file(scg_ctx* ctx, const scg_source* src, const char* constant
         const SingleMatcher& m = *matcher;
         c.ensure_ready();
         c.timing.setup_s += now_s() - t_setup;
-        static const bool tt = std::getenv("SCG_TIMING_TRACE") != nullptr;
-        if (tt) std::fprintf(stderr, "[tt] open %.3f ms, matcher+ready %.3f ms\n", (t_setup - t_start) * 1e3, (now_s() - t_setup) * 1e3);
 
         // several devices (scg_ctx_create_multi): the file's text is cut at record boundaries and every device counts its part
         if (split_over_devices && !ctx->peers.empty() &&
@@ -575,10 +573,8 @@ void count_single_file(scg_ctx* ctx, const scg_source* src, const char* constant
         d_counts.alloc((size_t)std::max(npool, 1) * sizeof(int32_t), true);
         TraceSink sink;
         sink.enabled = trace != nullptr;
-        const double t_core = now_s();
         const long long nreads = count_single_core(c, source.reader.get(), m, nthreads, d_counts.as<int32_t>(), sink);
         double t0 = now_s();
-        if (tt) std::fprintf(stderr, "[tt] alloc %.3f ms, core %.3f ms (device_s so far %.3f ms)\n", (t_core - t_setup) * 1e3, (t0 - t_core) * 1e3, c.timing.device_s * 1e3);
         SCG_CUDA_CHECK(cudaMemcpyAsync(counts, d_counts.ptr, (size_t)npool * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         SCG_CUDA_CHECK(cudaStreamSynchronize(c.stream));
         c.timing.device_s += now_s() - t0;
