@@ -413,6 +413,7 @@ cudaKernel_t specialised_single_kernel(const SpecSingleConfig& cfg, int device, 
         << "#define SPEC_RAGGED " << cfg.ragged << "\n"
         << "#define SPEC_HIST " << cfg.hist << "\n"
         << "#define SPEC_PRED " << cfg.pred << "\n"
+        << "#define SPEC_UWARP " << jit_env_int("SCG_SPEC_UWARP", 0, 0, 1) << "\n"
         << "#define SPEC_SKIP_GENERAL " << (cfg.ulen > 0 ? 1 : 0) << "\n"
         << "#include \"spec_single.cuh\"\n";
     JitProgram prog;

@@ -121,6 +121,9 @@
 #ifndef SPEC_PRED
 #define SPEC_PRED 0
 #endif
+#ifndef SPEC_UWARP
+#define SPEC_UWARP 0
+#endif
 #ifndef SPEC_HIST
 #define SPEC_HIST 0
 #endif
@@ -969,13 +972,25 @@ extern "C" __global__ void __launch_bounds__(SPEC_BLOCK, SPEC_MIN_BLOCKS)
 #else
     const uint32_t hist_saddr = 0;
 #endif
+#if SPEC_UWARP
+    // An experiment (SCG_SPEC_UWARP=1): the number of the warp read from lane 0, so that the compiler can prove what is
+    // warp-uniform.  It then drops the R2UR traffic and a third of the BSSY/BSYNC pairs (316 instead of 341 instructions per tile,
+    // 48 registers) but moves the bookkeeping of the loop to the uniform datapath: MIO-throttle and scoreboard stalls, 51.9
+    // against 66.9 G reads/s.
+    const int wib = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+#else
     const int wib = threadIdx.x >> 5;
+#endif
     uint32_t(*queue)[QCAP] = queue_all[wib];
     int waiting = 0;   // warp-uniform
 
     const int lane = threadIdx.x & 31;
     const uint32_t lanes_below = (1u << lane) - 1u;
+#if SPEC_UWARP
+    const int warp = (int)(blockIdx.x * (blockDim.x >> 5)) + wib;
+#else
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+#endif
     const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     const uint32_t n = (uint32_t)reads.n;                       // the host sends at most 2^31 - 64 reads per launch
     const int ntiles = (int)((n + TILE - 1) / TILE);
