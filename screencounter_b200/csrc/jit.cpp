@@ -239,6 +239,8 @@ int specialised_blocks_per_sm(cudaKernel_t kernel) {
         cudaGetLastError();
         blocks = 4;
     }
+    // SCG_SPEC_MAX_BLOCKS: fewer blocks than fit (every block's tile ring is shared memory taken from L1, which the scattered probes need)
+    if (const char* v = std::getenv("SCG_SPEC_MAX_BLOCKS")) blocks = std::max(1, std::min(blocks, std::atoi(v)));
     cache[kernel] = blocks;
     return blocks;
 }
